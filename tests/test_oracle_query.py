@@ -1,0 +1,199 @@
+"""Oracle query path (block selection, time trim, version dedup, row predicates, group-by, the five
+aggregation functions, Top) checked against an independent numpy model and against the known answers
+in the reference's pkg/query/vectorized/measure/aggregation_test.go and
+pkg/query/aggregation/function.go semantics.  No GPU needed."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+T0 = 1_700_000_000_000_000_000
+STEP = 60_000_000_000
+
+
+def _build(sids, ts, ver, f_int=None, f_flt=None, region=None, code=None, nulls=None):
+    b = O.PartBuilder()
+    fields = []
+    if f_flt is not None:
+        fields.append(("latency", O.VT_FLOAT64, f_flt, None))
+    if f_int is not None:
+        fields.append(("calls", O.VT_INT64, f_int, nulls))
+    fams = []
+    cols = []
+    if region is not None:
+        cols.append(("region", O.VT_STR, region, None))
+    if code is not None:
+        cols.append(("code", O.VT_INT64, code, None))
+    if cols:
+        fams.append(("default", cols))
+    b.append(sids, ts, ver, fields, fams)
+    return b.finish()
+
+
+def _synthetic(n_series=7, n_pts=300, seed=1, with_null=False):
+    rng = np.random.default_rng(seed)
+    sids = np.repeat(np.arange(1, n_series + 1, dtype=np.uint64) * 11, n_pts)
+    ts = np.tile(T0 + np.arange(n_pts, dtype=np.int64) * STEP, n_series)
+    ver = np.ones(sids.size, dtype=np.int64)
+    f_flt = np.round(25 + rng.normal(0, 5, sids.size), 2)
+    f_int = rng.integers(-1000, 1000, sids.size)
+    region = [b"r%d" % (i % 8) for i in rng.integers(0, 8, sids.size)]
+    code = rng.integers(0, 5, sids.size) * 100
+    nulls = (rng.random(sids.size) < 0.1) if with_null else None
+    return sids, ts, ver, f_int, f_flt, region, code, nulls
+
+
+def test_known_answers_aggregation_test_go():
+    # aggregation_test.go:82-120: sum a=3, b=7 ; :150-200: count a=3, b=1
+    sids = np.array([1, 2, 1, 2], dtype=np.uint64)
+    ts = T0 + np.array([0, 0, 1, 1], dtype=np.int64) * STEP
+    part = _build(sids, ts, np.ones(4, np.int64), f_int=np.array([1, 3, 2, 4]))
+    r = O.run_query(O.Query([part], [1, 2], [("calls", O.AGG_SUM), ("calls", O.AGG_COUNT), ("calls", O.AGG_MIN),
+                                            ("calls", O.AGG_MAX), ("calls", O.AGG_MEAN)],
+                            groups=[0, 1], n_groups=2))
+    assert r.group_id.tolist() == [0, 1]
+    assert r.val_i64[0].tolist() == [3, 2, 1, 2, 1]   # mean = 3/2 -> 1 (integer division)
+    assert r.val_i64[1].tolist() == [7, 2, 3, 4, 3]   # mean = 7/2 -> 3
+    assert not r.is_float.any()
+
+
+def test_mean_quirks_function_go():
+    # function.go:31-40: result < 1 is clamped to 1; float mean
+    sids = np.array([1, 1, 2, 2], dtype=np.uint64)
+    ts = T0 + np.array([0, 1, 0, 1], dtype=np.int64) * STEP
+    part = _build(sids, ts, np.ones(4, np.int64), f_int=np.array([-5, 2, 10, 11]), f_flt=np.array([0.25, 0.5, 1.5, 4.0]))
+    r = O.run_query(O.Query([part], [1, 2], [("calls", O.AGG_MEAN), ("latency", O.AGG_MEAN), ("latency", O.AGG_COUNT)],
+                            groups=[0, 1], n_groups=2))
+    assert r.val_i64[:, 0].tolist() == [1, 10]          # (-3/2 -> -1) < 1 -> 1 ; 21/2 -> 10
+    assert r.val_f64[:, 1].tolist() == [1.0, 2.75]      # 0.375 < 1 -> 1
+    assert r.is_float.tolist() == [False, True, False]  # COUNT is always int64 (aggregation.go:425-430)
+    assert r.val_i64[:, 2].tolist() == [2, 2]
+
+
+def test_query_matches_numpy_model():
+    sids, ts, ver, f_int, f_flt, region, code, _ = _synthetic()
+    part = _build(sids, ts, ver, f_int, f_flt, region, code)
+    assert part.meta()["total_count"] == sids.size
+    usid = np.unique(sids)
+    groups = (np.arange(usid.size) % 3).astype(np.int32)
+    tmin, tmax = T0 + 40 * STEP, T0 + 220 * STEP
+    q = O.Query([part], usid, [("latency", O.AGG_SUM), ("latency", O.AGG_MAX), ("latency", O.AGG_MIN),
+                               ("calls", O.AGG_SUM), ("calls", O.AGG_MIN), ("calls", O.AGG_MAX), ("latency", O.AGG_MEAN)],
+                groups=groups, n_groups=3, tmin=tmin, tmax=tmax,
+                preds=[O.Pred("default", "region", O.OP_EQ, b"r3"), O.Pred("default", "code", O.OP_GE, 200)])
+    r = O.run_query(q)
+    reg = np.array(region)
+    m = (ts >= tmin) & (ts <= tmax) & (reg == b"r3") & (code >= 200)
+    gid_of = {int(s): int(g) for s, g in zip(usid, groups)}
+    g = np.array([gid_of[int(s)] for s in sids])
+    for row, grp in enumerate(r.group_id.tolist()):
+        mm = m & (g == grp)
+        assert r.rows[row] == mm.sum()
+        assert r.val_f64[row, 0] == pytest.approx(f_flt[mm].sum(), rel=1e-12)
+        assert r.val_f64[row, 1] == f_flt[mm].max()
+        assert r.val_f64[row, 2] == f_flt[mm].min()
+        assert r.val_i64[row, 3] == f_int[mm].sum()
+        assert r.val_i64[row, 4] == f_int[mm].min()
+        assert r.val_i64[row, 5] == f_int[mm].max()
+        mean = f_flt[mm].sum() / mm.sum()
+        assert r.val_f64[row, 6] == pytest.approx(max(mean, 1.0), rel=1e-12)
+    assert r.rows_matched == m.sum()
+
+
+def test_sequential_float_sum_is_row_order():
+    # function.go:133-135: s.sum += val in scan order (series-major, then time)
+    sids, ts, ver, _, f_flt, _, _, _ = _synthetic(n_series=3, n_pts=500, seed=3)
+    part = _build(sids, ts, ver, f_flt=f_flt)
+    r = O.run_query(O.Query([part], np.unique(sids), [("latency", O.AGG_SUM)]))
+    acc = 0.0
+    for v in f_flt.tolist():   # rows were generated already sorted (sid, ts)
+        acc += v
+    assert r.val_f64[0, 0] == acc
+
+
+def test_version_dedup_across_parts():
+    # query.go:995-1004 / query_batch.go:151-161: duplicate (sid, ts) keeps the highest version
+    n = 50
+    ts = T0 + np.arange(n, dtype=np.int64) * STEP
+    sid = np.full(n, 7, dtype=np.uint64)
+    p1 = _build(sid, ts, np.full(n, 1, np.int64), f_int=np.arange(n))
+    # second part overwrites the even timestamps with version 2 and adds a stale version-0 copy of the odd ones
+    ts2 = np.concatenate([ts[::2], ts[1::2]])
+    ver2 = np.concatenate([np.full(n // 2, 2, np.int64), np.zeros(n // 2, np.int64)])
+    val2 = np.concatenate([np.arange(n)[::2] + 1000, np.arange(n)[1::2] - 5000])
+    p2 = _build(np.full(n, 7, np.uint64), ts2, ver2, f_int=val2)
+    r = O.run_query(O.Query([p1, p2], [7], [("calls", O.AGG_SUM), ("calls", O.AGG_COUNT)]))
+    want = (np.arange(n)[::2] + 1000).sum() + np.arange(n)[1::2].sum()
+    assert r.val_i64[0].tolist() == [want, n]
+    rows = O.scan_rows(O.Query([p1, p2], [7], [("calls", O.AGG_SUM)]))
+    assert rows["ts"].tolist() == ts.tolist()
+    assert rows["version"].tolist() == [2 if i % 2 == 0 else 1 for i in range(n)]
+
+
+def test_in_part_duplicates_dropped_at_write():
+    # part.go:176-190: same (sid, ts) inside one flush keeps the first after sort = highest version
+    ts = T0 + np.array([0, 1, 1, 2], dtype=np.int64) * STEP
+    part = _build(np.full(4, 3, np.uint64), ts, np.array([1, 1, 9, 1], np.int64), f_int=np.array([10, 20, 30, 40]))
+    assert part.meta()["total_count"] == 3
+    rows = O.scan_rows(O.Query([part], [3], [("calls", O.AGG_SUM)]))
+    assert rows["fields"][0][2].tolist() == [10, 30, 40]
+
+
+def test_null_cells_are_skipped_but_rows_counted():
+    sids, ts, ver, f_int, f_flt, _, _, nulls = _synthetic(n_series=2, n_pts=100, seed=5, with_null=True)
+    part = _build(sids, ts, ver, f_int=f_int, f_flt=f_flt, nulls=nulls)
+    r = O.run_query(O.Query([part], np.unique(sids), [("calls", O.AGG_SUM), ("calls", O.AGG_COUNT), ("latency", O.AGG_COUNT)]))
+    assert r.val_i64[0].tolist() == [f_int[~nulls].sum(), (~nulls).sum(), sids.size]
+    assert r.rows[0] == sids.size
+
+
+def test_block_cut_and_time_prune():
+    # measure.go:41-46 / part.go:192-199: a block is cut when rows > 8192 -> 8193-row first block
+    n = 20000
+    ts = T0 + np.arange(n, dtype=np.int64) * STEP
+    part = _build(np.full(n, 5, np.uint64), ts, np.ones(n, np.int64), f_int=np.arange(n))
+    assert part.meta()["blocks_count"] == 3
+    r = O.run_query(O.Query([part], [5], [("calls", O.AGG_SUM)], tmin=int(ts[8193]), tmax=int(ts[8200])))
+    assert r.blocks_scanned == 1 and r.rows_scanned == 8193
+    assert r.val_i64[0, 0] == np.arange(8193, 8201).sum()
+    r = O.run_query(O.Query([part], [5], [("calls", O.AGG_COUNT)], tmin=int(ts[-1]) + 1))
+    assert r.group_id.size == 0
+
+
+def test_top_n_desc_and_ties():
+    # top.go:145-214: largest N first; ties -> earlier row (lower group) wins
+    sids = np.arange(1, 9, dtype=np.uint64)
+    vals = np.array([5, 9, 9, 1, 7, 9, 3, 7])
+    part = _build(sids, np.full(8, T0, np.int64), np.ones(8, np.int64), f_int=vals)
+    r = O.run_query(O.Query([part], sids, [("calls", O.AGG_SUM)], groups=np.arange(8, dtype=np.int32), n_groups=8,
+                            top_n=4, top_desc=True))
+    assert r.group_id.tolist() == [1, 2, 5, 4]
+    r = O.run_query(O.Query([part], sids, [("calls", O.AGG_SUM)], groups=np.arange(8, dtype=np.int32), n_groups=8,
+                            top_n=2, top_desc=False))
+    assert r.group_id.tolist() == [3, 6]
+
+
+def test_threaded_modes_agree():
+    sids, ts, ver, f_int, f_flt, region, code, _ = _synthetic(n_series=40, n_pts=400, seed=9)
+    part = _build(sids, ts, ver, f_int, f_flt, region, code)
+    usid = np.unique(sids)
+    groups = (np.arange(usid.size) % 5).astype(np.int32)
+    base = dict(groups=groups, n_groups=5, preds=[O.Pred("default", "region", O.OP_NE, b"r1")])
+    aggs = [("latency", O.AGG_MAX), ("calls", O.AGG_SUM), ("latency", O.AGG_MEAN)]
+    a = O.run_query(O.Query([part], usid, aggs, threads=1, **base))
+    b = O.run_query(O.Query([part], usid, aggs, threads=4, **base))
+    c = O.run_query(O.Query([part], usid, aggs, threads=4, per_thread_partials=True, **base))
+    assert (a.val_i64 == b.val_i64).all() and (a.val_f64 == b.val_f64).all()
+    assert (a.val_i64 == c.val_i64).all()
+    np.testing.assert_allclose(a.val_f64, c.val_f64, rtol=1e-12)
+
+
+def test_part_reopen_from_files():
+    sids, ts, ver, f_int, f_flt, region, code, _ = _synthetic(n_series=4, n_pts=50, seed=2)
+    part = _build(sids, ts, ver, f_int, f_flt, region, code)
+    files = part.files()
+    assert set(files) == {"meta.bin", "primary.bin", "timestamps.bin", "fv.bin", "default.tf", "default.tfm"}
+    again = O.Part.open(files)
+    q = lambda p: O.run_query(O.Query([p], np.unique(sids), [("latency", O.AGG_SUM), ("calls", O.AGG_MAX)]))
+    assert q(part).val_f64.tolist() == q(again).val_f64.tolist()
+    assert again.meta()["total_count"] == sids.size
