@@ -1,0 +1,203 @@
+/*
+ * bydb_gpu.h -- C ABI of libbydbgpu.so: the B200-native measure scan -> filter -> aggregate path.
+ *
+ * This is the drop-in boundary a cgo binding in BanyanDB would bind.  It
+ * replaces, for one query, the reference's HOT LOOPS 1-3:
+ *
+ *   bydb_part_register  <- banyand/measure/part.go:312-375 (mustOpenFilePart) +
+ *                          part_iter.go:184-208 (readPrimaryBlock -> blockMetadata cache)
+ *   bydb_part_release   <- banyand/measure/part.go:282-299 (partWrapper.decRef -> close)
+ *   bydb_scan_agg       <- banyand/measure/query.go:594-639 (searchBlocks) +
+ *                          query_batch.go:64-238 (PullBatch / loadCursorsForBatch / mergeBatch) +
+ *                          block.go:793-870 (blockCursor.loadData) +
+ *                          pkg/query/vectorized/measure/aggregation.go:193-334 (BatchAggregation) +
+ *                          pkg/query/vectorized/measure/top.go:145-214 (BatchTop)
+ *   bydb_scan_partials / bydb_reduce_finalize
+ *                       <- pkg/query/logical/measure/measure_plan_aggregation.go:67-124
+ *                          (emitPartial map phase / reduceAccumulator.Combine)
+ *
+ * Rules: C linkage, plain pointers and sizes; no pointer passed in is retained after the call
+ * returns (cgo rule); every function is thread-safe; functions return 0 or a negative errno-style
+ * code and never abort; bydb_last_error() returns a thread-local message.  There is NO CPU fallback
+ * behind this ABI: pages the device path cannot decode make the call fail with BYDB_ENOTSUP so the
+ * caller can route the query to its own CPU path outside this library.
+ */
+#ifndef BYDB_GPU_H
+#define BYDB_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BYDB_OK 0
+#define BYDB_ENOENT (-2)    /* unknown part handle / missing file            */
+#define BYDB_EIO (-5)       /* CUDA runtime failure                          */
+#define BYDB_ENOMEM (-12)   /* HBM budget exceeded / allocation failure      */
+#define BYDB_EINVAL (-22)   /* malformed argument or corrupt part            */
+#define BYDB_ENOTSUP (-95)  /* encoding not handled on the device path       */
+
+/* value types, pkg/pb/v1/value.go:39-47 */
+#define BYDB_VT_STR 1
+#define BYDB_VT_INT64 2
+#define BYDB_VT_FLOAT64 3
+#define BYDB_VT_BINARY 4
+
+/* aggregation functions, api/proto/banyandb/model/v1/common.proto:75-80 */
+#define BYDB_AGG_MEAN 1
+#define BYDB_AGG_MAX 2
+#define BYDB_AGG_MIN 3
+#define BYDB_AGG_COUNT 4
+#define BYDB_AGG_SUM 5
+
+/* row-predicate operators on a stored tag column */
+#define BYDB_OP_EQ 1
+#define BYDB_OP_NE 2
+#define BYDB_OP_LT 3
+#define BYDB_OP_LE 4
+#define BYDB_OP_GT 5
+#define BYDB_OP_GE 6
+
+typedef struct bydb_ctx bydb_ctx; /* owns one device, its streams and the HBM part cache */
+typedef uint64_t bydb_part_h;
+
+typedef struct {
+    int32_t device;            /* CUDA device ordinal                                    */
+    int32_t warps_per_sm;      /* scan workers per SM; 0 = default (16)                  */
+    uint64_t hbm_budget_bytes; /* cap on resident part bytes; 0 = no cap                 */
+    uint32_t flags;            /* reserved, 0                                            */
+    uint32_t reserved;
+} bydb_cfg;
+
+/* One file image of a part (banyand/measure/part.go:40-55).  name is one of "meta.bin",
+ * "primary.bin", "timestamps.bin", "fv.bin", "<family>.tf", "<family>.tfm". */
+typedef struct {
+    const char *name;
+    const uint8_t *data;
+    uint64_t len;
+} bydb_file;
+
+typedef struct {
+    uint32_t n_files;
+    const bydb_file *files;
+} bydb_part_files;
+
+typedef struct {
+    const char *family;   /* tag family name                                   */
+    const char *tag;      /* tag name                                          */
+    int32_t op;           /* BYDB_OP_*                                         */
+    int32_t value_type;   /* BYDB_VT_STR / BYDB_VT_BINARY / BYDB_VT_INT64      */
+    const uint8_t *lit;   /* literal bytes for STR/BINARY                      */
+    uint64_t lit_len;
+    int64_t lit_i64;      /* literal for INT64                                 */
+} bydb_pred;
+
+typedef struct {
+    const char *field; /* field name (model.MeasureAgg input)       */
+    int32_t func;      /* BYDB_AGG_*                                */
+    int32_t reserved;
+} bydb_agg;
+
+/* One query = selected series (+ their dense group ids) x parts x predicates x aggregations.
+ * Mirrors model.MeasureQueryOptions (pkg/query/model/model.go:75-88) after series resolution:
+ * series_ids is what searchSeriesList returned (ascending, query.go:601), series_group is the
+ * GroupBy key of each series densified by the caller in first-appearance order (entity / indexed
+ * tags live in the series index, not in the part: SURVEY.md F3). */
+typedef struct {
+    uint32_t n_parts;
+    const bydb_part_h *parts;
+    uint64_t n_series;
+    const uint64_t *series_ids;   /* ascending, unique                                   */
+    const int32_t *series_group;  /* [n_series] dense group id; NULL = one group (scalar) */
+    int32_t n_groups;             /* ignored when series_group is NULL                    */
+    int32_t reserved0;
+    int64_t tmin, tmax;           /* inclusive (pkg/timestamp/range.go:143)               */
+    uint32_t n_preds;
+    const bydb_pred *preds;       /* conjunction                                          */
+    uint32_t n_aggs;
+    const bydb_agg *aggs;
+    int32_t top_n;                /* 0 = no Top                                           */
+    int32_t top_agg;              /* index into aggs                                      */
+    int32_t top_desc;             /* 1 = largest first                                    */
+    uint32_t flags;               /* reserved, 0                                          */
+} bydb_query;
+
+typedef struct {
+    uint64_t rows_scanned;    /* rows of every selected block (before time trim)            */
+    uint64_t rows_matched;    /* rows folded into an aggregate                               */
+    uint64_t blocks_scanned;
+    uint64_t page_bytes;      /* encoded page bytes the scan kernel consumed                 */
+    uint64_t h2d_bytes;       /* host->device bytes moved by this call                       */
+    uint64_t d2h_bytes;       /* device->host bytes moved by this call                       */
+    double scan_kernel_ms;    /* CUDA-event time of the scan kernel on the call's stream     */
+    double device_ms;         /* CUDA-event time of all kernels of the call                  */
+    uint32_t kernel_launches; /* kernels launched by this call                               */
+    uint32_t reserved;
+} bydb_stats;
+
+/* Dense result table; arrays are owned by the library until bydb_result_free.
+ * Rows are groups in group-id order (groups that never appeared are omitted), or rank order when
+ * top_n > 0.  Column a has type is_float[a]: COUNT is always int64, everything else follows the
+ * field type (pkg/query/vectorized/measure/aggregation.go:425-430). */
+typedef struct {
+    int32_t n_rows;
+    int32_t n_aggs;
+    const int32_t *group_id;  /* [n_rows]            */
+    const int64_t *rows;      /* [n_rows]            */
+    const uint8_t *is_float;  /* [n_aggs]            */
+    const int64_t *val_i64;   /* [n_rows * n_aggs]   */
+    const double *val_f64;    /* [n_rows * n_aggs]   */
+    bydb_stats stats;
+    void *owner;              /* private             */
+} bydb_result;
+
+int bydb_init(const bydb_cfg *cfg, bydb_ctx **out);
+void bydb_shutdown(bydb_ctx *ctx);
+
+/* Upload an immutable part into HBM and build its block directory.  Idempotent per part_id. */
+int bydb_part_register(bydb_ctx *ctx, uint64_t part_id, const bydb_part_files *files, bydb_part_h *out);
+int bydb_part_release(bydb_ctx *ctx, bydb_part_h part);
+/* resident bytes / block / row counts of a registered part */
+int bydb_part_info(bydb_ctx *ctx, bydb_part_h part, uint64_t *hbm_bytes, uint64_t *n_blocks, uint64_t *n_rows);
+
+/* Scan -> filter -> aggregate over parts already resident in HBM. */
+int bydb_scan_agg(bydb_ctx *ctx, const bydb_query *q, bydb_result *out);
+
+/* Same, but the parts come as HOST file images: they are uploaded, scanned and dropped inside the
+ * call (the end-to-end path of a cold query).  q->parts / q->n_parts are ignored. */
+int bydb_scan_agg_host(bydb_ctx *ctx, uint32_t n_parts, const bydb_part_files *parts, const bydb_query *q, bydb_result *out);
+
+void bydb_result_free(bydb_ctx *ctx, bydb_result *r);
+
+/* ---- multi-GPU map/reduce: per-rank partial tables, one collective, one finalize ----
+ * Layout of a partial table for (n_groups G, n_fields F = distinct aggregated fields):
+ *   double  sum_f64[G*F]; double max_f64[G*F]; double negmin_f64[G*F];
+ *   int64   sum_i64[G*F]; int64 cnt[G*F]; int64 rows[G]; int64 max_i64[G*F]; int64 negmin_i64[G*F];
+ * so that ONE all-reduce(SUM) over [sum_f64] + [sum_i64,cnt,rows] and one all-reduce(MAX) over the
+ * max/negmin halves combine ranks (min is carried as max of the negation; int64 negation of
+ * INT64_MIN is handled by carrying ~x instead of -x).  bydb_partials_layout reports the byte
+ * offsets so the caller can issue the collectives on sub-ranges. */
+typedef struct {
+    uint64_t total_bytes;
+    uint64_t off_sum_f64, off_max_f64;   /* [sum_f64] , [max_f64 | negmin_f64]                 */
+    uint64_t off_sum_i64, off_max_i64;   /* [sum_i64 | cnt | rows] , [max_i64 | notmin_i64]    */
+    uint64_t n_sum_f64, n_max_f64, n_sum_i64, n_max_i64; /* element counts of the four ranges */
+} bydb_partials_layout_t;
+
+int bydb_partials_layout(const bydb_query *q, bydb_partials_layout_t *out);
+/* Run the scan and leave the partial table in caller-provided DEVICE memory (e.g. a torch tensor),
+ * enqueued on `stream` (a cudaStream_t passed as void*; NULL = the library's own stream, synchronised
+ * before return). */
+int bydb_scan_partials(bydb_ctx *ctx, const bydb_query *q, void *d_partials, uint64_t bytes, void *stream, bydb_stats *stats);
+/* Finalize a (reduced) partial table: MEAN finalisation, output typing, Top-N; copies the result to host. */
+int bydb_reduce_finalize(bydb_ctx *ctx, const bydb_query *q, const void *d_partials, uint64_t bytes, void *stream, bydb_result *out);
+
+const char *bydb_last_error(void);
+const char *bydb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

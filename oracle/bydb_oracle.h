@@ -97,7 +97,8 @@ int64_t ob_conv_bytes_to_int64(const uint8_t b[8]);       /* number.go:93-106 */
 int ob_float64_to_decimal_list(int64_t *dst, const double *src, size_t n, int16_t *exp); /* float.go:30-66 */
 void ob_decimal_list_to_float64(double *dst, const int64_t *vals, size_t n, int16_t exp); /* float.go:69-93 */
 int ob_float_to_decimal(double f, int64_t *mant, int16_t *exp);                          /* float.go:107-190 */
-double ob_pow10(int n);                                                                   /* Go math.Pow10 */
+double ob_pow10(int n);
+extern int ob_force_slow_float;                                                          /* tests only */                                                                   /* Go math.Pow10 */
 
 /* ---- pkg/encoding/bytes.go, dictionary.go, writer.go, reader.go ---- */
 void ob_bytes_block_encode(ob_buf *dst, const ob_bytes *a, size_t n);    /* bytes.go:45-72 */

@@ -430,6 +430,8 @@ static void shortest_digits(double f, char *digits, int *nd_out, int *dexp_out) 
     *dexp_out = atoi(p + 1);
 }
 
+int ob_force_slow_float = 0; /* tests: force the general shortest-digits search */
+
 /* float.go:107-124 floatToDecimal + :128-190 floatToDecimalSlow */
 int ob_float_to_decimal(double f, int64_t *mant, int16_t *exp) {
     if (isnan(f) || isinf(f)) return -1;
@@ -453,6 +455,34 @@ int ob_float_to_decimal(double f, int64_t *mant, int16_t *exp) {
         *mant = u;
         *exp = e;
         return 0;
+    }
+    /* Fast equivalent of the shortest-digits search for "short" decimals: the smallest k such that
+     * some integer m (|m| < 2^53) has fl(m / 10^k) == f.  m and 10^k (k <= 22) are exact doubles, so
+     * the correctly rounded quotient equals strtod("m e-k"): m*10^-k round-trips, and no decimal
+     * with fewer fractional digits does (smaller k failed), hence it is the shortest one.  Falls
+     * through to the general search when nothing is found (checked against it in the tests). */
+    if (!ob_force_slow_float) {
+        static const double p10[16] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+        double a = fabs(f);
+        if (a < 9007199254740992.0 && a >= 1e-15) {
+            for (int k = 1; k <= 15; k++) {
+                double t = a * p10[k];
+                if (t >= 9007199254740992.0) break;
+                double m0 = nearbyint(t);
+                for (int dm = -1; dm <= 1; dm++) {
+                    double m = m0 + dm;
+                    if (m < 1 || m >= 9007199254740992.0) continue;
+                    volatile double back = m / p10[k];
+                    if (back == a) {
+                        int64_t mi = (int64_t)m;
+                        if (mi % 10 == 0) continue; /* would have matched at k-1; keep searching */
+                        *mant = f < 0 ? -mi : mi;
+                        *exp = (int16_t)-k;
+                        return 0;
+                    }
+                }
+            }
+        }
     }
     /* slow path: shortest 'e' formatting d.ddd e sciExp -> mantissa digits without the dot */
     char digits[24];

@@ -212,6 +212,11 @@ def decimal_list_to_float64(ints: Sequence[int], exp: int) -> np.ndarray:
     return dst[:src.size]
 
 
+def force_slow_float(on: bool) -> None:
+    """Tests: disable the fast shortest-decimal path so both searches can be compared."""
+    C.c_int.in_dll(lib(), "ob_force_slow_float").value = int(on)
+
+
 def pow10(n: int) -> float:
     return lib().ob_pow10(n)
 

@@ -1,0 +1,348 @@
+"""ctypes binding of include/bydb_gpu.h (the same calls a cgo shim would make)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+VT_STR, VT_INT64, VT_FLOAT64, VT_BINARY = 1, 2, 3, 4
+AGG_MEAN, AGG_MAX, AGG_MIN, AGG_COUNT, AGG_SUM = 1, 2, 3, 4, 5
+OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE = 1, 2, 3, 4, 5, 6
+ENOENT, EIO, ENOMEM, EINVAL, ENOTSUP = -2, -5, -12, -22, -95
+
+
+class BydbError(RuntimeError):
+    """A negative return code of the C ABI plus bydb_last_error()."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"bydb error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+class _Cfg(C.Structure):
+    _fields_ = [("device", C.c_int32), ("warps_per_sm", C.c_int32), ("hbm_budget_bytes", C.c_uint64),
+                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class _File(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("len", C.c_uint64)]
+
+
+class _PartFiles(C.Structure):
+    _fields_ = [("n_files", C.c_uint32), ("files", C.POINTER(_File))]
+
+
+class _Pred(C.Structure):
+    _fields_ = [("family", C.c_char_p), ("tag", C.c_char_p), ("op", C.c_int32), ("value_type", C.c_int32),
+                ("lit", C.c_void_p), ("lit_len", C.c_uint64), ("lit_i64", C.c_int64)]
+
+
+class _Agg(C.Structure):
+    _fields_ = [("field", C.c_char_p), ("func", C.c_int32), ("reserved", C.c_int32)]
+
+
+class _Query(C.Structure):
+    _fields_ = [("n_parts", C.c_uint32), ("parts", C.POINTER(C.c_uint64)), ("n_series", C.c_uint64),
+                ("series_ids", C.c_void_p), ("series_group", C.c_void_p), ("n_groups", C.c_int32),
+                ("reserved0", C.c_int32), ("tmin", C.c_int64), ("tmax", C.c_int64), ("n_preds", C.c_uint32),
+                ("preds", C.POINTER(_Pred)), ("n_aggs", C.c_uint32), ("aggs", C.POINTER(_Agg)),
+                ("top_n", C.c_int32), ("top_agg", C.c_int32), ("top_desc", C.c_int32), ("flags", C.c_uint32)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [("rows_scanned", C.c_uint64), ("rows_matched", C.c_uint64), ("blocks_scanned", C.c_uint64),
+                ("page_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("scan_kernel_ms", C.c_double), ("device_ms", C.c_double), ("kernel_launches", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("n_rows", C.c_int32), ("n_aggs", C.c_int32), ("group_id", C.POINTER(C.c_int32)),
+                ("rows", C.POINTER(C.c_int64)), ("is_float", C.POINTER(C.c_uint8)),
+                ("val_i64", C.POINTER(C.c_int64)), ("val_f64", C.POINTER(C.c_double)), ("stats", _Stats),
+                ("owner", C.c_void_p)]
+
+
+class _Layout(C.Structure):
+    _fields_ = [("total_bytes", C.c_uint64), ("off_sum_f64", C.c_uint64), ("off_max_f64", C.c_uint64),
+                ("off_sum_i64", C.c_uint64), ("off_max_i64", C.c_uint64), ("n_sum_f64", C.c_uint64),
+                ("n_max_f64", C.c_uint64), ("n_sum_i64", C.c_uint64), ("n_max_i64", C.c_uint64)]
+
+
+# every symbol include/bydb_gpu.h declares (tests/test_capi_symbols.py checks the list against the header)
+EXPORTS = ["bydb_init", "bydb_shutdown", "bydb_part_register", "bydb_part_release", "bydb_part_info",
+           "bydb_scan_agg", "bydb_scan_agg_host", "bydb_result_free", "bydb_partials_layout",
+           "bydb_scan_partials", "bydb_reduce_finalize", "bydb_last_error", "bydb_version"]
+
+_lib = None
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libbydbgpu.so")
+
+
+def load_library():
+    """Loads libbydbgpu.so.  Fails loudly when the CUDA extension is missing: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `make -C {_HERE}` (or __graft_entry__.build()); "
+                          "the measure scan path has no CPU fallback")
+    L = C.CDLL(path)
+    L.bydb_last_error.restype = C.c_char_p
+    L.bydb_version.restype = C.c_char_p
+    L.bydb_init.argtypes = [C.POINTER(_Cfg), C.POINTER(C.c_void_p)]
+    L.bydb_shutdown.argtypes = [C.c_void_p]
+    L.bydb_part_register.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(_PartFiles), C.POINTER(C.c_uint64)]
+    L.bydb_part_release.argtypes = [C.c_void_p, C.c_uint64]
+    L.bydb_part_info.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.bydb_scan_agg.argtypes = [C.c_void_p, C.POINTER(_Query), C.POINTER(_Result)]
+    L.bydb_scan_agg_host.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_PartFiles), C.POINTER(_Query), C.POINTER(_Result)]
+    L.bydb_result_free.argtypes = [C.c_void_p, C.POINTER(_Result)]
+    L.bydb_partials_layout.argtypes = [C.POINTER(_Query), C.POINTER(_Layout)]
+    L.bydb_scan_partials.argtypes = [C.c_void_p, C.POINTER(_Query), C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(_Stats)]
+    L.bydb_reduce_finalize.argtypes = [C.c_void_p, C.POINTER(_Query), C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(_Result)]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise BydbError(rc, (load_library().bydb_last_error() or b"").decode())
+
+
+@dataclass
+class Pred:
+    family: str
+    tag: str
+    op: int
+    value: Union[int, bytes, str]
+
+
+@dataclass
+class Query:
+    """model.MeasureQueryOptions after series resolution (see bydb_query in bydb_gpu.h)."""
+    parts: Sequence[int]                      # part handles
+    series_ids: Sequence[int]                 # ascending
+    aggs: Sequence[tuple]                     # (field, AGG_*)
+    series_group: Optional[Sequence[int]] = None
+    n_groups: int = 1
+    tmin: int = -(1 << 63)
+    tmax: int = (1 << 63) - 1
+    preds: Sequence[Pred] = field(default_factory=list)
+    top_n: int = 0
+    top_agg: int = 0
+    top_desc: bool = True
+
+
+@dataclass
+class Stats:
+    rows_scanned: int = 0
+    rows_matched: int = 0
+    blocks_scanned: int = 0
+    page_bytes: int = 0
+    h2d_bytes: int = 0
+    d2h_bytes: int = 0
+    scan_kernel_ms: float = 0.0
+    device_ms: float = 0.0
+    kernel_launches: int = 0
+
+    @staticmethod
+    def of(s: _Stats) -> "Stats":
+        return Stats(s.rows_scanned, s.rows_matched, s.blocks_scanned, s.page_bytes, s.h2d_bytes, s.d2h_bytes,
+                     s.scan_kernel_ms, s.device_ms, s.kernel_launches)
+
+
+@dataclass
+class Result:
+    group_id: np.ndarray
+    rows: np.ndarray
+    is_float: np.ndarray
+    val_i64: np.ndarray   # [n_rows, n_aggs]
+    val_f64: np.ndarray
+    stats: Stats
+
+    def value(self, row: int, agg: int):
+        return float(self.val_f64[row, agg]) if self.is_float[agg] else int(self.val_i64[row, agg])
+
+
+def _part_files(files: Dict[str, Union[bytes, np.ndarray]], keep: list) -> _PartFiles:
+    arr = (_File * len(files))()
+    for i, (name, data) in enumerate(files.items()):
+        nb = name.encode()
+        keep.append(nb)
+        arr[i].name = nb
+        if isinstance(data, np.ndarray):
+            a = np.ascontiguousarray(data, dtype=np.uint8)
+            keep.append(a)
+            arr[i].data = a.ctypes.data
+            arr[i].len = a.size
+        elif hasattr(data, "data_ptr"):      # a (pinned) torch uint8 tensor
+            keep.append(data)
+            arr[i].data = data.data_ptr()
+            arr[i].len = data.numel()
+        else:
+            b = bytes(data)
+            buf = C.create_string_buffer(b, max(len(b), 1))
+            keep.append(buf)
+            arr[i].data = C.cast(buf, C.c_void_p).value
+            arr[i].len = len(b)
+    keep.append(arr)
+    pf = _PartFiles()
+    pf.n_files = len(files)
+    pf.files = arr
+    return pf
+
+
+def _mk_query(q: Query, keep: list) -> _Query:
+    cq = _Query()
+    parts = (C.c_uint64 * max(len(q.parts), 1))(*[int(p) for p in q.parts])
+    keep.append(parts)
+    cq.n_parts, cq.parts = len(q.parts), parts
+    sids = np.ascontiguousarray(q.series_ids, dtype=np.uint64)
+    keep.append(sids)
+    cq.n_series, cq.series_ids = sids.size, sids.ctypes.data
+    if q.series_group is not None:
+        g = np.ascontiguousarray(q.series_group, dtype=np.int32)
+        keep.append(g)
+        cq.series_group, cq.n_groups = g.ctypes.data, q.n_groups
+    else:
+        cq.series_group, cq.n_groups = None, 1
+    cq.tmin, cq.tmax = q.tmin, q.tmax
+    preds = (_Pred * max(len(q.preds), 1))()
+    for i, p in enumerate(q.preds):
+        fb, tb = p.family.encode(), p.tag.encode()
+        keep.extend([fb, tb])
+        preds[i].family, preds[i].tag, preds[i].op = fb, tb, p.op
+        if isinstance(p.value, (int, np.integer)):
+            preds[i].value_type, preds[i].lit_i64 = VT_INT64, int(p.value)
+        else:
+            vb = p.value.encode() if isinstance(p.value, str) else bytes(p.value)
+            buf = C.create_string_buffer(vb, max(len(vb), 1))
+            keep.append(buf)
+            preds[i].value_type = VT_STR
+            preds[i].lit = C.cast(buf, C.c_void_p).value
+            preds[i].lit_len = len(vb)
+    keep.append(preds)
+    cq.n_preds, cq.preds = len(q.preds), preds
+    aggs = (_Agg * max(len(q.aggs), 1))()
+    for i, (fname, func) in enumerate(q.aggs):
+        nb = fname.encode()
+        keep.append(nb)
+        aggs[i].field, aggs[i].func = nb, int(func)
+    keep.append(aggs)
+    cq.n_aggs, cq.aggs = len(q.aggs), aggs
+    cq.top_n, cq.top_agg, cq.top_desc = q.top_n, q.top_agg, int(q.top_desc)
+    return cq
+
+
+def _read_result(r: _Result) -> Result:
+    n, a = r.n_rows, r.n_aggs
+
+    def arr(ptr, count, dtype):
+        if count == 0:
+            return np.zeros(0, dtype=dtype)
+        return np.ctypeslib.as_array(ptr, (count,)).copy()
+
+    return Result(group_id=arr(r.group_id, n, np.int32), rows=arr(r.rows, n, np.int64),
+                  is_float=arr(r.is_float, a, np.uint8).astype(bool),
+                  val_i64=arr(r.val_i64, n * a, np.int64).reshape(n, a),
+                  val_f64=arr(r.val_f64, n * a, np.float64).reshape(n, a), stats=Stats.of(r.stats))
+
+
+class Context:
+    """bydb_ctx: one device, its streams and the HBM part cache."""
+
+    def __init__(self, device: int = 0, warps_per_sm: int = 0, hbm_budget_bytes: int = 0):
+        self._L = load_library()
+        cfg = _Cfg(device, warps_per_sm, hbm_budget_bytes, 0, 0)
+        h = C.c_void_p()
+        _check(self._L.bydb_init(C.byref(cfg), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.bydb_shutdown(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        self.close()
+
+    # ---- parts
+    def register_part(self, part_id: int, files: Dict[str, Union[bytes, np.ndarray]]) -> int:
+        keep: list = []
+        pf = _part_files(files, keep)
+        out = C.c_uint64(0)
+        _check(self._L.bydb_part_register(self._h, part_id, C.byref(pf), C.byref(out)))
+        return out.value
+
+    def release_part(self, handle: int):
+        _check(self._L.bydb_part_release(self._h, handle))
+
+    def part_info(self, handle: int) -> Dict[str, int]:
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(self._L.bydb_part_info(self._h, handle, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(hbm_bytes=a.value, n_blocks=b.value, n_rows=c.value)
+
+    # ---- queries
+    def scan_agg(self, q: Query) -> Result:
+        keep: list = []
+        cq = _mk_query(q, keep)
+        r = _Result()
+        _check(self._L.bydb_scan_agg(self._h, C.byref(cq), C.byref(r)))
+        try:
+            return _read_result(r)
+        finally:
+            self._L.bydb_result_free(self._h, C.byref(r))
+
+    def scan_agg_host(self, parts: Sequence[Dict[str, Union[bytes, np.ndarray]]], q: Query) -> Result:
+        keep: list = []
+        arr = (_PartFiles * len(parts))()
+        for i, files in enumerate(parts):
+            arr[i] = _part_files(files, keep)
+        cq = _mk_query(q, keep)
+        r = _Result()
+        _check(self._L.bydb_scan_agg_host(self._h, len(parts), arr, C.byref(cq), C.byref(r)))
+        try:
+            return _read_result(r)
+        finally:
+            self._L.bydb_result_free(self._h, C.byref(r))
+
+    # ---- multi-GPU map / reduce
+    def partials_layout(self, q: Query) -> Dict[str, int]:
+        keep: list = []
+        cq = _mk_query(q, keep)
+        lay = _Layout()
+        _check(self._L.bydb_partials_layout(C.byref(cq), C.byref(lay)))
+        return {k: getattr(lay, k) for k, _ in _Layout._fields_}
+
+    def scan_partials(self, q: Query, d_ptr: int, nbytes: int, stream: int = 0) -> Stats:
+        keep: list = []
+        cq = _mk_query(q, keep)
+        st = _Stats()
+        _check(self._L.bydb_scan_partials(self._h, C.byref(cq), d_ptr, nbytes, stream or None, C.byref(st)))
+        return Stats.of(st)
+
+    def reduce_finalize(self, q: Query, d_ptr: int, nbytes: int, stream: int = 0) -> Result:
+        keep: list = []
+        cq = _mk_query(q, keep)
+        r = _Result()
+        _check(self._L.bydb_reduce_finalize(self._h, C.byref(cq), d_ptr, nbytes, stream or None, C.byref(r)))
+        try:
+            return _read_result(r)
+        finally:
+            self._L.bydb_result_free(self._h, C.byref(r))

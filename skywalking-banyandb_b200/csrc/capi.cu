@@ -1,0 +1,811 @@
+// capi.cu -- the C ABI of libbydbgpu.so (include/bydb_gpu.h): context, HBM part cache, query
+// orchestration on CUDA streams.  Host logic only; every byte of page decoding happens in
+// scan_kernels.cu.  There is no CPU fallback here: unsupported encodings surface as BYDB_ENOTSUP.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/bydb_gpu.h"
+#include "part_dir.hpp"
+#include "scan_kernels.cuh"
+
+using namespace bydb;
+
+namespace {
+
+thread_local std::string g_last_error;
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(BYDB_EIO, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Part {
+    uint64_t id = 0;
+    PartDir dir;
+    uint8_t *d_arena = nullptr;       // all file images, each 256 B aligned and padded
+    uint8_t *d_dir = nullptr;         // DevBlock[] | DevCol[] | file pointer table
+    const DevBlock *d_blocks = nullptr;
+    const DevCol *d_cols = nullptr;
+    const uint8_t *const *d_files = nullptr;
+    uint64_t hbm_bytes = 0;
+    int device = 0;
+    ~Part() {
+        if (d_arena) cudaFree(d_arena);
+        if (d_dir) cudaFree(d_dir);
+    }
+};
+
+// One in-flight call: stream, events and a pinned staging buffer.
+struct ExecSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint8_t *pinned = nullptr;
+    size_t pinned_bytes = 0;
+    int ensure_pinned(size_t n) {
+        if (n <= pinned_bytes) return 0;
+        if (pinned) cudaFreeHost(pinned);
+        pinned = nullptr;
+        pinned_bytes = 0;
+        size_t want = align_up(n, 1 << 16);
+        if (cudaMallocHost(reinterpret_cast<void **>(&pinned), want) != cudaSuccess) return -1;
+        pinned_bytes = want;
+        return 0;
+    }
+};
+
+}  // namespace
+
+struct bydb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int ctas_per_sm = 2;
+    uint64_t hbm_budget = 0;
+    uint64_t hbm_used = 0;
+    std::mutex mu;
+    NameTable names;
+    std::unordered_map<bydb_part_h, std::shared_ptr<Part>> parts;
+    std::unordered_map<uint64_t, bydb_part_h> by_id;
+    bydb_part_h next_handle = 1;
+    std::vector<std::unique_ptr<ExecSlot>> free_slots;
+};
+
+namespace {
+
+struct SlotLease {
+    bydb_ctx *ctx;
+    std::unique_ptr<ExecSlot> slot;
+    SlotLease(bydb_ctx *c) : ctx(c) {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!c->free_slots.empty()) {
+            slot = std::move(c->free_slots.back());
+            c->free_slots.pop_back();
+        }
+    }
+    int init() {
+        if (slot) return 0;
+        slot.reset(new ExecSlot());
+        if (cudaStreamCreateWithFlags(&slot->stream, cudaStreamNonBlocking) != cudaSuccess) return -1;
+        for (auto &e : slot->ev)
+            if (cudaEventCreate(&e) != cudaSuccess) return -1;
+        return 0;
+    }
+    ~SlotLease() {
+        if (!slot) return;
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->free_slots.push_back(std::move(slot));
+    }
+};
+
+struct ResultOwner {
+    std::vector<int32_t> group_id;
+    std::vector<int64_t> rows;
+    std::vector<uint8_t> is_float;
+    std::vector<int64_t> val_i64;
+    std::vector<double> val_f64;
+};
+
+// query after name resolution
+struct Plan {
+    std::vector<std::shared_ptr<Part>> parts;
+    std::vector<std::string> fcols;       // distinct aggregated fields
+    std::vector<int> agg_fcol;
+    int32_t n_groups = 1;
+    uint32_t total_blocks = 0;
+    uint64_t n_series = 0;
+};
+
+const char *dev_err_text(uint32_t code) {
+    switch (code) {
+        case kErrPlainPage: return "numeric fallback page (EncodeTypePlain: null cells or non-decimal floats) is not decoded on the device yet";
+        case kErrZstdDict: return "dictionary page with a zstd-compressed value block is not decoded on the device yet";
+        case kErrBigBlock: return "row predicate on a block larger than the shared-memory row mask (8448 rows)";
+        case kErrCorrupt: return "corrupt page: varint stream / header does not match the block's row count";
+        case kErrTypeMix: return "a field is stored with different value types across blocks";
+        case kErrBadEnc: return "unknown encode type byte";
+        case kErrTagPlain: return "high-cardinality string tag page (plain bytes block) is not decoded on the device yet";
+        case kErrOverlap: return "a series lives in several parts with overlapping time spans: version dedup is not done on the device yet";
+        case kErrPredType: return "predicate literal type does not match the stored tag column type";
+    }
+    return "unknown device error";
+}
+int dev_err_code(uint32_t code) { return (code == kErrCorrupt || code == kErrBadEnc || code == kErrTypeMix || code == kErrPredType) ? BYDB_EINVAL : BYDB_ENOTSUP; }
+
+int validate_query(const bydb_query *q, bool need_parts) {
+    if (!q) return fail(BYDB_EINVAL, "query is NULL");
+    if (need_parts && (q->n_parts == 0 || !q->parts)) return fail(BYDB_EINVAL, "query has no parts");
+    if (q->n_parts > kMaxParts) return fail(BYDB_EINVAL, "too many parts in one query (max 64)");
+    if (q->n_series > 0 && !q->series_ids) return fail(BYDB_EINVAL, "series_ids is NULL");
+    if (q->n_series > 0x7fffffffull) return fail(BYDB_EINVAL, "too many series");
+    if (q->n_aggs == 0 || q->n_aggs > 32 || !q->aggs) return fail(BYDB_EINVAL, "need 1..32 aggregations");
+    if (q->n_preds > kMaxPreds) return fail(BYDB_EINVAL, "too many predicates (max 8)");
+    if (q->n_preds > 0 && !q->preds) return fail(BYDB_EINVAL, "preds is NULL");
+    if (q->series_group && q->n_groups < 1) return fail(BYDB_EINVAL, "n_groups must be >= 1 when series_group is given");
+    for (uint64_t i = 1; i < q->n_series; ++i)
+        if (q->series_ids[i] <= q->series_ids[i - 1]) return fail(BYDB_EINVAL, "series_ids must be ascending and unique (query.go:601)");
+    if (q->series_group)
+        for (uint64_t i = 0; i < q->n_series; ++i)
+            if (q->series_group[i] < 0 || q->series_group[i] >= q->n_groups) return fail(BYDB_EINVAL, "series_group out of range");
+    for (uint32_t a = 0; a < q->n_aggs; ++a) {
+        if (!q->aggs[a].field) return fail(BYDB_EINVAL, "aggregation without a field");
+        if (q->aggs[a].func < BYDB_AGG_MEAN || q->aggs[a].func > BYDB_AGG_SUM) return fail(BYDB_EINVAL, "unknown aggregation function");
+    }
+    for (uint32_t i = 0; i < q->n_preds; ++i) {
+        const bydb_pred &p = q->preds[i];
+        if (!p.family || !p.tag) return fail(BYDB_EINVAL, "predicate without family/tag");
+        if (p.op < BYDB_OP_EQ || p.op > BYDB_OP_GE) return fail(BYDB_EINVAL, "unknown predicate operator");
+        if (p.value_type != BYDB_VT_INT64 && p.value_type != BYDB_VT_STR && p.value_type != BYDB_VT_BINARY)
+            return fail(BYDB_EINVAL, "predicate literal must be int64, string or binary");
+        if (p.value_type != BYDB_VT_INT64 && p.lit_len > kMaxLit) return fail(BYDB_ENOTSUP, "string predicate literal longer than 64 bytes");
+        if (p.value_type != BYDB_VT_INT64 && p.lit_len > 0 && !p.lit) return fail(BYDB_EINVAL, "predicate literal is NULL");
+    }
+    if (q->top_n < 0 || (q->top_n > 0 && (q->top_agg < 0 || static_cast<uint32_t>(q->top_agg) >= q->n_aggs)))
+        return fail(BYDB_EINVAL, "bad top_n / top_agg");
+    return 0;
+}
+
+void distinct_fields(const bydb_query *q, std::vector<std::string> &fcols, std::vector<int> &agg_fcol) {
+    for (uint32_t a = 0; a < q->n_aggs; ++a) {
+        std::string f = q->aggs[a].field;
+        int idx = -1;
+        for (size_t i = 0; i < fcols.size(); ++i)
+            if (fcols[i] == f) idx = static_cast<int>(i);
+        if (idx < 0) {
+            fcols.push_back(f);
+            idx = static_cast<int>(fcols.size() - 1);
+        }
+        agg_fcol.push_back(idx);
+    }
+}
+
+// partial-table layout for (G groups, F fields); see bydb_gpu.h
+struct TableLayout {
+    size_t G, F, GF;
+    size_t off_sum_f64, off_max_f64, off_negmin_f64, off_sum_i64, off_cnt, off_rows, off_max_i64, off_notmin_i64, off_coltype, total;
+    TableLayout(size_t g, size_t f) : G(g), F(f), GF(g * f) {
+        size_t o = 0;
+        off_sum_f64 = o; o += GF * 8;
+        off_max_f64 = o; o += GF * 8;
+        off_negmin_f64 = o; o += GF * 8;
+        off_sum_i64 = o; o += GF * 8;
+        off_cnt = o; o += GF * 8;
+        off_rows = o; o += G * 8;
+        off_max_i64 = o; o += GF * 8;
+        off_notmin_i64 = o; o += GF * 8;
+        off_coltype = o; o += F * 8;
+        total = o;
+    }
+};
+
+int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_files *files, std::shared_ptr<Part> &out, uint64_t *h2d) {
+    if (!files || files->n_files == 0 || !files->files) return fail(BYDB_EINVAL, "no files");
+    std::vector<FileImage> imgs;
+    for (uint32_t i = 0; i < files->n_files; ++i) {
+        const bydb_file &f = files->files[i];
+        if (!f.name || (!f.data && f.len)) return fail(BYDB_EINVAL, "file without name/data");
+        imgs.push_back(FileImage{f.name, f.data, f.len});
+    }
+    auto part = std::make_shared<Part>();
+    part->id = part_id;
+    part->device = ctx->device;
+    std::string err;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);  // NameTable is shared
+        int rc = build_part_dir(imgs, ctx->names, part->dir, err);
+        if (rc) return fail(rc, "part " + std::to_string(part_id) + ": " + err);
+    }
+    // arena: each data file 256 B aligned with >= 256 B of slack after it (TMA over-read, bit windows)
+    std::vector<size_t> offs;
+    size_t arena = 0;
+    std::vector<const FileImage *> order;
+    for (const auto &name : part->dir.files) {
+        const FileImage *img = nullptr;
+        for (const auto &f : imgs)
+            if (f.name == name) img = &f;
+        if (!img) return fail(BYDB_ENOENT, "missing file " + name);
+        order.push_back(img);
+        offs.push_back(arena);
+        arena = align_up(arena + img->len + 256, 256);
+    }
+    const size_t nb = part->dir.blocks.size(), nc = part->dir.cols.size(), nf = order.size();
+    const size_t dir_bytes = align_up(nb * sizeof(DevBlock), 256) + align_up(nc * sizeof(DevCol), 256) + align_up(nf * sizeof(void *), 256);
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ctx->hbm_budget && ctx->hbm_used + arena + dir_bytes > ctx->hbm_budget) return fail(BYDB_ENOMEM, "HBM budget exceeded");
+        ctx->hbm_used += arena + dir_bytes;
+    }
+    part->hbm_bytes = arena + dir_bytes;
+    auto undo_budget = [&]() {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->hbm_used -= part->hbm_bytes;
+    };
+    if (cudaMalloc(reinterpret_cast<void **>(&part->d_arena), arena ? arena : 256) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void **>(&part->d_dir), dir_bytes ? dir_bytes : 256) != cudaSuccess) {
+        undo_budget();
+        return fail(BYDB_ENOMEM, "cudaMalloc failed for part " + std::to_string(part_id));
+    }
+    SlotLease lease(ctx);
+    if (lease.init()) {
+        undo_budget();
+        return fail(BYDB_EIO, "cannot create stream");
+    }
+    cudaStream_t s = lease.slot->stream;
+    cudaError_t e = cudaMemsetAsync(part->d_arena, 0, arena ? arena : 256, s);
+    for (size_t i = 0; i < nf && e == cudaSuccess; ++i)
+        if (order[i]->len) e = cudaMemcpyAsync(part->d_arena + offs[i], order[i]->data, order[i]->len, cudaMemcpyHostToDevice, s);
+    // directory
+    std::vector<uint8_t> hdir(dir_bytes ? dir_bytes : 1, 0);
+    size_t o = 0;
+    if (nb) memcpy(hdir.data() + o, part->dir.blocks.data(), nb * sizeof(DevBlock));
+    const size_t off_cols = align_up(nb * sizeof(DevBlock), 256);
+    if (nc) memcpy(hdir.data() + off_cols, part->dir.cols.data(), nc * sizeof(DevCol));
+    const size_t off_files = off_cols + align_up(nc * sizeof(DevCol), 256);
+    for (size_t i = 0; i < nf; ++i) {
+        const uint8_t *pfile = part->d_arena + offs[i];
+        memcpy(hdir.data() + off_files + i * sizeof(void *), &pfile, sizeof(void *));
+    }
+    (void)o;
+    if (e == cudaSuccess && dir_bytes) e = cudaMemcpyAsync(part->d_dir, hdir.data(), dir_bytes, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        undo_budget();
+        return fail(BYDB_EIO, std::string("part upload: ") + cudaGetErrorString(e));
+    }
+    part->d_blocks = reinterpret_cast<const DevBlock *>(part->d_dir);
+    part->d_cols = reinterpret_cast<const DevCol *>(part->d_dir + off_cols);
+    part->d_files = reinterpret_cast<const uint8_t *const *>(part->d_dir + off_files);
+    if (h2d) {
+        for (size_t i = 0; i < nf; ++i) *h2d += order[i]->len;
+        *h2d += dir_bytes;
+    }
+    out = part;
+    return 0;
+}
+
+struct Scratch {
+    uint8_t *base = nullptr;
+    size_t bytes = 0;
+    cudaStream_t stream = nullptr;
+    ~Scratch() {
+        if (base) cudaFreeAsync(base, stream);
+    }
+};
+
+// Runs plan -> scan -> series_reduce -> group_reduce on `stream`, leaving the partial table at
+// `d_table` (device).  Synchronises the stream.  Fills stats.
+int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cudaStream_t stream, uint8_t *d_table, const TableLayout &tl,
+             bydb_stats *stats) {
+    const size_t F = plan.fcols.size();
+    const size_t NS = q->n_series;
+    const size_t NB = plan.total_blocks;
+    const int32_t G = plan.n_groups;
+    // ---- host staging: sids | order | group_start
+    std::vector<int32_t> order(NS), gstart(static_cast<size_t>(G) + 1, 0);
+    if (q->series_group) {
+        for (size_t i = 0; i < NS; ++i) gstart[static_cast<size_t>(q->series_group[i]) + 1]++;
+        for (int32_t g = 0; g < G; ++g) gstart[g + 1] += gstart[g];
+        std::vector<int32_t> cur(gstart.begin(), gstart.end() - 1);
+        for (size_t i = 0; i < NS; ++i) order[cur[q->series_group[i]]++] = static_cast<int32_t>(i);
+    } else {
+        for (size_t i = 0; i < NS; ++i) order[i] = static_cast<int32_t>(i);
+        gstart[1] = static_cast<int32_t>(NS);
+    }
+    // ---- device scratch layout
+    size_t o = 0;
+    auto carve = [&](size_t bytes) {
+        size_t at = o;
+        o = align_up(o + bytes, 256);
+        return at;
+    };
+    const size_t off_zero = carve(256);  // work_count, work_next, err[2], stats[4], col_type[F]
+    const size_t off_sids = carve(NS * 8);
+    const size_t off_order = carve(NS * 4);
+    const size_t off_gstart = carve((static_cast<size_t>(G) + 1) * 4);
+    const size_t off_worklist = carve(NB * 4);
+    const size_t off_qsid = carve(NB * 4);
+    const size_t off_P = carve(NB * F * sizeof(BlockPartial));
+    const size_t off_Prows = carve(NB * 4);
+    const size_t off_S = carve(NS * F * sizeof(BlockPartial));
+    const size_t off_Srows = carve(NS * 8);
+    Scratch sc;
+    sc.stream = stream;
+    sc.bytes = o;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&sc.base), o, stream));
+    uint8_t *d = sc.base;
+    const size_t stage_bytes = NS * 8 + NS * 4 + (static_cast<size_t>(G) + 1) * 4;
+    if (slot.ensure_pinned(stage_bytes + 256)) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
+    uint8_t *h = slot.pinned;
+    if (NS) memcpy(h, q->series_ids, NS * 8);
+    if (NS) memcpy(h + NS * 8, order.data(), NS * 4);
+    memcpy(h + NS * 12, gstart.data(), (static_cast<size_t>(G) + 1) * 4);
+    CUDA_TRY(cudaMemsetAsync(d + off_zero, 0, 256, stream));
+    if (NS) CUDA_TRY(cudaMemcpyAsync(d + off_sids, h, NS * 8, cudaMemcpyHostToDevice, stream));
+    if (NS) CUDA_TRY(cudaMemcpyAsync(d + off_order, h + NS * 8, NS * 4, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(d + off_gstart, h + NS * 12, (static_cast<size_t>(G) + 1) * 4, cudaMemcpyHostToDevice, stream));
+    if (stats) stats->h2d_bytes += stage_bytes;
+
+    // zero page: [0] work_count [1] work_next [2..3] err [4..11] stats (u64 x4) [16..] col_type
+    uint32_t *z32 = reinterpret_cast<uint32_t *>(d + off_zero);
+    ScanParams sp;
+    memset(&sp, 0, sizeof sp);
+    ReduceParams rp;
+    memset(&rp, 0, sizeof rp);
+    uint32_t base = 0;
+    for (size_t i = 0; i < plan.parts.size(); ++i) {
+        DevPartRef r;
+        r.blocks = plan.parts[i]->d_blocks;
+        r.cols = plan.parts[i]->d_cols;
+        r.files = plan.parts[i]->d_files;
+        r.n_blocks = static_cast<uint32_t>(plan.parts[i]->dir.blocks.size());
+        r.block_base = base;
+        base += r.n_blocks;
+        sp.parts[i] = r;
+        rp.parts[i] = r;
+    }
+    sp.n_parts = rp.n_parts = static_cast<uint32_t>(plan.parts.size());
+    sp.total_blocks = static_cast<uint32_t>(NB);
+    sp.q_sids = reinterpret_cast<const uint64_t *>(d + off_sids);
+    sp.n_series = static_cast<uint32_t>(NS);
+    sp.n_fcols = static_cast<uint32_t>(F);
+    sp.n_preds = q->n_preds;
+    sp.tmin = q->tmin;
+    sp.tmax = q->tmax;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (size_t c = 0; c < F; ++c) sp.fcol_name[c] = ctx->names.find("f:" + plan.fcols[c]);
+        for (uint32_t i = 0; i < q->n_preds; ++i) {
+            const bydb_pred &p = q->preds[i];
+            DevPred &dp = sp.preds[i];
+            dp.name_id = ctx->names.find(std::string("t:") + p.family + "/" + p.tag);
+            dp.op = static_cast<uint8_t>(p.op);
+            dp.value_type = static_cast<uint8_t>(p.value_type == BYDB_VT_BINARY ? BYDB_VT_STR : p.value_type);
+            dp.lit_i64 = p.lit_i64;
+            dp.lit_len = p.value_type == BYDB_VT_INT64 ? 0 : static_cast<uint32_t>(p.lit_len);
+            if (dp.lit_len) memcpy(dp.lit, p.lit, dp.lit_len);
+        }
+    }
+    sp.worklist = reinterpret_cast<uint32_t *>(d + off_worklist);
+    sp.work_count = z32 + 0;
+    sp.work_next = z32 + 1;
+    sp.err = z32 + 2;
+    sp.stats = reinterpret_cast<unsigned long long *>(d + off_zero + 16);
+    sp.col_type = reinterpret_cast<int32_t *>(d + off_zero + 64);
+    sp.block_qsid = reinterpret_cast<int32_t *>(d + off_qsid);
+    sp.P = reinterpret_cast<BlockPartial *>(d + off_P);
+    sp.Prows = reinterpret_cast<uint32_t *>(d + off_Prows);
+
+    rp.n_series = static_cast<uint32_t>(NS);
+    rp.n_fcols = static_cast<uint32_t>(F);
+    rp.n_groups = G;
+    rp.q_sids = sp.q_sids;
+    rp.order = reinterpret_cast<const int32_t *>(d + off_order);
+    rp.group_start = reinterpret_cast<const int32_t *>(d + off_gstart);
+    rp.block_qsid = sp.block_qsid;
+    rp.P = sp.P;
+    rp.Prows = sp.Prows;
+    rp.col_type = sp.col_type;
+    rp.S = reinterpret_cast<BlockPartial *>(d + off_S);
+    rp.Srows = reinterpret_cast<int64_t *>(d + off_Srows);
+    rp.err = sp.err;
+    rp.sum_f64 = reinterpret_cast<double *>(d_table + tl.off_sum_f64);
+    rp.max_f64 = reinterpret_cast<double *>(d_table + tl.off_max_f64);
+    rp.negmin_f64 = reinterpret_cast<double *>(d_table + tl.off_negmin_f64);
+    rp.sum_i64 = reinterpret_cast<int64_t *>(d_table + tl.off_sum_i64);
+    rp.cnt = reinterpret_cast<int64_t *>(d_table + tl.off_cnt);
+    rp.rows = reinterpret_cast<int64_t *>(d_table + tl.off_rows);
+    rp.max_i64 = reinterpret_cast<int64_t *>(d_table + tl.off_max_i64);
+    rp.notmin_i64 = reinterpret_cast<int64_t *>(d_table + tl.off_notmin_i64);
+    rp.coltype = reinterpret_cast<int64_t *>(d_table + tl.off_coltype);
+
+    CUDA_TRY(cudaEventRecord(slot.ev[0], stream));
+    launch_plan_blocks(sp, stream);
+    CUDA_TRY(cudaEventRecord(slot.ev[1], stream));
+    launch_scan_blocks(sp, ctx->sm_count * ctx->ctas_per_sm, stream);
+    CUDA_TRY(cudaEventRecord(slot.ev[2], stream));
+    launch_series_reduce(rp, stream);
+    launch_group_reduce(rp, stream);
+    CUDA_TRY(cudaEventRecord(slot.ev[3], stream));
+    // read back the zero page (errors + stats)
+    if (slot.ensure_pinned(256)) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
+    CUDA_TRY(cudaMemcpyAsync(slot.pinned, d + off_zero, 256, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaGetLastError());
+    const uint32_t *hz = reinterpret_cast<const uint32_t *>(slot.pinned);
+    if (stats) {
+        const unsigned long long *hs = reinterpret_cast<const unsigned long long *>(slot.pinned + 16);
+        stats->rows_scanned += hs[0];
+        stats->rows_matched += hs[1];
+        stats->page_bytes += hs[2];
+        stats->blocks_scanned += hs[3];
+        float ms = 0;
+        cudaEventElapsedTime(&ms, slot.ev[1], slot.ev[2]);
+        stats->scan_kernel_ms += ms;
+        cudaEventElapsedTime(&ms, slot.ev[0], slot.ev[3]);
+        stats->device_ms += ms;
+        stats->kernel_launches += (NB ? 1u : 0u) + 1u + (NS ? 1u : 0u) + 1u;
+        stats->d2h_bytes += 256;
+    }
+    if (hz[2] != 0) {
+        char buf[96];
+        snprintf(buf, sizeof buf, " (block/series #%u)", hz[3]);
+        return fail(dev_err_code(hz[2]), std::string(dev_err_text(hz[2])) + buf);
+    }
+    return 0;
+}
+
+int finalize_to_host(bydb_ctx *ctx, const bydb_query *q, const Plan &plan, ExecSlot &slot, cudaStream_t stream, const uint8_t *d_table,
+                     const TableLayout &tl, bydb_result *out) {
+    const size_t F = plan.fcols.size();
+    const int32_t G = plan.n_groups;
+    const size_t A = q->n_aggs;
+    const size_t out_bytes = align_up(static_cast<size_t>(G) * A * 8, 256) * 2 + align_up(A, 256) + align_up(static_cast<size_t>(G) * 8, 256) +
+                             align_up(static_cast<size_t>(G) * F * 8, 256);
+    Scratch sc;
+    sc.stream = stream;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&sc.base), out_bytes, stream));
+    uint8_t *d = sc.base;
+    FinalizeParams fp;
+    memset(&fp, 0, sizeof fp);
+    fp.n_groups = G;
+    fp.n_fcols = static_cast<uint32_t>(F);
+    fp.n_aggs = static_cast<uint32_t>(A);
+    for (size_t a = 0; a < A; ++a) {
+        fp.agg_fcol[a] = plan.agg_fcol[a];
+        fp.agg_func[a] = q->aggs[a].func;
+    }
+    fp.sum_f64 = reinterpret_cast<const double *>(d_table + tl.off_sum_f64);
+    fp.max_f64 = reinterpret_cast<const double *>(d_table + tl.off_max_f64);
+    fp.negmin_f64 = reinterpret_cast<const double *>(d_table + tl.off_negmin_f64);
+    fp.sum_i64 = reinterpret_cast<const int64_t *>(d_table + tl.off_sum_i64);
+    fp.cnt = reinterpret_cast<const int64_t *>(d_table + tl.off_cnt);
+    fp.rows = reinterpret_cast<const int64_t *>(d_table + tl.off_rows);
+    fp.max_i64 = reinterpret_cast<const int64_t *>(d_table + tl.off_max_i64);
+    fp.notmin_i64 = reinterpret_cast<const int64_t *>(d_table + tl.off_notmin_i64);
+    fp.coltype = reinterpret_cast<const int64_t *>(d_table + tl.off_coltype);
+    const size_t o_i64 = 0, o_f64 = align_up(static_cast<size_t>(G) * A * 8, 256), o_isf = o_f64 * 2;
+    fp.out_i64 = reinterpret_cast<int64_t *>(d + o_i64);
+    fp.out_f64 = reinterpret_cast<double *>(d + o_f64);
+    fp.out_is_float = d + o_isf;
+    launch_finalize(fp, stream);
+    // D2H: values, typing, rows and counts (counts decide "null" for Top)
+    const size_t h_rows = align_up(o_isf + align_up(A, 256), 256);
+    const size_t h_cnt = h_rows + align_up(static_cast<size_t>(G) * 8, 256);
+    const size_t h_total = h_cnt + align_up(static_cast<size_t>(G) * F * 8, 256);
+    if (slot.ensure_pinned(h_total)) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
+    uint8_t *h = slot.pinned;
+    CUDA_TRY(cudaMemcpyAsync(h, d, o_isf + A, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(h + h_rows, d_table + tl.off_rows, static_cast<size_t>(G) * 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(h + h_cnt, d_table + tl.off_cnt, static_cast<size_t>(G) * F * 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaGetLastError());
+    out->stats.d2h_bytes += o_isf + A + static_cast<size_t>(G) * 8 + static_cast<size_t>(G) * F * 8;
+    out->stats.kernel_launches += 1;
+    const int64_t *v_i = reinterpret_cast<const int64_t *>(h + o_i64);
+    const double *v_f = reinterpret_cast<const double *>(h + o_f64);
+    const uint8_t *isf = h + o_isf;
+    const int64_t *rows = reinterpret_cast<const int64_t *>(h + h_rows);
+    const int64_t *cnt = reinterpret_cast<const int64_t *>(h + h_cnt);
+
+    auto owner = new ResultOwner();
+    std::vector<int32_t> emit;
+    for (int32_t g = 0; g < G; ++g)
+        if (rows[g] > 0) emit.push_back(g);
+    if (q->top_n > 0) {
+        // pkg/query/vectorized/measure/top.go:145-214: nulls lowest, ties -> earlier row wins
+        const int a = q->top_agg;
+        const int c = plan.agg_fcol[a];
+        const bool f = isf[a];
+        const bool desc = q->top_desc != 0;
+        const bool count_fn = q->aggs[a].func == BYDB_AGG_COUNT;
+        auto less = [&](int32_t x, int32_t y) {
+            const bool nx = !count_fn && cnt[static_cast<size_t>(x) * F + c] == 0, ny = !count_fn && cnt[static_cast<size_t>(y) * F + c] == 0;
+            if (nx != ny) return ny;
+            if (!nx) {
+                if (f) {
+                    const double vx = v_f[static_cast<size_t>(x) * A + a], vy = v_f[static_cast<size_t>(y) * A + a];
+                    if (vx != vy) return desc ? vx > vy : vx < vy;
+                } else {
+                    const int64_t vx = v_i[static_cast<size_t>(x) * A + a], vy = v_i[static_cast<size_t>(y) * A + a];
+                    if (vx != vy) return desc ? vx > vy : vx < vy;
+                }
+            }
+            return x < y;
+        };
+        const size_t n = std::min<size_t>(emit.size(), static_cast<size_t>(q->top_n));
+        std::partial_sort(emit.begin(), emit.begin() + n, emit.end(), less);
+        emit.resize(n);
+    }
+    const size_t R = emit.size();
+    owner->group_id.assign(emit.begin(), emit.end());
+    owner->rows.resize(R);
+    owner->is_float.assign(isf, isf + A);
+    owner->val_i64.resize(R * A);
+    owner->val_f64.resize(R * A);
+    for (size_t r = 0; r < R; ++r) {
+        const int32_t g = emit[r];
+        owner->rows[r] = rows[g];
+        for (size_t a = 0; a < A; ++a) {
+            owner->val_i64[r * A + a] = v_i[static_cast<size_t>(g) * A + a];
+            owner->val_f64[r * A + a] = v_f[static_cast<size_t>(g) * A + a];
+        }
+    }
+    out->n_rows = static_cast<int32_t>(R);
+    out->n_aggs = static_cast<int32_t>(A);
+    out->group_id = owner->group_id.data();
+    out->rows = owner->rows.data();
+    out->is_float = owner->is_float.data();
+    out->val_i64 = owner->val_i64.data();
+    out->val_f64 = owner->val_f64.data();
+    out->owner = owner;
+    return 0;
+}
+
+int make_plan(bydb_ctx *ctx, const bydb_query *q, const std::vector<std::shared_ptr<Part>> *given, Plan &plan) {
+    if (given) {
+        plan.parts = *given;
+    } else {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (uint32_t i = 0; i < q->n_parts; ++i) {
+            auto it = ctx->parts.find(q->parts[i]);
+            if (it == ctx->parts.end()) return fail(BYDB_ENOENT, "unknown part handle");
+            plan.parts.push_back(it->second);
+        }
+    }
+    distinct_fields(q, plan.fcols, plan.agg_fcol);
+    if (plan.fcols.size() > kMaxFcols) return fail(BYDB_EINVAL, "too many distinct aggregated fields (max 8)");
+    plan.n_groups = q->series_group ? q->n_groups : 1;
+    uint64_t nb = 0;
+    for (auto &p : plan.parts) nb += p->dir.blocks.size();
+    if (nb > 0x7fffffffull) return fail(BYDB_EINVAL, "too many blocks");
+    plan.total_blocks = static_cast<uint32_t>(nb);
+    plan.n_series = q->n_series;
+    return 0;
+}
+
+int scan_agg_impl(bydb_ctx *ctx, const bydb_query *q, const std::vector<std::shared_ptr<Part>> *given, bydb_result *out, uint64_t h2d_pre) {
+    Plan plan;
+    int rc = make_plan(ctx, q, given, plan);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    SlotLease lease(ctx);
+    if (lease.init()) return fail(BYDB_EIO, "cannot create stream");
+    ExecSlot &slot = *lease.slot;
+    TableLayout tl(static_cast<size_t>(plan.n_groups), plan.fcols.size());
+    Scratch table;
+    table.stream = slot.stream;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&table.base), tl.total, slot.stream));
+    memset(&out->stats, 0, sizeof out->stats);
+    out->stats.h2d_bytes = h2d_pre;
+    rc = run_scan(ctx, q, plan, slot, slot.stream, table.base, tl, &out->stats);
+    if (rc) return rc;
+    return finalize_to_host(ctx, q, plan, slot, slot.stream, table.base, tl, out);
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char *bydb_last_error(void) { return g_last_error.c_str(); }
+const char *bydb_version(void) { return "bydb-b200 0.1 (sm_100a)"; }
+
+int bydb_init(const bydb_cfg *cfg, bydb_ctx **out) {
+    if (!out) return fail(BYDB_EINVAL, "out is NULL");
+    *out = nullptr;
+    int dev = cfg ? cfg->device : 0;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return fail(BYDB_EIO, "no CUDA device: libbydbgpu has no CPU fallback");
+    if (dev < 0 || dev >= n) return fail(BYDB_EINVAL, "bad device ordinal");
+    CUDA_TRY(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) return fail(BYDB_ENOTSUP, std::string("device '") + prop.name + "' is not sm_100 (Blackwell); this library is built for sm_100a only");
+    auto ctx = new bydb_ctx();
+    ctx->device = dev;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->hbm_budget = cfg ? cfg->hbm_budget_bytes : 0;
+    if (upload_pow10_table()) {
+        delete ctx;
+        return fail(BYDB_EIO, "cannot upload constant tables (is the library built for this GPU?)");
+    }
+    int occ = scan_max_ctas_per_sm();
+    int want = (cfg && cfg->warps_per_sm > 0) ? (cfg->warps_per_sm + kWarpsPerCta - 1) / kWarpsPerCta : 2;
+    ctx->ctas_per_sm = std::max(1, std::min(want, occ));
+    *out = ctx;
+    return 0;
+}
+
+void bydb_shutdown(bydb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto &s : ctx->free_slots) {
+        if (s->stream) cudaStreamDestroy(s->stream);
+        for (auto &e : s->ev)
+            if (e) cudaEventDestroy(e);
+        if (s->pinned) cudaFreeHost(s->pinned);
+    }
+    ctx->free_slots.clear();
+    ctx->parts.clear();
+    delete ctx;
+}
+
+int bydb_part_register(bydb_ctx *ctx, uint64_t part_id, const bydb_part_files *files, bydb_part_h *out) {
+    if (!ctx || !out) return fail(BYDB_EINVAL, "ctx/out is NULL");
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        auto it = ctx->by_id.find(part_id);
+        if (it != ctx->by_id.end()) {  // idempotent per part_id
+            *out = it->second;
+            return 0;
+        }
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    std::shared_ptr<Part> part;
+    int rc = register_part_locked_free(ctx, part_id, files, part, nullptr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    bydb_part_h h = ctx->next_handle++;
+    ctx->parts[h] = part;
+    ctx->by_id[part_id] = h;
+    *out = h;
+    return 0;
+}
+
+int bydb_part_release(bydb_ctx *ctx, bydb_part_h h) {
+    if (!ctx) return fail(BYDB_EINVAL, "ctx is NULL");
+    std::shared_ptr<Part> victim;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        auto it = ctx->parts.find(h);
+        if (it == ctx->parts.end()) return fail(BYDB_ENOENT, "unknown part handle");
+        victim = it->second;
+        ctx->by_id.erase(victim->id);
+        ctx->parts.erase(it);
+        ctx->hbm_used -= victim->hbm_bytes;
+    }
+    cudaSetDevice(ctx->device);
+    victim.reset();  // frees HBM once no in-flight query holds the part
+    return 0;
+}
+
+int bydb_part_info(bydb_ctx *ctx, bydb_part_h h, uint64_t *hbm_bytes, uint64_t *n_blocks, uint64_t *n_rows) {
+    if (!ctx) return fail(BYDB_EINVAL, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->parts.find(h);
+    if (it == ctx->parts.end()) return fail(BYDB_ENOENT, "unknown part handle");
+    if (hbm_bytes) *hbm_bytes = it->second->hbm_bytes;
+    if (n_blocks) *n_blocks = it->second->dir.blocks.size();
+    if (n_rows) *n_rows = it->second->dir.total_rows;
+    return 0;
+}
+
+int bydb_scan_agg(bydb_ctx *ctx, const bydb_query *q, bydb_result *out) {
+    if (!ctx || !out) return fail(BYDB_EINVAL, "ctx/out is NULL");
+    memset(out, 0, sizeof *out);
+    int rc = validate_query(q, true);
+    if (rc) return rc;
+    return scan_agg_impl(ctx, q, nullptr, out, 0);
+}
+
+int bydb_scan_agg_host(bydb_ctx *ctx, uint32_t n_parts, const bydb_part_files *parts, const bydb_query *q, bydb_result *out) {
+    if (!ctx || !out) return fail(BYDB_EINVAL, "ctx/out is NULL");
+    memset(out, 0, sizeof *out);
+    int rc = validate_query(q, false);
+    if (rc) return rc;
+    if (n_parts == 0 || !parts || n_parts > kMaxParts) return fail(BYDB_EINVAL, "need 1..64 host parts");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    std::vector<std::shared_ptr<Part>> tmp;
+    uint64_t h2d = 0;
+    for (uint32_t i = 0; i < n_parts; ++i) {
+        std::shared_ptr<Part> p;
+        rc = register_part_locked_free(ctx, ~0ull - i, &parts[i], p, &h2d);
+        if (rc) break;
+        tmp.push_back(p);
+    }
+    if (!rc) rc = scan_agg_impl(ctx, q, &tmp, out, h2d);
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (auto &p : tmp) ctx->hbm_used -= p->hbm_bytes;
+    }
+    return rc;
+}
+
+void bydb_result_free(bydb_ctx *, bydb_result *r) {
+    if (!r) return;
+    delete static_cast<ResultOwner *>(r->owner);
+    memset(r, 0, sizeof *r);
+}
+
+int bydb_partials_layout(const bydb_query *q, bydb_partials_layout_t *out) {
+    if (!q || !out) return fail(BYDB_EINVAL, "NULL argument");
+    int rc = validate_query(q, false);
+    if (rc) return rc;
+    std::vector<std::string> fcols;
+    std::vector<int> agg_fcol;
+    distinct_fields(q, fcols, agg_fcol);
+    TableLayout tl(static_cast<size_t>(q->series_group ? q->n_groups : 1), fcols.size());
+    out->total_bytes = tl.total;
+    out->off_sum_f64 = tl.off_sum_f64;
+    out->n_sum_f64 = tl.GF;
+    out->off_max_f64 = tl.off_max_f64;
+    out->n_max_f64 = 2 * tl.GF;
+    out->off_sum_i64 = tl.off_sum_i64;
+    out->n_sum_i64 = 2 * tl.GF + tl.G;
+    out->off_max_i64 = tl.off_max_i64;
+    out->n_max_i64 = 2 * tl.GF + tl.F;
+    return 0;
+}
+
+int bydb_scan_partials(bydb_ctx *ctx, const bydb_query *q, void *d_partials, uint64_t bytes, void *stream, bydb_stats *stats) {
+    if (!ctx || !d_partials) return fail(BYDB_EINVAL, "ctx/d_partials is NULL");
+    int rc = validate_query(q, true);
+    if (rc) return rc;
+    Plan plan;
+    rc = make_plan(ctx, q, nullptr, plan);
+    if (rc) return rc;
+    TableLayout tl(static_cast<size_t>(plan.n_groups), plan.fcols.size());
+    if (bytes < tl.total) return fail(BYDB_EINVAL, "partial table buffer too small");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    SlotLease lease(ctx);
+    if (lease.init()) return fail(BYDB_EIO, "cannot create stream");
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : lease.slot->stream;
+    bydb_stats local;
+    memset(&local, 0, sizeof local);
+    rc = run_scan(ctx, q, plan, *lease.slot, s, static_cast<uint8_t *>(d_partials), tl, &local);
+    if (stats) *stats = local;
+    return rc;
+}
+
+int bydb_reduce_finalize(bydb_ctx *ctx, const bydb_query *q, const void *d_partials, uint64_t bytes, void *stream, bydb_result *out) {
+    if (!ctx || !d_partials || !out) return fail(BYDB_EINVAL, "NULL argument");
+    memset(out, 0, sizeof *out);
+    int rc = validate_query(q, false);
+    if (rc) return rc;
+    Plan plan;
+    distinct_fields(q, plan.fcols, plan.agg_fcol);
+    plan.n_groups = q->series_group ? q->n_groups : 1;
+    TableLayout tl(static_cast<size_t>(plan.n_groups), plan.fcols.size());
+    if (bytes < tl.total) return fail(BYDB_EINVAL, "partial table buffer too small");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    SlotLease lease(ctx);
+    if (lease.init()) return fail(BYDB_EIO, "cannot create stream");
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : lease.slot->stream;
+    return finalize_to_host(ctx, q, plan, *lease.slot, s, static_cast<const uint8_t *>(d_partials), tl, out);
+}
+
+}  // extern "C"

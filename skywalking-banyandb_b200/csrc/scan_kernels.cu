@@ -1,0 +1,1213 @@
+// scan_kernels.cu -- hand-written sm_100a kernels of the measure scan -> filter -> aggregate path.
+//
+//   plan_blocks    a1-a3  block selection: sid in query set AND [ts_min,ts_max] overlaps [tmin,tmax]
+//                         (banyand/measure/part_iter.go:79-250, query.go:594-639)
+//   scan_blocks    a4-a13 one warp per block: timestamps -> row range, tag pages -> row bitmask,
+//                         field pages (varint / delta / delta-of-delta, decimal floats) -> per-block
+//                         partial aggregates (block.go:299-418,793-870; column.go:287-364;
+//                         pkg/encoding/{int.go,delta.go,float.go,dictionary.go};
+//                         pkg/query/aggregation/function.go)
+//   series_reduce / group_reduce   deterministic (fixed order) combine of the per-block partials
+//                         into per-group partial tables (aggregation.go:193-312 fold order is
+//                         replaced by a fixed tree; sums stay within the 1e-9 contract)
+//   finalize       a13-a14 MEAN finalisation / output typing (function.go:31-40, aggregation.go:425-430)
+//
+// Pages are streamed from HBM into per-warp shared-memory stages with 1-D TMA bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx) and decoded with warp-shuffle scans; no tensor cores
+// (there is no dense contraction on this path).
+#include "scan_kernels.cuh"
+
+#include <cfloat>
+#include <cmath>
+
+#include "../../include/bydb_gpu.h"
+
+namespace bydb {
+
+__constant__ double c_pow10[309];  // Go math.Pow10(n), 0 <= n <= 308 (table product, see upload_pow10_table)
+
+// ------------------------------------------------------------------------------------------------
+// small PTX wrappers: mbarrier + 1-D bulk TMA
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// global -> shared bulk copy executed by the TMA unit; completion is signalled on `bar`
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-warp shared memory
+// ------------------------------------------------------------------------------------------------
+struct __align__(128) WarpSmem {
+    uint8_t stage[kStages][kStageBytes];
+    uint64_t bar[kStages];
+    uint32_t mask[kMaskWords];
+    uint32_t match[8];  // dictionary match set of the predicate being applied
+    uint32_t pad[2];
+};
+
+size_t scan_smem_bytes() { return sizeof(WarpSmem) * kWarpsPerCta; }
+
+struct PageStream {
+    const uint8_t *abase;  // 16 B aligned global address at or below the first body byte
+    uint32_t total;        // aligned length (multiple of 16)
+    uint32_t pstart, pend; // valid byte range inside [0,total)
+    uint32_t nstages;
+    uint32_t seq0;         // warp-monotonic stage sequence number of stage 0
+};
+
+__device__ __forceinline__ void stream_issue(const PageStream &s, WarpSmem *sm, uint32_t k) {
+    uint32_t off = k * kStageBytes;
+    uint32_t bytes = min(static_cast<uint32_t>(kStageBytes), s.total - off);
+    uint32_t slot = (s.seq0 + k) % kStages;
+    mbar_expect_tx(&sm->bar[slot], bytes);
+    tma_load_1d(sm->stage[slot], s.abase + off, bytes, &sm->bar[slot]);
+}
+__device__ __forceinline__ void stream_open(PageStream &s, WarpSmem *sm, uint32_t &seq, const uint8_t *body, uint32_t len, int lane) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(body);
+    s.abase = reinterpret_cast<const uint8_t *>(a & ~static_cast<uintptr_t>(15));
+    s.pstart = static_cast<uint32_t>(a & 15);
+    s.pend = s.pstart + len;
+    s.total = (s.pend + 15u) & ~15u;
+    s.nstages = (s.total + kStageBytes - 1) / kStageBytes;
+    s.seq0 = seq;
+    seq += s.nstages;
+    __syncwarp();  // every lane is done reading the stages of the previous page
+    if (lane == 0) {
+        uint32_t n = min(s.nstages, static_cast<uint32_t>(kStages));
+        for (uint32_t k = 0; k < n; ++k) stream_issue(s, sm, k);
+    }
+}
+__device__ __forceinline__ const uint8_t *stream_wait(const PageStream &s, WarpSmem *sm, uint32_t k) {
+    uint32_t n = s.seq0 + k;
+    uint32_t slot = n % kStages;
+    uint32_t parity = (n / kStages) & 1u;
+    while (!mbar_try_wait(&sm->bar[slot], parity)) {
+    }
+    return sm->stage[slot];
+}
+__device__ __forceinline__ void stream_release(const PageStream &s, WarpSmem *sm, uint32_t k, int lane) {
+    __syncwarp();
+    if (lane == 0 && k + kStages < s.nstages) stream_issue(s, sm, k + kStages);
+}
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t msb4(uint32_t x) {  // gathers the 4 byte-MSBs of x into bits 0..3
+    return (((x >> 7) & 0x01010101u) * 0x01020408u) >> 24 & 0xfu;
+}
+__device__ __forceinline__ int64_t zigzag64(uint64_t u) { return static_cast<int64_t>(u >> 1) ^ -static_cast<int64_t>(u & 1); }
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+    uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v), src);
+    uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), src);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int delta) {
+    uint32_t lo = __shfl_up_sync(0xffffffffu, static_cast<uint32_t>(v), delta);
+    uint32_t hi = __shfl_up_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), delta);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+    uint32_t lo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v), m);
+    uint32_t hi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), m);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// pkg/convert/number.go:93-106 BytesToInt64 (order-preserving form, NOT two's complement)
+__device__ __forceinline__ int64_t conv_bytes_to_int64(const uint8_t *b) {
+    uint64_t u = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) u = (u << 8) | __ldg(b + k);
+    if (u >> 63) return static_cast<int64_t>(u ^ (1ull << 63));
+    return static_cast<int64_t>(0ull - ((1ull << 63) - u));
+}
+
+// pkg/encoding/int.go:111-148: one zig-zag varint read sequentially (headers only)
+__device__ __forceinline__ bool read_varint_seq(const uint8_t *p, uint32_t len, int64_t &out, uint32_t &used) {
+    uint64_t u = 0;
+    for (uint32_t i = 0; i < len && i < 10; ++i) {
+        uint8_t c = __ldg(p + i);
+        u |= static_cast<uint64_t>(c & 0x7f) << (7 * i);
+        if (c < 0x80) {
+            out = zigzag64(u);
+            used = i + 1;
+            return true;
+        }
+    }
+    return false;
+}
+__device__ __forceinline__ bool read_varuint_seq(const uint8_t *&p, const uint8_t *end, uint64_t &out) {
+    uint64_t u = 0;
+    for (uint32_t i = 0; i < 10 && p < end; ++i) {
+        uint8_t c = __ldg(p++);
+        u |= static_cast<uint64_t>(c & 0x7f) << (7 * i);
+        if (c < 0x80) {
+            out = u;
+            return true;
+        }
+    }
+    return false;
+}
+
+__device__ __forceinline__ void set_err(const ScanParams &p, uint32_t code, uint32_t g, int lane) {
+    if (lane == 0 && atomicCAS(&p.err[0], 0u, code) == 0u) p.err[1] = g;
+}
+
+// pkg/encoding/float.go:69-93: int64 -> float64 by the page exponent; exactly the reference's
+// operation sequence (float64(v) * Pow10(e), or float64(v) / d1 / d2 ... with d_i = 10^min(rem,308)).
+__device__ __forceinline__ double scale_decimal(double x, int exp) {
+    if (exp >= 0) {
+        double s = exp <= 308 ? c_pow10[exp] : INFINITY;
+        return __dmul_rn(x, s);
+    }
+    int neg = -exp;
+    while (neg > 0) {
+        int step = neg < 308 ? neg : 308;
+        x = __ddiv_rn(x, c_pow10[step]);
+        neg -= step;
+    }
+    return x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row consumers
+// ------------------------------------------------------------------------------------------------
+enum { kRowsAll = 0, kRowsRange = 1, kRowsMask = 2 };
+
+struct AggAcc {
+    uint64_t lo;
+    int64_t hi;  // 128-bit exact sum (a block holds <= 2^31 rows of int64)
+    int64_t mn, mx;
+    uint32_t cnt;
+    __device__ __forceinline__ void init() {
+        lo = 0;
+        hi = 0;
+        mn = INT64_MAX;
+        mx = INT64_MIN;
+        cnt = 0;
+    }
+    __device__ __forceinline__ void add(int64_t v) {
+        uint64_t uv = static_cast<uint64_t>(v);
+        lo += uv;
+        hi += (v >> 63) + (lo < uv ? 1 : 0);
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+        cnt++;
+    }
+    __device__ __forceinline__ void add_scaled(int64_t v, uint64_t times) {  // += v * times (exact)
+        uint64_t a = static_cast<uint64_t>(v);
+        uint64_t plo = a * times;
+        int64_t phi = static_cast<int64_t>(__umul64hi(a, times)) - (v < 0 ? static_cast<int64_t>(times) : 0);
+        lo += plo;
+        hi += phi + (lo < plo ? 1 : 0);
+    }
+    __device__ __forceinline__ void warp_reduce() {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            uint64_t olo = shfl_xor_u64(lo, m);
+            int64_t ohi = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(hi), m));
+            int64_t omn = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(mn), m));
+            int64_t omx = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(mx), m));
+            uint32_t ocnt = __shfl_xor_sync(0xffffffffu, cnt, m);
+            lo += olo;
+            hi += ohi + (lo < olo ? 1 : 0);
+            mn = omn < mn ? omn : mn;
+            mx = omx > mx ? omx : mx;
+            cnt += ocnt;
+        }
+    }
+};
+
+template <int kMode>
+struct AggCons {
+    AggAcc acc;
+    uint32_t r0, r1;
+    const uint32_t *mask;
+    __device__ __forceinline__ void operator()(uint32_t row, int64_t v) {
+        bool a = true;
+        if (kMode == kRowsRange) a = row >= r0 && row <= r1;
+        if (kMode == kRowsMask) a = (mask[row >> 5] >> (row & 31)) & 1u;
+        if (a) acc.add(v);
+    }
+};
+
+// counts rows with ts < tmin and ts <= tmax (pkg/timestamp/range.go:143-169 on an ascending block)
+struct TsCons {
+    int64_t tmin, tmax;
+    uint32_t lt, le;
+    __device__ __forceinline__ void operator()(uint32_t, int64_t v) {
+        lt += v < tmin ? 1u : 0u;
+        le += v <= tmax ? 1u : 0u;
+    }
+};
+
+__device__ __forceinline__ bool cmp_op(int op, bool have, int cmp) {
+    switch (op) {
+        case BYDB_OP_EQ: return have && cmp == 0;
+        case BYDB_OP_NE: return !have || cmp != 0;
+        case BYDB_OP_LT: return have && cmp < 0;
+        case BYDB_OP_LE: return have && cmp <= 0;
+        case BYDB_OP_GT: return have && cmp > 0;
+        case BYDB_OP_GE: return have && cmp >= 0;
+    }
+    return false;
+}
+
+// int64 tag predicate: clears the mask bit of every non-matching row
+struct CmpCons {
+    int64_t lit;
+    int op;
+    uint32_t *mask;
+    uint32_t limit;  // rows the mask can hold
+    __device__ __forceinline__ void operator()(uint32_t row, int64_t v) {
+        int c = v < lit ? -1 : (v > lit ? 1 : 0);
+        if (!cmp_op(op, true, c) && row < limit) atomicAnd(&mask[row >> 5], ~(1u << (row & 31)));
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// the varint page decoder (pkg/encoding/int.go:111-148 + delta.go:45-70 / :91-118)
+//
+// One warp; every iteration takes 512 B (16 B per lane) of the body from the staged shared-memory
+// tile.  A lane decodes the varints that END inside its 16 bytes; the low bits of a value that
+// started in the previous lane arrive by one shuffle of that lane's unfinished tail.  Row indices
+// come from a warp scan of the per-lane terminator counts, value prefixes from a warp scan of the
+// per-lane delta sums (delta) or of the (count, sum, sum-of-prefix) triple (delta-of-delta).  All
+// int64 arithmetic wraps mod 2^64 like Go's, so the result is bit-exact.
+// ------------------------------------------------------------------------------------------------
+template <bool kDod, class Cons>
+__device__ __noinline__ bool decode_varint_page(WarpSmem *sm, uint32_t &seq, const uint8_t *body, uint32_t len, uint32_t count,
+                                                 int64_t first, Cons &cons, int lane) {
+    if (lane == 0) cons(0u, first);
+    if (len == 0) return count == 1;
+    PageStream st;
+    stream_open(st, sm, seq, body, len, lane);
+    const uint32_t nchunks = (st.total + kChunkBytes - 1) / kChunkBytes;
+    constexpr uint32_t kChunksPerStage = kStageBytes / kChunkBytes;
+    int64_t V0 = first;  // value of the row before this chunk's first varint (warp-uniform)
+    int64_t D0 = 0;      // delta-of-delta: running first difference
+    uint64_t carry_acc = 0;
+    uint32_t carry_sh = 0;
+    uint32_t row_base = 1;
+    const uint8_t *buf = nullptr;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const uint32_t k = c / kChunksPerStage;
+        if ((c % kChunksPerStage) == 0) buf = stream_wait(st, sm, k);
+        const uint32_t o = c * kChunkBytes + lane * 16;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (o < st.total) w = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes));
+        // valid bytes of this lane: [pstart,pend) intersected with [o,o+16)
+        int lo_i = static_cast<int>(st.pstart) - static_cast<int>(o);
+        int hi_i = static_cast<int>(st.pend) - static_cast<int>(o);
+        lo_i = lo_i < 0 ? 0 : (lo_i > 16 ? 16 : lo_i);
+        hi_i = hi_i < 0 ? 0 : (hi_i > 16 ? 16 : hi_i);
+        const uint32_t valid = ((1u << hi_i) - 1u) & ~((1u << lo_i) - 1u);
+        const uint32_t msb = msb4(w.x) | (msb4(w.y) << 4) | (msb4(w.z) << 8) | (msb4(w.w) << 12);
+        const uint32_t term = valid & ~msb;
+
+        // ---- raw payload per terminator position
+        uint64_t d[16];
+        uint64_t acc = 0;
+        uint32_t sh = 0;
+        const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t b = (words[j >> 2] >> (8 * (j & 3))) & 0xffu;
+            const bool isv = (valid >> j) & 1u;
+            const bool ist = (term >> j) & 1u;
+            if (isv) {
+                acc |= static_cast<uint64_t>(b & 0x7fu) << (sh & 63u);
+                sh += 7;
+            }
+            d[j] = acc;
+            if (ist) {
+                acc = 0;
+                sh = 0;
+            }
+        }
+        // ---- splice the head with the previous lane's unfinished tail, zig-zag, local sums
+        uint64_t prev_acc = shfl_up_u64(acc, 1);
+        uint32_t prev_sh = __shfl_up_sync(0xffffffffu, sh, 1);
+        if (lane == 0) {
+            prev_acc = carry_acc;
+            prev_sh = carry_sh;
+        }
+        carry_acc = shfl_u64(acc, 31);
+        carry_sh = __shfl_sync(0xffffffffu, sh, 31);
+        const int firstpos = __ffs(term) - 1;
+        const uint32_t n = __popc(term);
+        int64_t q = 0;  // sum of this lane's values
+        int64_t r = 0;  // delta-of-delta: sum of the running prefixes
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            uint64_t x = d[j];
+            if (j == firstpos) x = prev_acc | (x << (prev_sh & 63u));
+            const int64_t v = zigzag64(x);
+            d[j] = static_cast<uint64_t>(v);
+            if ((term >> j) & 1u) {
+                q += v;
+                if (kDod) r += q;
+            }
+        }
+        // ---- warp scans (inclusive), then exclusive views
+        uint32_t n_in = n;
+        int64_t q_in = q, r_in = r;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            uint32_t on = __shfl_up_sync(0xffffffffu, n_in, s);
+            int64_t oq = static_cast<int64_t>(shfl_up_u64(static_cast<uint64_t>(q_in), s));
+            int64_t orr = 0;
+            if (kDod) orr = static_cast<int64_t>(shfl_up_u64(static_cast<uint64_t>(r_in), s));
+            if (lane >= s) {
+                // (A then B): n = nA+nB, q = qA+qB, r = rA + rB + nB*qA
+                if (kDod) r_in = orr + r_in + static_cast<int64_t>(static_cast<uint64_t>(n_in) * static_cast<uint64_t>(oq));
+                q_in += oq;
+                n_in += on;
+            }
+        }
+        const uint32_t n_ex = n_in - n;
+        int64_t q_ex = static_cast<int64_t>(shfl_up_u64(static_cast<uint64_t>(q_in), 1));
+        int64_t r_ex = 0;
+        if (kDod) r_ex = static_cast<int64_t>(shfl_up_u64(static_cast<uint64_t>(r_in), 1));
+        if (lane == 0) {
+            q_ex = 0;
+            r_ex = 0;
+        }
+        // ---- second pass: true values -> consumer
+        uint32_t row = row_base + n_ex;
+        if (!kDod) {
+            int64_t v = V0 + q_ex;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if ((term >> j) & 1u) {
+                    v += static_cast<int64_t>(d[j]);
+                    cons(row, v);
+                    row++;
+                }
+            }
+        } else {
+            int64_t D = D0 + q_ex;
+            int64_t v = V0 + static_cast<int64_t>(static_cast<uint64_t>(n_ex) * static_cast<uint64_t>(D0)) + r_ex;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if ((term >> j) & 1u) {
+                    D += static_cast<int64_t>(d[j]);
+                    v += D;
+                    cons(row, v);
+                    row++;
+                }
+            }
+        }
+        // ---- carries to the next chunk
+        const uint32_t n_tot = __shfl_sync(0xffffffffu, n_in, 31);
+        const int64_t q_tot = static_cast<int64_t>(shfl_u64(static_cast<uint64_t>(q_in), 31));
+        if (!kDod) {
+            V0 += q_tot;
+        } else {
+            const int64_t r_tot = static_cast<int64_t>(shfl_u64(static_cast<uint64_t>(r_in), 31));
+            V0 += static_cast<int64_t>(static_cast<uint64_t>(n_tot) * static_cast<uint64_t>(D0)) + r_tot;
+            D0 += q_tot;
+        }
+        row_base += n_tot;
+        if ((c % kChunksPerStage) == kChunksPerStage - 1 || c == nchunks - 1) stream_release(st, sm, k, lane);
+    }
+    // the body must hold exactly count-1 varints and end on a terminator
+    return row_base == count && carry_sh == 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row mask helpers (per-warp shared memory bitmask)
+// ------------------------------------------------------------------------------------------------
+// clears bits [a,b) ; cooperative over the warp
+__device__ __forceinline__ void warp_clear_range(uint32_t *mask, uint32_t a, uint32_t b, int lane) {
+    if (a >= b) return;
+    const uint32_t wa = a >> 5, wb = (b - 1) >> 5;
+    for (uint32_t w = wa + lane; w <= wb; w += 32) {
+        uint32_t keep = 0;
+        if (w == wa) keep |= (1u << (a & 31)) - 1u;
+        if (w == wb && (b & 31)) keep |= ~((1u << (b & 31)) - 1u);
+        atomicAnd(&mask[w], keep);
+    }
+}
+// clears bits [a,b) ; executed by one lane (short runs)
+__device__ __forceinline__ void lane_clear_range(uint32_t *mask, uint32_t a, uint32_t b) {
+    if (a >= b) return;
+    const uint32_t wa = a >> 5, wb = (b - 1) >> 5;
+    for (uint32_t w = wa; w <= wb; ++w) {
+        uint32_t keep = 0;
+        if (w == wa) keep |= (1u << (a & 31)) - 1u;
+        if (w == wb && (b & 31)) keep |= ~((1u << (b & 31)) - 1u);
+        atomicAnd(&mask[w], keep);
+    }
+}
+
+__device__ __forceinline__ uint64_t load_be64_unaligned(const uint8_t *p) {
+    uint64_t u = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) u = (u << 8) | __ldg(p + k);
+    return u;
+}
+
+// Dictionary tag page -> mask (pkg/encoding/dictionary.go:69-114, bytes.go:45-127, writer.go/reader.go).
+// page points just after the 0x0A type byte.  Returns a DevErr.
+__device__ __noinline__ uint32_t apply_dict_pred(WarpSmem *sm, const DevPred &pr, const uint8_t *page, uint32_t size, uint32_t count, int lane) {
+    const uint8_t *p = page;
+    const uint8_t *end = page + size;
+    uint64_t nvals;
+    if (!read_varuint_seq(p, end, nvals) || nvals == 0 || nvals > 256) return kErrCorrupt;
+    // lens block: compressBlock(encodeUint64List(len+1 | 0 for nil))
+    if (end - p < 2) return kErrCorrupt;
+    uint8_t t = __ldg(p++);
+    if (t == 1) return kErrZstdDict;
+    if (t != 0) return kErrCorrupt;
+    uint32_t llen = __ldg(p++);
+    if (static_cast<uint32_t>(end - p) < llen || llen < 1) return kErrCorrupt;
+    const uint8_t wt = __ldg(p);
+    if (wt > 3) return kErrCorrupt;
+    const uint32_t width = 1u << wt;
+    if (llen != 1 + nvals * width) return kErrCorrupt;
+    const uint8_t *lens = p + 1;
+    p += llen;
+    // data block
+    if (end - p < 2) return kErrCorrupt;
+    t = __ldg(p++);
+    if (t == 1) return kErrZstdDict;
+    if (t != 0) return kErrCorrupt;
+    uint32_t dlen = __ldg(p++);
+    if (static_cast<uint32_t>(end - p) < dlen) return kErrCorrupt;
+    const uint8_t *data = p;
+    p += dlen;
+    // ---- match set over the dictionary values
+    uint32_t off_carry = 0;
+    bool bad = false;  // lane-local; folded warp-wide before any return
+    for (uint32_t base = 0; base < nvals; base += 32) {
+        const uint32_t k = base + lane;
+        uint32_t L = 0;
+        if (k < nvals) {
+            for (uint32_t i = 0; i < width; ++i) L = (L << 8) | __ldg(lens + k * width + i);
+        }
+        const bool have = L > 0;
+        const uint32_t vlen = have ? L - 1 : 0;
+        uint32_t incl = vlen;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, incl, s);
+            if (lane >= s) incl += o;
+        }
+        const uint32_t off = off_carry + incl - vlen;
+        off_carry += __shfl_sync(0xffffffffu, incl, 31);
+        bool m = false;
+        if (k < nvals) {
+            int cmp = 0;
+            if (have && off + vlen > dlen) {
+                bad = true;
+            } else if (have) {
+                const uint32_t ml = vlen < pr.lit_len ? vlen : pr.lit_len;
+                for (uint32_t i = 0; i < ml && cmp == 0; ++i) {
+                    const int a = __ldg(data + off + i), b = pr.lit[i];
+                    cmp = a < b ? -1 : (a > b ? 1 : 0);
+                }
+                if (cmp == 0) cmp = vlen < pr.lit_len ? -1 : (vlen > pr.lit_len ? 1 : 0);
+            }
+            m = cmp_op(pr.op, have, cmp);
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, m);
+        if (lane == 0) sm->match[base >> 5] = bal;
+    }
+    if (__any_sync(0xffffffffu, bad)) return kErrCorrupt;
+    __syncwarp();
+    // ---- bit-packed RLE pairs: [u32 BE n][u8 width][n x width bits, MSB first]
+    if (end - p < 4) return kErrCorrupt;
+    const uint32_t nrle = static_cast<uint32_t>(load_be64_unaligned(p) >> 32);
+    p += 4;
+    if (nrle == 0) return count == 0 ? kErrNone : kErrCorrupt;
+    if (nrle & 1u) return kErrCorrupt;
+    if (end - p < 1) return kErrCorrupt;
+    const uint32_t wbits = __ldg(p++);
+    if (wbits == 0 || wbits > 32) return kErrCorrupt;
+    if (static_cast<uint64_t>(end - p) * 8 < static_cast<uint64_t>(nrle) * wbits) return kErrCorrupt;
+    const uint8_t *bits = p;
+    const uint32_t nruns = nrle >> 1;
+    const uint64_t vmask = (wbits == 32) ? 0xffffffffull : ((1ull << wbits) - 1ull);
+    uint32_t row_carry = 0;
+    for (uint32_t base = 0; base < nruns; base += 32) {
+        const uint32_t ri = base + lane;
+        uint32_t value = 0, cnt = 0;
+        if (ri < nruns) {
+            // reads up to 7 bytes past the last needed byte: file images are padded in HBM
+            uint64_t bo = static_cast<uint64_t>(2 * ri) * wbits;
+            uint64_t x = load_be64_unaligned(bits + (bo >> 3));
+            value = static_cast<uint32_t>((x >> (64 - (bo & 7) - wbits)) & vmask);
+            bo += wbits;
+            x = load_be64_unaligned(bits + (bo >> 3));
+            cnt = static_cast<uint32_t>((x >> (64 - (bo & 7) - wbits)) & vmask);
+        }
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, incl, s);
+            if (lane >= s) incl += o;
+        }
+        uint32_t start = row_carry + incl - cnt;
+        uint32_t stop = start + cnt;
+        row_carry += __shfl_sync(0xffffffffu, incl, 31);
+        if (ri < nruns && value >= nvals) {
+            bad = true;
+            value = 0;
+        }
+        if (stop > count) stop = count;  // guarded; the total is verified below
+        if (start > count) start = count;
+        const bool clear = ri < nruns && cnt > 0 && !((sm->match[value >> 5] >> (value & 31)) & 1u);
+        const bool is_long = clear && (stop - start) > 128;
+        if (clear && !is_long) lane_clear_range(sm->mask, start, stop);
+        uint32_t lm = __ballot_sync(0xffffffffu, is_long);
+        while (lm) {
+            const int src = __ffs(lm) - 1;
+            lm &= lm - 1;
+            warp_clear_range(sm->mask, __shfl_sync(0xffffffffu, start, src), __shfl_sync(0xffffffffu, stop, src), lane);
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) || row_carry != count) return kErrCorrupt;  // dictionary.go:108-110
+    return kErrNone;
+}
+
+// Sum of (first + i*d) over the active rows of an arithmetic page (EncodeTypeConst: d = 0,
+// EncodeTypeDeltaConst), int_list.go:73-96.  Lanes split the active set.
+template <int kMode>
+__device__ __forceinline__ void agg_arith_page(AggAcc &acc, int64_t first, int64_t d, uint32_t count, uint32_t r0, uint32_t r1,
+                                               const uint32_t *mask, int lane) {
+    acc.init();
+    if (kMode != kRowsMask) {
+        // contiguous rows [r0,r1]: lane 0 owns the closed form
+        if (lane == 0) {
+            const uint64_t n = static_cast<uint64_t>(r1) - r0 + 1;
+            acc.cnt = static_cast<uint32_t>(n);
+            acc.add_scaled(first, n);
+            // sum of indices r0..r1 = n*(r0+r1)/2 (fits 64 bits: rows < 2^31)
+            const uint64_t si = (n * (static_cast<uint64_t>(r0) + r1)) >> 1;
+            acc.add_scaled(d, si);
+            const int64_t va = first + static_cast<int64_t>(static_cast<uint64_t>(d) * r0);
+            const int64_t vb = first + static_cast<int64_t>(static_cast<uint64_t>(d) * r1);
+            acc.mn = va < vb ? va : vb;
+            acc.mx = va < vb ? vb : va;
+        }
+        return;
+    }
+    const uint32_t nwords = (count + 31) >> 5;
+    for (uint32_t w = lane; w < nwords; w += 32) {
+        uint32_t m = mask[w];
+        while (m) {
+            const uint32_t b = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t row = (w << 5) + b;
+            acc.add(first + static_cast<int64_t>(static_cast<uint64_t>(d) * row));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan_blocks: block selection
+// ------------------------------------------------------------------------------------------------
+__global__ void plan_blocks_kernel(const __grid_constant__ ScanParams p) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    bool sel = false;
+    if (g < p.total_blocks) {
+        uint32_t pi = 0;
+        while (pi + 1 < p.n_parts && g >= p.parts[pi + 1].block_base) ++pi;
+        const DevBlock &b = p.parts[pi].blocks[g - p.parts[pi].block_base];
+        // binary search of the block's series in the query's ascending series list (query.go:601)
+        uint32_t lo = 0, hi = p.n_series;
+        const uint64_t sid = b.sid;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (p.q_sids[mid] < sid) lo = mid + 1;
+            else hi = mid;
+        }
+        int32_t qi = -1;
+        if (lo < p.n_series && p.q_sids[lo] == sid) qi = static_cast<int32_t>(lo);
+        // part_iter.go:232-241: the block must overlap the inclusive time range
+        sel = qi >= 0 && !(b.ts_max < p.tmin || b.ts_min > p.tmax);
+        p.block_qsid[g] = sel ? qi : -1;
+        p.Prows[g] = 0;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, sel);
+    if (bal) {
+        const int lane = threadIdx.x & 31;
+        uint32_t base = 0;
+        if (lane == __ffs(bal) - 1) base = atomicAdd(p.work_count, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+        if (sel) p.worklist[base + __popc(bal & ((1u << lane) - 1u))] = g;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scan_blocks: one warp per block
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool find_col(const DevPartRef &part, const DevBlock &blk, uint16_t name_id, DevCol &out, int lane) {
+    bool found = false;
+    for (uint32_t base = 0; base < blk.n_cols; base += 32) {
+        const uint32_t i = base + lane;
+        DevCol c{};
+        bool hit = false;
+        if (i < blk.n_cols) {
+            c = part.cols[blk.col_begin + i];
+            hit = c.name_id == name_id;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) {
+            const int src = __ffs(bal) - 1;
+            out.off = shfl_u64(c.off, src);
+            out.size = __shfl_sync(0xffffffffu, c.size, src);
+            out.name_id = name_id;
+            out.value_type = static_cast<uint8_t>(__shfl_sync(0xffffffffu, static_cast<uint32_t>(c.value_type), src));
+            out.file_id = static_cast<uint8_t>(__shfl_sync(0xffffffffu, static_cast<uint32_t>(c.file_id), src));
+            found = true;
+            break;
+        }
+    }
+    return found;
+}
+
+template <int kMode>
+__device__ __forceinline__ uint32_t agg_field_page(WarpSmem *sm, uint32_t &seq, const uint8_t *page, uint32_t size, bool is_float,
+                                                   uint32_t count, uint32_t r0, uint32_t r1, AggAcc &out, int &exp_out, int lane) {
+    if (size < 1) return kErrCorrupt;
+    const uint32_t enc = __ldg(page);
+    if (enc == 9) return kErrPlainPage;  // EncodeTypePlain fallback page (column.go:147-153,203-208)
+    const uint32_t hdr = is_float ? 11u : 9u;
+    if (size < hdr) return kErrCorrupt;
+    exp_out = 0;
+    if (is_float) exp_out = static_cast<int16_t>((static_cast<uint32_t>(__ldg(page + 1)) << 8) | __ldg(page + 2));
+    const int64_t first = conv_bytes_to_int64(page + hdr - 8);
+    const uint8_t *body = page + hdr;
+    const uint32_t blen = size - hdr;
+    if (enc == 1 || enc == 2) {
+        int64_t d = 0;
+        if (enc == 1) {
+            if (blen != 0) return kErrCorrupt;
+        } else {
+            uint32_t used = 0;
+            if (!read_varint_seq(body, blen, d, used) || used != blen) return kErrCorrupt;
+        }
+        agg_arith_page<kMode>(out, first, d, count, r0, r1, sm->mask, lane);
+        out.warp_reduce();
+        return kErrNone;
+    }
+    if (enc != 3 && enc != 4) return kErrBadEnc;
+    AggCons<kMode> cons;
+    cons.acc.init();
+    cons.r0 = r0;
+    cons.r1 = r1;
+    cons.mask = sm->mask;
+    bool ok;
+    if (enc == 3) ok = decode_varint_page<false>(sm, seq, body, blen, count, first, cons, lane);
+    else ok = decode_varint_page<true>(sm, seq, body, blen, count, first, cons, lane);
+    ok = __all_sync(0xffffffffu, ok);
+    if (!ok) return kErrCorrupt;
+    cons.acc.warp_reduce();
+    out = cons.acc;
+    return kErrNone;
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_blocks_kernel(const __grid_constant__ ScanParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    WarpSmem *sm = reinterpret_cast<WarpSmem *>(smem_raw) + warp;
+    if (lane == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&sm->bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t seq = 0;
+    const uint32_t nwork = *p.work_count;
+    for (;;) {
+        uint32_t wi = 0;
+        if (lane == 0) wi = atomicAdd(p.work_next, 1u);
+        wi = __shfl_sync(0xffffffffu, wi, 0);
+        if (wi >= nwork) break;
+        const uint32_t g = p.worklist[wi];
+        uint32_t pi = 0;
+        while (pi + 1 < p.n_parts && g >= p.parts[pi + 1].block_base) ++pi;
+        const DevPartRef &part = p.parts[pi];
+        const DevBlock blk = part.blocks[g - part.block_base];
+        const uint32_t count = blk.count;
+        uint32_t page_bytes = 0;
+        uint32_t err = kErrNone;
+
+        // ---- 1. time range -> rows [r0,r1] (block.go:825-829, range.go:143-169)
+        uint32_t r0 = 0, r1 = count - 1;
+        bool empty = false;
+        if (p.tmin > blk.ts_min || p.tmax < blk.ts_max) {
+            const uint8_t *tsp = part.files[0] + blk.ts_off;
+            if (blk.ts_enc == 1) {
+                // all timestamps equal ts_min, which plan_blocks already proved inside the range
+            } else if (blk.ts_enc == 2) {
+                int64_t d = 0;
+                uint32_t used = 0;
+                if (!read_varint_seq(tsp, blk.ver_off, d, used) || used != blk.ver_off || d <= 0) {
+                    err = kErrCorrupt;
+                } else {
+                    const uint64_t ud = static_cast<uint64_t>(d);
+                    if (p.tmin > blk.ts_min) {
+                        const uint64_t diff = static_cast<uint64_t>(p.tmin) - static_cast<uint64_t>(blk.ts_min);
+                        const uint64_t q = (diff + ud - 1) / ud;
+                        r0 = q > count ? count : static_cast<uint32_t>(q);
+                    }
+                    if (p.tmax < blk.ts_max) {
+                        const uint64_t diff = static_cast<uint64_t>(p.tmax) - static_cast<uint64_t>(blk.ts_min);
+                        const uint64_t q = diff / ud;
+                        r1 = q >= count ? count - 1 : static_cast<uint32_t>(q);
+                    }
+                    empty = r0 > r1;
+                }
+                page_bytes += blk.ver_off;
+            } else {
+                TsCons tc;
+                tc.tmin = p.tmin;
+                tc.tmax = p.tmax;
+                tc.lt = 0;
+                tc.le = 0;
+                bool ok;
+                if (blk.ts_enc == 3) ok = decode_varint_page<false>(sm, seq, tsp, blk.ver_off, count, blk.ts_min, tc, lane);
+                else ok = decode_varint_page<true>(sm, seq, tsp, blk.ver_off, count, blk.ts_min, tc, lane);
+                if (!__all_sync(0xffffffffu, ok)) err = kErrCorrupt;
+                uint32_t lt = tc.lt, le = tc.le;
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) {
+                    lt += __shfl_xor_sync(0xffffffffu, lt, m);
+                    le += __shfl_xor_sync(0xffffffffu, le, m);
+                }
+                r0 = lt;
+                if (le == 0 || lt >= le) empty = true;
+                else r1 = le - 1;
+                page_bytes += blk.ver_off;
+            }
+        }
+
+        // ---- 2. tag predicates -> row bitmask
+        uint32_t rows = empty ? 0 : (r1 - r0 + 1);
+        const bool use_mask = p.n_preds > 0;
+        if (use_mask && !empty && err == kErrNone) {
+            if (count > kMaskWords * 32) {
+                err = kErrBigBlock;
+            } else {
+                const uint32_t nwords = (count + 31) >> 5;
+                for (uint32_t w = lane; w < kMaskWords; w += 32) {
+                    uint32_t v = 0;
+                    if (w < nwords) v = (w == nwords - 1 && (count & 31)) ? ((1u << (count & 31)) - 1u) : 0xffffffffu;
+                    sm->mask[w] = v;
+                }
+                __syncwarp();
+                for (uint32_t pi2 = 0; pi2 < p.n_preds && err == kErrNone; ++pi2) {
+                    const DevPred &pr = p.preds[pi2];
+                    DevCol col;
+                    if (!find_col(part, blk, pr.name_id, col, lane)) {
+                        // column absent in this block: every cell is nil (block.go:226-233)
+                        if (!cmp_op(pr.op, false, 0)) warp_clear_range(sm->mask, 0, count, lane);
+                        __syncwarp();
+                        continue;
+                    }
+                    const uint8_t *page = part.files[col.file_id] + col.off;
+                    page_bytes += col.size;
+                    if (col.size < 1) {
+                        err = kErrCorrupt;
+                        break;
+                    }
+                    const uint32_t enc = __ldg(page);
+                    if (pr.value_type == BYDB_VT_INT64) {
+                        if (col.value_type != BYDB_VT_INT64) {
+                            err = kErrPredType;
+                        } else if (enc == 9) {
+                            err = kErrPlainPage;
+                        } else if (col.size < 9) {
+                            err = kErrCorrupt;
+                        } else {
+                            const int64_t first = conv_bytes_to_int64(page + 1);
+                            const uint8_t *body = page + 9;
+                            const uint32_t blen = col.size - 9;
+                            if (enc == 1 || enc == 2) {
+                                int64_t d = 0;
+                                uint32_t used = 0;
+                                if (enc == 2 && (!read_varint_seq(body, blen, d, used) || used != blen)) err = kErrCorrupt;
+                                if (enc == 1 && blen != 0) err = kErrCorrupt;
+                                if (err == kErrNone) {
+                                    for (uint32_t row = lane; row < count; row += 32) {
+                                        const int64_t v = first + static_cast<int64_t>(static_cast<uint64_t>(d) * row);
+                                        const int c = v < pr.lit_i64 ? -1 : (v > pr.lit_i64 ? 1 : 0);
+                                        if (!cmp_op(pr.op, true, c)) atomicAnd(&sm->mask[row >> 5], ~(1u << (row & 31)));
+                                    }
+                                }
+                            } else if (enc == 3 || enc == 4) {
+                                CmpCons cc;
+                                cc.lit = pr.lit_i64;
+                                cc.op = pr.op;
+                                cc.mask = sm->mask;
+                                cc.limit = count;
+                                bool ok;
+                                if (enc == 3) ok = decode_varint_page<false>(sm, seq, body, blen, count, first, cc, lane);
+                                else ok = decode_varint_page<true>(sm, seq, body, blen, count, first, cc, lane);
+                                if (!__all_sync(0xffffffffu, ok)) err = kErrCorrupt;
+                            } else {
+                                err = kErrBadEnc;
+                            }
+                        }
+                    } else {
+                        if (col.value_type != BYDB_VT_STR && col.value_type != BYDB_VT_BINARY) err = kErrPredType;
+                        else if (enc == 9) err = kErrTagPlain;
+                        else if (enc != 10) err = kErrBadEnc;
+                        else err = apply_dict_pred(sm, pr, page + 1, col.size - 1, count, lane);
+                        err = __reduce_max_sync(0xffffffffu, err);
+                    }
+                    __syncwarp();
+                }
+                // fold the time range into the mask, then count the surviving rows
+                if (err == kErrNone) {
+                    warp_clear_range(sm->mask, 0, r0, lane);
+                    warp_clear_range(sm->mask, r1 + 1, count, lane);
+                    __syncwarp();
+                    uint32_t c = 0;
+                    for (uint32_t w = lane; w < nwords; w += 32) c += __popc(sm->mask[w]);
+#pragma unroll
+                    for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+                    rows = c;
+                }
+            }
+        }
+
+        // ---- 3. field pages -> per-block partial aggregates
+        for (uint32_t c = 0; c < p.n_fcols; ++c) {
+            BlockPartial bp;
+            bp.sum.i = 0;
+            bp.mn.i = 0;
+            bp.mx.i = 0;
+            bp.cnt = 0;
+            DevCol col;
+            if (err == kErrNone && rows > 0 && find_col(part, blk, p.fcol_name[c], col, lane)) {
+                const bool is_float = col.value_type == BYDB_VT_FLOAT64;
+                if (!is_float && col.value_type != BYDB_VT_INT64) {
+                    err = kErrTypeMix;
+                } else {
+                    if (lane == 0) {
+                        const int32_t old = atomicCAS(&p.col_type[c], 0, static_cast<int32_t>(col.value_type));
+                        if (old != 0 && old != static_cast<int32_t>(col.value_type)) err = kErrTypeMix;
+                    }
+                    err = __shfl_sync(0xffffffffu, err, 0);
+                    const uint8_t *page = part.files[col.file_id] + col.off;
+                    page_bytes += col.size;
+                    AggAcc acc;
+                    acc.init();
+                    int exp = 0;
+                    uint32_t e2;
+                    if (use_mask) e2 = agg_field_page<kRowsMask>(sm, seq, page, col.size, is_float, count, r0, r1, acc, exp, lane);
+                    else if (r0 == 0 && r1 == count - 1) e2 = agg_field_page<kRowsAll>(sm, seq, page, col.size, is_float, count, r0, r1, acc, exp, lane);
+                    else e2 = agg_field_page<kRowsRange>(sm, seq, page, col.size, is_float, count, r0, r1, acc, exp, lane);
+                    if (err == kErrNone) err = e2;
+                    if (err == kErrNone && acc.cnt > 0) {
+                        bp.cnt = acc.cnt;
+                        if (is_float) {
+                            // block sum in the exact decimal-integer domain, converted once
+                            double s;
+                            if (acc.hi == (static_cast<int64_t>(acc.lo) >> 63)) s = __ll2double_rn(static_cast<int64_t>(acc.lo));
+                            else s = __ll2double_rn(acc.hi) * 18446744073709551616.0 + __ull2double_rn(acc.lo);
+                            bp.sum.f = scale_decimal(s, exp);
+                            // min/max: int -> float64 conversion and the scaling are monotone, so
+                            // converting the integer extreme gives the bit-exact float extreme
+                            bp.mn.f = scale_decimal(__ll2double_rn(acc.mn), exp);
+                            bp.mx.f = scale_decimal(__ll2double_rn(acc.mx), exp);
+                        } else {
+                            bp.sum.i = static_cast<int64_t>(acc.lo);  // wraps mod 2^64 like Go's int64 sum
+                            bp.mn.i = acc.mn;
+                            bp.mx.i = acc.mx;
+                        }
+                    }
+                }
+            }
+            if (lane == 0) p.P[static_cast<size_t>(g) * p.n_fcols + c] = bp;
+        }
+        if (err != kErrNone) {
+            set_err(p, err, g, lane);
+            rows = 0;
+        }
+        if (lane == 0) {
+            p.Prows[g] = rows;
+            atomicAdd(&p.stats[0], static_cast<unsigned long long>(count));
+            atomicAdd(&p.stats[1], static_cast<unsigned long long>(rows));
+            atomicAdd(&p.stats[2], static_cast<unsigned long long>(page_bytes));
+            atomicAdd(&p.stats[3], 1ull);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic reduction of the per-block partials
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void combine(BlockPartial &a, const BlockPartial &b, bool is_float) {
+    if (b.cnt == 0) return;
+    if (a.cnt == 0) {
+        a = b;
+        return;
+    }
+    if (is_float) {
+        a.sum.f += b.sum.f;
+        a.mn.f = b.mn.f < a.mn.f ? b.mn.f : a.mn.f;
+        a.mx.f = b.mx.f > a.mx.f ? b.mx.f : a.mx.f;
+    } else {
+        a.sum.i = static_cast<int64_t>(static_cast<uint64_t>(a.sum.i) + static_cast<uint64_t>(b.sum.i));
+        a.mn.i = b.mn.i < a.mn.i ? b.mn.i : a.mn.i;
+        a.mx.i = b.mx.i > a.mx.i ? b.mx.i : a.mx.i;
+    }
+    a.cnt += b.cnt;
+}
+
+// one thread per query series: walks the series' blocks part by part (blocks of one series are
+// contiguous inside a part, block_metadata.go:170-175) and detects overlapping time spans across
+// parts, which would need the version dedup of query.go:995-1004.
+__global__ void series_reduce_kernel(const __grid_constant__ ReduceParams p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_series) return;
+    const uint64_t sid = p.q_sids[i];
+    BlockPartial acc[kMaxFcols];
+    for (uint32_t c = 0; c < p.n_fcols; ++c) {
+        acc[c].sum.i = 0;
+        acc[c].mn.i = 0;
+        acc[c].mx.i = 0;
+        acc[c].cnt = 0;
+    }
+    int64_t rows = 0;
+    int64_t span_lo[4], span_hi[4];
+    int nspan = 0;
+    bool overlap = false;
+    for (uint32_t pi = 0; pi < p.n_parts; ++pi) {
+        const DevPartRef &part = p.parts[pi];
+        uint32_t lo = 0, hi = part.n_blocks;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (part.blocks[mid].sid < sid) lo = mid + 1;
+            else hi = mid;
+        }
+        int64_t plo = INT64_MAX, phi = INT64_MIN;
+        for (uint32_t b = lo; b < part.n_blocks && part.blocks[b].sid == sid; ++b) {
+            const uint32_t g = part.block_base + b;
+            if (p.block_qsid[g] < 0) continue;
+            plo = part.blocks[b].ts_min < plo ? part.blocks[b].ts_min : plo;
+            phi = part.blocks[b].ts_max > phi ? part.blocks[b].ts_max : phi;
+            rows += p.Prows[g];
+            for (uint32_t c = 0; c < p.n_fcols; ++c)
+                combine(acc[c], p.P[static_cast<size_t>(g) * p.n_fcols + c], p.col_type[c] == BYDB_VT_FLOAT64);
+        }
+        if (plo <= phi) {
+            for (int s = 0; s < nspan; ++s)
+                if (!(phi < span_lo[s] || plo > span_hi[s])) overlap = true;
+            if (nspan < 4) {
+                span_lo[nspan] = plo;
+                span_hi[nspan] = phi;
+                ++nspan;
+            } else {  // merge into the last span: conservative
+                span_lo[3] = plo < span_lo[3] ? plo : span_lo[3];
+                span_hi[3] = phi > span_hi[3] ? phi : span_hi[3];
+            }
+        }
+    }
+    if (overlap && atomicCAS(&p.err[0], 0u, static_cast<uint32_t>(kErrOverlap)) == 0u) p.err[1] = i;
+    for (uint32_t c = 0; c < p.n_fcols; ++c) p.S[static_cast<size_t>(i) * p.n_fcols + c] = acc[c];
+    p.Srows[i] = rows;
+}
+
+// one CTA per group: fixed-stride accumulation + fixed shuffle tree => run-to-run identical sums
+__global__ void __launch_bounds__(256) group_reduce_kernel(const __grid_constant__ ReduceParams p) {
+    const int32_t g = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    __shared__ BlockPartial s_part[8];
+    __shared__ int64_t s_rows[8];
+    const int32_t lo = p.group_start[g], hi = p.group_start[g + 1];
+    const size_t GF = static_cast<size_t>(p.n_groups) * p.n_fcols;
+    (void)GF;
+    int64_t rows = 0;
+    for (int32_t k = lo + tid; k < hi; k += blockDim.x) rows += p.Srows[p.order[k]];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) rows += static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(rows), m));
+    if (lane == 0) s_rows[warp] = rows;
+    __syncthreads();
+    if (tid == 0) {
+        int64_t r = 0;
+        for (int w = 0; w < 8; ++w) r += s_rows[w];
+        p.rows[g] = r;
+    }
+    for (uint32_t c = 0; c < p.n_fcols; ++c) {
+        const bool is_float = p.col_type[c] == BYDB_VT_FLOAT64;
+        BlockPartial acc;
+        acc.sum.i = 0;
+        acc.mn.i = 0;
+        acc.mx.i = 0;
+        acc.cnt = 0;
+        for (int32_t k = lo + tid; k < hi; k += blockDim.x) combine(acc, p.S[static_cast<size_t>(p.order[k]) * p.n_fcols + c], is_float);
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            BlockPartial o;
+            o.sum.i = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(acc.sum.i), m));
+            o.mn.i = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(acc.mn.i), m));
+            o.mx.i = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(acc.mx.i), m));
+            o.cnt = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(acc.cnt), m));
+            // combine in lane order so that both partners compute the same value
+            BlockPartial a = (lane & m) ? o : acc, b = (lane & m) ? acc : o;
+            combine(a, b, is_float);
+            acc = a;
+        }
+        __syncthreads();
+        if (lane == 0) s_part[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            BlockPartial t = s_part[0];
+            for (int w = 1; w < 8; ++w) combine(t, s_part[w], is_float);
+            const size_t o = static_cast<size_t>(g) * p.n_fcols + c;
+            const bool have = t.cnt > 0;
+            p.cnt[o] = t.cnt;
+            p.sum_f64[o] = (have && is_float) ? t.sum.f : 0.0;
+            p.max_f64[o] = (have && is_float) ? t.mx.f : -INFINITY;
+            p.negmin_f64[o] = (have && is_float) ? -t.mn.f : -INFINITY;
+            p.sum_i64[o] = (have && !is_float) ? t.sum.i : 0;
+            p.max_i64[o] = (have && !is_float) ? t.mx.i : INT64_MIN;
+            p.notmin_i64[o] = (have && !is_float) ? ~t.mn.i : INT64_MIN;
+            if (g == 0) p.coltype[c] = p.col_type[c];
+        }
+    }
+}
+
+// finalisation: pkg/query/aggregation/function.go Val() + output typing aggregation.go:425-430
+__global__ void finalize_kernel(const __grid_constant__ FinalizeParams p) {
+    const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0) {
+        for (uint32_t a = 0; a < p.n_aggs; ++a)
+            p.out_is_float[a] = (p.agg_func[a] != BYDB_AGG_COUNT && p.coltype[p.agg_fcol[a]] == BYDB_VT_FLOAT64) ? 1 : 0;
+    }
+    if (g >= p.n_groups) return;
+    for (uint32_t a = 0; a < p.n_aggs; ++a) {
+        const uint32_t c = p.agg_fcol[a];
+        const size_t o = static_cast<size_t>(g) * p.n_fcols + c;
+        const size_t oo = static_cast<size_t>(g) * p.n_aggs + a;
+        const int64_t typ = p.coltype[c];
+        const int64_t cnt = p.cnt[o];
+        int64_t vi = 0;
+        double vf = 0.0;
+        const int fn = p.agg_func[a];
+        if (typ != 0) {
+            if (fn == BYDB_AGG_COUNT) {
+                vi = cnt;
+            } else if (typ == BYDB_VT_FLOAT64) {
+                switch (fn) {
+                    case BYDB_AGG_SUM: vf = p.sum_f64[o]; break;
+                    case BYDB_AGG_MAX: vf = cnt > 0 ? p.max_f64[o] : -DBL_MAX; break;  // aggregation.go:169-191 sentinels
+                    case BYDB_AGG_MIN: vf = cnt > 0 ? -p.negmin_f64[o] : DBL_MAX; break;
+                    case BYDB_AGG_MEAN: {
+                        if (cnt > 0) {
+                            vf = __ddiv_rn(p.sum_f64[o], __ll2double_rn(cnt));
+                            if (vf < 1.0) vf = 1.0;  // function.go:31-40
+                        }
+                        break;
+                    }
+                }
+            } else {
+                switch (fn) {
+                    case BYDB_AGG_SUM: vi = p.sum_i64[o]; break;
+                    case BYDB_AGG_MAX: vi = cnt > 0 ? p.max_i64[o] : INT64_MIN; break;
+                    case BYDB_AGG_MIN: vi = cnt > 0 ? ~p.notmin_i64[o] : INT64_MAX; break;
+                    case BYDB_AGG_MEAN: {
+                        if (cnt > 0) {
+                            vi = p.sum_i64[o] / cnt;  // Go integer division truncates toward zero
+                            if (vi < 1) vi = 1;
+                        }
+                        break;
+                    }
+                }
+            }
+        }
+        p.out_i64[oo] = vi;
+        p.out_f64[oo] = vf;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+void launch_plan_blocks(const ScanParams &p, cudaStream_t s) {
+    if (p.total_blocks == 0) return;
+    const int threads = 256;
+    plan_blocks_kernel<<<(p.total_blocks + threads - 1) / threads, threads, 0, s>>>(p);
+}
+
+static bool g_scan_attr_set = false;
+void launch_scan_blocks(const ScanParams &p, int grid, cudaStream_t s) {
+    const size_t smem = scan_smem_bytes();
+    if (!g_scan_attr_set) {
+        cudaFuncSetAttribute(scan_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        g_scan_attr_set = true;
+    }
+    scan_blocks_kernel<<<grid, kWarpsPerCta * 32, smem, s>>>(p);
+}
+
+int scan_max_ctas_per_sm() {
+    int n = 0;
+    cudaFuncSetAttribute(scan_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scan_smem_bytes()));
+    g_scan_attr_set = true;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, scan_blocks_kernel, kWarpsPerCta * 32, scan_smem_bytes()) != cudaSuccess) return 1;
+    return n < 1 ? 1 : n;
+}
+
+void launch_series_reduce(const ReduceParams &p, cudaStream_t s) {
+    if (p.n_series == 0) return;
+    const int threads = 128;
+    series_reduce_kernel<<<(p.n_series + threads - 1) / threads, threads, 0, s>>>(p);
+}
+void launch_group_reduce(const ReduceParams &p, cudaStream_t s) {
+    if (p.n_groups <= 0) return;
+    group_reduce_kernel<<<p.n_groups, 256, 0, s>>>(p);
+}
+void launch_finalize(const FinalizeParams &p, cudaStream_t s) {
+    const int threads = 128;
+    const int n = p.n_groups > 0 ? p.n_groups : 1;
+    finalize_kernel<<<(n + threads - 1) / threads, threads, 0, s>>>(p);
+}
+
+// Go math.Pow10 (src/math/pow10.go): pow10postab32[n/32] * pow10tab[n%32].  The product is done
+// on the host in IEEE double (no FMA: a single multiply), exactly like the Go runtime.
+int upload_pow10_table() {
+    static const double tab[32] = {1e00, 1e01, 1e02, 1e03, 1e04, 1e05, 1e06, 1e07, 1e08, 1e09, 1e10,
+                                   1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21,
+                                   1e22, 1e23, 1e24, 1e25, 1e26, 1e27, 1e28, 1e29, 1e30, 1e31};
+    static const double postab32[10] = {1e00, 1e32, 1e64, 1e96, 1e128, 1e160, 1e192, 1e224, 1e256, 1e288};
+    double h[309];
+    for (int n = 0; n <= 308; ++n) {
+        volatile double a = postab32[n / 32], b = tab[n % 32];
+        volatile double r = a * b;
+        h[n] = r;
+    }
+    return cudaMemcpyToSymbol(c_pow10, h, sizeof(h)) == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace bydb

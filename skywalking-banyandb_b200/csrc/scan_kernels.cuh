@@ -1,0 +1,128 @@
+// scan_kernels.cuh -- device-side types shared between the kernels (scan_kernels.cu) and the host
+// orchestration (capi.cu).  See DESIGN.md for the HBM layout and the roofline of each kernel.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "part_dir.hpp"
+
+namespace bydb {
+
+constexpr int kWarpsPerCta = 8;          // 256 threads; every warp is an independent block worker
+constexpr int kStageBytes = 4096;        // one TMA bulk copy (cp.async.bulk) per stage
+constexpr int kStages = 2;               // per-warp ring: decode stage k while stage k+1 lands
+constexpr int kChunkBytes = 512;         // 32 lanes x 16 B per decode iteration
+constexpr int kMaskWords = 264;          // row bitmask: 8448 rows (memPart blocks hold <= 8193 rows)
+constexpr int kMaxFcols = 8;             // distinct aggregated fields per query
+constexpr int kMaxPreds = 8;             // conjunctive row predicates per query
+constexpr int kMaxLit = 64;              // inline literal bytes of a string predicate
+constexpr int kMaxParts = 64;            // parts per query
+
+// device error codes written to ScanParams::err[0] (first error wins); err[1] = global block index
+enum DevErr : uint32_t {
+    kErrNone = 0,
+    kErrPlainPage = 1,      // numeric fallback page (EncodeTypePlain, column.go:147-153): needs zstd on device
+    kErrZstdDict = 2,       // dictionary whose value block is zstd-compressed (>=128 B, bytes.go:291-304)
+    kErrBigBlock = 3,       // predicate on a block with more rows than the smem row mask holds
+    kErrCorrupt = 4,        // varint stream does not decode to `count` values / bad header
+    kErrTypeMix = 5,        // one field name with int64 and float64 pages in the same query
+    kErrBadEnc = 6,         // unknown encode type byte
+    kErrTagPlain = 7,       // high-cardinality (>256 values) string tag page: plain bytes block
+    kErrOverlap = 8,        // same series in several parts with overlapping time spans: needs version dedup
+    kErrPredType = 9,       // predicate literal type does not match the stored tag column type
+};
+
+struct DevPartRef {
+    const DevBlock *blocks;
+    const DevCol *cols;
+    const uint8_t *const *files;  // device array of file base pointers (indexed by DevCol::file_id)
+    uint32_t n_blocks;
+    uint32_t block_base;          // global index of blocks[0] in this query
+};
+
+struct DevPred {
+    int64_t lit_i64;
+    uint32_t lit_len;
+    uint16_t name_id;
+    uint8_t op;
+    uint8_t value_type;
+    uint8_t lit[kMaxLit];
+};
+
+// per (block, field) partial aggregate; `i` views are used for int64 fields, `f` for float64 fields
+struct BlockPartial {
+    union { double f; int64_t i; } sum, mn, mx;
+    int64_t cnt;
+};
+static_assert(sizeof(BlockPartial) == 32, "BlockPartial layout");
+
+struct ScanParams {
+    DevPartRef parts[kMaxParts];
+    uint32_t n_parts;
+    uint32_t total_blocks;
+    const uint64_t *q_sids;       // ascending
+    uint32_t n_series;
+    uint32_t n_fcols;
+    uint32_t n_preds;
+    uint32_t pad0;
+    int64_t tmin, tmax;
+    uint16_t fcol_name[kMaxFcols];
+    DevPred preds[kMaxPreds];
+    uint32_t *worklist;           // [total_blocks] global block indices selected by plan_blocks
+    uint32_t *work_count;
+    uint32_t *work_next;
+    int32_t *block_qsid;          // [total_blocks] query-series index or -1
+    BlockPartial *P;              // [total_blocks * n_fcols]
+    uint32_t *Prows;              // [total_blocks] rows that passed range + predicates
+    int32_t *col_type;            // [n_fcols] 0 unknown / BYDB_VT_INT64 / BYDB_VT_FLOAT64
+    uint32_t *err;                // [2]
+    unsigned long long *stats;    // [0] rows_scanned [1] rows_matched [2] page_bytes [3] blocks
+};
+
+struct ReduceParams {
+    DevPartRef parts[kMaxParts];
+    uint32_t n_parts;
+    uint32_t n_series;
+    uint32_t n_fcols;
+    int32_t n_groups;
+    const uint64_t *q_sids;
+    const int32_t *order;         // [n_series] query-series indices sorted by (group, series)
+    const int32_t *group_start;   // [n_groups + 1] into order
+    const int32_t *block_qsid;
+    const BlockPartial *P;
+    const uint32_t *Prows;
+    const int32_t *col_type;
+    BlockPartial *S;              // [n_series * n_fcols] per-series partials
+    int64_t *Srows;               // [n_series]
+    uint32_t *err;
+    // partial table (see bydb_gpu.h): written by group_reduce
+    double *sum_f64, *max_f64, *negmin_f64;
+    int64_t *sum_i64, *cnt, *rows, *max_i64, *notmin_i64, *coltype;
+};
+
+struct FinalizeParams {
+    int32_t n_groups;
+    uint32_t n_fcols;
+    uint32_t n_aggs;
+    uint32_t pad;
+    int32_t agg_fcol[32];
+    int32_t agg_func[32];
+    const double *sum_f64, *max_f64, *negmin_f64;
+    const int64_t *sum_i64, *cnt, *rows, *max_i64, *notmin_i64, *coltype;
+    int64_t *out_i64;             // [n_groups * n_aggs]
+    double *out_f64;              // [n_groups * n_aggs]
+    uint8_t *out_is_float;        // [n_aggs]
+};
+
+size_t scan_smem_bytes();
+void launch_plan_blocks(const ScanParams &p, cudaStream_t s);
+void launch_scan_blocks(const ScanParams &p, int grid, cudaStream_t s);
+void launch_series_reduce(const ReduceParams &p, cudaStream_t s);
+void launch_group_reduce(const ReduceParams &p, cudaStream_t s);
+void launch_finalize(const FinalizeParams &p, cudaStream_t s);
+int upload_pow10_table();
+int scan_max_ctas_per_sm();
+
+}  // namespace bydb

@@ -13,3 +13,24 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def _load_pkg():
+    import __graft_entry__ as ge
+    return ge.load_package()
+
+
+import pytest  # noqa: E402
+
+
+@pytest.fixture(scope="session")
+def bydb():
+    """The product package (skywalking-banyandb_b200/) under its import name bydb_b200."""
+    return _load_pkg()
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx(bydb):
+    ctx = bydb.Context(device=0)
+    yield ctx
+    ctx.close()

@@ -1,0 +1,350 @@
+"""-m gpu: parity of the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+Bar: bit-exact for int64 count/min/max/sum and float64 min/max; <= 1e-9 relative for float64 sum/mean."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.helpers import STEP, T0, assert_parity, build_part, grid, run_both
+
+pytestmark = pytest.mark.gpu
+
+ALL5 = [O.AGG_SUM, O.AGG_COUNT, O.AGG_MIN, O.AGG_MAX, O.AGG_MEAN]
+_pid = [10]
+
+
+def _next_pid(n=1):
+    _pid[0] += 100
+    return _pid[0]
+
+
+def test_c1_scalar_sum_no_filter(bydb, gpu_ctx):
+    # BASELINE config 1: single part, 1k series x 1k points, 1 float64 field, sum() no filter
+    rng = np.random.default_rng(0xB200)
+    sids, ts, ver = grid(1000, 1000)
+    lat = np.round(25 + rng.normal(0, 5, sids.size), 2)
+    part = build_part(sids, ts, ver, [("latency", O.VT_FLOAT64, lat, None)])
+    oq = O.Query([part], np.unique(sids), [("latency", O.AGG_SUM)])
+    got, want = run_both(bydb, gpu_ctx, [part], oq, _next_pid())
+    assert_parity(got, want, oq.aggs, "C1")
+    assert got.stats.rows_scanned == 1_000_000 and got.stats.rows_matched == 1_000_000
+    # the exact decimal sum is an independent known answer
+    exact = int(np.round(lat * 100).astype(np.int64).sum()) / 100.0
+    assert abs(got.val_f64[0, 0] - exact) <= 1e-9 * abs(exact)
+
+
+def test_groups_time_range_dict_pred_all_functions(bydb, gpu_ctx):
+    rng = np.random.default_rng(11)
+    sids, ts, ver = grid(37, 2500, sid0=5, sid_step=3)
+    lat = np.round(25 + rng.normal(0, 5, sids.size), 2)
+    calls = rng.integers(-5000, 5000, sids.size)
+    region = [b"r%d" % v for v in rng.integers(0, 8, sids.size)]
+    part = build_part(sids, ts, ver, [("latency", O.VT_FLOAT64, lat, None), ("calls", O.VT_INT64, calls, None)],
+                      [("default", [("region", O.VT_STR, region, None)])])
+    usid = np.unique(sids)
+    groups = (np.arange(usid.size) % 6).astype(np.int32)
+    aggs = [("latency", f) for f in ALL5] + [("calls", f) for f in ALL5]
+    oq = O.Query([part], usid, aggs, groups=groups, n_groups=6, tmin=T0 + 300 * STEP + 1, tmax=T0 + 2100 * STEP,
+                 preds=[O.Pred("default", "region", O.OP_EQ, b"r3")])
+    got, want = run_both(bydb, gpu_ctx, [part], oq, _next_pid())
+    assert_parity(got, want, aggs, "grouped")
+    assert got.stats.rows_matched == want.rows_matched
+
+
+@pytest.mark.parametrize("kind", ["const", "delta_const", "delta_small", "delta_wide", "dod_monotone", "dod_counter_resets",
+                                  "full_range", "negative", "two_byte", "one_byte"])
+def test_int64_encodings(bydb, gpu_ctx, kind):
+    rng = np.random.default_rng(hash(kind) & 0xFFFF)
+    n_series, n_pts = 9, 8193 + 700   # 8193-row first block (measure.go:41-46 quirk) + a short tail block
+    sids, ts, ver = grid(n_series, n_pts)
+    n = sids.size
+    if kind == "const":
+        v = np.full(n, 42, dtype=np.int64)
+    elif kind == "delta_const":
+        v = np.tile(np.arange(n_pts, dtype=np.int64) * -7 + 100, n_series)
+    elif kind == "delta_small":
+        v = rng.integers(-50, 50, n)
+    elif kind == "delta_wide":
+        v = rng.integers(-(1 << 40), 1 << 40, n)
+    elif kind == "dod_monotone":
+        v = np.concatenate([np.cumsum(rng.integers(0, 1000, n_pts)) for _ in range(n_series)])
+    elif kind == "dod_counter_resets":
+        base = np.cumsum(rng.integers(1, 50, n_pts))
+        base[n_pts // 3:] -= base[n_pts // 3]        # one reset -> isIncremental -> delta-of-delta
+        base[n_pts // 3] = 0
+        v = np.tile(base, n_series)
+    elif kind == "full_range":
+        v = rng.integers(-(1 << 62), 1 << 62, n) * 2 + rng.integers(0, 2, n)
+        v[::1000] = np.iinfo(np.int64).max
+        v[1::1000] = np.iinfo(np.int64).min
+    elif kind == "negative":
+        v = -np.abs(rng.integers(1, 1 << 20, n))
+    elif kind == "two_byte":
+        v = rng.integers(-700, 700, n).cumsum() % 100000
+    else:
+        v = np.cumsum(rng.integers(-3, 4, n))
+    v = np.asarray(v, dtype=np.int64)
+    part = build_part(sids, ts, ver, [("calls", O.VT_INT64, v, None)])
+    usid = np.unique(sids)
+    aggs = [("calls", f) for f in ALL5]
+    for tmin, tmax in [(-(1 << 63), (1 << 63) - 1), (T0 + 17 * STEP, T0 + 8500 * STEP)]:
+        oq = O.Query([part], usid, aggs, groups=(np.arange(usid.size) % 2).astype(np.int32), n_groups=2, tmin=tmin, tmax=tmax)
+        got, want = run_both(bydb, gpu_ctx, [part], oq, _next_pid())
+        assert_parity(got, want, aggs, f"int64/{kind}")
+
+
+@pytest.mark.parametrize("kind", ["two_decimals", "ints_as_float", "mixed_exponents", "tiny", "huge_scale", "negative_mix", "random_walk_3dp"])
+def test_float64_decimal_pages(bydb, gpu_ctx, kind):
+    rng = np.random.default_rng(hash(kind) & 0xFFFF)
+    n_series, n_pts = 6, 5000
+    sids, ts, ver = grid(n_series, n_pts)
+    n = sids.size
+    if kind == "two_decimals":
+        v = np.round(25 + rng.normal(0, 5, n), 2)
+    elif kind == "ints_as_float":
+        v = rng.integers(0, 1000, n).astype(np.float64) * 100.0   # trailing zeros -> positive exponent
+    elif kind == "mixed_exponents":
+        v = np.where(rng.random(n) < 0.5, np.round(rng.random(n) * 10, 4), rng.integers(0, 50, n) * 10.0)
+    elif kind == "tiny":
+        v = rng.integers(1, 9999, n) * 1e-12
+    elif kind == "huge_scale":
+        v = rng.integers(1, 999, n).astype(np.float64) * 1e25
+    elif kind == "negative_mix":
+        v = np.round(rng.normal(0, 100, n), 1)
+    else:
+        v = np.round(np.cumsum(rng.normal(0, 0.1, n)), 3)
+    part = build_part(sids, ts, ver, [("latency", O.VT_FLOAT64, v, None)])
+    usid = np.unique(sids)
+    aggs = [("latency", f) for f in ALL5]
+    oq = O.Query([part], usid, aggs, groups=(np.arange(usid.size) % 3).astype(np.int32), n_groups=3,
+                 tmin=T0 + 3 * STEP, tmax=T0 + 4711 * STEP)
+    got, want = run_both(bydb, gpu_ctx, [part], oq, _next_pid())
+    assert_parity(got, want, aggs, f"float64/{kind}")
+
+
+@pytest.mark.parametrize("kind", ["irregular", "accelerating", "single_row_blocks"])
+def test_timestamp_encodings_and_ranges(bydb, gpu_ctx, kind):
+    rng = np.random.default_rng(hash(kind) & 0xFFFF)
+    n_series = 5
+    rows = []
+    for s in range(n_series):
+        if kind == "irregular":      # Delta page
+            t = T0 + np.cumsum(rng.integers(1, 10, 3000) * 1_000_000_000)
+        elif kind == "accelerating":  # monotone deltas -> delta-of-delta page
+            t = T0 + np.cumsum(np.arange(1, 3001, dtype=np.int64) * 1_000_000)
+        else:
+            t = T0 + np.arange(1, dtype=np.int64)
+        rows.append((np.full(t.size, s + 1, np.uint64), t.astype(np.int64)))
+    sids = np.concatenate([r[0] for r in rows])
+    ts = np.concatenate([r[1] for r in rows])
+    v = rng.integers(0, 1000, sids.size)
+    part = build_part(sids, ts, np.ones(sids.size, np.int64), [("calls", O.VT_INT64, v, None)])
+    usid = np.unique(sids)
+    aggs = [("calls", O.AGG_SUM), ("calls", O.AGG_COUNT), ("calls", O.AGG_MIN)]
+    lo, hi = int(ts.min()), int(ts.max())
+    ranges = [(-(1 << 63), (1 << 63) - 1), (lo + (hi - lo) // 3, lo + 2 * (hi - lo) // 3), (lo, lo), (hi, hi + 5),
+              (int(ts[7]), int(ts[7])), (int(ts[7]) + 1, int(ts[9]) - 1 if ts.size > 9 else hi)]
+    for tmin, tmax in ranges:
+        oq = O.Query([part], usid, aggs, tmin=tmin, tmax=tmax)
+        got, want = run_both(bydb, gpu_ctx, [part], oq, _next_pid())
+        assert_parity(got, want, aggs, f"ts/{kind}/{tmin}-{tmax}")
+
+
+def test_int64_tag_predicates_all_ops_and_conjunction(bydb, gpu_ctx):
+    rng = np.random.default_rng(21)
+    sids, ts, ver = grid(8, 4000)
+    n = sids.size
+    calls = rng.integers(0, 100, n)
+    code = rng.integers(0, 6, n) * 100            # Delta page
+    seq = np.tile(np.arange(4000, dtype=np.int64), 8)   # DeltaConst page
+    flag = np.full(n, 3, dtype=np.int64)          # Const page
+    region = [b"r%d" % v for v in np.repeat(rng.integers(0, 4, n // 50), 50)]   # runs of 50
+    part = build_part(sids, ts, ver, [("calls", O.VT_INT64, calls, None)],
+                      [("default", [("code", O.VT_INT64, code, None), ("seq", O.VT_INT64, seq, None),
+                                    ("flag", O.VT_INT64, flag, None), ("region", O.VT_STR, region, None)])])
+    usid = np.unique(sids)
+    aggs = [("calls", O.AGG_SUM), ("calls", O.AGG_COUNT)]
+    cases = []
+    for op in (O.OP_EQ, O.OP_NE, O.OP_LT, O.OP_LE, O.OP_GT, O.OP_GE):
+        cases.append([O.Pred("default", "code", op, 300)])
+        cases.append([O.Pred("default", "seq", op, 1234)])
+        cases.append([O.Pred("default", "flag", op, 3)])
+        cases.append([O.Pred("default", "region", op, b"r2")])
+    cases.append([O.Pred("default", "code", O.OP_GE, 200), O.Pred("default", "region", O.OP_NE, b"r0"), O.Pred("default", "seq", O.OP_LT, 3000)])
+    cases.append([O.Pred("default", "nosuchtag", O.OP_EQ, b"x")])
+    cases.append([O.Pred("default", "nosuchtag", O.OP_NE, b"x")])
+    cases.append([O.Pred("nofamily", "region", O.OP_NE, 5)])
+    cases.append([O.Pred("default", "region", O.OP_EQ, b"zzz")])
+    for preds in cases:
+        oq = O.Query([part], usid, aggs, tmin=T0 + 100 * STEP, tmax=T0 + 3900 * STEP, preds=preds)
+        got, want = run_both(bydb, gpu_ctx, [part], oq, _next_pid())
+        assert_parity(got, want, aggs, f"preds/{[(p.tag, p.op) for p in preds]}")
+
+
+def test_dictionary_tag_shapes(bydb, gpu_ctx):
+    rng = np.random.default_rng(5)
+    sids, ts, ver = grid(6, 8193)
+    n = sids.size
+    calls = rng.integers(0, 100, n)
+    per_row = [b"r%d" % v for v in rng.integers(0, 8, n)]                       # run length ~1
+    per_series = [b"zone-%d" % (s % 3) for s in sids.tolist()]                   # one run per block
+    many = [b"v%03d" % v for v in rng.integers(0, 25, n)]                        # 25 short values (<128 B of lens)
+    with_nil = [None if v == 0 else (b"" if v == 1 else b"k%d" % v) for v in rng.integers(0, 5, n)]
+    part = build_part(sids, ts, ver, [("calls", O.VT_INT64, calls, None)],
+                      [("default", [("per_row", O.VT_STR, per_row, None), ("per_series", O.VT_STR, per_series, None),
+                                    ("many", O.VT_STR, many, None), ("with_nil", O.VT_STR, with_nil, None)])])
+    usid = np.unique(sids)
+    aggs = [("calls", O.AGG_SUM), ("calls", O.AGG_MAX)]
+    for preds in ([O.Pred("default", "per_row", O.OP_EQ, b"r5")], [O.Pred("default", "per_series", O.OP_EQ, b"zone-1")],
+                  [O.Pred("default", "per_series", O.OP_GT, b"zone-0")], [O.Pred("default", "many", O.OP_LE, b"v010")],
+                  [O.Pred("default", "with_nil", O.OP_EQ, b"")], [O.Pred("default", "with_nil", O.OP_NE, b"k3")],
+                  [O.Pred("default", "per_row", O.OP_NE, b"r1"), O.Pred("default", "many", O.OP_EQ, b"v007")]):
+        oq = O.Query([part], usid, aggs, groups=(np.arange(usid.size) % 2).astype(np.int32), n_groups=2, preds=preds)
+        got, want = run_both(bydb, gpu_ctx, [part], oq, _next_pid())
+        assert_parity(got, want, aggs, f"dict/{[(p.tag, p.op, p.value) for p in preds]}")
+
+
+def test_multiple_parts_series_subset_and_topn(bydb, gpu_ctx):
+    rng = np.random.default_rng(77)
+    parts = []
+    all_sids = np.arange(1, 201, dtype=np.uint64) * 7
+    for k in range(3):   # time-disjoint parts, like consecutive flushes
+        sids = np.repeat(all_sids, 400)
+        ts = np.tile(T0 + (k * 400 + np.arange(400, dtype=np.int64)) * STEP, all_sids.size)
+        lat = np.round(rng.gamma(2.0, 20.0, sids.size), 2)
+        parts.append(build_part(sids, ts, np.ones(sids.size, np.int64), [("latency", O.VT_FLOAT64, lat, None)]))
+    sel = all_sids[::2]                      # every other series
+    groups = (np.arange(sel.size) // 4).astype(np.int32)     # 25 services x 4 series
+    aggs = [("latency", O.AGG_SUM), ("latency", O.AGG_COUNT)]
+    oq = O.Query(parts, sel, aggs, groups=groups, n_groups=25, tmin=T0 + 150 * STEP, tmax=T0 + 1000 * STEP, top_n=10, top_desc=True)
+    got, want = run_both(bydb, gpu_ctx, parts, oq, _next_pid())
+    assert got.group_id.tolist() == want.group_id.tolist()
+    assert_parity(got, want, aggs, "multi-part top10")
+    oq.top_desc, oq.top_n, oq.top_agg = False, 3, 1
+    got, want = run_both(bydb, gpu_ctx, parts, oq, _next_pid())
+    assert_parity(got, want, aggs, "multi-part bottom3")
+
+
+def test_empty_and_missing(bydb, gpu_ctx):
+    sids, ts, ver = grid(4, 100)
+    part = build_part(sids, ts, ver, [("calls", O.VT_INT64, np.arange(sids.size), None)])
+    aggs = [("calls", O.AGG_SUM), ("nosuchfield", O.AGG_MAX), ("calls", O.AGG_COUNT)]
+    for q in (O.Query([part], [99, 100], aggs),                                  # no series matches
+              O.Query([part], np.unique(sids), aggs, tmin=T0 - 10, tmax=T0 - 1),  # nothing in range
+              O.Query([part], np.unique(sids), aggs),                             # unknown field next to a real one
+              O.Query([part], [], aggs)):
+        got, want = run_both(bydb, gpu_ctx, [part], q, _next_pid())
+        assert_parity(got, want, aggs, "empty/missing")
+
+
+def test_unsupported_pages_fail_loudly_not_silently(bydb, gpu_ctx):
+    # null cells force the EncodeTypePlain fallback page (column.go:147-153): the device path must refuse
+    sids, ts, ver = grid(2, 300)
+    nulls = np.zeros(sids.size, dtype=np.uint8)
+    nulls[5] = 1
+    part = build_part(sids, ts, ver, [("calls", O.VT_INT64, np.arange(sids.size), nulls)])
+    h = gpu_ctx.register_part(_next_pid(), part.files())
+    with pytest.raises(bydb.BydbError) as ei:
+        gpu_ctx.scan_agg(bydb.Query([h], np.unique(sids), [("calls", O.AGG_SUM)]))
+    assert ei.value.code == -95
+    gpu_ctx.release_part(h)
+    # the same series in two parts with overlapping time spans needs version dedup (query.go:995-1004)
+    p1 = build_part(sids, ts, ver, [("calls", O.VT_INT64, np.arange(sids.size), None)])
+    p2 = build_part(sids, ts, ver + 1, [("calls", O.VT_INT64, np.arange(sids.size) + 7, None)])
+    h1, h2 = gpu_ctx.register_part(_next_pid(), p1.files()), gpu_ctx.register_part(_next_pid(), p2.files())
+    with pytest.raises(bydb.BydbError) as ei:
+        gpu_ctx.scan_agg(bydb.Query([h1, h2], np.unique(sids), [("calls", O.AGG_SUM)]))
+    assert ei.value.code == -95
+    gpu_ctx.release_part(h1)
+    gpu_ctx.release_part(h2)
+
+
+def test_scan_agg_host_and_idempotent_register(bydb, gpu_ctx):
+    rng = np.random.default_rng(3)
+    sids, ts, ver = grid(20, 1000)
+    lat = np.round(rng.normal(50, 10, sids.size), 2)
+    part = build_part(sids, ts, ver, [("latency", O.VT_FLOAT64, lat, None)])
+    aggs = [("latency", O.AGG_MEAN), ("latency", O.AGG_MAX)]
+    oq = O.Query([part], np.unique(sids), aggs)
+    want = O.run_query(oq)
+    files = {k: np.frombuffer(v, dtype=np.uint8) for k, v in part.files().items()}
+    got = gpu_ctx.scan_agg_host([files], bydb.Query([], np.unique(sids), aggs))
+    assert_parity(got, want, aggs, "host path")
+    assert got.stats.h2d_bytes >= sum(v.size for k, v in files.items() if k in ("timestamps.bin", "fv.bin"))
+    pid = _next_pid()
+    h1 = gpu_ctx.register_part(pid, part.files())
+    h2 = gpu_ctx.register_part(pid, part.files())
+    assert h1 == h2
+    info = gpu_ctx.part_info(h1)
+    assert info["n_rows"] == sids.size and info["n_blocks"] == 20
+    gpu_ctx.release_part(h1)
+    with pytest.raises(bydb.BydbError):
+        gpu_ctx.part_info(h1)
+
+
+def test_operator_gpuscanagg_matches_batch_aggregation_contract(bydb, gpu_ctx):
+    # reads like pkg/query/vectorized/measure/aggregation_test.go: schema (tag key + field), AggSpecs, NextBatch until EOF
+    rng = np.random.default_rng(8)
+    sids, ts, ver = grid(30, 500)
+    calls = rng.integers(0, 50, sids.size)
+    part = build_part(sids, ts, ver, [("calls", O.VT_INT64, calls, None)])
+    h = gpu_ctx.register_part(_next_pid(), part.files())
+    V = bydb
+    schema = V.BatchSchema([V.ColumnDef("service_id", V.ColumnRole.RoleTag, V.ColumnType.ColumnTypeString, "default"),
+                            V.ColumnDef("calls", V.ColumnRole.RoleField, V.ColumnType.ColumnTypeInt64)])
+    usid = np.unique(sids)[::-1].copy()      # index order is not ascending
+    svc = ["svc_%02d" % (int(s) % 7) for s in usid]
+    op = V.GPUScanAgg(gpu_ctx, schema, [0], [V.AggSpec("sum_v", V.AggSum, 1), V.AggSpec("n", V.AggCount, 1), V.AggSpec("mean_v", V.AggMean, 1)],
+                      V.ScanSpec(parts=[h], series_ids=usid, series_tags={("default", "service_id"): svc}), batch_size=4)
+    op.Init()
+    assert [c.Name for c in op.OutputSchema().Columns] == ["service_id", "sum_v", "n", "mean_v"]
+    out = {}
+    order = []
+    while True:
+        b = op.NextBatch()
+        if b is None:
+            break
+        assert 0 < b.Len <= 4 and b.Selection is None
+        for i in range(b.Len):
+            out[b.Columns[0][i]] = (int(b.Columns[1][i]), int(b.Columns[2][i]), int(b.Columns[3][i]))
+            order.append(b.Columns[0][i])
+    assert op.NextBatch() is None
+    op.Close()
+    op.Close()   # idempotent
+    first_seen = []
+    for s in svc:
+        if s not in first_seen:
+            first_seen.append(s)
+    assert order == first_seen           # group-insertion order (aggregation.go:211-213)
+    sid_svc = dict(zip(usid.tolist(), svc))
+    for name in first_seen:
+        m = np.array([sid_svc[int(s)] == name for s in sids])
+        tot, n = int(calls[m].sum()), int(m.sum())
+        assert out[name] == (tot, n, max(tot // n, 1))
+    gpu_ctx.release_part(h)
+
+
+def test_large_property_checks(bydb, gpu_ctx):
+    # size-independent properties at a size the oracle would take long on: count == rows, sum over groups ==
+    # scalar sum (int64, exact), min <= mean <= max, idempotence (same query twice -> identical bits)
+    rng = np.random.default_rng(99)
+    n_series, n_pts = 200, 20000
+    sids, ts, ver = grid(n_series, n_pts)
+    lat = np.round(25 + rng.normal(0, 5, sids.size), 2)
+    calls = rng.integers(0, 1000, sids.size)
+    part = build_part(sids, ts, ver, [("latency", O.VT_FLOAT64, lat, None), ("calls", O.VT_INT64, calls, None)])
+    h = gpu_ctx.register_part(_next_pid(), part.files())
+    usid = np.unique(sids)
+    aggs = [("calls", O.AGG_SUM), ("calls", O.AGG_COUNT), ("latency", O.AGG_MIN), ("latency", O.AGG_MEAN), ("latency", O.AGG_MAX), ("latency", O.AGG_SUM)]
+    q1 = bydb.Query([h], usid, aggs)
+    qg = bydb.Query([h], usid, aggs, series_group=(np.arange(usid.size) % 16).astype(np.int32), n_groups=16)
+    a, b, g = gpu_ctx.scan_agg(q1), gpu_ctx.scan_agg(q1), gpu_ctx.scan_agg(qg)
+    assert a.val_i64.tolist() == b.val_i64.tolist() and a.val_f64.view(np.uint64).tolist() == b.val_f64.view(np.uint64).tolist()
+    assert a.val_i64[0, 1] == sids.size == a.rows[0]
+    assert a.val_i64[0, 0] == int(calls.sum()) == int(g.val_i64[:, 0].sum())
+    assert g.val_i64[:, 1].sum() == sids.size
+    assert a.val_f64[0, 2] == lat.min() and a.val_f64[0, 4] == lat.max()
+    assert a.val_f64[0, 2] <= a.val_f64[0, 3] <= a.val_f64[0, 4]
+    exact = int(np.round(lat * 100).astype(np.int64).sum()) / 100.0
+    assert abs(a.val_f64[0, 5] - exact) <= 1e-9 * exact
+    assert abs(g.val_f64[:, 5].sum() - exact) <= 1e-9 * exact
+    gpu_ctx.release_part(h)

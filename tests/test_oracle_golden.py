@@ -291,3 +291,27 @@ def test_string_column_high_cardinality_is_plain():
 def test_zstd_roundtrip():
     data = bytes(range(256)) * 40
     assert O.zstd_decompress(O.zstd_compress(data)) == data
+
+
+def test_fast_and_general_shortest_decimal_agree():
+    # the oracle's fast path for short decimals must equal the general strconv-style search
+    rng = np.random.default_rng(1234)
+    vals = np.concatenate([
+        np.round(rng.normal(25, 5, 3000), 2), np.round(rng.random(3000) * 100, 4), rng.integers(1, 9999, 2000) * 1e-12,
+        np.round(np.cumsum(rng.normal(0, 0.1, 2000)), 3), rng.random(500), rng.random(500) * 1e-7,
+        np.array([0.1, 0.2, 0.3, 0.1 + 0.2, 1 / 3, 2.5e-10, 123456.789, 0.007, 7 * 0.001, 5e-324, 1.7976931348623157e308]),
+    ])
+    got_fast, got_slow = [], []
+    for v in vals.tolist():
+        O.force_slow_float(False)
+        try:
+            got_fast.append(tuple(x for x in (O.float64_to_decimal_list([v])[0].tolist(), O.float64_to_decimal_list([v])[1])))
+        except ValueError:
+            got_fast.append(None)
+        O.force_slow_float(True)
+        try:
+            got_slow.append(tuple(x for x in (O.float64_to_decimal_list([v])[0].tolist(), O.float64_to_decimal_list([v])[1])))
+        except ValueError:
+            got_slow.append(None)
+    O.force_slow_float(False)
+    assert got_fast == got_slow
