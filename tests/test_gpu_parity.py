@@ -105,7 +105,7 @@ def test_float64_decimal_pages(bydb, gpu_ctx, kind):
     elif kind == "mixed_exponents":
         v = np.where(rng.random(n) < 0.5, np.round(rng.random(n) * 10, 4), rng.integers(0, 50, n) * 10.0)
     elif kind == "tiny":
-        v = rng.integers(1, 9999, n) * 1e-12
+        v = rng.integers(1, 9999, n) / 1e12     # exact division keeps the short decimal
     elif kind == "huge_scale":
         v = rng.integers(1, 999, n).astype(np.float64) * 1e25
     elif kind == "negative_mix":
