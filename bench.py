@@ -224,20 +224,14 @@ def main():
         lay = ctx.partials_layout(q)
         table = torch.zeros(lay["total_bytes"] // 8, dtype=torch.float64, device="cuda")
         tf64 = table
-        ti64 = table.view(torch.int64)
+        from importlib import import_module
+        multi = import_module("bydb_b200.multi")
         stream = torch.cuda.current_stream().cuda_stream
 
         def step():
             st = ctx.scan_partials(q, table.data_ptr(), lay["total_bytes"], stream)
             stats_acc.append(st)
-            a, n = lay["off_sum_f64"] // 8, lay["n_sum_f64"]
-            dist.all_reduce(tf64[a:a + n], op=dist.ReduceOp.SUM)
-            a, n = lay["off_max_f64"] // 8, lay["n_max_f64"]
-            dist.all_reduce(tf64[a:a + n], op=dist.ReduceOp.MAX)
-            a, n = lay["off_sum_i64"] // 8, lay["n_sum_i64"]
-            dist.all_reduce(ti64[a:a + n], op=dist.ReduceOp.SUM)
-            a, n = lay["off_max_i64"] // 8, lay["n_max_i64"]
-            dist.all_reduce(ti64[a:a + n], op=dist.ReduceOp.MAX)
+            multi.allreduce_partial_table(tf64, lay, dist)   # <= 4 tiny NCCL all-reduces (SUM / MAX ranges)
             if rank == 0:
                 return ctx.reduce_finalize(q, table.data_ptr(), lay["total_bytes"], stream)
             torch.cuda.current_stream().synchronize()

@@ -63,9 +63,8 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 struct __align__(128) WarpSmem {
     uint8_t stage[kStages][kStageBytes];
     uint64_t bar[kStages];
-    uint32_t mask[kMaskWords];
+    uint32_t mask[kMaskWords + 2];  // +2: the fast path reads a 64-bit window at the last word
     uint32_t match[8];  // dictionary match set of the predicate being applied
-    uint32_t pad[2];
 };
 
 size_t scan_smem_bytes() { return sizeof(WarpSmem) * kWarpsPerCta; }
@@ -242,15 +241,15 @@ struct AggAcc {
     }
 };
 
-template <int kMode>
+// general-path consumer: the row mode is a runtime value to keep one instantiation of the decoder
 struct AggCons {
     AggAcc acc;
     uint32_t r0, r1;
     const uint32_t *mask;
+    int mode;
     __device__ __forceinline__ void operator()(uint32_t row, int64_t v) {
-        bool a = true;
-        if (kMode == kRowsRange) a = row >= r0 && row <= r1;
-        if (kMode == kRowsMask) a = (mask[row >> 5] >> (row & 31)) & 1u;
+        bool a = row >= r0 && row <= r1;
+        if (mode == kRowsMask) a = (mask[row >> 5] >> (row & 31)) & 1u;
         if (a) acc.add(v);
     }
 };
@@ -301,9 +300,13 @@ struct CmpCons {
 // ------------------------------------------------------------------------------------------------
 template <bool kDod, class Cons>
 __device__ __noinline__ bool decode_varint_page(WarpSmem *sm, uint32_t &seq, const uint8_t *body, uint32_t len, uint32_t count,
-                                                 int64_t first, Cons &cons, int lane) {
+                                                 int64_t first, Cons &cons_io, int lane) {
+    Cons cons = cons_io;  // register copy: the by-reference object of a noinline call lives in local memory
     if (lane == 0) cons(0u, first);
-    if (len == 0) return count == 1;
+    if (len == 0) {
+        cons_io = cons;
+        return count == 1;
+    }
     PageStream st;
     stream_open(st, sm, seq, body, len, lane);
     const uint32_t nchunks = (st.total + kChunkBytes - 1) / kChunkBytes;
@@ -328,28 +331,35 @@ __device__ __noinline__ bool decode_varint_page(WarpSmem *sm, uint32_t &seq, con
         const uint32_t valid = ((1u << hi_i) - 1u) & ~((1u << lo_i) - 1u);
         const uint32_t msb = msb4(w.x) | (msb4(w.y) << 4) | (msb4(w.z) << 8) | (msb4(w.w) << 12);
         const uint32_t term = valid & ~msb;
+        const uint32_t n = __popc(term);
 
-        // ---- raw payload per terminator position
-        uint64_t d[16];
+        // ---- pass A: lane-local sums; the head value is decoded from this lane's bytes only and
+        //      corrected below by what the previous lane's unfinished tail contributes
         uint64_t acc = 0;
         uint32_t sh = 0;
-        const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+        uint64_t head_x = 0;
+        bool seen = false;
+        int64_t q = 0;  // sum of this lane's values
+        int64_t r = 0;  // delta-of-delta: sum of the running prefixes
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const uint32_t b = (words[j >> 2] >> (8 * (j & 3))) & 0xffu;
-            const bool isv = (valid >> j) & 1u;
-            const bool ist = (term >> j) & 1u;
-            if (isv) {
+            const uint32_t wj = j < 4 ? w.x : (j < 8 ? w.y : (j < 12 ? w.z : w.w));
+            const uint32_t b = (wj >> (8 * (j & 3))) & 0xffu;
+            if ((valid >> j) & 1u) {
                 acc |= static_cast<uint64_t>(b & 0x7fu) << (sh & 63u);
                 sh += 7;
             }
-            d[j] = acc;
-            if (ist) {
+            if ((term >> j) & 1u) {
+                if (!seen) {
+                    head_x = acc;
+                    seen = true;
+                }
+                q += zigzag64(acc);
+                if (kDod) r += q;
                 acc = 0;
                 sh = 0;
             }
         }
-        // ---- splice the head with the previous lane's unfinished tail, zig-zag, local sums
         uint64_t prev_acc = shfl_up_u64(acc, 1);
         uint32_t prev_sh = __shfl_up_sync(0xffffffffu, sh, 1);
         if (lane == 0) {
@@ -358,20 +368,10 @@ __device__ __noinline__ bool decode_varint_page(WarpSmem *sm, uint32_t &seq, con
         }
         carry_acc = shfl_u64(acc, 31);
         carry_sh = __shfl_sync(0xffffffffu, sh, 31);
-        const int firstpos = __ffs(term) - 1;
-        const uint32_t n = __popc(term);
-        int64_t q = 0;  // sum of this lane's values
-        int64_t r = 0;  // delta-of-delta: sum of the running prefixes
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            uint64_t x = d[j];
-            if (j == firstpos) x = prev_acc | (x << (prev_sh & 63u));
-            const int64_t v = zigzag64(x);
-            d[j] = static_cast<uint64_t>(v);
-            if ((term >> j) & 1u) {
-                q += v;
-                if (kDod) r += q;
-            }
+        if (n > 0 && prev_sh != 0) {
+            const int64_t dlt = zigzag64(prev_acc | (head_x << (prev_sh & 63u))) - zigzag64(head_x);
+            q += dlt;
+            if (kDod) r += static_cast<int64_t>(static_cast<uint64_t>(n) * static_cast<uint64_t>(dlt));
         }
         // ---- warp scans (inclusive), then exclusive views
         uint32_t n_in = n;
@@ -397,29 +397,32 @@ __device__ __noinline__ bool decode_varint_page(WarpSmem *sm, uint32_t &seq, con
             q_ex = 0;
             r_ex = 0;
         }
-        // ---- second pass: true values -> consumer
+        // ---- pass B: decode again, now starting from the previous lane's tail, with the true base
         uint32_t row = row_base + n_ex;
-        if (!kDod) {
-            int64_t v = V0 + q_ex;
+        int64_t D = D0 + q_ex;
+        int64_t v = kDod ? V0 + static_cast<int64_t>(static_cast<uint64_t>(n_ex) * static_cast<uint64_t>(D0)) + r_ex : V0 + q_ex;
+        acc = prev_acc;
+        sh = prev_sh;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                if ((term >> j) & 1u) {
-                    v += static_cast<int64_t>(d[j]);
-                    cons(row, v);
-                    row++;
-                }
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t wj = j < 4 ? w.x : (j < 8 ? w.y : (j < 12 ? w.z : w.w));
+            const uint32_t b = (wj >> (8 * (j & 3))) & 0xffu;
+            if ((valid >> j) & 1u) {
+                acc |= static_cast<uint64_t>(b & 0x7fu) << (sh & 63u);
+                sh += 7;
             }
-        } else {
-            int64_t D = D0 + q_ex;
-            int64_t v = V0 + static_cast<int64_t>(static_cast<uint64_t>(n_ex) * static_cast<uint64_t>(D0)) + r_ex;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                if ((term >> j) & 1u) {
-                    D += static_cast<int64_t>(d[j]);
+            if ((term >> j) & 1u) {
+                const int64_t x = zigzag64(acc);
+                if (kDod) {
+                    D += x;
                     v += D;
-                    cons(row, v);
-                    row++;
+                } else {
+                    v += x;
                 }
+                cons(row, v);
+                row++;
+                acc = 0;
+                sh = 0;
             }
         }
         // ---- carries to the next chunk
@@ -435,8 +438,173 @@ __device__ __noinline__ bool decode_varint_page(WarpSmem *sm, uint32_t &seq, con
         row_base += n_tot;
         if ((c % kChunksPerStage) == kChunksPerStage - 1 || c == nchunks - 1) stream_release(st, sm, k, lane);
     }
+    cons_io = cons;
     // the body must hold exactly count-1 varints and end on a terminator
     return row_base == count && carry_sh == 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path: EncodeTypeDelta pages whose varints are all <= 3 bytes (|delta| < 2^20 -- the common case
+// for metric pages).  One pass per 512 B chunk, everything in 32-bit registers:
+//   * a lane decodes its values with no dependency on its neighbour (the head value is decoded from
+//     this lane's bytes only and corrected afterwards by the difference the neighbour's tail makes),
+//   * it keeps the running LOCAL prefix P_j of its deltas and folds the active rows into
+//     (sum of P_j, min P_j, max P_j, count) -- |P_j| < 2^24, so int32 cannot wrap and order is preserved,
+//   * one warp scan of the per-lane totals gives the lane's base value; the lane then contributes
+//     cnt*base + sum(P), base + min(P), base + max(P) -- exactly the values of the two-pass decoder.
+// Returns 0 = done, 1 = a chunk with a longer varint was met (caller re-runs the general decoder
+// on the whole page), 2 = corrupt.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stream_drain(const PageStream &s, WarpSmem *sm, uint32_t k) {
+    const uint32_t issued = min(s.nstages, k + static_cast<uint32_t>(kStages));
+    for (uint32_t j = k + 1; j < issued; ++j) (void)stream_wait(s, sm, j);
+}
+
+template <int kMode>
+__device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const uint8_t *body, uint32_t len, uint32_t count, int64_t first,
+                                            uint32_t r0, uint32_t r1, AggAcc &acc_io, int lane) {
+    AggAcc acc = acc_io;  // register copy (see decode_varint_page)
+    if (lane == 0) {
+        bool a = true;
+        if (kMode == kRowsRange) a = r0 == 0;
+        if (kMode == kRowsMask) a = sm->mask[0] & 1u;
+        if (a) acc.add(first);
+    }
+    if (len == 0) {
+        acc_io = acc;
+        return count == 1 ? 0 : 2;
+    }
+    PageStream st;
+    stream_open(st, sm, seq, body, len, lane);
+    const uint32_t nchunks = (st.total + kChunkBytes - 1) / kChunkBytes;
+    constexpr uint32_t kChunksPerStage = kStageBytes / kChunkBytes;
+    int64_t V0 = first;
+    uint32_t carry_acc = 0, carry_sh = 0;
+    uint32_t row_base = 1;
+    const uint8_t *buf = nullptr;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const uint32_t k = c / kChunksPerStage;
+        if ((c % kChunksPerStage) == 0) buf = stream_wait(st, sm, k);
+        const uint32_t o = c * kChunkBytes + lane * 16;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (o < st.total) w = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes));
+        int lo_i = static_cast<int>(st.pstart) - static_cast<int>(o);
+        int hi_i = static_cast<int>(st.pend) - static_cast<int>(o);
+        lo_i = lo_i < 0 ? 0 : (lo_i > 16 ? 16 : lo_i);
+        hi_i = hi_i < 0 ? 0 : (hi_i > 16 ? 16 : hi_i);
+        const uint32_t valid = ((1u << hi_i) - 1u) & ~((1u << lo_i) - 1u);
+        const uint32_t msb = msb4(w.x) | (msb4(w.y) << 4) | (msb4(w.z) << 8) | (msb4(w.w) << 12);
+        const uint32_t term = valid & ~msb;
+        const uint32_t cont = valid & msb;
+        // longest varint check: no run of 3 continuation bytes inside the lane, and the run that
+        // crosses from the previous lane (its trailing continuation bytes + our leading ones) <= 2
+        const uint32_t lead = term ? static_cast<uint32_t>(__ffs(term) - 1 - lo_i) : static_cast<uint32_t>(hi_i - lo_i);
+        const uint32_t trail = term ? static_cast<uint32_t>(hi_i - 1 - (31 - __clz(term))) : static_cast<uint32_t>(hi_i - lo_i);
+        uint32_t trail_prev = __shfl_up_sync(0xffffffffu, trail, 1);
+        if (lane == 0) trail_prev = carry_sh / 7;
+        const bool wide = (cont & (cont >> 1) & (cont >> 2)) != 0 || (trail_prev + lead) > 2 || (term == 0 && valid != 0 && (trail_prev + lead) > 2);
+        if (__any_sync(0xffffffffu, wide)) {
+            stream_drain(st, sm, k);
+            __syncwarp();
+            return 1;
+        }
+        // rows of this lane
+        const uint32_t n = __popc(term);
+        uint32_t n_in = n;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint32_t on = __shfl_up_sync(0xffffffffu, n_in, s);
+            if (lane >= s) n_in += on;
+        }
+        const uint32_t row0 = row_base + n_in - n;
+        uint32_t aw;  // bit i = i-th value of this lane is an active row
+        if (kMode == kRowsAll) {
+            aw = (1u << n) - 1u;
+        } else if (kMode == kRowsRange) {
+            const uint32_t a = r0 > row0 ? r0 - row0 : 0u;
+            const uint32_t b = (r1 + 1u) < (row0 + n) ? (r1 + 1u > row0 ? r1 + 1u - row0 : 0u) : n;
+            aw = a < b ? (((1u << b) - 1u) & ~((1u << a) - 1u)) : 0u;
+        } else {
+            const uint32_t wi = row0 >> 5;
+            const uint64_t m64 = static_cast<uint64_t>(sm->mask[wi]) | (static_cast<uint64_t>(sm->mask[wi + 1]) << 32);
+            aw = static_cast<uint32_t>(m64 >> (row0 & 31)) & ((1u << n) - 1u);
+        }
+        // ---- decode: local prefix P, folded over the active rows
+        uint32_t accv = 0, sh = 0, kbit = 1u;
+        int32_t P = 0, sumP = 0, minP = INT32_MAX, maxP = INT32_MIN;
+        int32_t head_v = 0;       // first value decoded from this lane's bytes only
+        uint32_t head_x = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t wj = j < 4 ? w.x : (j < 8 ? w.y : (j < 12 ? w.z : w.w));
+            const uint32_t b = (wj >> (8 * (j & 3))) & 0xffu;
+            if ((valid >> j) & 1u) {
+                accv |= (b & 0x7fu) << sh;
+                sh += 7;
+            }
+            if ((term >> j) & 1u) {
+                const int32_t v = static_cast<int32_t>(accv >> 1) ^ -static_cast<int32_t>(accv & 1u);
+                if (kbit == 1u) {
+                    head_x = accv;
+                    head_v = v;
+                }
+                P += v;
+                if (aw & kbit) {
+                    sumP += P;
+                    minP = P < minP ? P : minP;
+                    maxP = P > maxP ? P : maxP;
+                }
+                kbit <<= 1;
+                accv = 0;
+                sh = 0;
+            }
+        }
+        // ---- head correction by the previous lane's unfinished tail
+        uint32_t prev_acc = __shfl_up_sync(0xffffffffu, accv, 1);
+        uint32_t prev_sh = __shfl_up_sync(0xffffffffu, sh, 1);
+        if (lane == 0) {
+            prev_acc = carry_acc;
+            prev_sh = carry_sh;
+        }
+        carry_acc = __shfl_sync(0xffffffffu, accv, 31);
+        carry_sh = __shfl_sync(0xffffffffu, sh, 31);
+        const uint32_t cntA = __popc(aw);
+        if (n > 0 && prev_sh != 0) {
+            const uint32_t x = prev_acc | (head_x << prev_sh);
+            const int32_t vt = static_cast<int32_t>(x >> 1) ^ -static_cast<int32_t>(x & 1u);
+            const int32_t dlt = vt - head_v;
+            P += dlt;
+            sumP += dlt * static_cast<int32_t>(cntA);
+            if (cntA) {
+                minP += dlt;
+                maxP += dlt;
+            }
+        }
+        // ---- base value of the lane: scan of the lane totals
+        int32_t s_in = P;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int32_t os = __shfl_up_sync(0xffffffffu, s_in, s);
+            if (lane >= s) s_in += os;
+        }
+        const int64_t base = V0 + static_cast<int64_t>(s_in - P);
+        if (cntA) {
+            acc.add_scaled(base, cntA);
+            const int64_t sp = sumP;
+            const uint64_t usp = static_cast<uint64_t>(sp);
+            acc.lo += usp;
+            acc.hi += (sp >> 63) + (acc.lo < usp ? 1 : 0);
+            const int64_t vmin = base + minP, vmax = base + maxP;
+            acc.mn = vmin < acc.mn ? vmin : acc.mn;
+            acc.mx = vmax > acc.mx ? vmax : acc.mx;
+            acc.cnt += cntA;
+        }
+        V0 += static_cast<int64_t>(__shfl_sync(0xffffffffu, s_in, 31));
+        row_base += __shfl_sync(0xffffffffu, n_in, 31);
+        if ((c % kChunksPerStage) == kChunksPerStage - 1 || c == nchunks - 1) stream_release(st, sm, k, lane);
+    }
+    acc_io = acc;
+    return (row_base == count && carry_sh == 0) ? 0 : 2;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -718,11 +886,25 @@ __device__ __forceinline__ uint32_t agg_field_page(WarpSmem *sm, uint32_t &seq, 
         return kErrNone;
     }
     if (enc != 3 && enc != 4) return kErrBadEnc;
-    AggCons<kMode> cons;
+    if (enc == 3) {
+        AggAcc fa;
+        fa.init();
+        int rc = delta_page_fast<kMode>(sm, seq, body, blen, count, first, r0, r1, fa, lane);
+        rc = __reduce_max_sync(0xffffffffu, static_cast<unsigned>(rc));
+        if (rc == 0) {
+            fa.warp_reduce();
+            out = fa;
+            return kErrNone;
+        }
+        if (rc == 2) return kErrCorrupt;
+        // rc == 1: a varint longer than 3 bytes -> general two-pass decoder below
+    }
+    AggCons cons;
     cons.acc.init();
     cons.r0 = r0;
     cons.r1 = r1;
     cons.mask = sm->mask;
+    cons.mode = kMode;
     bool ok;
     if (enc == 3) ok = decode_varint_page<false>(sm, seq, body, blen, count, first, cons, lane);
     else ok = decode_varint_page<true>(sm, seq, body, blen, count, first, cons, lane);

@@ -107,7 +107,7 @@ def test_float64_decimal_pages(bydb, gpu_ctx, kind):
     elif kind == "tiny":
         v = rng.integers(1, 9999, n) / 1e12     # exact division keeps the short decimal
     elif kind == "huge_scale":
-        v = rng.integers(1, 999, n).astype(np.float64) * 1e25
+        v = np.array([float("%de25" % k) for k in rng.integers(1, 999, n)])   # correctly rounded k*10^25
     elif kind == "negative_mix":
         v = np.round(rng.normal(0, 100, n), 1)
     else:
