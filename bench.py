@@ -271,30 +271,45 @@ def main():
     # ------------------------------------------------------------------ end to end: host buffers in, result out
     e2e = None
     if not args.no_e2e:
-        pinned = {}
+        pinned, keep_pinned = {}, []
         for k, v in files.items():
-            tns = torch.empty(max(v.size, 1), dtype=torch.uint8, pin_memory=True)
+            tns = torch.empty(v.size + 256, dtype=torch.uint8, pin_memory=True)   # 256 B of readable slack after each image
             tns[:v.size].copy_(torch.from_numpy(np.ascontiguousarray(v)))
-            pinned[k] = tns[:v.size].numpy() if v.size else np.zeros(0, np.uint8)
-        qh = query_of(pkg, [], sids, n_points)
+            keep_pinned.append(tns)
+            pinned[k] = tns[:v.size].numpy()
+
+        def e2e_leg(flags, steps):
+            qh = query_of(pkg, [], sids, n_points)
+            qh.flags = flags
+            ctx.scan_agg_host([pinned], qh)
+            barrier()
+            t0 = time.perf_counter()
+            st = None
+            for _ in range(steps):
+                st = ctx.scan_agg_host([pinned], qh).stats
+            barrier()
+            d = time.perf_counter() - t0
+            if world > 1:
+                m = torch.tensor([d], dtype=torch.float64, device="cuda")
+                dist.all_reduce(m, op=dist.ReduceOp.MAX)
+                d = float(m[0])
+            return {"value": total_rows_step * steps / d, "unit": "datapoints/s", "h2d_bytes_per_step": int(st.h2d_bytes),
+                    "d2h_bytes_per_step": int(st.d2h_bytes), "ms_per_step": d / steps * 1e3, "steps": steps}
+
         e2e_steps = max(3, min(args.steps, 10))
-        ctx.scan_agg_host([pinned], qh)
-        barrier()
-        t = time.perf_counter()
-        h2d = d2h = 0
-        for _ in range(e2e_steps):
-            r = ctx.scan_agg_host([pinned], qh)
-            h2d, d2h = r.stats.h2d_bytes, r.stats.d2h_bytes
-        barrier()
-        dte = time.perf_counter() - t
-        if world > 1:
-            mx = torch.tensor([dte], dtype=torch.float64, device="cuda")
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            dte = float(mx[0])
-        e2e = {"value": total_rows_step * e2e_steps / dte, "unit": "datapoints/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": dte / e2e_steps * 1e3, "steps": e2e_steps,
-               "note": "bydb_scan_agg_host: every file of the part is uploaded from pinned host memory, scanned, result copied back"
-                       + ("; per rank, no cross-rank reduce in this leg" if world > 1 else "")}
+        from bydb_b200.capi import Q_HOST_ZERO_COPY
+        staged = e2e_leg(0, max(3, e2e_steps // 2))
+        staged["note"] = "bydb_scan_agg_host: every file of the part is copied from pinned host memory to HBM, scanned, result copied back"
+        try:
+            e2e = e2e_leg(Q_HOST_ZERO_COPY, e2e_steps)
+            e2e["note"] = ("bydb_scan_agg_host(BYDB_Q_HOST_ZERO_COPY): part files stay in pinned host memory; every step parses the "
+                           "block index, uploads the block directory and the kernels pull exactly the pages the query touches over "
+                           "PCIe (h2d = directory + page bytes), result copied back"
+                           + ("; per rank, no cross-rank reduce in this leg" if world > 1 else ""))
+            e2e["staged_upload"] = staged
+        except Exception as ex:  # keep the bench line alive: report the staged leg as e2e
+            e2e = staged
+            e2e["zero_copy_error"] = str(ex)[:200]
 
     if rank != 0:
         if world > 1:

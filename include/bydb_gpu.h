@@ -100,6 +100,11 @@ typedef struct {
     int32_t reserved;
 } bydb_agg;
 
+/* bydb_query.flags */
+#define BYDB_Q_HOST_ZERO_COPY 1u /* bydb_scan_agg_host only: the file images are in pinned, device-mapped host memory,
+                                    16-byte aligned, with >= 64 readable bytes after each buffer; the kernels then read
+                                    only the pages the query touches, in place over PCIe (no staging copy) */
+
 /* One query = selected series (+ their dense group ids) x parts x predicates x aggregations.
  * Mirrors model.MeasureQueryOptions (pkg/query/model/model.go:75-88) after series resolution:
  * series_ids is what searchSeriesList returned (ascending, query.go:601), series_group is the
@@ -121,7 +126,7 @@ typedef struct {
     int32_t top_n;                /* 0 = no Top                                           */
     int32_t top_agg;              /* index into aggs                                      */
     int32_t top_desc;             /* 1 = largest first                                    */
-    uint32_t flags;               /* reserved, 0                                          */
+    uint32_t flags;               /* BYDB_Q_*                                             */
 } bydb_query;
 
 typedef struct {

@@ -706,13 +706,13 @@ typedef struct {
 static int top_desc;
 static int top_cmp(const void *pa, const void *pb) {
     const topent *a = (const topent *)pa, *b = (const topent *)pb;
-    if (a->null != b->null) return a->null ? 1 : -1;
-    int c;
-    if (a->is_float) c = a->f < b->f ? -1 : (a->f > b->f ? 1 : 0);
+    int c; /* cmpTopVal, top.go:88-117: nulls sort LOWEST as values (last for desc, first for asc) */
+    if (a->null || b->null) c = (a->null && b->null) ? 0 : (a->null ? -1 : 1);
+    else if (a->is_float) c = a->f < b->f ? -1 : (a->f > b->f ? 1 : 0);
     else c = a->i < b->i ? -1 : (a->i > b->i ? 1 : 0);
     if (top_desc) c = -c;
     if (c) return c;
-    return a->g < b->g ? -1 : (a->g > b->g ? 1 : 0);
+    return a->g < b->g ? -1 : (a->g > b->g ? 1 : 0); /* earlier row wins, top.go:62-76 */
 }
 
 int ob_query_run(const ob_query *q, ob_result *out) {

@@ -5,7 +5,7 @@ TAG=${1:-r01}
 OUT=gpurun_out
 mkdir -p $OUT
 echo "== pytest -m gpu" | tee $OUT/${TAG}_pytest.log
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee -a $OUT/${TAG}_pytest.log
+timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee -a $OUT/${TAG}_pytest.log
 echo "== smoke"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee $OUT/${TAG}_smoke.log
 echo "== bench (b200 arm)"

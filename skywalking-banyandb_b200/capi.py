@@ -141,6 +141,10 @@ class Query:
     top_n: int = 0
     top_agg: int = 0
     top_desc: bool = True
+    flags: int = 0
+
+
+Q_HOST_ZERO_COPY = 1
 
 
 @dataclass
@@ -241,6 +245,7 @@ def _mk_query(q: Query, keep: list) -> _Query:
     keep.append(aggs)
     cq.n_aggs, cq.aggs = len(q.aggs), aggs
     cq.top_n, cq.top_agg, cq.top_desc = q.top_n, q.top_agg, int(q.top_desc)
+    cq.flags = q.flags
     return cq
 
 

@@ -138,12 +138,13 @@ const char *dev_err_text(uint32_t code) {
         case kErrTypeMix: return "a field is stored with different value types across blocks";
         case kErrBadEnc: return "unknown encode type byte";
         case kErrTagPlain: return "high-cardinality string tag page (plain bytes block) is not decoded on the device yet";
-        case kErrOverlap: return "a series lives in several parts with overlapping time spans: version dedup is not done on the device yet";
+        case kErrOverlap: return "a series lives in several parts with overlapping time spans and the dedup pass did not run (internal error)";
         case kErrPredType: return "predicate literal type does not match the stored tag column type";
+        case kErrTmaTimeout: return "internal error: a TMA bulk copy did not complete";
     }
     return "unknown device error";
 }
-int dev_err_code(uint32_t code) { return (code == kErrCorrupt || code == kErrBadEnc || code == kErrTypeMix || code == kErrPredType) ? BYDB_EINVAL : BYDB_ENOTSUP; }
+int dev_err_code(uint32_t code) { return (code == kErrCorrupt || code == kErrBadEnc || code == kErrTypeMix || code == kErrPredType) ? BYDB_EINVAL : (code == kErrTmaTimeout) ? BYDB_EIO : BYDB_ENOTSUP; }
 
 int validate_query(const bydb_query *q, bool need_parts) {
     if (!q) return fail(BYDB_EINVAL, "query is NULL");
@@ -211,7 +212,10 @@ struct TableLayout {
     }
 };
 
-int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_files *files, std::shared_ptr<Part> &out, uint64_t *h2d) {
+// zero_copy: the data files stay in (pinned, device-mapped) host memory and the kernels read the
+// pages they need straight over PCIe; only the block directory is uploaded.
+int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_files *files, std::shared_ptr<Part> &out, uint64_t *h2d,
+                              bool zero_copy = false) {
     if (!files || files->n_files == 0 || !files->files) return fail(BYDB_EINVAL, "no files");
     std::vector<FileImage> imgs;
     for (uint32_t i = 0; i < files->n_files; ++i) {
@@ -241,6 +245,20 @@ int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_f
         offs.push_back(arena);
         arena = align_up(arena + img->len + 256, 256);
     }
+    std::vector<const uint8_t *> mapped(order.size(), nullptr);
+    if (zero_copy) {
+        for (size_t i = 0; i < order.size(); ++i) {
+            if (order[i]->len == 0) continue;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, order[i]->data) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+                cudaGetLastError();
+                return fail(BYDB_EINVAL, "BYDB_Q_HOST_ZERO_COPY needs file images in pinned, device-mapped host memory (" + order[i]->name + ")");
+            }
+            if (reinterpret_cast<uintptr_t>(at.devicePointer) & 15) return fail(BYDB_EINVAL, "zero-copy file images must be 16-byte aligned");
+            mapped[i] = static_cast<const uint8_t *>(at.devicePointer);
+        }
+        arena = 0;
+    }
     const size_t nb = part->dir.blocks.size(), nc = part->dir.cols.size(), nf = order.size();
     const size_t dir_bytes = align_up(nb * sizeof(DevBlock), 256) + align_up(nc * sizeof(DevCol), 256) + align_up(nf * sizeof(void *), 256);
     {
@@ -264,9 +282,12 @@ int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_f
         return fail(BYDB_EIO, "cannot create stream");
     }
     cudaStream_t s = lease.slot->stream;
-    cudaError_t e = cudaMemsetAsync(part->d_arena, 0, arena ? arena : 256, s);
-    for (size_t i = 0; i < nf && e == cudaSuccess; ++i)
-        if (order[i]->len) e = cudaMemcpyAsync(part->d_arena + offs[i], order[i]->data, order[i]->len, cudaMemcpyHostToDevice, s);
+    cudaError_t e = cudaSuccess;
+    if (!zero_copy) {
+        e = cudaMemsetAsync(part->d_arena, 0, arena ? arena : 256, s);
+        for (size_t i = 0; i < nf && e == cudaSuccess; ++i)
+            if (order[i]->len) e = cudaMemcpyAsync(part->d_arena + offs[i], order[i]->data, order[i]->len, cudaMemcpyHostToDevice, s);
+    }
     // directory
     std::vector<uint8_t> hdir(dir_bytes ? dir_bytes : 1, 0);
     size_t o = 0;
@@ -275,7 +296,7 @@ int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_f
     if (nc) memcpy(hdir.data() + off_cols, part->dir.cols.data(), nc * sizeof(DevCol));
     const size_t off_files = off_cols + align_up(nc * sizeof(DevCol), 256);
     for (size_t i = 0; i < nf; ++i) {
-        const uint8_t *pfile = part->d_arena + offs[i];
+        const uint8_t *pfile = zero_copy ? mapped[i] : part->d_arena + offs[i];
         memcpy(hdir.data() + off_files + i * sizeof(void *), &pfile, sizeof(void *));
     }
     (void)o;
@@ -289,7 +310,8 @@ int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_f
     part->d_cols = reinterpret_cast<const DevCol *>(part->d_dir + off_cols);
     part->d_files = reinterpret_cast<const uint8_t *const *>(part->d_dir + off_files);
     if (h2d) {
-        for (size_t i = 0; i < nf; ++i) *h2d += order[i]->len;
+        if (!zero_copy)
+            for (size_t i = 0; i < nf; ++i) *h2d += order[i]->len;
         *h2d += dir_bytes;
     }
     out = part;
@@ -341,6 +363,10 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
     const size_t off_Prows = carve(NB * 4);
     const size_t off_S = carve(NS * F * sizeof(BlockPartial));
     const size_t off_Srows = carve(NS * 8);
+    const size_t n_first = NS * plan.parts.size();
+    const bool use_first = n_first > 0 && n_first <= (16u << 20);
+    const size_t off_first = carve(use_first ? n_first * 4 : 0);
+    const size_t off_dd_index = carve(NB * 4), off_dd_rowoff = carve(NB * 8), off_dd_list = carve(NB * 4);
     Scratch sc;
     sc.stream = stream;
     sc.bytes = o;
@@ -353,6 +379,7 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
     if (NS) memcpy(h + NS * 8, order.data(), NS * 4);
     memcpy(h + NS * 12, gstart.data(), (static_cast<size_t>(G) + 1) * 4);
     CUDA_TRY(cudaMemsetAsync(d + off_zero, 0, 256, stream));
+    if (use_first) CUDA_TRY(cudaMemsetAsync(d + off_first, 0xff, n_first * 4, stream));
     if (NS) CUDA_TRY(cudaMemcpyAsync(d + off_sids, h, NS * 8, cudaMemcpyHostToDevice, stream));
     if (NS) CUDA_TRY(cudaMemcpyAsync(d + off_order, h + NS * 8, NS * 4, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(d + off_gstart, h + NS * 12, (static_cast<size_t>(G) + 1) * 4, cudaMemcpyHostToDevice, stream));
@@ -405,6 +432,7 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
     sp.stats = reinterpret_cast<unsigned long long *>(d + off_zero + 16);
     sp.col_type = reinterpret_cast<int32_t *>(d + off_zero + 64);
     sp.block_qsid = reinterpret_cast<int32_t *>(d + off_qsid);
+    sp.first_block = use_first ? reinterpret_cast<uint32_t *>(d + off_first) : nullptr;
     sp.P = reinterpret_cast<BlockPartial *>(d + off_P);
     sp.Prows = reinterpret_cast<uint32_t *>(d + off_Prows);
 
@@ -415,6 +443,7 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
     rp.order = reinterpret_cast<const int32_t *>(d + off_order);
     rp.group_start = reinterpret_cast<const int32_t *>(d + off_gstart);
     rp.block_qsid = sp.block_qsid;
+    rp.first_block = sp.first_block;
     rp.P = sp.P;
     rp.Prows = sp.Prows;
     rp.col_type = sp.col_type;
@@ -433,6 +462,45 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
 
     CUDA_TRY(cudaEventRecord(slot.ev[0], stream));
     launch_plan_blocks(sp, stream);
+    // ---- version dedup: only when two parts of the query overlap in time at all (host-side precheck on
+    //      the part directories); then the device finds the series that really overlap
+    Scratch dd_scratch;
+    dd_scratch.stream = stream;
+    uint32_t extra_launches = 0;
+    bool parts_overlap = false;
+    for (size_t a = 0; a < plan.parts.size() && !parts_overlap; ++a)
+        for (size_t b = a + 1; b < plan.parts.size() && !parts_overlap; ++b) {
+            const PartDir &x = plan.parts[a]->dir, &y = plan.parts[b]->dir;
+            if (x.blocks.empty() || y.blocks.empty()) continue;
+            const int64_t lo = std::max(std::max(x.min_ts, y.min_ts), q->tmin), hi = std::min(std::min(x.max_ts, y.max_ts), q->tmax);
+            parts_overlap = lo <= hi;
+        }
+    if (parts_overlap && NB > 0 && NS > 0) {
+        sp.dd_index = reinterpret_cast<int32_t *>(d + off_dd_index);
+        sp.dd_row_off = reinterpret_cast<unsigned long long *>(d + off_dd_rowoff);
+        sp.dd_list = reinterpret_cast<uint32_t *>(d + off_dd_list);
+        sp.dd_counts = reinterpret_cast<unsigned long long *>(d + off_zero + 96);
+        CUDA_TRY(cudaMemsetAsync(sp.dd_index, 0xff, NB * 4, stream));
+        launch_detect_overlap(sp, stream);
+        if (slot.ensure_pinned(256)) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
+        CUDA_TRY(cudaMemcpyAsync(slot.pinned, d + off_zero + 96, 16, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        const unsigned long long n_ddb = reinterpret_cast<unsigned long long *>(slot.pinned)[0];
+        const unsigned long long n_ddr = reinterpret_cast<unsigned long long *>(slot.pinned)[1];
+        extra_launches += 1;
+        if (stats) stats->d2h_bytes += 16;
+        if (n_ddb > 0) {
+            const size_t b_ts = align_up(n_ddr * 8, 256), b_sh = align_up(n_ddb * kMaskWords * 4, 256);
+            CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&dd_scratch.base), 2 * b_ts + b_sh, stream));
+            sp.dd_ts = reinterpret_cast<int64_t *>(dd_scratch.base);
+            sp.dd_ver = reinterpret_cast<int64_t *>(dd_scratch.base + b_ts);
+            sp.dd_shadow = reinterpret_cast<uint32_t *>(dd_scratch.base + 2 * b_ts);
+            sp.n_dd_blocks = static_cast<uint32_t>(n_ddb);
+            launch_dedup(sp, ctx->sm_count * ctx->ctas_per_sm, stream);
+            extra_launches += 2;
+        }
+        rp.dedup_done = 1;
+    }
     CUDA_TRY(cudaEventRecord(slot.ev[1], stream));
     launch_scan_blocks(sp, ctx->sm_count * ctx->ctas_per_sm, stream);
     CUDA_TRY(cudaEventRecord(slot.ev[2], stream));
@@ -456,7 +524,7 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
         stats->scan_kernel_ms += ms;
         cudaEventElapsedTime(&ms, slot.ev[0], slot.ev[3]);
         stats->device_ms += ms;
-        stats->kernel_launches += (NB ? 1u : 0u) + 1u + (NS ? 1u : 0u) + 1u;
+        stats->kernel_launches += (NB ? 1u : 0u) + 1u + (NS ? 1u : 0u) + 1u + extra_launches;
         stats->d2h_bytes += 256;
     }
     if (hz[2] != 0) {
@@ -472,11 +540,23 @@ int finalize_to_host(bydb_ctx *ctx, const bydb_query *q, const Plan &plan, ExecS
     const size_t F = plan.fcols.size();
     const int32_t G = plan.n_groups;
     const size_t A = q->n_aggs;
-    const size_t out_bytes = align_up(static_cast<size_t>(G) * A * 8, 256) * 2 + align_up(A, 256) + align_up(static_cast<size_t>(G) * 8, 256) +
-                             align_up(static_cast<size_t>(G) * F * 8, 256);
+    const size_t cap = q->top_n > 0 ? std::min<size_t>(static_cast<size_t>(q->top_n), static_cast<size_t>(G)) : static_cast<size_t>(G);
+    if (q->top_n > kMaxDeviceTopN) return fail(BYDB_ENOTSUP, "top_n larger than 2048 is not supported on the device path");
+    // device scratch: finalized values [G x A] (i64, f64), typing [A], keys [G], key states [G]; then the selected rows
+    size_t o = 0;
+    auto carve = [&](size_t bytes) {
+        size_t at = o;
+        o = align_up(o + bytes, 256);
+        return at;
+    };
+    const size_t o_vi = carve(static_cast<size_t>(G) * A * 8), o_vf = carve(static_cast<size_t>(G) * A * 8), o_keys = carve(static_cast<size_t>(G) * 8),
+                 o_kst = carve(static_cast<size_t>(G));
+    const size_t o_out = o;  // everything from here is copied back in one transfer
+    const size_t o_cnt = carve(16), o_isf = carve(A), o_sg = carve(cap * 4), o_sr = carve(cap * 8), o_si = carve(cap * A * 8), o_sf = carve(cap * A * 8);
+    const size_t out_bytes = o - o_out;
     Scratch sc;
     sc.stream = stream;
-    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&sc.base), out_bytes, stream));
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&sc.base), o, stream));
     uint8_t *d = sc.base;
     FinalizeParams fp;
     memset(&fp, 0, sizeof fp);
@@ -496,73 +576,52 @@ int finalize_to_host(bydb_ctx *ctx, const bydb_query *q, const Plan &plan, ExecS
     fp.max_i64 = reinterpret_cast<const int64_t *>(d_table + tl.off_max_i64);
     fp.notmin_i64 = reinterpret_cast<const int64_t *>(d_table + tl.off_notmin_i64);
     fp.coltype = reinterpret_cast<const int64_t *>(d_table + tl.off_coltype);
-    const size_t o_i64 = 0, o_f64 = align_up(static_cast<size_t>(G) * A * 8, 256), o_isf = o_f64 * 2;
-    fp.out_i64 = reinterpret_cast<int64_t *>(d + o_i64);
-    fp.out_f64 = reinterpret_cast<double *>(d + o_f64);
+    fp.out_i64 = reinterpret_cast<int64_t *>(d + o_vi);
+    fp.out_f64 = reinterpret_cast<double *>(d + o_vf);
     fp.out_is_float = d + o_isf;
     launch_finalize(fp, stream);
-    // D2H: values, typing, rows and counts (counts decide "null" for Top)
-    const size_t h_rows = align_up(o_isf + align_up(A, 256), 256);
-    const size_t h_cnt = h_rows + align_up(static_cast<size_t>(G) * 8, 256);
-    const size_t h_total = h_cnt + align_up(static_cast<size_t>(G) * F * 8, 256);
-    if (slot.ensure_pinned(h_total)) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
+    // output rows are chosen and ordered on the device (stable compaction, or Top-N)
+    SelectParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.n_groups = G;
+    sp.n_fcols = static_cast<uint32_t>(F);
+    sp.n_aggs = static_cast<uint32_t>(A);
+    sp.top_n = q->top_n;
+    sp.top_agg = q->top_n > 0 ? q->top_agg : 0;
+    sp.top_desc = q->top_desc;
+    sp.top_fcol = plan.agg_fcol[sp.top_agg];
+    sp.top_is_count = q->aggs[sp.top_agg].func == BYDB_AGG_COUNT;
+    sp.rows = fp.rows;
+    sp.cnt = fp.cnt;
+    sp.val_i64 = fp.out_i64;
+    sp.val_f64 = fp.out_f64;
+    sp.is_float = fp.out_is_float;
+    sp.keys = reinterpret_cast<uint64_t *>(d + o_keys);
+    sp.kstate = d + o_kst;
+    sp.sel_count = reinterpret_cast<uint32_t *>(d + o_cnt);
+    sp.sel_group = reinterpret_cast<int32_t *>(d + o_sg);
+    sp.sel_rows = reinterpret_cast<int64_t *>(d + o_sr);
+    sp.sel_i64 = reinterpret_cast<int64_t *>(d + o_si);
+    sp.sel_f64 = reinterpret_cast<double *>(d + o_sf);
+    launch_select_rows(sp, stream);
+    if (slot.ensure_pinned(out_bytes)) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
     uint8_t *h = slot.pinned;
-    CUDA_TRY(cudaMemcpyAsync(h, d, o_isf + A, cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaMemcpyAsync(h + h_rows, d_table + tl.off_rows, static_cast<size_t>(G) * 8, cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaMemcpyAsync(h + h_cnt, d_table + tl.off_cnt, static_cast<size_t>(G) * F * 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(h, d + o_out, out_bytes, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     CUDA_TRY(cudaGetLastError());
-    out->stats.d2h_bytes += o_isf + A + static_cast<size_t>(G) * 8 + static_cast<size_t>(G) * F * 8;
-    out->stats.kernel_launches += 1;
-    const int64_t *v_i = reinterpret_cast<const int64_t *>(h + o_i64);
-    const double *v_f = reinterpret_cast<const double *>(h + o_f64);
-    const uint8_t *isf = h + o_isf;
-    const int64_t *rows = reinterpret_cast<const int64_t *>(h + h_rows);
-    const int64_t *cnt = reinterpret_cast<const int64_t *>(h + h_cnt);
-
+    out->stats.d2h_bytes += out_bytes;
+    out->stats.kernel_launches += 2;
+    const size_t R = std::min<size_t>(*reinterpret_cast<const uint32_t *>(h + (o_cnt - o_out)), cap);
     auto owner = new ResultOwner();
-    std::vector<int32_t> emit;
-    for (int32_t g = 0; g < G; ++g)
-        if (rows[g] > 0) emit.push_back(g);
-    if (q->top_n > 0) {
-        // pkg/query/vectorized/measure/top.go:145-214: nulls lowest, ties -> earlier row wins
-        const int a = q->top_agg;
-        const int c = plan.agg_fcol[a];
-        const bool f = isf[a];
-        const bool desc = q->top_desc != 0;
-        const bool count_fn = q->aggs[a].func == BYDB_AGG_COUNT;
-        auto less = [&](int32_t x, int32_t y) {
-            const bool nx = !count_fn && cnt[static_cast<size_t>(x) * F + c] == 0, ny = !count_fn && cnt[static_cast<size_t>(y) * F + c] == 0;
-            if (nx != ny) return ny;
-            if (!nx) {
-                if (f) {
-                    const double vx = v_f[static_cast<size_t>(x) * A + a], vy = v_f[static_cast<size_t>(y) * A + a];
-                    if (vx != vy) return desc ? vx > vy : vx < vy;
-                } else {
-                    const int64_t vx = v_i[static_cast<size_t>(x) * A + a], vy = v_i[static_cast<size_t>(y) * A + a];
-                    if (vx != vy) return desc ? vx > vy : vx < vy;
-                }
-            }
-            return x < y;
-        };
-        const size_t n = std::min<size_t>(emit.size(), static_cast<size_t>(q->top_n));
-        std::partial_sort(emit.begin(), emit.begin() + n, emit.end(), less);
-        emit.resize(n);
-    }
-    const size_t R = emit.size();
-    owner->group_id.assign(emit.begin(), emit.end());
-    owner->rows.resize(R);
-    owner->is_float.assign(isf, isf + A);
-    owner->val_i64.resize(R * A);
-    owner->val_f64.resize(R * A);
-    for (size_t r = 0; r < R; ++r) {
-        const int32_t g = emit[r];
-        owner->rows[r] = rows[g];
-        for (size_t a = 0; a < A; ++a) {
-            owner->val_i64[r * A + a] = v_i[static_cast<size_t>(g) * A + a];
-            owner->val_f64[r * A + a] = v_f[static_cast<size_t>(g) * A + a];
-        }
-    }
+    const int32_t *sg = reinterpret_cast<const int32_t *>(h + (o_sg - o_out));
+    const int64_t *sr = reinterpret_cast<const int64_t *>(h + (o_sr - o_out));
+    const int64_t *si = reinterpret_cast<const int64_t *>(h + (o_si - o_out));
+    const double *sf = reinterpret_cast<const double *>(h + (o_sf - o_out));
+    owner->group_id.assign(sg, sg + R);
+    owner->rows.assign(sr, sr + R);
+    owner->is_float.assign(h + (o_isf - o_out), h + (o_isf - o_out) + A);
+    owner->val_i64.assign(si, si + R * A);
+    owner->val_f64.assign(sf, sf + R * A);
     out->n_rows = static_cast<int32_t>(R);
     out->n_aggs = static_cast<int32_t>(A);
     out->group_id = owner->group_id.data();
@@ -733,11 +792,12 @@ int bydb_scan_agg_host(bydb_ctx *ctx, uint32_t n_parts, const bydb_part_files *p
     uint64_t h2d = 0;
     for (uint32_t i = 0; i < n_parts; ++i) {
         std::shared_ptr<Part> p;
-        rc = register_part_locked_free(ctx, ~0ull - i, &parts[i], p, &h2d);
+        rc = register_part_locked_free(ctx, ~0ull - i, &parts[i], p, &h2d, (q->flags & BYDB_Q_HOST_ZERO_COPY) != 0);
         if (rc) break;
         tmp.push_back(p);
     }
     if (!rc) rc = scan_agg_impl(ctx, q, &tmp, out, h2d);
+    if (!rc && (q->flags & BYDB_Q_HOST_ZERO_COPY)) out->stats.h2d_bytes += out->stats.page_bytes;  // pages were read in place over PCIe
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         for (auto &p : tmp) ctx->hbm_used -= p->hbm_bytes;

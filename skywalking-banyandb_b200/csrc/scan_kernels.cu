@@ -65,6 +65,8 @@ struct __align__(128) WarpSmem {
     uint64_t bar[kStages];
     uint32_t mask[kMaskWords + 2];  // +2: the fast path reads a 64-bit window at the last word
     uint32_t match[8];  // dictionary match set of the predicate being applied
+    uint32_t fault;     // set when a TMA wait timed out
+    uint32_t pad;
 };
 
 size_t scan_smem_bytes() { return sizeof(WarpSmem) * kWarpsPerCta; }
@@ -103,7 +105,12 @@ __device__ __forceinline__ const uint8_t *stream_wait(const PageStream &s, WarpS
     uint32_t n = s.seq0 + k;
     uint32_t slot = n % kStages;
     uint32_t parity = (n / kStages) & 1u;
-    while (!mbar_try_wait(&sm->bar[slot], parity)) {
+    // bounded spin: a lost transaction must surface as an error, never as a hung GPU
+    for (uint32_t spins = 0; !mbar_try_wait(&sm->bar[slot], parity); ++spins) {
+        if (spins > (1u << 24)) {
+            sm->fault = 1;
+            break;
+        }
     }
     return sm->stage[slot];
 }
@@ -504,7 +511,10 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const u
         if (lane == 0) trail_prev = carry_sh / 7;
         const bool wide = (cont & (cont >> 1) & (cont >> 2)) != 0 || (trail_prev + lead) > 2 || (term == 0 && valid != 0 && (trail_prev + lead) > 2);
         if (__any_sync(0xffffffffu, wide)) {
+            // give the unissued stage numbers back: the mbarrier phases only advance for stages that
+            // were really issued, and the next page must continue from exactly that count
             stream_drain(st, sm, k);
+            seq = st.seq0 + min(st.nstages, k + static_cast<uint32_t>(kStages));
             __syncwarp();
             return 1;
         }
@@ -821,6 +831,11 @@ __global__ void plan_blocks_kernel(const __grid_constant__ ScanParams p) {
         sel = qi >= 0 && !(b.ts_max < p.tmin || b.ts_min > p.tmax);
         p.block_qsid[g] = sel ? qi : -1;
         p.Prows[g] = 0;
+        // head of this series' run of blocks inside the part: lets series_reduce skip its binary search
+        if (p.first_block && qi >= 0) {
+            const uint32_t lb = g - p.parts[pi].block_base;
+            if (lb == 0 || p.parts[pi].blocks[lb - 1].sid != sid) p.first_block[static_cast<size_t>(pi) * p.n_series + qi] = g;
+        }
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, sel);
     if (bal) {
@@ -921,6 +936,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_blocks_kernel(const
     const int warp = threadIdx.x >> 5;
     WarpSmem *sm = reinterpret_cast<WarpSmem *>(smem_raw) + warp;
     if (lane == 0) {
+        sm->fault = 0;
         for (int s = 0; s < kStages; ++s) mbar_init(&sm->bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -993,15 +1009,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_blocks_kernel(const
 
         // ---- 2. tag predicates -> row bitmask
         uint32_t rows = empty ? 0 : (r1 - r0 + 1);
-        const bool use_mask = p.n_preds > 0;
+        const int32_t ddi = p.dd_index ? p.dd_index[g] : -1;
+        const bool use_mask = p.n_preds > 0 || ddi >= 0;
         if (use_mask && !empty && err == kErrNone) {
             if (count > kMaskWords * 32) {
                 err = kErrBigBlock;
             } else {
                 const uint32_t nwords = (count + 31) >> 5;
+                const uint32_t *shadow = ddi >= 0 ? p.dd_shadow + static_cast<size_t>(ddi) * kMaskWords : nullptr;
                 for (uint32_t w = lane; w < kMaskWords; w += 32) {
                     uint32_t v = 0;
                     if (w < nwords) v = (w == nwords - 1 && (count & 31)) ? ((1u << (count & 31)) - 1u) : 0xffffffffu;
+                    if (shadow && w < nwords) v &= shadow[w];
                     sm->mask[w] = v;
                 }
                 __syncwarp();
@@ -1131,6 +1150,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_blocks_kernel(const
             }
             if (lane == 0) p.P[static_cast<size_t>(g) * p.n_fcols + c] = bp;
         }
+        if (sm->fault) err = kErrTmaTimeout;
         if (err != kErrNone) {
             set_err(p, err, g, lane);
             rows = 0;
@@ -1141,6 +1161,165 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_blocks_kernel(const
             atomicAdd(&p.stats[1], static_cast<unsigned long long>(rows));
             atomicAdd(&p.stats[2], static_cast<unsigned long long>(page_bytes));
             atomicAdd(&p.stats[3], 1ull);
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// version dedup across parts (banyand/measure/query.go:912-942,995-1004; query_batch.go:151-161):
+// a (series, timestamp) present in several parts keeps only the row with the highest version.
+//   detect_overlap  thread per query series: parts whose selected time spans intersect -> flag blocks
+//   dedup_decode    warp per flagged block: timestamps + versions -> global arrays
+//   dedup_shadow    warp per flagged block: binary-search every row's timestamp in the other parts'
+//                   blocks of the series; clear the row's bit in the shadow mask when a higher
+//                   version (or the same version in an earlier part) exists
+// scan_blocks then starts the row mask of a flagged block from its shadow mask.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t series_first_block(const ScanParams &p, uint32_t pi, uint32_t qi, uint64_t sid) {
+    const DevPartRef &part = p.parts[pi];
+    if (p.first_block) {
+        const uint32_t g0 = p.first_block[static_cast<size_t>(pi) * p.n_series + qi];
+        return g0 == 0xffffffffu ? part.n_blocks : g0 - part.block_base;
+    }
+    uint32_t lo = 0, hi = part.n_blocks;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (part.blocks[mid].sid < sid) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void detect_overlap_kernel(const __grid_constant__ ScanParams p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_series) return;
+    const uint64_t sid = p.q_sids[i];
+    // spans of the selected blocks per part; conservative merge beyond 8 parts
+    int64_t lo[8], hi[8];
+    int ns = 0;
+    bool overlap = false;
+    for (uint32_t pi = 0; pi < p.n_parts; ++pi) {
+        const DevPartRef &part = p.parts[pi];
+        int64_t plo = INT64_MAX, phi = INT64_MIN;
+        for (uint32_t b = series_first_block(p, pi, i, sid); b < part.n_blocks && part.blocks[b].sid == sid; ++b) {
+            if (p.block_qsid[part.block_base + b] < 0) continue;
+            plo = part.blocks[b].ts_min < plo ? part.blocks[b].ts_min : plo;
+            phi = part.blocks[b].ts_max > phi ? part.blocks[b].ts_max : phi;
+        }
+        if (plo > phi) continue;
+        for (int s = 0; s < ns; ++s)
+            if (!(phi < lo[s] || plo > hi[s])) overlap = true;
+        if (ns < 8) {
+            lo[ns] = plo;
+            hi[ns] = phi;
+            ++ns;
+        } else {
+            lo[7] = plo < lo[7] ? plo : lo[7];
+            hi[7] = phi > hi[7] ? phi : hi[7];
+        }
+    }
+    if (!overlap) return;
+    for (uint32_t pi = 0; pi < p.n_parts; ++pi) {
+        const DevPartRef &part = p.parts[pi];
+        for (uint32_t b = series_first_block(p, pi, i, sid); b < part.n_blocks && part.blocks[b].sid == sid; ++b) {
+            const uint32_t g = part.block_base + b;
+            if (p.block_qsid[g] < 0) continue;
+            const unsigned long long idx = atomicAdd(&p.dd_counts[0], 1ull);
+            p.dd_row_off[g] = atomicAdd(&p.dd_counts[1], static_cast<unsigned long long>(part.blocks[b].count));
+            p.dd_index[g] = static_cast<int32_t>(idx);
+            p.dd_list[idx] = g;
+        }
+    }
+}
+
+struct StoreCons {
+    int64_t *out;
+    __device__ __forceinline__ void operator()(uint32_t row, int64_t v) { out[row] = v; }
+};
+
+// decodes one int64 list body (timestamps or versions) into out[0..count)
+__device__ __forceinline__ bool decode_list_to(WarpSmem *sm, uint32_t &seq, const uint8_t *body, uint32_t len, uint32_t enc, int64_t first, uint32_t count,
+                                               int64_t *out, int lane) {
+    if (enc == 1 || enc == 2) {
+        int64_t d = 0;
+        uint32_t used = 0;
+        if (enc == 1 && len != 0) return false;
+        if (enc == 2 && (!read_varint_seq(body, len, d, used) || used != len)) return false;
+        for (uint32_t r = lane; r < count; r += 32) out[r] = first + static_cast<int64_t>(static_cast<uint64_t>(d) * r);
+        return true;
+    }
+    StoreCons sc;
+    sc.out = out;
+    bool ok;
+    if (enc == 3) ok = decode_varint_page<false>(sm, seq, body, len, count, first, sc, lane);
+    else if (enc == 4) ok = decode_varint_page<true>(sm, seq, body, len, count, first, sc, lane);
+    else ok = false;
+    return __all_sync(0xffffffffu, ok);
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) dedup_kernel(const __grid_constant__ ScanParams p, int phase) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    WarpSmem *sm = reinterpret_cast<WarpSmem *>(smem_raw) + warp;
+    if (lane == 0) {
+        sm->fault = 0;
+        for (int s = 0; s < kStages; ++s) mbar_init(&sm->bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t seq = 0;
+    const uint32_t gw = blockIdx.x * kWarpsPerCta + warp, nw = gridDim.x * kWarpsPerCta;
+    for (uint32_t k = gw; k < p.n_dd_blocks; k += nw) {
+        const uint32_t g = p.dd_list[k];
+        uint32_t pi = 0;
+        while (pi + 1 < p.n_parts && g >= p.parts[pi + 1].block_base) ++pi;
+        const DevPartRef &part = p.parts[pi];
+        const DevBlock blk = part.blocks[g - part.block_base];
+        const unsigned long long off = p.dd_row_off[g];
+        if (phase == 0) {
+            const uint8_t *tsp = part.files[0] + blk.ts_off;
+            bool ok = decode_list_to(sm, seq, tsp, blk.ver_off, blk.ts_enc, blk.ts_min, blk.count, p.dd_ts + off, lane);
+            ok = ok && decode_list_to(sm, seq, tsp + blk.ver_off, blk.ts_size - blk.ver_off, blk.ver_enc, blk.ver_first, blk.count, p.dd_ver + off, lane);
+            if (!ok || blk.count > kMaskWords * 32) set_err(p, !ok ? kErrCorrupt : kErrBigBlock, g, lane);
+            continue;
+        }
+        // phase 1: shadow mask
+        uint32_t *shadow = p.dd_shadow + static_cast<size_t>(k) * kMaskWords;
+        const uint32_t nwords = (blk.count + 31) >> 5;
+        if (blk.count > kMaskWords * 32) continue;
+        const int32_t qi = p.block_qsid[g];
+        for (uint32_t w = 0; w < nwords; ++w) {
+            const uint32_t row = (w << 5) + lane;
+            bool keep = row < blk.count;
+            if (keep) {
+                const int64_t t = p.dd_ts[off + row], v = p.dd_ver[off + row];
+                for (uint32_t qp = 0; qp < p.n_parts && keep; ++qp) {
+                    if (qp == pi) continue;
+                    const DevPartRef &other = p.parts[qp];
+                    for (uint32_t b = series_first_block(p, qp, static_cast<uint32_t>(qi), blk.sid); b < other.n_blocks && other.blocks[b].sid == blk.sid; ++b) {
+                        const DevBlock &ob = other.blocks[b];
+                        if (ob.ts_min > t) break;
+                        if (ob.ts_max < t) continue;
+                        const uint32_t og = other.block_base + b;
+                        if (p.dd_index[og] < 0) continue;
+                        const int64_t *ots = p.dd_ts + p.dd_row_off[og];
+                        uint32_t lo = 0, hi = ob.count;
+                        while (lo < hi) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (ots[mid] < t) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        if (lo < ob.count && ots[lo] == t) {
+                            const int64_t ov = p.dd_ver[p.dd_row_off[og] + lo];
+                            if (ov > v || (ov == v && qp < pi)) keep = false;
+                        }
+                    }
+                }
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) shadow[w] = bal;
         }
     }
 }
@@ -1187,10 +1366,15 @@ __global__ void series_reduce_kernel(const __grid_constant__ ReduceParams p) {
     for (uint32_t pi = 0; pi < p.n_parts; ++pi) {
         const DevPartRef &part = p.parts[pi];
         uint32_t lo = 0, hi = part.n_blocks;
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (part.blocks[mid].sid < sid) lo = mid + 1;
-            else hi = mid;
+        if (p.first_block) {
+            const uint32_t g0 = p.first_block[static_cast<size_t>(pi) * p.n_series + i];
+            lo = g0 == 0xffffffffu ? part.n_blocks : g0 - part.block_base;
+        } else {
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (part.blocks[mid].sid < sid) lo = mid + 1;
+                else hi = mid;
+            }
         }
         int64_t plo = INT64_MAX, phi = INT64_MIN;
         for (uint32_t b = lo; b < part.n_blocks && part.blocks[b].sid == sid; ++b) {
@@ -1215,7 +1399,7 @@ __global__ void series_reduce_kernel(const __grid_constant__ ReduceParams p) {
             }
         }
     }
-    if (overlap && atomicCAS(&p.err[0], 0u, static_cast<uint32_t>(kErrOverlap)) == 0u) p.err[1] = i;
+    if (overlap && !p.dedup_done && atomicCAS(&p.err[0], 0u, static_cast<uint32_t>(kErrOverlap)) == 0u) p.err[1] = i;
     for (uint32_t c = 0; c < p.n_fcols; ++c) p.S[static_cast<size_t>(i) * p.n_fcols + c] = acc[c];
     p.Srows[i] = rows;
 }
@@ -1334,6 +1518,210 @@ __global__ void finalize_kernel(const __grid_constant__ FinalizeParams p) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// select_rows: which groups become output rows, in which order (one CTA; G is small next to the scan)
+//   top_n == 0 : stable compaction of the groups with rows > 0 (group-id = first-appearance order,
+//                pkg/query/vectorized/measure/aggregation.go:211-213)
+//   top_n  > 0 : pkg/query/vectorized/measure/top.go:62-117 -- order by the aggregate, nulls lowest,
+//                ties -> earlier row.  MSB-first radix select (8 x 8 bit histograms in shared memory)
+//                finds the N-th key, an ordered pass resolves the ties by group id, a bitonic sort
+//                orders the <= 2048 selected rows.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_tot, uint32_t &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, s);
+        if (lane >= s) incl += o;
+    }
+    __syncthreads();
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+    total = 0;
+    for (int w = 0; w < nw; ++w) {
+        const uint32_t t = warp_tot[w];
+        if (w < warp) base += t;
+        total += t;
+    }
+    return base + incl - v;
+}
+
+__device__ __forceinline__ uint64_t order_key_i64(int64_t v) { return static_cast<uint64_t>(v) ^ (1ull << 63); }
+__device__ __forceinline__ uint64_t order_key_f64(double d) {
+    const uint64_t b = static_cast<uint64_t>(__double_as_longlong(d));
+    return (b >> 63) ? ~b : (b | (1ull << 63));
+}
+
+__global__ void __launch_bounds__(1024) select_rows_kernel(const __grid_constant__ SelectParams p) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint64_t s_key[kMaxDeviceTopN];
+    __shared__ int32_t s_gid[kMaxDeviceTopN];
+    __shared__ uint64_t s_prefix;
+    __shared__ uint32_t s_remaining, s_count, s_nn, s_nulls;
+    const int tid = threadIdx.x;
+    const int32_t G = p.n_groups;
+    const uint32_t A = p.n_aggs;
+    auto emit = [&](uint32_t pos, int32_t g) {
+        p.sel_group[pos] = g;
+        p.sel_rows[pos] = p.rows[g];
+        for (uint32_t a = 0; a < A; ++a) {
+            p.sel_i64[static_cast<size_t>(pos) * A + a] = p.val_i64[static_cast<size_t>(g) * A + a];
+            p.sel_f64[static_cast<size_t>(pos) * A + a] = p.val_f64[static_cast<size_t>(g) * A + a];
+        }
+    };
+    if (p.top_n <= 0) {
+        uint32_t base = 0;
+        for (int32_t g0 = 0; g0 < G; g0 += blockDim.x) {
+            const int32_t g = g0 + tid;
+            const uint32_t f = (g < G && p.rows[g] > 0) ? 1u : 0u;
+            uint32_t tot;
+            const uint32_t pos = base + block_excl_scan(f, s_warp, tot);
+            if (f) emit(pos, g);
+            base += tot;
+            __syncthreads();
+        }
+        if (tid == 0) *p.sel_count = base;
+        return;
+    }
+    // ---- keys: 0 for rows that do not compete; nulls are counted apart (they sort lowest as values)
+    const bool isf = p.is_float[p.top_agg] != 0;
+    uint32_t my_nn = 0, my_null = 0;
+    for (int32_t g = tid; g < G; g += blockDim.x) {
+        uint64_t k = 0;
+        uint8_t st = 0;  // 0 = no output row, 1 = null aggregate, 2 = competes with key k
+        if (p.rows[g] > 0) {
+            const bool null = !p.top_is_count && p.cnt[static_cast<size_t>(g) * p.n_fcols + p.top_fcol] == 0;
+            if (null) {
+                st = 1;
+                ++my_null;
+            } else {
+                const size_t o = static_cast<size_t>(g) * A + p.top_agg;
+                k = isf ? order_key_f64(p.val_f64[o]) : order_key_i64(p.val_i64[o]);
+                if (!p.top_desc) k = ~k;  // ascending: the smallest value gets the largest key
+                st = 2;
+                ++my_nn;
+            }
+        }
+        p.keys[g] = k;
+        p.kstate[g] = st;
+    }
+    uint32_t tot;
+    (void)block_excl_scan(my_nn, s_warp, tot);
+    if (tid == 0) s_nn = tot;
+    __syncthreads();
+    (void)block_excl_scan(my_null, s_warp, tot);
+    if (tid == 0) s_nulls = tot;
+    __syncthreads();
+    const uint32_t N = static_cast<uint32_t>(p.top_n);
+    const uint32_t n_nulls_first = p.top_desc ? 0u : min(N, s_nulls);                  // asc: nulls lead
+    const uint32_t M = min(N - n_nulls_first, s_nn);                                     // competing rows to take
+    const uint32_t n_nulls_last = p.top_desc ? min(N - M, s_nulls) : 0u;               // desc: nulls trail
+    // ---- radix select of the M-th largest competing key
+    if (tid == 0) {
+        s_prefix = 0;
+        s_remaining = M;
+    }
+    __syncthreads();
+    if (M > 0) {
+        for (int pass = 7; pass >= 0; --pass) {
+            for (int i = tid; i < 256; i += blockDim.x) s_hist[i] = 0;
+            __syncthreads();
+            const uint64_t prefix = s_prefix;
+            for (int32_t g = tid; g < G; g += blockDim.x) {
+                if (p.kstate[g] != 2) continue;
+                const uint64_t k = p.keys[g];
+                if (pass < 7 && (k >> (8 * (pass + 1))) != prefix) continue;
+                atomicAdd(&s_hist[(k >> (8 * pass)) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t rem = s_remaining, above = 0;
+                int d = 255;
+                for (; d > 0; --d) {
+                    if (above + s_hist[d] >= rem) break;
+                    above += s_hist[d];
+                }
+                s_remaining = rem - above;
+                s_prefix = (prefix << 8) | static_cast<uint64_t>(d);
+            }
+            __syncthreads();
+        }
+    }
+    const uint64_t T = s_prefix;
+    const uint32_t take_eq = s_remaining;
+    // ---- collect: keys above T in any order, keys equal to T in group order
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    uint32_t eq_base = 0;
+    for (int32_t g0 = 0; g0 < G && M > 0; g0 += blockDim.x) {
+        const int32_t g = g0 + tid;
+        const uint64_t k = g < G ? p.keys[g] : 0;
+        const bool comp = g < G && p.kstate[g] == 2;
+        const uint32_t eq = (comp && k == T) ? 1u : 0u;
+        uint32_t tot_eq;
+        const uint32_t rank = eq_base + block_excl_scan(eq, s_warp, tot_eq);
+        if (comp && (k > T || (eq && rank < take_eq))) {
+            const uint32_t pos = atomicAdd(&s_count, 1u);
+            if (pos < kMaxDeviceTopN) {
+                s_key[pos] = k;
+                s_gid[pos] = g;
+            }
+        }
+        eq_base += tot_eq;
+        __syncthreads();
+    }
+    __syncthreads();
+    // ---- bitonic sort (key desc, group asc)
+    uint32_t P2 = 1;
+    while (P2 < M) P2 <<= 1;
+    for (uint32_t i = M + tid; i < P2; i += blockDim.x) {
+        s_key[i] = 0;
+        s_gid[i] = INT32_MAX;
+    }
+    __syncthreads();
+    for (uint32_t k2 = 2; k2 <= P2; k2 <<= 1) {
+        for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = tid; i < P2; i += blockDim.x) {
+                const uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    const bool up = (i & k2) == 0;
+                    const uint64_t ka = s_key[i], kb = s_key[ixj];
+                    const int32_t ga = s_gid[i], gb = s_gid[ixj];
+                    const bool a_first = ka > kb || (ka == kb && ga < gb);  // a precedes b in the output
+                    if (a_first != up) {
+                        s_key[i] = kb;
+                        s_key[ixj] = ka;
+                        s_gid[i] = gb;
+                        s_gid[ixj] = ga;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- emit: [nulls (asc only)] [sorted competing rows] [nulls (desc only)]
+    for (uint32_t i = tid; i < M; i += blockDim.x) emit(n_nulls_first + i, s_gid[i]);
+    const uint32_t n_nulls = n_nulls_first + n_nulls_last;
+    if (n_nulls > 0) {
+        uint32_t base = 0;
+        const uint32_t at = p.top_desc ? M : 0u;
+        for (int32_t g0 = 0; g0 < G; g0 += blockDim.x) {
+            const int32_t g = g0 + tid;
+            const uint32_t f = (g < G && p.kstate[g] == 1) ? 1u : 0u;
+            uint32_t tot2;
+            const uint32_t pos = base + block_excl_scan(f, s_warp, tot2);
+            if (f && pos < n_nulls) emit(at + pos, g);
+            base += tot2;
+            __syncthreads();
+        }
+    }
+    if (tid == 0) *p.sel_count = M + n_nulls;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
@@ -1361,6 +1749,22 @@ int scan_max_ctas_per_sm() {
     return n < 1 ? 1 : n;
 }
 
+void launch_detect_overlap(const ScanParams &p, cudaStream_t s) {
+    if (p.n_series == 0) return;
+    const int threads = 128;
+    detect_overlap_kernel<<<(p.n_series + threads - 1) / threads, threads, 0, s>>>(p);
+}
+void launch_dedup(const ScanParams &p, int grid, cudaStream_t s) {
+    if (p.n_dd_blocks == 0) return;
+    const size_t smem = scan_smem_bytes();
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        attr = true;
+    }
+    dedup_kernel<<<grid, kWarpsPerCta * 32, smem, s>>>(p, 0);
+    dedup_kernel<<<grid, kWarpsPerCta * 32, smem, s>>>(p, 1);
+}
 void launch_series_reduce(const ReduceParams &p, cudaStream_t s) {
     if (p.n_series == 0) return;
     const int threads = 128;
@@ -1370,6 +1774,7 @@ void launch_group_reduce(const ReduceParams &p, cudaStream_t s) {
     if (p.n_groups <= 0) return;
     group_reduce_kernel<<<p.n_groups, 256, 0, s>>>(p);
 }
+void launch_select_rows(const SelectParams &p, cudaStream_t s) { select_rows_kernel<<<1, 1024, 0, s>>>(p); }
 void launch_finalize(const FinalizeParams &p, cudaStream_t s) {
     const int threads = 128;
     const int n = p.n_groups > 0 ? p.n_groups : 1;

@@ -32,6 +32,7 @@ enum DevErr : uint32_t {
     kErrTagPlain = 7,       // high-cardinality (>256 values) string tag page: plain bytes block
     kErrOverlap = 8,        // same series in several parts with overlapping time spans: needs version dedup
     kErrPredType = 9,       // predicate literal type does not match the stored tag column type
+    kErrTmaTimeout = 10,    // a bulk copy never completed (internal error)
 };
 
 struct DevPartRef {
@@ -74,11 +75,21 @@ struct ScanParams {
     uint32_t *work_count;
     uint32_t *work_next;
     int32_t *block_qsid;          // [total_blocks] query-series index or -1
+    uint32_t *first_block;        // [n_parts * n_series] first block of the series in the part (0xffffffff = none); may be NULL
     BlockPartial *P;              // [total_blocks * n_fcols]
     uint32_t *Prows;              // [total_blocks] rows that passed range + predicates
     int32_t *col_type;            // [n_fcols] 0 unknown / BYDB_VT_INT64 / BYDB_VT_FLOAT64
     uint32_t *err;                // [2]
     unsigned long long *stats;    // [0] rows_scanned [1] rows_matched [2] page_bytes [3] blocks
+    // ---- version dedup across overlapping parts (query.go:995-1004); all NULL when no parts overlap
+    int32_t *dd_index;            // [total_blocks] compact index of a block that needs dedup, or -1
+    unsigned long long *dd_row_off; // [total_blocks] offset of the block's rows in dd_ts / dd_ver
+    uint32_t *dd_list;            // [n_dd_blocks] global block indices
+    unsigned long long *dd_counts; // [0] flagged blocks, [1] flagged rows
+    int64_t *dd_ts, *dd_ver;      // decoded timestamps / versions of the flagged blocks
+    uint32_t *dd_shadow;          // [n_dd_blocks * kMaskWords] 1 = row survives the dedup
+    uint32_t n_dd_blocks;
+    uint32_t pad1;
 };
 
 struct ReduceParams {
@@ -91,12 +102,15 @@ struct ReduceParams {
     const int32_t *order;         // [n_series] query-series indices sorted by (group, series)
     const int32_t *group_start;   // [n_groups + 1] into order
     const int32_t *block_qsid;
+    const uint32_t *first_block;  // see ScanParams
     const BlockPartial *P;
     const uint32_t *Prows;
     const int32_t *col_type;
     BlockPartial *S;              // [n_series * n_fcols] per-series partials
     int64_t *Srows;               // [n_series]
     uint32_t *err;
+    uint32_t dedup_done;          // 1 = overlapping parts were resolved by the dedup kernels
+    uint32_t pad2;
     // partial table (see bydb_gpu.h): written by group_reduce
     double *sum_f64, *max_f64, *negmin_f64;
     int64_t *sum_i64, *cnt, *rows, *max_i64, *notmin_i64, *coltype;
@@ -116,12 +130,34 @@ struct FinalizeParams {
     uint8_t *out_is_float;        // [n_aggs]
 };
 
+// output row selection on the device: stable compaction of the groups that appeared, or Top-N
+constexpr int kMaxDeviceTopN = 2048;
+struct SelectParams {
+    int32_t n_groups;
+    uint32_t n_fcols, n_aggs;
+    int32_t top_n, top_agg, top_desc, top_fcol, top_is_count;
+    const int64_t *rows, *cnt;
+    const int64_t *val_i64;       // finalized values [n_groups * n_aggs]
+    const double *val_f64;
+    const uint8_t *is_float;      // [n_aggs]
+    uint64_t *keys;               // scratch [n_groups]
+    uint8_t *kstate;              // scratch [n_groups]
+    int32_t *sel_group;           // outputs, capacity = top_n > 0 ? min(top_n, n_groups) : n_groups
+    int64_t *sel_rows;
+    int64_t *sel_i64;
+    double *sel_f64;
+    uint32_t *sel_count;
+};
+void launch_select_rows(const SelectParams &p, cudaStream_t s);
+
 size_t scan_smem_bytes();
 void launch_plan_blocks(const ScanParams &p, cudaStream_t s);
 void launch_scan_blocks(const ScanParams &p, int grid, cudaStream_t s);
 void launch_series_reduce(const ReduceParams &p, cudaStream_t s);
 void launch_group_reduce(const ReduceParams &p, cudaStream_t s);
 void launch_finalize(const FinalizeParams &p, cudaStream_t s);
+void launch_detect_overlap(const ScanParams &p, cudaStream_t s);
+void launch_dedup(const ScanParams &p, int grid, cudaStream_t s);
 int upload_pow10_table();
 int scan_max_ctas_per_sm();
 

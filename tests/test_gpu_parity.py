@@ -224,6 +224,25 @@ def test_multiple_parts_series_subset_and_topn(bydb, gpu_ctx):
     assert_parity(got, want, aggs, "multi-part bottom3")
 
 
+def test_topn_adjacent_values_ties_and_float_order(bydb, gpu_ctx):
+    # top.go:62-117: full-precision ordering (values differing by 1 / 1 ulp), ties -> earlier group, both directions
+    rng = np.random.default_rng(31)
+    n_groups = 300
+    sids = np.arange(1, n_groups + 1, dtype=np.uint64)
+    ivals = rng.integers(-5, 6, n_groups) + 1000            # many ties and neighbours
+    fvals = np.round(rng.integers(-3, 4, n_groups) * 0.01 + 7.5, 2)
+    part = build_part(sids, np.full(n_groups, T0, np.int64), np.ones(n_groups, np.int64),
+                      [("calls", O.VT_INT64, ivals, None), ("latency", O.VT_FLOAT64, fvals, None)])
+    groups = np.arange(n_groups, dtype=np.int32)
+    aggs = [("calls", O.AGG_SUM), ("latency", O.AGG_MAX), ("calls", O.AGG_COUNT)]
+    for top_agg in (0, 1, 2):
+        for desc in (True, False):
+            for n in (1, 7, 64, 299, 300, 1000):
+                oq = O.Query([part], sids, aggs, groups=groups, n_groups=n_groups, top_n=n, top_agg=top_agg, top_desc=desc)
+                got, want = run_both(bydb, gpu_ctx, [part], oq, _next_pid())
+                assert_parity(got, want, aggs, f"top/{top_agg}/{desc}/{n}")
+
+
 def test_empty_and_missing(bydb, gpu_ctx):
     sids, ts, ver = grid(4, 100)
     part = build_part(sids, ts, ver, [("calls", O.VT_INT64, np.arange(sids.size), None)])
@@ -247,15 +266,58 @@ def test_unsupported_pages_fail_loudly_not_silently(bydb, gpu_ctx):
         gpu_ctx.scan_agg(bydb.Query([h], np.unique(sids), [("calls", O.AGG_SUM)]))
     assert ei.value.code == -95
     gpu_ctx.release_part(h)
-    # the same series in two parts with overlapping time spans needs version dedup (query.go:995-1004)
-    p1 = build_part(sids, ts, ver, [("calls", O.VT_INT64, np.arange(sids.size), None)])
-    p2 = build_part(sids, ts, ver + 1, [("calls", O.VT_INT64, np.arange(sids.size) + 7, None)])
-    h1, h2 = gpu_ctx.register_part(_next_pid(), p1.files()), gpu_ctx.register_part(_next_pid(), p2.files())
-    with pytest.raises(bydb.BydbError) as ei:
-        gpu_ctx.scan_agg(bydb.Query([h1, h2], np.unique(sids), [("calls", O.AGG_SUM)]))
-    assert ei.value.code == -95
-    gpu_ctx.release_part(h1)
-    gpu_ctx.release_part(h2)
+
+
+def test_version_dedup_across_overlapping_parts(bydb, gpu_ctx):
+    # query.go:995-1004 / query_batch.go:151-161: a (series, timestamp) present in several parts keeps the highest version
+    rng = np.random.default_rng(17)
+    n_series, n_pts = 12, 9000
+    sids, ts, _ = grid(n_series, n_pts)
+    base = rng.integers(0, 1000, sids.size)
+    lat = np.round(rng.normal(20, 3, sids.size), 2)
+    p1 = build_part(sids, ts, np.full(sids.size, 5, np.int64), [("calls", O.VT_INT64, base, None), ("latency", O.VT_FLOAT64, lat, None)])
+    # part 2 rewrites a random 30% of the points of the even series: half of them newer (version 9), half stale (version 2)
+    m = (rng.random(sids.size) < 0.3) & (sids % 2 == 0)
+    ver2 = np.where(rng.random(m.sum()) < 0.5, 9, 2).astype(np.int64)
+    p2 = build_part(sids[m], ts[m], ver2, [("calls", O.VT_INT64, base[m] + 100000, None), ("latency", O.VT_FLOAT64, lat[m] + 1000, None)])
+    # part 3: late data for series 3 only, newest version, plus points beyond the others' range
+    m3 = sids == 3
+    ts3 = np.concatenate([ts[m3][::7], ts[m3][-1] + (1 + np.arange(50)) * STEP])
+    p3 = build_part(np.full(ts3.size, 3, np.uint64), ts3, np.full(ts3.size, 11, np.int64),
+                    [("calls", O.VT_INT64, np.arange(ts3.size) - 7, None), ("latency", O.VT_FLOAT64, np.full(ts3.size, 0.5), None)])
+    usid = np.unique(sids)
+    aggs = [("calls", f) for f in ALL5] + [("latency", O.AGG_SUM), ("latency", O.AGG_MAX)]
+    for kw in (dict(), dict(tmin=T0 + 1000 * STEP, tmax=T0 + 8500 * STEP),
+               dict(groups=(np.arange(usid.size) % 3).astype(np.int32), n_groups=3)):
+        oq = O.Query([p1, p2, p3], usid, aggs, **kw)
+        got, want = run_both(bydb, gpu_ctx, [p1, p2, p3], oq, _next_pid())
+        assert_parity(got, want, aggs, f"dedup/{list(kw)}")
+    # order of the parts must not matter
+    oq = O.Query([p3, p1, p2], usid, aggs)
+    got, want = run_both(bydb, gpu_ctx, [p3, p1, p2], oq, _next_pid())
+    assert_parity(got, want, aggs, "dedup/reordered")
+
+
+def test_version_dedup_irregular_timestamps_and_predicate(bydb, gpu_ctx):
+    rng = np.random.default_rng(23)
+    rows1, rows2 = [], []
+    for s in range(1, 6):
+        t = T0 + np.cumsum(rng.integers(1, 10, 4000)) * 1_000_000_000
+        rows1.append((np.full(t.size, s, np.uint64), t))
+        pick = rng.random(t.size) < 0.4
+        rows2.append((np.full(pick.sum(), s, np.uint64), t[pick]))
+    sid1, ts1 = np.concatenate([r[0] for r in rows1]), np.concatenate([r[1] for r in rows1])
+    sid2, ts2 = np.concatenate([r[0] for r in rows2]), np.concatenate([r[1] for r in rows2])
+    v1, v2 = rng.integers(0, 100, sid1.size), rng.integers(1000, 2000, sid2.size)
+    reg1 = [b"r%d" % x for x in rng.integers(0, 3, sid1.size)]
+    reg2 = [b"r%d" % x for x in rng.integers(0, 3, sid2.size)]
+    p1 = build_part(sid1, ts1, np.full(sid1.size, 1, np.int64), [("calls", O.VT_INT64, v1, None)], [("default", [("region", O.VT_STR, reg1, None)])])
+    p2 = build_part(sid2, ts2, np.full(sid2.size, 2, np.int64), [("calls", O.VT_INT64, v2, None)], [("default", [("region", O.VT_STR, reg2, None)])])
+    aggs = [("calls", O.AGG_SUM), ("calls", O.AGG_COUNT), ("calls", O.AGG_MAX)]
+    for preds in ([], [O.Pred("default", "region", O.OP_EQ, b"r1")]):
+        oq = O.Query([p1, p2], np.arange(1, 6, dtype=np.uint64), aggs, preds=preds, tmin=int(ts1.min()) + 5, tmax=int(ts1.max()) - 5)
+        got, want = run_both(bydb, gpu_ctx, [p1, p2], oq, _next_pid())
+        assert_parity(got, want, aggs, f"dedup-irregular/{len(preds)}")
 
 
 def test_scan_agg_host_and_idempotent_register(bydb, gpu_ctx):
@@ -270,6 +332,19 @@ def test_scan_agg_host_and_idempotent_register(bydb, gpu_ctx):
     got = gpu_ctx.scan_agg_host([files], bydb.Query([], np.unique(sids), aggs))
     assert_parity(got, want, aggs, "host path")
     assert got.stats.h2d_bytes >= sum(v.size for k, v in files.items() if k in ("timestamps.bin", "fv.bin"))
+    # zero-copy: pinned, padded host buffers are read in place by the kernels
+    import torch
+    keep, pinned = [], {}
+    for k, v in files.items():
+        t = torch.empty(v.size + 256, dtype=torch.uint8, pin_memory=True)
+        t[:v.size].copy_(torch.from_numpy(v.copy()))
+        keep.append(t)
+        pinned[k] = t[:v.size].numpy()
+    got = gpu_ctx.scan_agg_host([pinned], bydb.Query([], np.unique(sids), aggs, flags=1))
+    assert_parity(got, want, aggs, "host zero-copy path")
+    assert got.stats.h2d_bytes < sum(v.size for v in files.values())
+    with pytest.raises(bydb.BydbError):     # pageable memory must be refused, not silently copied
+        gpu_ctx.scan_agg_host([files], bydb.Query([], np.unique(sids), aggs, flags=1))
     pid = _next_pid()
     h1 = gpu_ctx.register_part(pid, part.files())
     h2 = gpu_ctx.register_part(pid, part.files())
