@@ -44,9 +44,15 @@ struct Part {
     const uint8_t *const *d_files = nullptr;
     uint64_t hbm_bytes = 0;
     int device = 0;
+    cudaStream_t pool_stream = nullptr;  // transient parts (host path) live in the stream-ordered pool
     ~Part() {
-        if (d_arena) cudaFree(d_arena);
-        if (d_dir) cudaFree(d_dir);
+        if (pool_stream) {
+            if (d_arena) cudaFreeAsync(d_arena, pool_stream);
+            if (d_dir) cudaFreeAsync(d_dir, pool_stream);
+        } else {
+            if (d_arena) cudaFree(d_arena);
+            if (d_dir) cudaFree(d_dir);
+        }
     }
 };
 
@@ -73,7 +79,8 @@ struct ExecSlot {
 struct bydb_ctx {
     int device = 0;
     int sm_count = 0;
-    int ctas_per_sm = 2;
+    int ctas_per_sm = 2;       // slow lane (general decoder)
+    int ctas_per_sm_fast = 2;  // fast lane
     uint64_t hbm_budget = 0;
     uint64_t hbm_used = 0;
     std::mutex mu;
@@ -215,7 +222,7 @@ struct TableLayout {
 // zero_copy: the data files stay in (pinned, device-mapped) host memory and the kernels read the
 // pages they need straight over PCIe; only the block directory is uploaded.
 int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_files *files, std::shared_ptr<Part> &out, uint64_t *h2d,
-                              bool zero_copy = false) {
+                              bool zero_copy = false, bool transient = false) {
     if (!files || files->n_files == 0 || !files->files) return fail(BYDB_EINVAL, "no files");
     std::vector<FileImage> imgs;
     for (uint32_t i = 0; i < files->n_files; ++i) {
@@ -271,17 +278,25 @@ int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_f
         std::lock_guard<std::mutex> lk(ctx->mu);
         ctx->hbm_used -= part->hbm_bytes;
     };
-    if (cudaMalloc(reinterpret_cast<void **>(&part->d_arena), arena ? arena : 256) != cudaSuccess ||
-        cudaMalloc(reinterpret_cast<void **>(&part->d_dir), dir_bytes ? dir_bytes : 256) != cudaSuccess) {
-        undo_budget();
-        return fail(BYDB_ENOMEM, "cudaMalloc failed for part " + std::to_string(part_id));
-    }
     SlotLease lease(ctx);
     if (lease.init()) {
         undo_budget();
         return fail(BYDB_EIO, "cannot create stream");
     }
     cudaStream_t s = lease.slot->stream;
+    bool alloc_ok;
+    if (transient) {
+        part->pool_stream = s;
+        alloc_ok = cudaMallocAsync(reinterpret_cast<void **>(&part->d_arena), arena ? arena : 256, s) == cudaSuccess &&
+                   cudaMallocAsync(reinterpret_cast<void **>(&part->d_dir), dir_bytes ? dir_bytes : 256, s) == cudaSuccess;
+    } else {
+        alloc_ok = cudaMalloc(reinterpret_cast<void **>(&part->d_arena), arena ? arena : 256) == cudaSuccess &&
+                   cudaMalloc(reinterpret_cast<void **>(&part->d_dir), dir_bytes ? dir_bytes : 256) == cudaSuccess;
+    }
+    if (!alloc_ok) {
+        undo_budget();
+        return fail(BYDB_ENOMEM, "device allocation failed for part " + std::to_string(part_id));
+    }
     cudaError_t e = cudaSuccess;
     if (!zero_copy) {
         e = cudaMemsetAsync(part->d_arena, 0, arena ? arena : 256, s);
@@ -289,18 +304,20 @@ int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_f
             if (order[i]->len) e = cudaMemcpyAsync(part->d_arena + offs[i], order[i]->data, order[i]->len, cudaMemcpyHostToDevice, s);
     }
     // directory
-    std::vector<uint8_t> hdir(dir_bytes ? dir_bytes : 1, 0);
-    size_t o = 0;
-    if (nb) memcpy(hdir.data() + o, part->dir.blocks.data(), nb * sizeof(DevBlock));
+    if (lease.slot->ensure_pinned(dir_bytes ? dir_bytes : 256)) {
+        undo_budget();
+        return fail(BYDB_ENOMEM, "cudaMallocHost failed");
+    }
+    uint8_t *hdir = lease.slot->pinned;  // the directory goes up from pinned staging in one copy
+    if (nb) memcpy(hdir, part->dir.blocks.data(), nb * sizeof(DevBlock));
     const size_t off_cols = align_up(nb * sizeof(DevBlock), 256);
-    if (nc) memcpy(hdir.data() + off_cols, part->dir.cols.data(), nc * sizeof(DevCol));
+    if (nc) memcpy(hdir + off_cols, part->dir.cols.data(), nc * sizeof(DevCol));
     const size_t off_files = off_cols + align_up(nc * sizeof(DevCol), 256);
     for (size_t i = 0; i < nf; ++i) {
         const uint8_t *pfile = zero_copy ? mapped[i] : part->d_arena + offs[i];
-        memcpy(hdir.data() + off_files + i * sizeof(void *), &pfile, sizeof(void *));
+        memcpy(hdir + off_files + i * sizeof(void *), &pfile, sizeof(void *));
     }
-    (void)o;
-    if (e == cudaSuccess && dir_bytes) e = cudaMemcpyAsync(part->d_dir, hdir.data(), dir_bytes, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && dir_bytes) e = cudaMemcpyAsync(part->d_dir, hdir, dir_bytes, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) {
         undo_budget();
@@ -358,6 +375,7 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
     const size_t off_order = carve(NS * 4);
     const size_t off_gstart = carve((static_cast<size_t>(G) + 1) * 4);
     const size_t off_worklist = carve(NB * 4);
+    const size_t off_slowlist = carve(NB * 4);
     const size_t off_qsid = carve(NB * 4);
     const size_t off_P = carve(NB * F * sizeof(BlockPartial));
     const size_t off_Prows = carve(NB * 4);
@@ -414,6 +432,11 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         for (size_t c = 0; c < F; ++c) sp.fcol_name[c] = ctx->names.find("f:" + plan.fcols[c]);
+        for (uint32_t a = 0; a < q->n_aggs; ++a) {
+            const int fn = q->aggs[a].func;
+            uint8_t need = (fn == BYDB_AGG_SUM || fn == BYDB_AGG_MEAN) ? 1 : (fn == BYDB_AGG_MIN || fn == BYDB_AGG_MAX) ? 2 : 0;
+            sp.fcol_need[plan.agg_fcol[a]] |= need;
+        }
         for (uint32_t i = 0; i < q->n_preds; ++i) {
             const bydb_pred &p = q->preds[i];
             DevPred &dp = sp.preds[i];
@@ -428,6 +451,9 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
     sp.worklist = reinterpret_cast<uint32_t *>(d + off_worklist);
     sp.work_count = z32 + 0;
     sp.work_next = z32 + 1;
+    sp.slow_list = reinterpret_cast<uint32_t *>(d + off_slowlist);
+    sp.slow_count = z32 + 28;  // bytes 112..119 of the zero page
+    sp.slow_next = z32 + 29;
     sp.err = z32 + 2;
     sp.stats = reinterpret_cast<unsigned long long *>(d + off_zero + 16);
     sp.col_type = reinterpret_cast<int32_t *>(d + off_zero + 64);
@@ -502,7 +528,7 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
         rp.dedup_done = 1;
     }
     CUDA_TRY(cudaEventRecord(slot.ev[1], stream));
-    launch_scan_blocks(sp, ctx->sm_count * ctx->ctas_per_sm, stream);
+    launch_scan_blocks(sp, ctx->sm_count * ctx->ctas_per_sm_fast, ctx->sm_count * ctx->ctas_per_sm, stream);
     CUDA_TRY(cudaEventRecord(slot.ev[2], stream));
     launch_series_reduce(rp, stream);
     launch_group_reduce(rp, stream);
@@ -524,7 +550,7 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
         stats->scan_kernel_ms += ms;
         cudaEventElapsedTime(&ms, slot.ev[0], slot.ev[3]);
         stats->device_ms += ms;
-        stats->kernel_launches += (NB ? 1u : 0u) + 1u + (NS ? 1u : 0u) + 1u + extra_launches;
+        stats->kernel_launches += (NB ? 1u : 0u) + 2u + (NS ? 1u : 0u) + 1u + extra_launches;
         stats->d2h_bytes += 256;
     }
     if (hz[2] != 0) {
@@ -701,9 +727,11 @@ int bydb_init(const bydb_cfg *cfg, bydb_ctx **out) {
         delete ctx;
         return fail(BYDB_EIO, "cannot upload constant tables (is the library built for this GPU?)");
     }
-    int occ = scan_max_ctas_per_sm();
-    int want = (cfg && cfg->warps_per_sm > 0) ? (cfg->warps_per_sm + kWarpsPerCta - 1) / kWarpsPerCta : 2;
-    ctx->ctas_per_sm = std::max(1, std::min(want, occ));
+    int occ_fast = 1, occ_slow = 1;
+    scan_max_ctas_per_sm(&occ_fast, &occ_slow);
+    int want = (cfg && cfg->warps_per_sm > 0) ? (cfg->warps_per_sm + kWarpsPerCta - 1) / kWarpsPerCta : 64;
+    ctx->ctas_per_sm = std::max(1, std::min(want, occ_slow));
+    ctx->ctas_per_sm_fast = std::max(1, std::min(want, occ_fast));
     *out = ctx;
     return 0;
 }
@@ -792,7 +820,7 @@ int bydb_scan_agg_host(bydb_ctx *ctx, uint32_t n_parts, const bydb_part_files *p
     uint64_t h2d = 0;
     for (uint32_t i = 0; i < n_parts; ++i) {
         std::shared_ptr<Part> p;
-        rc = register_part_locked_free(ctx, ~0ull - i, &parts[i], p, &h2d, (q->flags & BYDB_Q_HOST_ZERO_COPY) != 0);
+        rc = register_part_locked_free(ctx, ~0ull - i, &parts[i], p, &h2d, (q->flags & BYDB_Q_HOST_ZERO_COPY) != 0, true);
         if (rc) break;
         tmp.push_back(p);
     }

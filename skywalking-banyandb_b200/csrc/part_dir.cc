@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 #include "../../include/bydb_gpu.h"
 
@@ -129,6 +130,192 @@ const FileImage *find_file(const std::vector<FileImage> &files, const std::strin
 }
 }  // namespace
 
+// Parses one decompressed primary block (a run of blockMetadata records) into blocks/cols.
+// Column names are resolved through a positional cache first (consecutive blocks share a schema),
+// so the shared NameTable is only touched on a miss.
+namespace {
+struct NameSlot {
+    std::string raw;
+    uint16_t id = 0;
+};
+struct ParseCtx {
+    const std::vector<FileImage> *files;
+    const FileImage *tsf, *fvf;
+    NameTable *names;
+    std::mutex *names_mu;
+    std::vector<std::string> *file_table;  // shared, guarded by names_mu
+    std::vector<NameSlot> field_cache;
+    std::vector<NameSlot> tag_cache;
+    struct FamSlot {
+        std::string name;
+        const FileImage *tfm = nullptr, *tf = nullptr;
+        int file_id = -1;
+    };
+    std::vector<FamSlot> fam_cache;
+};
+
+uint16_t resolve_name(ParseCtx &cx, std::vector<NameSlot> &cache, size_t pos, const char *prefix, const std::string &fam, const uint8_t *p, size_t n) {
+    if (pos < cache.size() && cache[pos].raw.size() == n && memcmp(cache[pos].raw.data(), p, n) == 0) return cache[pos].id;
+    std::string key(prefix);
+    if (!fam.empty()) key += fam + "/";
+    key.append(reinterpret_cast<const char *>(p), n);
+    uint16_t id;
+    {
+        std::lock_guard<std::mutex> lk(*cx.names_mu);
+        id = cx.names->intern(key);
+    }
+    if (pos >= cache.size()) cache.resize(pos + 1);
+    cache[pos].raw.assign(reinterpret_cast<const char *>(p), n);
+    cache[pos].id = id;
+    return id;
+}
+
+int parse_primary_block(ParseCtx &cx, const uint8_t *data, size_t len, std::vector<DevBlock> &blocks, std::vector<DevCol> &cols, std::string &err) {
+    Cur c{data, data + len};
+    while (c.p < c.end) {
+        // blockMetadata.unmarshal, block_metadata.go:133-168 (+ timestampsMetadata :279-293)
+        DevBlock b{};
+        b.sid = c.u64be();
+        (void)c.varu();  // uncompressedSizeBytes: accounting only
+        uint64_t count = c.varu();
+        b.ts_off = c.varu();
+        uint64_t ts_size = c.varu();
+        b.ts_min = static_cast<int64_t>(c.u64be());
+        b.ts_max = static_cast<int64_t>(c.u64be());
+        uint8_t enc = c.u8();
+        uint64_t ver_off = c.varu();
+        b.ver_first = static_cast<int64_t>(c.u64be());
+        b.ver_enc = c.u8();
+        if (c.bad || count == 0 || count > 0x7fffffffu || ts_size > 0xffffffffu || ver_off > ts_size || b.ts_off + ts_size > cx.tsf->len) {
+            err = "corrupt blockMetadata (timestamps)";
+            return BYDB_EINVAL;
+        }
+        if (enc < 5 || enc > 8 || b.ver_enc < 1 || b.ver_enc > 4) {  // encoding.go:87-130
+            err = "unexpected timestamps encode type";
+            return BYDB_EINVAL;
+        }
+        b.ts_enc = static_cast<uint8_t>(enc - 4);
+        b.count = static_cast<uint32_t>(count);
+        b.ts_size = static_cast<uint32_t>(ts_size);
+        b.ver_off = static_cast<uint32_t>(ver_off);
+        b.col_begin = static_cast<uint32_t>(cols.size());
+        // tag families: name -> dataBlock into <name>.tfm (columnFamilyMetadata of this block)
+        uint64_t nfam = c.varu();
+        struct Fam {
+            size_t slot;
+            uint64_t off, size;
+        };
+        Fam fams[16];
+        if (nfam > 16) {
+            err = "more than 16 tag families in a block";
+            return BYDB_ENOTSUP;
+        }
+        for (uint64_t i = 0; i < nfam && !c.bad; ++i) {
+            uint64_t nl = c.varu();
+            if (c.bad || c.left() < nl) {
+                c.bad = true;
+                break;
+            }
+            const uint8_t *np = c.p;
+            c.p += nl;
+            size_t slot = cx.fam_cache.size();
+            for (size_t k = 0; k < cx.fam_cache.size(); ++k)
+                if (cx.fam_cache[k].name.size() == nl && memcmp(cx.fam_cache[k].name.data(), np, nl) == 0) slot = k;
+            if (slot == cx.fam_cache.size()) {
+                ParseCtx::FamSlot fs;
+                fs.name.assign(reinterpret_cast<const char *>(np), nl);
+                fs.tfm = find_file(*cx.files, fs.name + ".tfm");
+                fs.tf = find_file(*cx.files, fs.name + ".tf");
+                if (fs.tf) {
+                    std::lock_guard<std::mutex> lk(*cx.names_mu);
+                    const std::string fname = fs.name + ".tf";
+                    for (size_t k = 0; k < cx.file_table->size(); ++k)
+                        if ((*cx.file_table)[k] == fname) fs.file_id = static_cast<int>(k);
+                    if (fs.file_id < 0 && cx.file_table->size() < 255) {
+                        cx.file_table->push_back(fname);
+                        fs.file_id = static_cast<int>(cx.file_table->size() - 1);
+                    }
+                }
+                cx.fam_cache.push_back(std::move(fs));
+            }
+            fams[i].slot = slot;
+            fams[i].off = c.varu();
+            fams[i].size = c.varu();
+        }
+        // fields: columnFamilyMetadata.unmarshal, column_metadata.go:108-122
+        uint64_t nf = c.varu();
+        for (uint64_t i = 0; i < nf && !c.bad; ++i) {
+            DevCol col{};
+            uint64_t nl = c.varu();
+            if (c.bad || c.left() < nl) {
+                c.bad = true;
+                break;
+            }
+            const uint8_t *np = c.p;
+            c.p += nl;
+            col.value_type = c.u8();
+            col.off = c.varu();
+            uint64_t size = c.varu();
+            if (c.bad || size > 0xffffffffu || col.off + size > cx.fvf->len) {
+                err = "corrupt field columnMetadata";
+                return BYDB_EINVAL;
+            }
+            col.size = static_cast<uint32_t>(size);
+            col.name_id = resolve_name(cx, cx.field_cache, i, "f:", std::string(), np, nl);
+            col.file_id = 1;
+            cols.push_back(col);
+        }
+        if (c.bad) {
+            err = "corrupt blockMetadata";
+            return BYDB_EINVAL;
+        }
+        size_t tag_pos = 0;
+        for (uint64_t fi = 0; fi < nfam; ++fi) {
+            const ParseCtx::FamSlot &fs = cx.fam_cache[fams[fi].slot];
+            if (!fs.tfm || !fs.tf || fs.file_id < 0 || fams[fi].off + fams[fi].size > fs.tfm->len) {
+                err = "tag family '" + fs.name + "': missing or truncated .tf/.tfm";
+                return BYDB_EINVAL;
+            }
+            Cur t{fs.tfm->data + fams[fi].off, fs.tfm->data + fams[fi].off + fams[fi].size};
+            uint64_t nc = t.varu();
+            for (uint64_t i = 0; i < nc && !t.bad; ++i, ++tag_pos) {
+                DevCol col{};
+                uint64_t nl = t.varu();
+                if (t.bad || t.left() < nl) {
+                    t.bad = true;
+                    break;
+                }
+                const uint8_t *np = t.p;
+                t.p += nl;
+                col.value_type = t.u8();
+                col.off = t.varu();
+                uint64_t size = t.varu();
+                if (t.bad || size > 0xffffffffu || col.off + size > fs.tf->len) {
+                    err = "corrupt tag columnMetadata";
+                    return BYDB_EINVAL;
+                }
+                col.size = static_cast<uint32_t>(size);
+                col.name_id = resolve_name(cx, cx.tag_cache, tag_pos, "t:", fs.name, np, nl);
+                col.file_id = static_cast<uint8_t>(fs.file_id);
+                cols.push_back(col);
+            }
+            if (t.bad) {
+                err = "corrupt columnFamilyMetadata";
+                return BYDB_EINVAL;
+            }
+        }
+        size_t ncols = cols.size() - b.col_begin;
+        if (ncols > 0xffff) {
+            err = "too many columns in a block";
+            return BYDB_EINVAL;
+        }
+        b.n_cols = static_cast<uint16_t>(ncols);
+        blocks.push_back(b);
+    }
+    return 0;
+}
+}  // namespace
+
 int build_part_dir(const std::vector<FileImage> &files, NameTable &names, PartDir &out, std::string &err) {
     const FileImage *meta = find_file(files, "meta.bin");
     const FileImage *primary = find_file(files, "primary.bin");
@@ -139,14 +326,6 @@ int build_part_dir(const std::vector<FileImage> &files, NameTable &names, PartDi
         return BYDB_ENOENT;
     }
     out.files = {"timestamps.bin", "fv.bin"};
-    auto file_id = [&](const std::string &name) -> int {
-        for (size_t i = 0; i < out.files.size(); ++i)
-            if (out.files[i] == name) return static_cast<int>(i);
-        if (!find_file(files, name) || out.files.size() >= 255) return -1;
-        out.files.push_back(name);
-        return static_cast<int>(out.files.size() - 1);
-    };
-
     // meta.bin = zstd(concat primaryBlockMetadata), 40 B records (primary_metadata.go:60-83)
     std::vector<uint8_t> raw;
     int rc = zstd_decompress(meta->data, meta->len, raw, err);
@@ -169,6 +348,10 @@ int build_part_dir(const std::vector<FileImage> &files, NameTable &names, PartDi
             p.mx = static_cast<int64_t>(c.u64be());
             p.off = c.u64be();
             p.size = c.u64be();
+            if (p.off + p.size > primary->len) {
+                err = "primary block outside primary.bin";
+                return BYDB_EINVAL;
+            }
         }
         for (size_t i = 1; i < pbms.size(); ++i)
             if (pbms[i].sid < pbms[i - 1].sid) {  // primary_metadata.go:127-134
@@ -176,120 +359,58 @@ int build_part_dir(const std::vector<FileImage> &files, NameTable &names, PartDi
                 return BYDB_EINVAL;
             }
     }
+    // primary blocks are independent zstd frames: decompress + parse them on a few threads
+    const size_t np = pbms.size();
+    unsigned hw = std::thread::hardware_concurrency();
+    const size_t nt = std::max<size_t>(1, std::min<size_t>({np, hw ? hw : 4, size_t{16}}));
+    std::vector<std::vector<DevBlock>> tb(nt);
+    std::vector<std::vector<DevCol>> tc(nt);
+    std::vector<int> trc(nt, 0);
+    std::vector<std::string> terr(nt);
+    std::mutex names_mu;
+    auto work = [&](size_t t) {
+        ParseCtx cx;
+        cx.files = &files;
+        cx.tsf = tsf;
+        cx.fvf = fvf;
+        cx.names = &names;
+        cx.names_mu = &names_mu;
+        cx.file_table = &out.files;
+        std::vector<uint8_t> blk;
+        for (size_t i = np * t / nt; i < np * (t + 1) / nt && trc[t] == 0; ++i) {
+            trc[t] = zstd_decompress(primary->data + pbms[i].off, static_cast<size_t>(pbms[i].size), blk, terr[t]);
+            if (trc[t] == 0) trc[t] = parse_primary_block(cx, blk.data(), blk.size(), tb[t], tc[t], terr[t]);
+        }
+    };
+    if (nt == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+    }
+    for (size_t t = 0; t < nt; ++t)
+        if (trc[t]) {
+            err = terr[t];
+            return trc[t];
+        }
     out.blocks.clear();
     out.cols.clear();
     out.total_rows = 0;
     out.max_block_rows = 0;
     out.min_ts = INT64_MAX;
     out.max_ts = INT64_MIN;
-    std::vector<uint8_t> blk;
-    for (const auto &pb : pbms) {
-        if (pb.off + pb.size > primary->len) {
-            err = "primary block outside primary.bin";
-            return BYDB_EINVAL;
-        }
-        rc = zstd_decompress(primary->data + pb.off, static_cast<size_t>(pb.size), blk, err);
-        if (rc) return rc;
-        Cur c{blk.data(), blk.data() + blk.size()};
-        while (c.p < c.end) {
-            // blockMetadata.unmarshal, block_metadata.go:133-168 (+ timestampsMetadata :279-293)
-            DevBlock b{};
-            b.sid = c.u64be();
-            (void)c.varu();  // uncompressedSizeBytes: accounting only
-            uint64_t count = c.varu();
-            b.ts_off = c.varu();
-            uint64_t ts_size = c.varu();
-            b.ts_min = static_cast<int64_t>(c.u64be());
-            b.ts_max = static_cast<int64_t>(c.u64be());
-            uint8_t enc = c.u8();
-            uint64_t ver_off = c.varu();
-            b.ver_first = static_cast<int64_t>(c.u64be());
-            b.ver_enc = c.u8();
-            if (c.bad || count == 0 || count > 0x7fffffffu || ts_size > 0xffffffffu || ver_off > ts_size ||
-                b.ts_off + ts_size > tsf->len) {
-                err = "corrupt blockMetadata (timestamps)";
-                return BYDB_EINVAL;
-            }
-            if (enc < 5 || enc > 8 || b.ver_enc < 1 || b.ver_enc > 4) {  // encoding.go:87-130
-                err = "unexpected timestamps encode type";
-                return BYDB_EINVAL;
-            }
-            b.ts_enc = static_cast<uint8_t>(enc - 4);
-            b.count = static_cast<uint32_t>(count);
-            b.ts_size = static_cast<uint32_t>(ts_size);
-            b.ver_off = static_cast<uint32_t>(ver_off);
-            b.col_begin = static_cast<uint32_t>(out.cols.size());
-            // tag families: name -> dataBlock into <name>.tfm (columnFamilyMetadata of this block)
-            uint64_t nfam = c.varu();
-            struct Fam {
-                std::string name;
-                uint64_t off, size;
-            };
-            std::vector<Fam> fams;
-            for (uint64_t i = 0; i < nfam && !c.bad; ++i) {
-                Fam f;
-                f.name = c.str();
-                f.off = c.varu();
-                f.size = c.varu();
-                fams.push_back(std::move(f));
-            }
-            // fields: columnFamilyMetadata.unmarshal, column_metadata.go:108-122
-            uint64_t nf = c.varu();
-            for (uint64_t i = 0; i < nf && !c.bad; ++i) {
-                DevCol col{};
-                std::string name = c.str();
-                col.value_type = c.u8();
-                col.off = c.varu();
-                uint64_t size = c.varu();
-                if (c.bad || size > 0xffffffffu || col.off + size > fvf->len) {
-                    err = "corrupt field columnMetadata";
-                    return BYDB_EINVAL;
-                }
-                col.size = static_cast<uint32_t>(size);
-                col.name_id = names.intern("f:" + name);
-                col.file_id = 1;
-                out.cols.push_back(col);
-            }
-            if (c.bad) {
-                err = "corrupt blockMetadata";
-                return BYDB_EINVAL;
-            }
-            for (const auto &f : fams) {
-                const FileImage *tfm = find_file(files, f.name + ".tfm");
-                int fid = file_id(f.name + ".tf");
-                if (!tfm || fid < 0 || f.off + f.size > tfm->len) {
-                    err = "tag family '" + f.name + "': missing or truncated .tf/.tfm";
-                    return BYDB_EINVAL;
-                }
-                const FileImage *tf = find_file(files, f.name + ".tf");
-                Cur t{tfm->data + f.off, tfm->data + f.off + f.size};
-                uint64_t nc = t.varu();
-                for (uint64_t i = 0; i < nc && !t.bad; ++i) {
-                    DevCol col{};
-                    std::string name = t.str();
-                    col.value_type = t.u8();
-                    col.off = t.varu();
-                    uint64_t size = t.varu();
-                    if (t.bad || size > 0xffffffffu || col.off + size > tf->len) {
-                        err = "corrupt tag columnMetadata";
-                        return BYDB_EINVAL;
-                    }
-                    col.size = static_cast<uint32_t>(size);
-                    col.name_id = names.intern("t:" + f.name + "/" + name);
-                    col.file_id = static_cast<uint8_t>(fid);
-                    out.cols.push_back(col);
-                }
-                if (t.bad) {
-                    err = "corrupt columnFamilyMetadata";
-                    return BYDB_EINVAL;
-                }
-            }
-            size_t ncols = out.cols.size() - b.col_begin;
-            if (ncols > 0xffff) {
-                err = "too many columns in a block";
-                return BYDB_EINVAL;
-            }
-            b.n_cols = static_cast<uint16_t>(ncols);
+    size_t nb = 0, nc = 0;
+    for (size_t t = 0; t < nt; ++t) {
+        nb += tb[t].size();
+        nc += tc[t].size();
+    }
+    out.blocks.reserve(nb);
+    out.cols.reserve(nc);
+    for (size_t t = 0; t < nt; ++t) {
+        const uint32_t shift = static_cast<uint32_t>(out.cols.size());
+        for (DevBlock b : tb[t]) {
+            b.col_begin += shift;
             // block_metadata.go:323-336 validateBlockMetadataOrder (also across primary blocks)
             if (!out.blocks.empty()) {
                 const DevBlock &pre = out.blocks.back();
@@ -304,6 +425,7 @@ int build_part_dir(const std::vector<FileImage> &files, NameTable &names, PartDi
             out.max_ts = std::max(out.max_ts, b.ts_max);
             out.blocks.push_back(b);
         }
+        out.cols.insert(out.cols.end(), tc[t].begin(), tc[t].end());
     }
     return 0;
 }

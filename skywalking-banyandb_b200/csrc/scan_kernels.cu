@@ -467,7 +467,44 @@ __device__ __forceinline__ void stream_drain(const PageStream &s, WarpSmem *sm, 
     for (uint32_t j = k + 1; j < issued; ++j) (void)stream_wait(s, sm, j);
 }
 
-template <int kMode>
+// one lane's 16 bytes: local prefix P of its deltas folded over the active rows.
+// kFull: all 16 bytes are valid (interior chunk) -> no per-byte validity logic.
+// kNeed: bit0 = sum wanted, bit1 = min/max wanted.
+enum { kNeedSum = 1, kNeedMinMax = 2 };
+template <bool kFull, int kNeed>
+__device__ __forceinline__ void fast_lane_decode(const uint4 &w, uint32_t valid, uint32_t term, uint32_t aw, uint32_t &accv, uint32_t &sh, int32_t &P,
+                                                 int32_t &sumP, int32_t &minP, int32_t &maxP, uint32_t &head_x, int32_t &head_v) {
+    uint32_t kbit = 1u;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t wj = j < 4 ? w.x : (j < 8 ? w.y : (j < 12 ? w.z : w.w));
+        const uint32_t b = (wj >> (8 * (j & 3))) & 0xffu;
+        if (kFull || ((valid >> j) & 1u)) {
+            accv |= (b & 0x7fu) << sh;
+            sh += 7;
+        }
+        if ((term >> j) & 1u) {
+            const int32_t v = static_cast<int32_t>(accv >> 1) ^ -static_cast<int32_t>(accv & 1u);
+            if (kbit == 1u) {
+                head_x = accv;
+                head_v = v;
+            }
+            P += v;
+            if (aw & kbit) {
+                if (kNeed & kNeedSum) sumP += P;
+                if (kNeed & kNeedMinMax) {
+                    minP = P < minP ? P : minP;
+                    maxP = P > maxP ? P : maxP;
+                }
+            }
+            kbit <<= 1;
+            accv = 0;
+            sh = 0;
+        }
+    }
+}
+
+template <int kMode, int kNeed>
 __device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const uint8_t *body, uint32_t len, uint32_t count, int64_t first,
                                             uint32_t r0, uint32_t r1, AggAcc &acc_io, int lane) {
     AggAcc acc = acc_io;  // register copy (see decode_varint_page)
@@ -509,7 +546,7 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const u
         const uint32_t trail = term ? static_cast<uint32_t>(hi_i - 1 - (31 - __clz(term))) : static_cast<uint32_t>(hi_i - lo_i);
         uint32_t trail_prev = __shfl_up_sync(0xffffffffu, trail, 1);
         if (lane == 0) trail_prev = carry_sh / 7;
-        const bool wide = (cont & (cont >> 1) & (cont >> 2)) != 0 || (trail_prev + lead) > 2 || (term == 0 && valid != 0 && (trail_prev + lead) > 2);
+        const bool wide = (cont & (cont >> 1) & (cont >> 2)) != 0 || (trail_prev + lead) > 2;
         if (__any_sync(0xffffffffu, wide)) {
             // give the unissued stage numbers back: the mbarrier phases only advance for stages that
             // were really issued, and the next page must continue from exactly that count
@@ -540,35 +577,12 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const u
             aw = static_cast<uint32_t>(m64 >> (row0 & 31)) & ((1u << n) - 1u);
         }
         // ---- decode: local prefix P, folded over the active rows
-        uint32_t accv = 0, sh = 0, kbit = 1u;
+        uint32_t accv = 0, sh = 0;
         int32_t P = 0, sumP = 0, minP = INT32_MAX, maxP = INT32_MIN;
-        int32_t head_v = 0;       // first value decoded from this lane's bytes only
+        int32_t head_v = 0;  // first value decoded from this lane's bytes only
         uint32_t head_x = 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const uint32_t wj = j < 4 ? w.x : (j < 8 ? w.y : (j < 12 ? w.z : w.w));
-            const uint32_t b = (wj >> (8 * (j & 3))) & 0xffu;
-            if ((valid >> j) & 1u) {
-                accv |= (b & 0x7fu) << sh;
-                sh += 7;
-            }
-            if ((term >> j) & 1u) {
-                const int32_t v = static_cast<int32_t>(accv >> 1) ^ -static_cast<int32_t>(accv & 1u);
-                if (kbit == 1u) {
-                    head_x = accv;
-                    head_v = v;
-                }
-                P += v;
-                if (aw & kbit) {
-                    sumP += P;
-                    minP = P < minP ? P : minP;
-                    maxP = P > maxP ? P : maxP;
-                }
-                kbit <<= 1;
-                accv = 0;
-                sh = 0;
-            }
-        }
+        if (__all_sync(0xffffffffu, valid == 0xffffu)) fast_lane_decode<true, kNeed>(w, valid, term, aw, accv, sh, P, sumP, minP, maxP, head_x, head_v);
+        else fast_lane_decode<false, kNeed>(w, valid, term, aw, accv, sh, P, sumP, minP, maxP, head_x, head_v);
         // ---- head correction by the previous lane's unfinished tail
         uint32_t prev_acc = __shfl_up_sync(0xffffffffu, accv, 1);
         uint32_t prev_sh = __shfl_up_sync(0xffffffffu, sh, 1);
@@ -584,8 +598,8 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const u
             const int32_t vt = static_cast<int32_t>(x >> 1) ^ -static_cast<int32_t>(x & 1u);
             const int32_t dlt = vt - head_v;
             P += dlt;
-            sumP += dlt * static_cast<int32_t>(cntA);
-            if (cntA) {
+            if (kNeed & kNeedSum) sumP += dlt * static_cast<int32_t>(cntA);
+            if ((kNeed & kNeedMinMax) && cntA) {
                 minP += dlt;
                 maxP += dlt;
             }
@@ -599,14 +613,18 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const u
         }
         const int64_t base = V0 + static_cast<int64_t>(s_in - P);
         if (cntA) {
-            acc.add_scaled(base, cntA);
-            const int64_t sp = sumP;
-            const uint64_t usp = static_cast<uint64_t>(sp);
-            acc.lo += usp;
-            acc.hi += (sp >> 63) + (acc.lo < usp ? 1 : 0);
-            const int64_t vmin = base + minP, vmax = base + maxP;
-            acc.mn = vmin < acc.mn ? vmin : acc.mn;
-            acc.mx = vmax > acc.mx ? vmax : acc.mx;
+            if (kNeed & kNeedSum) {
+                acc.add_scaled(base, cntA);
+                const int64_t sp = sumP;
+                const uint64_t usp = static_cast<uint64_t>(sp);
+                acc.lo += usp;
+                acc.hi += (sp >> 63) + (acc.lo < usp ? 1 : 0);
+            }
+            if (kNeed & kNeedMinMax) {
+                const int64_t vmin = base + minP, vmax = base + maxP;
+                acc.mn = vmin < acc.mn ? vmin : acc.mn;
+                acc.mx = vmax > acc.mx ? vmax : acc.mx;
+            }
             acc.cnt += cntA;
         }
         V0 += static_cast<int64_t>(__shfl_sync(0xffffffffu, s_in, 31));
@@ -875,8 +893,11 @@ __device__ __forceinline__ bool find_col(const DevPartRef &part, const DevBlock 
     return found;
 }
 
-template <int kMode>
-__device__ __forceinline__ uint32_t agg_field_page(WarpSmem *sm, uint32_t &seq, const uint8_t *page, uint32_t size, bool is_float,
+// kDeferSlow is returned by the fast lane when a page needs the general decoder
+constexpr uint32_t kDeferSlow = 0xffffffffu;
+
+template <int kMode, bool kFastLane>
+__device__ __forceinline__ uint32_t agg_field_page(WarpSmem *sm, uint32_t &seq, const uint8_t *page, uint32_t size, bool is_float, uint32_t need,
                                                    uint32_t count, uint32_t r0, uint32_t r1, AggAcc &out, int &exp_out, int lane) {
     if (size < 1) return kErrCorrupt;
     const uint32_t enc = __ldg(page);
@@ -904,7 +925,10 @@ __device__ __forceinline__ uint32_t agg_field_page(WarpSmem *sm, uint32_t &seq, 
     if (enc == 3) {
         AggAcc fa;
         fa.init();
-        int rc = delta_page_fast<kMode>(sm, seq, body, blen, count, first, r0, r1, fa, lane);
+        int rc;
+        if (need == kNeedSum) rc = delta_page_fast<kMode, kNeedSum>(sm, seq, body, blen, count, first, r0, r1, fa, lane);
+        else if (need == kNeedMinMax) rc = delta_page_fast<kMode, kNeedMinMax>(sm, seq, body, blen, count, first, r0, r1, fa, lane);
+        else rc = delta_page_fast<kMode, kNeedSum | kNeedMinMax>(sm, seq, body, blen, count, first, r0, r1, fa, lane);
         rc = __reduce_max_sync(0xffffffffu, static_cast<unsigned>(rc));
         if (rc == 0) {
             fa.warp_reduce();
@@ -912,25 +936,30 @@ __device__ __forceinline__ uint32_t agg_field_page(WarpSmem *sm, uint32_t &seq, 
             return kErrNone;
         }
         if (rc == 2) return kErrCorrupt;
-        // rc == 1: a varint longer than 3 bytes -> general two-pass decoder below
+        // rc == 1: a varint longer than 3 bytes -> general two-pass decoder
     }
-    AggCons cons;
-    cons.acc.init();
-    cons.r0 = r0;
-    cons.r1 = r1;
-    cons.mask = sm->mask;
-    cons.mode = kMode;
-    bool ok;
-    if (enc == 3) ok = decode_varint_page<false>(sm, seq, body, blen, count, first, cons, lane);
-    else ok = decode_varint_page<true>(sm, seq, body, blen, count, first, cons, lane);
-    ok = __all_sync(0xffffffffu, ok);
-    if (!ok) return kErrCorrupt;
-    cons.acc.warp_reduce();
-    out = cons.acc;
-    return kErrNone;
+    if (kFastLane) {
+        return kDeferSlow;
+    } else {
+        AggCons cons;
+        cons.acc.init();
+        cons.r0 = r0;
+        cons.r1 = r1;
+        cons.mask = sm->mask;
+        cons.mode = kMode;
+        bool ok;
+        if (enc == 3) ok = decode_varint_page<false>(sm, seq, body, blen, count, first, cons, lane);
+        else ok = decode_varint_page<true>(sm, seq, body, blen, count, first, cons, lane);
+        ok = __all_sync(0xffffffffu, ok);
+        if (!ok) return kErrCorrupt;
+        cons.acc.warp_reduce();
+        out = cons.acc;
+        return kErrNone;
+    }
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_blocks_kernel(const __grid_constant__ ScanParams p) {
+template <bool kFastLane>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blocks_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -942,13 +971,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_blocks_kernel(const
     }
     __syncthreads();
     uint32_t seq = 0;
-    const uint32_t nwork = *p.work_count;
+    // fast lane: the planned work list; slow lane: the blocks the fast lane deferred
+    const uint32_t nwork = kFastLane ? *p.work_count : *p.slow_count;
+    const uint32_t *list = kFastLane ? p.worklist : p.slow_list;
+    uint32_t *cursor = kFastLane ? p.work_next : p.slow_next;
     for (;;) {
         uint32_t wi = 0;
-        if (lane == 0) wi = atomicAdd(p.work_next, 1u);
+        if (lane == 0) wi = atomicAdd(cursor, 1u);
         wi = __shfl_sync(0xffffffffu, wi, 0);
         if (wi >= nwork) break;
-        const uint32_t g = p.worklist[wi];
+        const uint32_t g = list[wi];
+        bool defer = false;
         uint32_t pi = 0;
         while (pi + 1 < p.n_parts && g >= p.parts[pi + 1].block_base) ++pi;
         const DevPartRef &part = p.parts[pi];
@@ -984,6 +1017,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_blocks_kernel(const
                     empty = r0 > r1;
                 }
                 page_bytes += blk.ver_off;
+            } else if (kFastLane) {
+                defer = true;  // irregular timestamps need the general decoder
             } else {
                 TsCons tc;
                 tc.tmin = p.tmin;
@@ -1011,7 +1046,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_blocks_kernel(const
         uint32_t rows = empty ? 0 : (r1 - r0 + 1);
         const int32_t ddi = p.dd_index ? p.dd_index[g] : -1;
         const bool use_mask = p.n_preds > 0 || ddi >= 0;
-        if (use_mask && !empty && err == kErrNone) {
+        if (use_mask && !empty && err == kErrNone && !defer) {
             if (count > kMaskWords * 32) {
                 err = kErrBigBlock;
             } else {
@@ -1024,7 +1059,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_blocks_kernel(const
                     sm->mask[w] = v;
                 }
                 __syncwarp();
-                for (uint32_t pi2 = 0; pi2 < p.n_preds && err == kErrNone; ++pi2) {
+                for (uint32_t pi2 = 0; pi2 < p.n_preds && err == kErrNone && !defer; ++pi2) {
                     const DevPred &pr = p.preds[pi2];
                     DevCol col;
                     if (!find_col(part, blk, pr.name_id, col, lane)) {
@@ -1063,6 +1098,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_blocks_kernel(const
                                         if (!cmp_op(pr.op, true, c)) atomicAnd(&sm->mask[row >> 5], ~(1u << (row & 31)));
                                     }
                                 }
+                            } else if ((enc == 3 || enc == 4) && kFastLane) {
+                                defer = true;
                             } else if (enc == 3 || enc == 4) {
                                 CmpCons cc;
                                 cc.lit = pr.lit_i64;
@@ -1087,7 +1124,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_blocks_kernel(const
                     __syncwarp();
                 }
                 // fold the time range into the mask, then count the surviving rows
-                if (err == kErrNone) {
+                if (err == kErrNone && !defer) {
                     warp_clear_range(sm->mask, 0, r0, lane);
                     warp_clear_range(sm->mask, r1 + 1, count, lane);
                     __syncwarp();
@@ -1108,7 +1145,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_blocks_kernel(const
             bp.mx.i = 0;
             bp.cnt = 0;
             DevCol col;
-            if (err == kErrNone && rows > 0 && find_col(part, blk, p.fcol_name[c], col, lane)) {
+            if (err == kErrNone && !defer && rows > 0 && find_col(part, blk, p.fcol_name[c], col, lane)) {
                 const bool is_float = col.value_type == BYDB_VT_FLOAT64;
                 if (!is_float && col.value_type != BYDB_VT_INT64) {
                     err = kErrTypeMix;
@@ -1119,16 +1156,31 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_blocks_kernel(const
                     }
                     err = __shfl_sync(0xffffffffu, err, 0);
                     const uint8_t *page = part.files[col.file_id] + col.off;
-                    page_bytes += col.size;
                     AggAcc acc;
                     acc.init();
                     int exp = 0;
-                    uint32_t e2;
-                    if (use_mask) e2 = agg_field_page<kRowsMask>(sm, seq, page, col.size, is_float, count, r0, r1, acc, exp, lane);
-                    else if (r0 == 0 && r1 == count - 1) e2 = agg_field_page<kRowsAll>(sm, seq, page, col.size, is_float, count, r0, r1, acc, exp, lane);
-                    else e2 = agg_field_page<kRowsRange>(sm, seq, page, col.size, is_float, count, r0, r1, acc, exp, lane);
+                    uint32_t e2 = kErrNone;
+                    const uint32_t need = p.fcol_need[c];
+                    if (need == 0) {
+                        // COUNT only: numeric pages hold no nulls (a null forces the Plain fallback page), so the
+                        // count is the number of surviving rows and the page body is never read
+                        if (col.size < 1) e2 = kErrCorrupt;
+                        else if (__ldg(page) == 9) e2 = kErrPlainPage;
+                        acc.cnt = rows;
+                        page_bytes += 1;
+                    } else {
+                        page_bytes += col.size;
+                        if (use_mask) e2 = agg_field_page<kRowsMask, kFastLane>(sm, seq, page, col.size, is_float, need, count, r0, r1, acc, exp, lane);
+                        else if (r0 == 0 && r1 == count - 1)
+                            e2 = agg_field_page<kRowsAll, kFastLane>(sm, seq, page, col.size, is_float, need, count, r0, r1, acc, exp, lane);
+                        else e2 = agg_field_page<kRowsRange, kFastLane>(sm, seq, page, col.size, is_float, need, count, r0, r1, acc, exp, lane);
+                    }
+                    if (e2 == kDeferSlow) {
+                        defer = true;
+                        e2 = kErrNone;
+                    }
                     if (err == kErrNone) err = e2;
-                    if (err == kErrNone && acc.cnt > 0) {
+                    if (err == kErrNone && !defer && acc.cnt > 0) {
                         bp.cnt = acc.cnt;
                         if (is_float) {
                             // block sum in the exact decimal-integer domain, converted once
@@ -1148,9 +1200,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_blocks_kernel(const
                     }
                 }
             }
-            if (lane == 0) p.P[static_cast<size_t>(g) * p.n_fcols + c] = bp;
+            if (lane == 0 && !defer) p.P[static_cast<size_t>(g) * p.n_fcols + c] = bp;
         }
         if (sm->fault) err = kErrTmaTimeout;
+        if (kFastLane && defer && err == kErrNone) {
+            // hand the whole block to the slow lane (launched right after this kernel)
+            if (lane == 0) p.slow_list[atomicAdd(p.slow_count, 1u)] = g;
+            continue;
+        }
         if (err != kErrNone) {
             set_err(p, err, g, lane);
             rows = 0;
@@ -1732,21 +1789,28 @@ void launch_plan_blocks(const ScanParams &p, cudaStream_t s) {
 }
 
 static bool g_scan_attr_set = false;
-void launch_scan_blocks(const ScanParams &p, int grid, cudaStream_t s) {
+static void scan_set_attrs() {
+    if (g_scan_attr_set) return;
+    const int smem = static_cast<int>(scan_smem_bytes());
+    cudaFuncSetAttribute(scan_blocks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(scan_blocks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    g_scan_attr_set = true;
+}
+// fast lane over the planned blocks, then the slow lane over whatever the fast lane deferred
+void launch_scan_blocks(const ScanParams &p, int grid_fast, int grid_slow, cudaStream_t s) {
+    scan_set_attrs();
     const size_t smem = scan_smem_bytes();
-    if (!g_scan_attr_set) {
-        cudaFuncSetAttribute(scan_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        g_scan_attr_set = true;
-    }
-    scan_blocks_kernel<<<grid, kWarpsPerCta * 32, smem, s>>>(p);
+    scan_blocks_kernel<true><<<grid_fast, kWarpsPerCta * 32, smem, s>>>(p);
+    scan_blocks_kernel<false><<<grid_slow, kWarpsPerCta * 32, smem, s>>>(p);
 }
 
-int scan_max_ctas_per_sm() {
-    int n = 0;
-    cudaFuncSetAttribute(scan_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scan_smem_bytes()));
-    g_scan_attr_set = true;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, scan_blocks_kernel, kWarpsPerCta * 32, scan_smem_bytes()) != cudaSuccess) return 1;
-    return n < 1 ? 1 : n;
+void scan_max_ctas_per_sm(int *fast, int *slow) {
+    scan_set_attrs();
+    int a = 1, b = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, scan_blocks_kernel<true>, kWarpsPerCta * 32, scan_smem_bytes());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, scan_blocks_kernel<false>, kWarpsPerCta * 32, scan_smem_bytes());
+    *fast = a < 1 ? 1 : a;
+    *slow = b < 1 ? 1 : b;
 }
 
 void launch_detect_overlap(const ScanParams &p, cudaStream_t s) {

@@ -11,7 +11,7 @@
 namespace bydb {
 
 constexpr int kWarpsPerCta = 8;          // 256 threads; every warp is an independent block worker
-constexpr int kStageBytes = 4096;        // one TMA bulk copy (cp.async.bulk) per stage
+constexpr int kStageBytes = 2048;        // one TMA bulk copy (cp.async.bulk) per stage
 constexpr int kStages = 2;               // per-warp ring: decode stage k while stage k+1 lands
 constexpr int kChunkBytes = 512;         // 32 lanes x 16 B per decode iteration
 constexpr int kMaskWords = 264;          // row bitmask: 8448 rows (memPart blocks hold <= 8193 rows)
@@ -70,10 +70,14 @@ struct ScanParams {
     uint32_t pad0;
     int64_t tmin, tmax;
     uint16_t fcol_name[kMaxFcols];
+    uint8_t fcol_need[kMaxFcols]; // bit0: sum wanted (SUM/MEAN), bit1: min/max wanted; 0 = COUNT only
     DevPred preds[kMaxPreds];
     uint32_t *worklist;           // [total_blocks] global block indices selected by plan_blocks
     uint32_t *work_count;
     uint32_t *work_next;
+    uint32_t *slow_list;          // [total_blocks] blocks the fast lane deferred to the general decoder
+    uint32_t *slow_count;
+    uint32_t *slow_next;
     int32_t *block_qsid;          // [total_blocks] query-series index or -1
     uint32_t *first_block;        // [n_parts * n_series] first block of the series in the part (0xffffffff = none); may be NULL
     BlockPartial *P;              // [total_blocks * n_fcols]
@@ -152,13 +156,13 @@ void launch_select_rows(const SelectParams &p, cudaStream_t s);
 
 size_t scan_smem_bytes();
 void launch_plan_blocks(const ScanParams &p, cudaStream_t s);
-void launch_scan_blocks(const ScanParams &p, int grid, cudaStream_t s);
+void launch_scan_blocks(const ScanParams &p, int grid_fast, int grid_slow, cudaStream_t s);
 void launch_series_reduce(const ReduceParams &p, cudaStream_t s);
 void launch_group_reduce(const ReduceParams &p, cudaStream_t s);
 void launch_finalize(const FinalizeParams &p, cudaStream_t s);
 void launch_detect_overlap(const ScanParams &p, cudaStream_t s);
 void launch_dedup(const ScanParams &p, int grid, cudaStream_t s);
 int upload_pow10_table();
-int scan_max_ctas_per_sm();
+void scan_max_ctas_per_sm(int *fast, int *slow);
 
 }  // namespace bydb

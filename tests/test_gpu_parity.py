@@ -142,7 +142,8 @@ def test_timestamp_encodings_and_ranges(bydb, gpu_ctx, kind):
     aggs = [("calls", O.AGG_SUM), ("calls", O.AGG_COUNT), ("calls", O.AGG_MIN)]
     lo, hi = int(ts.min()), int(ts.max())
     ranges = [(-(1 << 63), (1 << 63) - 1), (lo + (hi - lo) // 3, lo + 2 * (hi - lo) // 3), (lo, lo), (hi, hi + 5),
-              (int(ts[7]), int(ts[7])), (int(ts[7]) + 1, int(ts[9]) - 1 if ts.size > 9 else hi)]
+              (int(ts[min(7, ts.size - 1)]), int(ts[min(7, ts.size - 1)])),
+              (int(ts[min(7, ts.size - 1)]) + 1, int(ts[9]) - 1 if ts.size > 9 else hi)]
     for tmin, tmax in ranges:
         oq = O.Query([part], usid, aggs, tmin=tmin, tmax=tmax)
         got, want = run_both(bydb, gpu_ctx, [part], oq, _next_pid())
