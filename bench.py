@@ -330,7 +330,7 @@ def main():
     out = {"metric": "measure datapoints scanned+aggregated/sec", "value": value, "unit": "datapoints/s", "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": cfg, "datapoints_per_step": total_rows_step, "device_ms_per_step": dev_ms,
-           "scan_kernel_ms": scan_ms, "roofline": roofline, "clocks": clocks, "gpu_launches": launches, "e2e": e2e}
+           "scan_kernel_ms": scan_ms, "blocks_slow_lane": int(stats_acc[-1].blocks_slow_lane), "slow_lane_reasons": int(stats_acc[-1].slow_lane_reasons), "roofline": roofline, "clocks": clocks, "gpu_launches": launches, "e2e": e2e}
     if last is not None:
         out["result"] = {"mean_latency": float(last.val_f64[0, 0]), "max_walk": float(last.val_f64[0, 1]), "rows_matched": int(last.rows[0])}
     if world == 1 and not args.no_cpu:

@@ -139,6 +139,8 @@ typedef struct {
     double scan_kernel_ms;    /* CUDA-event time of the scan kernel on the call's stream     */
     double device_ms;         /* CUDA-event time of all kernels of the call                  */
     uint32_t kernel_launches; /* kernels launched by this call                               */
+    uint32_t blocks_slow_lane; /* blocks the fast lane handed to the general decoder          */
+    uint32_t slow_lane_reasons; /* OR of: 1 irregular timestamps, 2 int64 tag page, 4<<c field c needs the general decoder */
     uint32_t reserved;
 } bydb_stats;
 

@@ -59,7 +59,7 @@ class _Stats(C.Structure):
     _fields_ = [("rows_scanned", C.c_uint64), ("rows_matched", C.c_uint64), ("blocks_scanned", C.c_uint64),
                 ("page_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("scan_kernel_ms", C.c_double), ("device_ms", C.c_double), ("kernel_launches", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("blocks_slow_lane", C.c_uint32), ("slow_lane_reasons", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class _Result(C.Structure):
@@ -158,11 +158,13 @@ class Stats:
     scan_kernel_ms: float = 0.0
     device_ms: float = 0.0
     kernel_launches: int = 0
+    blocks_slow_lane: int = 0
+    slow_lane_reasons: int = 0
 
     @staticmethod
     def of(s: _Stats) -> "Stats":
         return Stats(s.rows_scanned, s.rows_matched, s.blocks_scanned, s.page_bytes, s.h2d_bytes, s.d2h_bytes,
-                     s.scan_kernel_ms, s.device_ms, s.kernel_launches)
+                     s.scan_kernel_ms, s.device_ms, s.kernel_launches, s.blocks_slow_lane, s.slow_lane_reasons)
 
 
 @dataclass

@@ -545,6 +545,8 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
         stats->rows_matched += hs[1];
         stats->page_bytes += hs[2];
         stats->blocks_scanned += hs[3];
+        stats->blocks_slow_lane += static_cast<uint32_t>(hs[4]);
+        stats->slow_lane_reasons |= static_cast<uint32_t>(hs[5]);
         float ms = 0;
         cudaEventElapsedTime(&ms, slot.ev[1], slot.ev[2]);
         stats->scan_kernel_ms += ms;
@@ -726,6 +728,15 @@ int bydb_init(const bydb_cfg *cfg, bydb_ctx **out) {
     if (upload_pow10_table()) {
         delete ctx;
         return fail(BYDB_EIO, "cannot upload constant tables (is the library built for this GPU?)");
+    }
+    {
+        // keep freed stream-ordered allocations in the pool: every query allocates its scratch with
+        // cudaMallocAsync, and the default threshold (0) would hand the memory back at each sync
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
     }
     int occ_fast = 1, occ_slow = 1;
     scan_max_ctas_per_sm(&occ_fast, &occ_slow);

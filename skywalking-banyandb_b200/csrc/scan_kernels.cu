@@ -982,6 +982,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
         if (wi >= nwork) break;
         const uint32_t g = list[wi];
         bool defer = false;
+        uint32_t defer_why = 0;
         uint32_t pi = 0;
         while (pi + 1 < p.n_parts && g >= p.parts[pi + 1].block_base) ++pi;
         const DevPartRef &part = p.parts[pi];
@@ -1019,6 +1020,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
                 page_bytes += blk.ver_off;
             } else if (kFastLane) {
                 defer = true;  // irregular timestamps need the general decoder
+                defer_why |= 1u;
             } else {
                 TsCons tc;
                 tc.tmin = p.tmin;
@@ -1100,6 +1102,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
                                 }
                             } else if ((enc == 3 || enc == 4) && kFastLane) {
                                 defer = true;
+                                defer_why |= 2u;
                             } else if (enc == 3 || enc == 4) {
                                 CmpCons cc;
                                 cc.lit = pr.lit_i64;
@@ -1177,6 +1180,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
                     }
                     if (e2 == kDeferSlow) {
                         defer = true;
+                        defer_why |= 4u << c;
                         e2 = kErrNone;
                     }
                     if (err == kErrNone) err = e2;
@@ -1205,7 +1209,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
         if (sm->fault) err = kErrTmaTimeout;
         if (kFastLane && defer && err == kErrNone) {
             // hand the whole block to the slow lane (launched right after this kernel)
-            if (lane == 0) p.slow_list[atomicAdd(p.slow_count, 1u)] = g;
+            if (lane == 0) {
+                p.slow_list[atomicAdd(p.slow_count, 1u)] = g;
+                atomicAdd(&p.stats[4], 1ull);
+                atomicOr(&p.stats[5], static_cast<unsigned long long>(defer_why));
+            }
             continue;
         }
         if (err != kErrNone) {

