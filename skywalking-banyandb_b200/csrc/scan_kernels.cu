@@ -893,6 +893,177 @@ __device__ __forceinline__ bool find_col(const DevPartRef &part, const DevBlock 
     return found;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast path for EncodeTypeDeltaOfDelta pages with narrow (<= 3 byte) second differences
+// (monotone counters, series that start below zero: int_list.go:150-179).  Two light passes per
+// chunk: (1) per-lane (count, sum, sum-of-prefixes) of the second differences in 32-bit registers,
+// one warp scan of the triple with the composition law r = rA + rB + nB*qA gives every lane its
+// (value, first difference) on entry; (2) the lane decodes again and folds the true values.
+// The first varint (the first DIFFERENCE, often wide) is read sequentially up front.
+// Returns like delta_page_fast.
+// ------------------------------------------------------------------------------------------------
+template <int kMode, int kNeed>
+__device__ __noinline__ int dod_page_fast(WarpSmem *sm, uint32_t &seq, const uint8_t *body, uint32_t len, uint32_t count, int64_t first,
+                                          uint32_t r0, uint32_t r1, AggAcc &acc_io, int lane) {
+    AggAcc acc = acc_io;
+    auto active0 = [&](uint32_t row) -> bool {
+        if (kMode == kRowsRange) return row >= r0 && row <= r1;
+        if (kMode == kRowsMask) return (sm->mask[row >> 5] >> (row & 31)) & 1u;
+        return true;
+    };
+    if (count < 2) return 2;
+    int64_t d1 = 0;
+    uint32_t used = 0;
+    if (!read_varint_seq(body, len, d1, used)) return 2;
+    if (lane == 0) {
+        if (active0(0)) acc.add(first);
+        if (active0(1)) acc.add(first + d1);
+    }
+    body += used;
+    len -= used;
+    if (len == 0) {
+        acc_io = acc;
+        return count == 2 ? 0 : 2;
+    }
+    PageStream st;
+    stream_open(st, sm, seq, body, len, lane);
+    const uint32_t nchunks = (st.total + kChunkBytes - 1) / kChunkBytes;
+    constexpr uint32_t kChunksPerStage = kStageBytes / kChunkBytes;
+    int64_t V0 = first + d1;  // value of the row before this chunk's first varint
+    int64_t D0 = d1;          // running first difference
+    uint32_t carry_acc = 0, carry_sh = 0;
+    uint32_t row_base = 2;
+    const uint8_t *buf = nullptr;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const uint32_t k = c / kChunksPerStage;
+        if ((c % kChunksPerStage) == 0) buf = stream_wait(st, sm, k);
+        const uint32_t o = c * kChunkBytes + lane * 16;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (o < st.total) w = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes));
+        int lo_i = static_cast<int>(st.pstart) - static_cast<int>(o);
+        int hi_i = static_cast<int>(st.pend) - static_cast<int>(o);
+        lo_i = lo_i < 0 ? 0 : (lo_i > 16 ? 16 : lo_i);
+        hi_i = hi_i < 0 ? 0 : (hi_i > 16 ? 16 : hi_i);
+        const uint32_t valid = ((1u << hi_i) - 1u) & ~((1u << lo_i) - 1u);
+        const uint32_t msb = msb4(w.x) | (msb4(w.y) << 4) | (msb4(w.z) << 8) | (msb4(w.w) << 12);
+        const uint32_t term = valid & ~msb;
+        const uint32_t cont = valid & msb;
+        const uint32_t lead = term ? static_cast<uint32_t>(__ffs(term) - 1 - lo_i) : static_cast<uint32_t>(hi_i - lo_i);
+        const uint32_t trail = term ? static_cast<uint32_t>(hi_i - 1 - (31 - __clz(term))) : static_cast<uint32_t>(hi_i - lo_i);
+        uint32_t trail_prev = __shfl_up_sync(0xffffffffu, trail, 1);
+        if (lane == 0) trail_prev = carry_sh / 7;
+        const bool wide = (cont & (cont >> 1) & (cont >> 2)) != 0 || (trail_prev + lead) > 2;
+        if (__any_sync(0xffffffffu, wide)) {
+            stream_drain(st, sm, k);
+            seq = st.seq0 + min(st.nstages, k + static_cast<uint32_t>(kStages));
+            __syncwarp();
+            return 1;
+        }
+        const uint32_t n = __popc(term);
+        // ---- pass 1: lane-local (q, r) with every value counted (aw = all ones)
+        uint32_t accv = 0, sh = 0;
+        int32_t P = 0, sumP = 0, mnu = 0, mxu = 0;
+        int32_t head_v = 0;
+        uint32_t head_x = 0;
+        const bool full = __all_sync(0xffffffffu, valid == 0xffffu);
+        if (full) fast_lane_decode<true, kNeedSum>(w, valid, term, 0xffffffffu, accv, sh, P, sumP, mnu, mxu, head_x, head_v);
+        else fast_lane_decode<false, kNeedSum>(w, valid, term, 0xffffffffu, accv, sh, P, sumP, mnu, mxu, head_x, head_v);
+        uint32_t prev_acc = __shfl_up_sync(0xffffffffu, accv, 1);
+        uint32_t prev_sh = __shfl_up_sync(0xffffffffu, sh, 1);
+        if (lane == 0) {
+            prev_acc = carry_acc;
+            prev_sh = carry_sh;
+        }
+        carry_acc = __shfl_sync(0xffffffffu, accv, 31);
+        carry_sh = __shfl_sync(0xffffffffu, sh, 31);
+        if (n > 0 && prev_sh != 0) {
+            const uint32_t x = prev_acc | (head_x << prev_sh);
+            const int32_t dlt = (static_cast<int32_t>(x >> 1) ^ -static_cast<int32_t>(x & 1u)) - head_v;
+            P += dlt;
+            sumP += dlt * static_cast<int32_t>(n);
+        }
+        // ---- scan of (n, q, r)
+        uint32_t n_in = n;
+        int64_t q_in = P, r_in = sumP;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint32_t on = __shfl_up_sync(0xffffffffu, n_in, s);
+            const int64_t oq = static_cast<int64_t>(shfl_up_u64(static_cast<uint64_t>(q_in), s));
+            const int64_t orr = static_cast<int64_t>(shfl_up_u64(static_cast<uint64_t>(r_in), s));
+            if (lane >= s) {
+                r_in = orr + r_in + static_cast<int64_t>(n_in) * oq;  // current lane is B: nB * qA
+                q_in += oq;
+                n_in += on;
+            }
+        }
+        const uint32_t n_ex = n_in - n;
+        int64_t q_ex = static_cast<int64_t>(shfl_up_u64(static_cast<uint64_t>(q_in), 1));
+        int64_t r_ex = static_cast<int64_t>(shfl_up_u64(static_cast<uint64_t>(r_in), 1));
+        if (lane == 0) {
+            q_ex = 0;
+            r_ex = 0;
+        }
+        // ---- pass 2: true values of this lane's rows
+        const uint32_t row0 = row_base + n_ex;
+        uint32_t aw;
+        if (kMode == kRowsAll) {
+            aw = (1u << n) - 1u;
+        } else if (kMode == kRowsRange) {
+            const uint32_t a = r0 > row0 ? r0 - row0 : 0u;
+            const uint32_t b = (r1 + 1u) < (row0 + n) ? (r1 + 1u > row0 ? r1 + 1u - row0 : 0u) : n;
+            aw = a < b ? (((1u << b) - 1u) & ~((1u << a) - 1u)) : 0u;
+        } else {
+            const uint32_t wi = row0 >> 5;
+            const uint64_t m64 = static_cast<uint64_t>(sm->mask[wi]) | (static_cast<uint64_t>(sm->mask[wi + 1]) << 32);
+            aw = static_cast<uint32_t>(m64 >> (row0 & 31)) & ((1u << n) - 1u);
+        }
+        if (__any_sync(0xffffffffu, aw != 0)) {
+            int64_t D = D0 + q_ex;
+            int64_t v = V0 + static_cast<int64_t>(n_ex) * D0 + r_ex;
+            accv = prev_acc;
+            sh = prev_sh;
+            uint32_t kbit = 1u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t wj = j < 4 ? w.x : (j < 8 ? w.y : (j < 12 ? w.z : w.w));
+                const uint32_t b = (wj >> (8 * (j & 3))) & 0xffu;
+                if ((valid >> j) & 1u) {
+                    accv |= (b & 0x7fu) << sh;
+                    sh += 7;
+                }
+                if ((term >> j) & 1u) {
+                    D += static_cast<int64_t>(static_cast<int32_t>(accv >> 1) ^ -static_cast<int32_t>(accv & 1u));
+                    v += D;
+                    if (aw & kbit) {
+                        if (kNeed & kNeedSum) {
+                            const uint64_t uv = static_cast<uint64_t>(v);
+                            acc.lo += uv;
+                            acc.hi += (v >> 63) + (acc.lo < uv ? 1 : 0);
+                        }
+                        if (kNeed & kNeedMinMax) {
+                            acc.mn = v < acc.mn ? v : acc.mn;
+                            acc.mx = v > acc.mx ? v : acc.mx;
+                        }
+                        acc.cnt++;
+                    }
+                    kbit <<= 1;
+                    accv = 0;
+                    sh = 0;
+                }
+            }
+        }
+        const uint32_t n_tot = __shfl_sync(0xffffffffu, n_in, 31);
+        const int64_t q_tot = static_cast<int64_t>(shfl_u64(static_cast<uint64_t>(q_in), 31));
+        const int64_t r_tot = static_cast<int64_t>(shfl_u64(static_cast<uint64_t>(r_in), 31));
+        V0 += static_cast<int64_t>(n_tot) * D0 + r_tot;
+        D0 += q_tot;
+        row_base += n_tot;
+        if ((c % kChunksPerStage) == kChunksPerStage - 1 || c == nchunks - 1) stream_release(st, sm, k, lane);
+    }
+    acc_io = acc;
+    return (row_base == count && carry_sh == 0) ? 0 : 2;
+}
+
 // kDeferSlow is returned by the fast lane when a page needs the general decoder
 constexpr uint32_t kDeferSlow = 0xffffffffu;
 
@@ -922,13 +1093,17 @@ __device__ __forceinline__ uint32_t agg_field_page(WarpSmem *sm, uint32_t &seq, 
         return kErrNone;
     }
     if (enc != 3 && enc != 4) return kErrBadEnc;
-    if (enc == 3) {
+    {
         AggAcc fa;
         fa.init();
         int rc;
-        if (need == kNeedSum) rc = delta_page_fast<kMode, kNeedSum>(sm, seq, body, blen, count, first, r0, r1, fa, lane);
-        else if (need == kNeedMinMax) rc = delta_page_fast<kMode, kNeedMinMax>(sm, seq, body, blen, count, first, r0, r1, fa, lane);
-        else rc = delta_page_fast<kMode, kNeedSum | kNeedMinMax>(sm, seq, body, blen, count, first, r0, r1, fa, lane);
+        if (enc == 3) {
+            if (need == kNeedSum) rc = delta_page_fast<kMode, kNeedSum>(sm, seq, body, blen, count, first, r0, r1, fa, lane);
+            else if (need == kNeedMinMax) rc = delta_page_fast<kMode, kNeedMinMax>(sm, seq, body, blen, count, first, r0, r1, fa, lane);
+            else rc = delta_page_fast<kMode, kNeedSum | kNeedMinMax>(sm, seq, body, blen, count, first, r0, r1, fa, lane);
+        } else {
+            rc = dod_page_fast<kMode, kNeedSum | kNeedMinMax>(sm, seq, body, blen, count, first, r0, r1, fa, lane);
+        }
         rc = __reduce_max_sync(0xffffffffu, static_cast<unsigned>(rc));
         if (rc == 0) {
             fa.warp_reduce();
