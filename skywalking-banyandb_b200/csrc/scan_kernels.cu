@@ -467,41 +467,112 @@ __device__ __forceinline__ void stream_drain(const PageStream &s, WarpSmem *sm, 
     for (uint32_t j = k + 1; j < issued; ++j) (void)stream_wait(s, sm, j);
 }
 
-// one lane's 16 bytes: local prefix P of its deltas folded over the active rows.
-// kFull: all 16 bytes are valid (interior chunk) -> no per-byte validity logic.
+// one lane's 32 bytes: local prefix P of its deltas folded over the active rows.
+// kFull: all 32 bytes are valid (interior chunk) -> no per-byte validity logic.
 // kNeed: bit0 = sum wanted, bit1 = min/max wanted.
 enum { kNeedSum = 1, kNeedMinMax = 2 };
+constexpr uint32_t kFastLaneBytes = 32;
+constexpr uint32_t kFastChunkBytes = 32 * kFastLaneBytes;  // 1 KB per warp iteration
+
+__device__ __forceinline__ uint32_t low_bits(uint32_t n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
+
 template <bool kFull, int kNeed>
-__device__ __forceinline__ void fast_lane_decode(const uint4 &w, uint32_t valid, uint32_t term, uint32_t aw, uint32_t &accv, uint32_t &sh, int32_t &P,
-                                                 int32_t &sumP, int32_t &minP, int32_t &maxP, uint32_t &head_x, int32_t &head_v) {
-    uint32_t kbit = 1u;
+__device__ __forceinline__ void fast_lane_decode(const uint4 &wa, const uint4 &wb, uint32_t valid, uint32_t term, uint32_t aw, uint32_t &accv,
+                                                 uint32_t &sh, int32_t &P, int32_t &sumP, int32_t &minP, int32_t &maxP) {
+    // 8 words x 4 bytes: the word loop stays rolled so that the body (the hottest code of the whole
+    // path) is ~70 instructions and stays resident in the instruction caches of every scheduler
+    uint32_t w0 = wa.x, w1 = wa.y, w2 = wa.z, w3 = wa.w, w4 = wb.x, w5 = wb.y, w6 = wb.z, w7 = wb.w;
+    uint32_t vm = valid, tm = term;
+#pragma unroll 1
+    for (int q8 = 0; q8 < 8; ++q8) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const uint32_t wj = j < 4 ? w.x : (j < 8 ? w.y : (j < 12 ? w.z : w.w));
-        const uint32_t b = (wj >> (8 * (j & 3))) & 0xffu;
-        if (kFull || ((valid >> j) & 1u)) {
-            accv |= (b & 0x7fu) << sh;
-            sh += 7;
-        }
-        if ((term >> j) & 1u) {
-            const int32_t v = static_cast<int32_t>(accv >> 1) ^ -static_cast<int32_t>(accv & 1u);
-            if (kbit == 1u) {
-                head_x = accv;
-                head_v = v;
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t b = (w0 >> (8 * j)) & 0xffu;
+            if (kFull || ((vm >> j) & 1u)) {
+                accv |= (b & 0x7fu) << sh;
+                sh += 7;
             }
-            P += v;
-            if (aw & kbit) {
-                if (kNeed & kNeedSum) sumP += P;
-                if (kNeed & kNeedMinMax) {
-                    minP = P < minP ? P : minP;
-                    maxP = P > maxP ? P : maxP;
+            if ((tm >> j) & 1u) {
+                P += static_cast<int32_t>(accv >> 1) ^ -static_cast<int32_t>(accv & 1u);
+                if (aw & 1u) {
+                    if (kNeed & kNeedSum) sumP += P;
+                    if (kNeed & kNeedMinMax) {
+                        minP = P < minP ? P : minP;
+                        maxP = P > maxP ? P : maxP;
+                    }
                 }
+                aw >>= 1;
+                accv = 0;
+                sh = 0;
             }
-            kbit <<= 1;
-            accv = 0;
-            sh = 0;
         }
+        w0 = w1;
+        w1 = w2;
+        w2 = w3;
+        w3 = w4;
+        w4 = w5;
+        w5 = w6;
+        w6 = w7;
+        vm >>= 4;
+        tm >>= 4;
     }
+}
+
+// what the previous lane's unfinished tail adds to this lane's first value (narrow mode: the value's own
+// bytes are the first <= 3 bytes of the lane, its low bits are prev_acc)
+__device__ __forceinline__ int32_t head_delta(uint32_t w0, uint32_t term, uint32_t prev_acc, uint32_t prev_sh) {
+    const uint32_t fp = static_cast<uint32_t>(__ffs(term) - 1);                 // <= 2
+    const uint32_t x = w0 & (0xffffffu >> (8u * (2u - fp)));                     // bytes 0..fp
+    const uint32_t hx = (x & 0x7fu) | ((x >> 1) & 0x3f80u) | ((x >> 2) & 0x1fc000u);
+    const uint32_t full = prev_acc | (hx << prev_sh);
+    const int32_t v_true = static_cast<int32_t>(full >> 1) ^ -static_cast<int32_t>(full & 1u);
+    const int32_t v_own = static_cast<int32_t>(hx >> 1) ^ -static_cast<int32_t>(hx & 1u);
+    return v_true - v_own;
+}
+
+// per-chunk front end shared by the two fast decoders: load 32 B per lane, byte masks, narrow check
+struct FastChunk {
+    uint4 wa, wb;
+    uint32_t valid, term, n;
+    bool wide;
+};
+__device__ __forceinline__ void fast_chunk_load(FastChunk &fc, const PageStream &st, const uint8_t *buf, uint32_t c, uint32_t carry_sh, int lane) {
+    const uint32_t o = c * kFastChunkBytes + lane * kFastLaneBytes;
+    fc.wa = make_uint4(0, 0, 0, 0);
+    fc.wb = make_uint4(0, 0, 0, 0);
+    if (o < st.total) fc.wa = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes));
+    if (o + 16 < st.total) fc.wb = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes) + 16);
+    int lo_i = static_cast<int>(st.pstart) - static_cast<int>(o);
+    int hi_i = static_cast<int>(st.pend) - static_cast<int>(o);
+    lo_i = lo_i < 0 ? 0 : (lo_i > 32 ? 32 : lo_i);
+    hi_i = hi_i < 0 ? 0 : (hi_i > 32 ? 32 : hi_i);
+    fc.valid = low_bits(hi_i) & ~low_bits(lo_i);
+    const uint32_t msb = msb4(fc.wa.x) | (msb4(fc.wa.y) << 4) | (msb4(fc.wa.z) << 8) | (msb4(fc.wa.w) << 12) | (msb4(fc.wb.x) << 16) |
+                         (msb4(fc.wb.y) << 20) | (msb4(fc.wb.z) << 24) | (msb4(fc.wb.w) << 28);
+    fc.term = fc.valid & ~msb;
+    const uint32_t cont = fc.valid & msb;
+    fc.n = __popc(fc.term);
+    // longest varint check: no run of 3 continuation bytes inside the lane, and the run that
+    // crosses from the previous lane (its trailing continuation bytes + our leading ones) <= 2
+    const uint32_t lead = fc.term ? static_cast<uint32_t>(__ffs(fc.term) - 1 - lo_i) : static_cast<uint32_t>(hi_i - lo_i);
+    const uint32_t trail = fc.term ? static_cast<uint32_t>(hi_i - 1 - (31 - __clz(fc.term))) : static_cast<uint32_t>(hi_i - lo_i);
+    uint32_t trail_prev = __shfl_up_sync(0xffffffffu, trail, 1);
+    if (lane == 0) trail_prev = carry_sh / 7;
+    fc.wide = __any_sync(0xffffffffu, (cont & (cont >> 1) & (cont >> 2)) != 0 || (trail_prev + lead) > 2);
+}
+
+// rows of the lane -> bit i of the result = i-th value of this lane is an active row
+template <int kMode>
+__device__ __forceinline__ uint32_t fast_active_window(const WarpSmem *sm, uint32_t row0, uint32_t n, uint32_t r0, uint32_t r1) {
+    if (kMode == kRowsAll) return low_bits(n);
+    if (kMode == kRowsRange) {
+        const uint32_t a = r0 > row0 ? r0 - row0 : 0u;
+        const uint32_t b = (r1 + 1u) < (row0 + n) ? (r1 + 1u > row0 ? r1 + 1u - row0 : 0u) : n;
+        return a < b ? (low_bits(b) & ~low_bits(a)) : 0u;
+    }
+    const uint32_t wi = row0 >> 5;
+    const uint64_t m64 = static_cast<uint64_t>(sm->mask[wi]) | (static_cast<uint64_t>(sm->mask[wi + 1]) << 32);
+    return static_cast<uint32_t>(m64 >> (row0 & 31)) & low_bits(n);
 }
 
 template <int kMode, int kNeed>
@@ -520,8 +591,8 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const u
     }
     PageStream st;
     stream_open(st, sm, seq, body, len, lane);
-    const uint32_t nchunks = (st.total + kChunkBytes - 1) / kChunkBytes;
-    constexpr uint32_t kChunksPerStage = kStageBytes / kChunkBytes;
+    const uint32_t nchunks = (st.total + kFastChunkBytes - 1) / kFastChunkBytes;
+    constexpr uint32_t kChunksPerStage = kStageBytes / kFastChunkBytes;
     int64_t V0 = first;
     uint32_t carry_acc = 0, carry_sh = 0;
     uint32_t row_base = 1;
@@ -529,25 +600,9 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const u
     for (uint32_t c = 0; c < nchunks; ++c) {
         const uint32_t k = c / kChunksPerStage;
         if ((c % kChunksPerStage) == 0) buf = stream_wait(st, sm, k);
-        const uint32_t o = c * kChunkBytes + lane * 16;
-        uint4 w = make_uint4(0, 0, 0, 0);
-        if (o < st.total) w = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes));
-        int lo_i = static_cast<int>(st.pstart) - static_cast<int>(o);
-        int hi_i = static_cast<int>(st.pend) - static_cast<int>(o);
-        lo_i = lo_i < 0 ? 0 : (lo_i > 16 ? 16 : lo_i);
-        hi_i = hi_i < 0 ? 0 : (hi_i > 16 ? 16 : hi_i);
-        const uint32_t valid = ((1u << hi_i) - 1u) & ~((1u << lo_i) - 1u);
-        const uint32_t msb = msb4(w.x) | (msb4(w.y) << 4) | (msb4(w.z) << 8) | (msb4(w.w) << 12);
-        const uint32_t term = valid & ~msb;
-        const uint32_t cont = valid & msb;
-        // longest varint check: no run of 3 continuation bytes inside the lane, and the run that
-        // crosses from the previous lane (its trailing continuation bytes + our leading ones) <= 2
-        const uint32_t lead = term ? static_cast<uint32_t>(__ffs(term) - 1 - lo_i) : static_cast<uint32_t>(hi_i - lo_i);
-        const uint32_t trail = term ? static_cast<uint32_t>(hi_i - 1 - (31 - __clz(term))) : static_cast<uint32_t>(hi_i - lo_i);
-        uint32_t trail_prev = __shfl_up_sync(0xffffffffu, trail, 1);
-        if (lane == 0) trail_prev = carry_sh / 7;
-        const bool wide = (cont & (cont >> 1) & (cont >> 2)) != 0 || (trail_prev + lead) > 2;
-        if (__any_sync(0xffffffffu, wide)) {
+        FastChunk fc;
+        fast_chunk_load(fc, st, buf, c, carry_sh, lane);
+        if (fc.wide) {
             // give the unissued stage numbers back: the mbarrier phases only advance for stages that
             // were really issued, and the next page must continue from exactly that count
             stream_drain(st, sm, k);
@@ -555,34 +610,28 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const u
             __syncwarp();
             return 1;
         }
-        // rows of this lane
-        const uint32_t n = __popc(term);
-        uint32_t n_in = n;
-#pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            const uint32_t on = __shfl_up_sync(0xffffffffu, n_in, s);
-            if (lane >= s) n_in += on;
-        }
-        const uint32_t row0 = row_base + n_in - n;
-        uint32_t aw;  // bit i = i-th value of this lane is an active row
+        const uint32_t n = fc.n;
+        // rows of this lane (only the masked / ranged modes need the per-lane row index)
+        uint32_t n_tot, aw;
         if (kMode == kRowsAll) {
-            aw = (1u << n) - 1u;
-        } else if (kMode == kRowsRange) {
-            const uint32_t a = r0 > row0 ? r0 - row0 : 0u;
-            const uint32_t b = (r1 + 1u) < (row0 + n) ? (r1 + 1u > row0 ? r1 + 1u - row0 : 0u) : n;
-            aw = a < b ? (((1u << b) - 1u) & ~((1u << a) - 1u)) : 0u;
+            n_tot = __reduce_add_sync(0xffffffffu, n);
+            aw = low_bits(n);
         } else {
-            const uint32_t wi = row0 >> 5;
-            const uint64_t m64 = static_cast<uint64_t>(sm->mask[wi]) | (static_cast<uint64_t>(sm->mask[wi + 1]) << 32);
-            aw = static_cast<uint32_t>(m64 >> (row0 & 31)) & ((1u << n) - 1u);
+            uint32_t n_in = n;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const uint32_t on = __shfl_up_sync(0xffffffffu, n_in, s);
+                if (lane >= s) n_in += on;
+            }
+            n_tot = __shfl_sync(0xffffffffu, n_in, 31);
+            aw = fast_active_window<kMode>(sm, row_base + n_in - n, n, r0, r1);
         }
+        const uint32_t cntA = __popc(aw);
         // ---- decode: local prefix P, folded over the active rows
         uint32_t accv = 0, sh = 0;
         int32_t P = 0, sumP = 0, minP = INT32_MAX, maxP = INT32_MIN;
-        int32_t head_v = 0;  // first value decoded from this lane's bytes only
-        uint32_t head_x = 0;
-        if (__all_sync(0xffffffffu, valid == 0xffffu)) fast_lane_decode<true, kNeed>(w, valid, term, aw, accv, sh, P, sumP, minP, maxP, head_x, head_v);
-        else fast_lane_decode<false, kNeed>(w, valid, term, aw, accv, sh, P, sumP, minP, maxP, head_x, head_v);
+        if (__all_sync(0xffffffffu, fc.valid == 0xffffffffu)) fast_lane_decode<true, kNeed>(fc.wa, fc.wb, fc.valid, fc.term, aw, accv, sh, P, sumP, minP, maxP);
+        else fast_lane_decode<false, kNeed>(fc.wa, fc.wb, fc.valid, fc.term, aw, accv, sh, P, sumP, minP, maxP);
         // ---- head correction by the previous lane's unfinished tail
         uint32_t prev_acc = __shfl_up_sync(0xffffffffu, accv, 1);
         uint32_t prev_sh = __shfl_up_sync(0xffffffffu, sh, 1);
@@ -592,11 +641,8 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const u
         }
         carry_acc = __shfl_sync(0xffffffffu, accv, 31);
         carry_sh = __shfl_sync(0xffffffffu, sh, 31);
-        const uint32_t cntA = __popc(aw);
         if (n > 0 && prev_sh != 0) {
-            const uint32_t x = prev_acc | (head_x << prev_sh);
-            const int32_t vt = static_cast<int32_t>(x >> 1) ^ -static_cast<int32_t>(x & 1u);
-            const int32_t dlt = vt - head_v;
+            const int32_t dlt = head_delta(fc.wa.x, fc.term, prev_acc, prev_sh);
             P += dlt;
             if (kNeed & kNeedSum) sumP += dlt * static_cast<int32_t>(cntA);
             if ((kNeed & kNeedMinMax) && cntA) {
@@ -628,7 +674,7 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const u
             acc.cnt += cntA;
         }
         V0 += static_cast<int64_t>(__shfl_sync(0xffffffffu, s_in, 31));
-        row_base += __shfl_sync(0xffffffffu, n_in, 31);
+        row_base += n_tot;
         if ((c % kChunksPerStage) == kChunksPerStage - 1 || c == nchunks - 1) stream_release(st, sm, k, lane);
     }
     acc_io = acc;
@@ -927,8 +973,8 @@ __device__ __noinline__ int dod_page_fast(WarpSmem *sm, uint32_t &seq, const uin
     }
     PageStream st;
     stream_open(st, sm, seq, body, len, lane);
-    const uint32_t nchunks = (st.total + kChunkBytes - 1) / kChunkBytes;
-    constexpr uint32_t kChunksPerStage = kStageBytes / kChunkBytes;
+    const uint32_t nchunks = (st.total + kFastChunkBytes - 1) / kFastChunkBytes;
+    constexpr uint32_t kChunksPerStage = kStageBytes / kFastChunkBytes;
     int64_t V0 = first + d1;  // value of the row before this chunk's first varint
     int64_t D0 = d1;          // running first difference
     uint32_t carry_acc = 0, carry_sh = 0;
@@ -937,37 +983,21 @@ __device__ __noinline__ int dod_page_fast(WarpSmem *sm, uint32_t &seq, const uin
     for (uint32_t c = 0; c < nchunks; ++c) {
         const uint32_t k = c / kChunksPerStage;
         if ((c % kChunksPerStage) == 0) buf = stream_wait(st, sm, k);
-        const uint32_t o = c * kChunkBytes + lane * 16;
-        uint4 w = make_uint4(0, 0, 0, 0);
-        if (o < st.total) w = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes));
-        int lo_i = static_cast<int>(st.pstart) - static_cast<int>(o);
-        int hi_i = static_cast<int>(st.pend) - static_cast<int>(o);
-        lo_i = lo_i < 0 ? 0 : (lo_i > 16 ? 16 : lo_i);
-        hi_i = hi_i < 0 ? 0 : (hi_i > 16 ? 16 : hi_i);
-        const uint32_t valid = ((1u << hi_i) - 1u) & ~((1u << lo_i) - 1u);
-        const uint32_t msb = msb4(w.x) | (msb4(w.y) << 4) | (msb4(w.z) << 8) | (msb4(w.w) << 12);
-        const uint32_t term = valid & ~msb;
-        const uint32_t cont = valid & msb;
-        const uint32_t lead = term ? static_cast<uint32_t>(__ffs(term) - 1 - lo_i) : static_cast<uint32_t>(hi_i - lo_i);
-        const uint32_t trail = term ? static_cast<uint32_t>(hi_i - 1 - (31 - __clz(term))) : static_cast<uint32_t>(hi_i - lo_i);
-        uint32_t trail_prev = __shfl_up_sync(0xffffffffu, trail, 1);
-        if (lane == 0) trail_prev = carry_sh / 7;
-        const bool wide = (cont & (cont >> 1) & (cont >> 2)) != 0 || (trail_prev + lead) > 2;
-        if (__any_sync(0xffffffffu, wide)) {
+        FastChunk fc;
+        fast_chunk_load(fc, st, buf, c, carry_sh, lane);
+        if (fc.wide) {
             stream_drain(st, sm, k);
             seq = st.seq0 + min(st.nstages, k + static_cast<uint32_t>(kStages));
             __syncwarp();
             return 1;
         }
-        const uint32_t n = __popc(term);
-        // ---- pass 1: lane-local (q, r) with every value counted (aw = all ones)
+        const uint32_t n = fc.n;
+        // ---- pass 1: lane-local (q, r) with every value counted
         uint32_t accv = 0, sh = 0;
         int32_t P = 0, sumP = 0, mnu = 0, mxu = 0;
-        int32_t head_v = 0;
-        uint32_t head_x = 0;
-        const bool full = __all_sync(0xffffffffu, valid == 0xffffu);
-        if (full) fast_lane_decode<true, kNeedSum>(w, valid, term, 0xffffffffu, accv, sh, P, sumP, mnu, mxu, head_x, head_v);
-        else fast_lane_decode<false, kNeedSum>(w, valid, term, 0xffffffffu, accv, sh, P, sumP, mnu, mxu, head_x, head_v);
+        const bool full = __all_sync(0xffffffffu, fc.valid == 0xffffffffu);
+        if (full) fast_lane_decode<true, kNeedSum>(fc.wa, fc.wb, fc.valid, fc.term, 0xffffffffu, accv, sh, P, sumP, mnu, mxu);
+        else fast_lane_decode<false, kNeedSum>(fc.wa, fc.wb, fc.valid, fc.term, 0xffffffffu, accv, sh, P, sumP, mnu, mxu);
         uint32_t prev_acc = __shfl_up_sync(0xffffffffu, accv, 1);
         uint32_t prev_sh = __shfl_up_sync(0xffffffffu, sh, 1);
         if (lane == 0) {
@@ -977,8 +1007,7 @@ __device__ __noinline__ int dod_page_fast(WarpSmem *sm, uint32_t &seq, const uin
         carry_acc = __shfl_sync(0xffffffffu, accv, 31);
         carry_sh = __shfl_sync(0xffffffffu, sh, 31);
         if (n > 0 && prev_sh != 0) {
-            const uint32_t x = prev_acc | (head_x << prev_sh);
-            const int32_t dlt = (static_cast<int32_t>(x >> 1) ^ -static_cast<int32_t>(x & 1u)) - head_v;
+            const int32_t dlt = head_delta(fc.wa.x, fc.term, prev_acc, prev_sh);
             P += dlt;
             sumP += dlt * static_cast<int32_t>(n);
         }
@@ -1004,52 +1033,52 @@ __device__ __noinline__ int dod_page_fast(WarpSmem *sm, uint32_t &seq, const uin
             r_ex = 0;
         }
         // ---- pass 2: true values of this lane's rows
-        const uint32_t row0 = row_base + n_ex;
-        uint32_t aw;
-        if (kMode == kRowsAll) {
-            aw = (1u << n) - 1u;
-        } else if (kMode == kRowsRange) {
-            const uint32_t a = r0 > row0 ? r0 - row0 : 0u;
-            const uint32_t b = (r1 + 1u) < (row0 + n) ? (r1 + 1u > row0 ? r1 + 1u - row0 : 0u) : n;
-            aw = a < b ? (((1u << b) - 1u) & ~((1u << a) - 1u)) : 0u;
-        } else {
-            const uint32_t wi = row0 >> 5;
-            const uint64_t m64 = static_cast<uint64_t>(sm->mask[wi]) | (static_cast<uint64_t>(sm->mask[wi + 1]) << 32);
-            aw = static_cast<uint32_t>(m64 >> (row0 & 31)) & ((1u << n) - 1u);
-        }
+        uint32_t aw = fast_active_window<kMode>(sm, row_base + n_ex, n, r0, r1);
         if (__any_sync(0xffffffffu, aw != 0)) {
             int64_t D = D0 + q_ex;
             int64_t v = V0 + static_cast<int64_t>(n_ex) * D0 + r_ex;
             accv = prev_acc;
             sh = prev_sh;
-            uint32_t kbit = 1u;
+            uint32_t w0 = fc.wa.x, w1 = fc.wa.y, w2 = fc.wa.z, w3 = fc.wa.w, w4 = fc.wb.x, w5 = fc.wb.y, w6 = fc.wb.z, w7 = fc.wb.w;
+            uint32_t vm = fc.valid, tm = fc.term;
+#pragma unroll 1
+            for (int q8 = 0; q8 < 8; ++q8) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const uint32_t wj = j < 4 ? w.x : (j < 8 ? w.y : (j < 12 ? w.z : w.w));
-                const uint32_t b = (wj >> (8 * (j & 3))) & 0xffu;
-                if ((valid >> j) & 1u) {
-                    accv |= (b & 0x7fu) << sh;
-                    sh += 7;
-                }
-                if ((term >> j) & 1u) {
-                    D += static_cast<int64_t>(static_cast<int32_t>(accv >> 1) ^ -static_cast<int32_t>(accv & 1u));
-                    v += D;
-                    if (aw & kbit) {
-                        if (kNeed & kNeedSum) {
-                            const uint64_t uv = static_cast<uint64_t>(v);
-                            acc.lo += uv;
-                            acc.hi += (v >> 63) + (acc.lo < uv ? 1 : 0);
-                        }
-                        if (kNeed & kNeedMinMax) {
-                            acc.mn = v < acc.mn ? v : acc.mn;
-                            acc.mx = v > acc.mx ? v : acc.mx;
-                        }
-                        acc.cnt++;
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t b = (w0 >> (8 * j)) & 0xffu;
+                    if ((vm >> j) & 1u) {
+                        accv |= (b & 0x7fu) << sh;
+                        sh += 7;
                     }
-                    kbit <<= 1;
-                    accv = 0;
-                    sh = 0;
+                    if ((tm >> j) & 1u) {
+                        D += static_cast<int64_t>(static_cast<int32_t>(accv >> 1) ^ -static_cast<int32_t>(accv & 1u));
+                        v += D;
+                        if (aw & 1u) {
+                            if (kNeed & kNeedSum) {
+                                const uint64_t uv = static_cast<uint64_t>(v);
+                                acc.lo += uv;
+                                acc.hi += (v >> 63) + (acc.lo < uv ? 1 : 0);
+                            }
+                            if (kNeed & kNeedMinMax) {
+                                acc.mn = v < acc.mn ? v : acc.mn;
+                                acc.mx = v > acc.mx ? v : acc.mx;
+                            }
+                            acc.cnt++;
+                        }
+                        aw >>= 1;
+                        accv = 0;
+                        sh = 0;
+                    }
                 }
+                w0 = w1;
+                w1 = w2;
+                w2 = w3;
+                w3 = w4;
+                w4 = w5;
+                w5 = w6;
+                w6 = w7;
+                vm >>= 4;
+                tm >>= 4;
             }
         }
         const uint32_t n_tot = __shfl_sync(0xffffffffu, n_in, 31);

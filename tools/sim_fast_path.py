@@ -21,6 +21,7 @@ def enc(vals):
 
 def sim(body, pstart, count, first, active):
     """returns (rc, sum, mn, mx, cnt) like the kernel; active: bool per row"""
+    LB = 32  # bytes per lane (kFastLaneBytes)
     total = ((pstart + len(body)) + 15) & ~15
     buf = bytes(pstart) + body + bytes(total - pstart - len(body))
     pend = pstart + len(body)
@@ -28,16 +29,16 @@ def sim(body, pstart, count, first, active):
     if active[0]:
         S += first; mn = mx = first; cnt += 1
     V0 = first; carry_acc = 0; carry_sh = 0; row_base = 1
-    nchunks = (total + 511) // 512
+    nchunks = (total + 32 * LB - 1) // (32 * LB)
     for c in range(nchunks):
         lanes = []
         for lane in range(32):
-            o = c * 512 + lane * 16
-            w = buf[o:o + 16] if o < total else bytes(16)
-            w = w + bytes(16 - len(w))
-            lo = min(max(pstart - o, 0), 16); hi = min(max(pend - o, 0), 16)
+            o = c * 32 * LB + lane * LB
+            w = buf[o:o + LB] if o < total else bytes(LB)
+            w = w + bytes(LB - len(w))
+            lo = min(max(pstart - o, 0), LB); hi = min(max(pend - o, 0), LB)
             valid = ((1 << hi) - 1) & ~((1 << lo) - 1)
-            msb = sum(((w[j] >> 7) & 1) << j for j in range(16))
+            msb = sum(((w[j] >> 7) & 1) << j for j in range(LB))
             term = valid & ~msb; cont = valid & msb
             lanes.append(dict(w=w, lo=lo, hi=hi, valid=valid, term=term, cont=cont))
         # wide check
@@ -70,7 +71,7 @@ def sim(body, pstart, count, first, active):
                 if active[row0 + i]:
                     aw |= 1 << i
             acc = 0; sh = 0; kbit = 1; P = 0; sumP = 0; minP = 2**31 - 1; maxP = -2**31; head_v = 0; head_x = 0
-            for j in range(16):
+            for j in range(LB):
                 b = L['w'][j]
                 if (L['valid'] >> j) & 1:
                     acc |= (b & 0x7f) << sh; sh += 7
@@ -88,8 +89,12 @@ def sim(body, pstart, count, first, active):
             pa, ps = (lanes[lane - 1]['acc'], lanes[lane - 1]['sh']) if lane else (carry_acc, carry_sh)
             cntA = bin(L['aw']).count('1')
             if L['n'] > 0 and ps != 0:
-                x = pa | (L['head_x'] << ps)
-                dlt = zz(x) - L['head_v']
+                term = L['term']; fp = (term & -term).bit_length() - 1
+                assert fp <= 2 and L['lo'] == 0
+                xb = int.from_bytes(L['w'][:4], 'little') & (0xffffff >> (8 * (2 - fp)))
+                hx = (xb & 0x7f) | ((xb >> 1) & 0x3f80) | ((xb >> 2) & 0x1fc000)
+                assert hx == L['head_x']
+                dlt = zz(pa | (hx << ps)) - zz(hx)
                 L['P'] += dlt; L['sumP'] += dlt * cntA
                 if cntA:
                     L['minP'] += dlt; L['maxP'] += dlt
