@@ -62,6 +62,7 @@ struct ExecSlot {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     uint8_t *pinned = nullptr;
     size_t pinned_bytes = 0;
+    uint8_t *zpage = nullptr;  // 256 B pinned: read-back of the per-query zero page (errors + counters)
     int ensure_pinned(size_t n) {
         if (n <= pinned_bytes) return 0;
         if (pinned) cudaFreeHost(pinned);
@@ -109,6 +110,7 @@ struct SlotLease {
         if (cudaStreamCreateWithFlags(&slot->stream, cudaStreamNonBlocking) != cudaSuccess) return -1;
         for (auto &e : slot->ev)
             if (cudaEventCreate(&e) != cudaSuccess) return -1;
+        if (cudaMallocHost(reinterpret_cast<void **>(&slot->zpage), 256) != cudaSuccess) return -1;
         return 0;
     }
     ~SlotLease() {
@@ -508,11 +510,10 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
         sp.dd_counts = reinterpret_cast<unsigned long long *>(d + off_zero + 96);
         CUDA_TRY(cudaMemsetAsync(sp.dd_index, 0xff, NB * 4, stream));
         launch_detect_overlap(sp, stream);
-        if (slot.ensure_pinned(256)) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
-        CUDA_TRY(cudaMemcpyAsync(slot.pinned, d + off_zero + 96, 16, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(slot.zpage + 128, d + off_zero + 96, 16, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
-        const unsigned long long n_ddb = reinterpret_cast<unsigned long long *>(slot.pinned)[0];
-        const unsigned long long n_ddr = reinterpret_cast<unsigned long long *>(slot.pinned)[1];
+        const unsigned long long n_ddb = reinterpret_cast<unsigned long long *>(slot.zpage + 128)[0];
+        const unsigned long long n_ddr = reinterpret_cast<unsigned long long *>(slot.zpage + 128)[1];
         extra_launches += 1;
         if (stats) stats->d2h_bytes += 16;
         if (n_ddb > 0) {
@@ -533,14 +534,21 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
     launch_series_reduce(rp, stream);
     launch_group_reduce(rp, stream);
     CUDA_TRY(cudaEventRecord(slot.ev[3], stream));
-    // read back the zero page (errors + stats)
-    if (slot.ensure_pinned(256)) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
-    CUDA_TRY(cudaMemcpyAsync(slot.pinned, d + off_zero, 256, cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaStreamSynchronize(stream));
-    CUDA_TRY(cudaGetLastError());
-    const uint32_t *hz = reinterpret_cast<const uint32_t *>(slot.pinned);
+    // read back the zero page (errors + counters); the caller synchronises and then calls collect_scan
+    CUDA_TRY(cudaMemcpyAsync(slot.zpage, d + off_zero, 256, cudaMemcpyDeviceToHost, stream));
     if (stats) {
-        const unsigned long long *hs = reinterpret_cast<const unsigned long long *>(slot.pinned + 16);
+        stats->kernel_launches += (NB ? 1u : 0u) + 2u + (NS ? 1u : 0u) + 1u + extra_launches;
+        stats->d2h_bytes += 256;
+    }
+    // the scratch must outlive the kernels: it is freed stream-ordered (after them) when `sc` goes out of scope
+    return 0;
+}
+
+// after the stream is synchronised: device errors + counters of the scan
+int collect_scan(ExecSlot &slot, bydb_stats *stats) {
+    const uint32_t *hz = reinterpret_cast<const uint32_t *>(slot.zpage);
+    if (stats) {
+        const unsigned long long *hs = reinterpret_cast<const unsigned long long *>(slot.zpage + 16);
         stats->rows_scanned += hs[0];
         stats->rows_matched += hs[1];
         stats->page_bytes += hs[2];
@@ -552,8 +560,6 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
         stats->scan_kernel_ms += ms;
         cudaEventElapsedTime(&ms, slot.ev[0], slot.ev[3]);
         stats->device_ms += ms;
-        stats->kernel_launches += (NB ? 1u : 0u) + 2u + (NS ? 1u : 0u) + 1u + extra_launches;
-        stats->d2h_bytes += 256;
     }
     if (hz[2] != 0) {
         char buf[96];
@@ -697,9 +703,21 @@ int scan_agg_impl(bydb_ctx *ctx, const bydb_query *q, const std::vector<std::sha
     CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&table.base), tl.total, slot.stream));
     memset(&out->stats, 0, sizeof out->stats);
     out->stats.h2d_bytes = h2d_pre;
+    {
+        // size the pinned staging once: it must not be reallocated while copies from/to it are in flight
+        const size_t G = static_cast<size_t>(plan.n_groups), A = q->n_aggs, NS = q->n_series;
+        if (slot.ensure_pinned(NS * 12 + (G + 1) * 4 + G * (12 + 16 * A) + 16 * A + 8192)) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
+    }
     rc = run_scan(ctx, q, plan, slot, slot.stream, table.base, tl, &out->stats);
     if (rc) return rc;
-    return finalize_to_host(ctx, q, plan, slot, slot.stream, table.base, tl, out);
+    // finalisation is enqueued behind the scan; one synchronisation covers both
+    rc = finalize_to_host(ctx, q, plan, slot, slot.stream, table.base, tl, out);
+    int rc2 = collect_scan(slot, &out->stats);
+    if (rc2) {
+        bydb_result_free(ctx, out);
+        return rc2;
+    }
+    return rc;
 }
 
 }  // namespace
@@ -756,6 +774,7 @@ void bydb_shutdown(bydb_ctx *ctx) {
         for (auto &e : s->ev)
             if (e) cudaEventDestroy(e);
         if (s->pinned) cudaFreeHost(s->pinned);
+        if (s->zpage) cudaFreeHost(s->zpage);
     }
     ctx->free_slots.clear();
     ctx->parts.clear();
@@ -886,6 +905,11 @@ int bydb_scan_partials(bydb_ctx *ctx, const bydb_query *q, void *d_partials, uin
     bydb_stats local;
     memset(&local, 0, sizeof local);
     rc = run_scan(ctx, q, plan, *lease.slot, s, static_cast<uint8_t *>(d_partials), tl, &local);
+    if (!rc) {
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaGetLastError());
+        rc = collect_scan(*lease.slot, &local);
+    }
     if (stats) *stats = local;
     return rc;
 }

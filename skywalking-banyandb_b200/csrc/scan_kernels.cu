@@ -1614,11 +1614,27 @@ __device__ __forceinline__ void combine(BlockPartial &a, const BlockPartial &b, 
     a.cnt += b.cnt;
 }
 
-// one thread per query series: walks the series' blocks part by part (blocks of one series are
-// contiguous inside a part, block_metadata.go:170-175) and detects overlapping time spans across
-// parts, which would need the version dedup of query.go:995-1004.
-__global__ void series_reduce_kernel(const __grid_constant__ ReduceParams p) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// one WARP per query series: the series' blocks are contiguous inside a part (block_metadata.go:170-175),
+// so lanes take consecutive blocks, and a fixed shuffle tree combines them (deterministic).  Also detects
+// overlapping time spans across parts, which need the version dedup of query.go:995-1004.
+__device__ __forceinline__ void warp_combine(BlockPartial &acc, bool is_float, int lane) {
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+        BlockPartial o;
+        o.sum.i = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(acc.sum.i), m));
+        o.mn.i = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(acc.mn.i), m));
+        o.mx.i = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(acc.mx.i), m));
+        o.cnt = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(acc.cnt), m));
+        // lower lane first, so both partners compute the same value and block order is respected
+        BlockPartial a = (lane & m) ? o : acc, b = (lane & m) ? acc : o;
+        combine(a, b, is_float);
+        acc = a;
+    }
+}
+
+__global__ void __launch_bounds__(256) series_reduce_kernel(const __grid_constant__ ReduceParams p) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= p.n_series) return;
     const uint64_t sid = p.q_sids[i];
     BlockPartial acc[kMaxFcols];
@@ -1646,14 +1662,40 @@ __global__ void series_reduce_kernel(const __grid_constant__ ReduceParams p) {
             }
         }
         int64_t plo = INT64_MAX, phi = INT64_MIN;
-        for (uint32_t b = lo; b < part.n_blocks && part.blocks[b].sid == sid; ++b) {
+        for (uint32_t base = lo; base < part.n_blocks; base += 32) {
+            const uint32_t b = base + lane;
+            const bool mine = b < part.n_blocks && part.blocks[b].sid == sid;
             const uint32_t g = part.block_base + b;
-            if (p.block_qsid[g] < 0) continue;
-            plo = part.blocks[b].ts_min < plo ? part.blocks[b].ts_min : plo;
-            phi = part.blocks[b].ts_max > phi ? part.blocks[b].ts_max : phi;
-            rows += p.Prows[g];
-            for (uint32_t c = 0; c < p.n_fcols; ++c)
-                combine(acc[c], p.P[static_cast<size_t>(g) * p.n_fcols + c], p.col_type[c] == BYDB_VT_FLOAT64);
+            const bool sel = mine && p.block_qsid[g] >= 0;
+            int64_t r = 0, tlo = INT64_MAX, thi = INT64_MIN;
+            if (sel) {
+                r = p.Prows[g];
+                tlo = part.blocks[b].ts_min;
+                thi = part.blocks[b].ts_max;
+            }
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                r += static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(r), m));
+                const int64_t ol = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(tlo), m));
+                const int64_t oh = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(thi), m));
+                tlo = ol < tlo ? ol : tlo;
+                thi = oh > thi ? oh : thi;
+            }
+            rows += r;
+            plo = tlo < plo ? tlo : plo;
+            phi = thi > phi ? thi : phi;
+            for (uint32_t c = 0; c < p.n_fcols; ++c) {
+                BlockPartial bp;
+                bp.sum.i = 0;
+                bp.mn.i = 0;
+                bp.mx.i = 0;
+                bp.cnt = 0;
+                if (sel) bp = p.P[static_cast<size_t>(g) * p.n_fcols + c];
+                const bool is_float = p.col_type[c] == BYDB_VT_FLOAT64;
+                warp_combine(bp, is_float, lane);
+                combine(acc[c], bp, is_float);
+            }
+            if (__ballot_sync(0xffffffffu, mine) != 0xffffffffu) break;
         }
         if (plo <= phi) {
             for (int s = 0; s < nspan; ++s)
@@ -1668,6 +1710,7 @@ __global__ void series_reduce_kernel(const __grid_constant__ ReduceParams p) {
             }
         }
     }
+    if (lane != 0) return;
     if (overlap && !p.dedup_done && atomicCAS(&p.err[0], 0u, static_cast<uint32_t>(kErrOverlap)) == 0u) p.err[1] = i;
     for (uint32_t c = 0; c < p.n_fcols; ++c) p.S[static_cast<size_t>(i) * p.n_fcols + c] = acc[c];
     p.Srows[i] = rows;
@@ -2043,8 +2086,8 @@ void launch_dedup(const ScanParams &p, int grid, cudaStream_t s) {
 }
 void launch_series_reduce(const ReduceParams &p, cudaStream_t s) {
     if (p.n_series == 0) return;
-    const int threads = 128;
-    series_reduce_kernel<<<(p.n_series + threads - 1) / threads, threads, 0, s>>>(p);
+    const int threads = 256;  // 8 series (one warp each) per CTA
+    series_reduce_kernel<<<(p.n_series + 7) / 8, threads, 0, s>>>(p);
 }
 void launch_group_reduce(const ReduceParams &p, cudaStream_t s) {
     if (p.n_groups <= 0) return;
