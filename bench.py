@@ -294,7 +294,8 @@ def main():
                 dist.all_reduce(m, op=dist.ReduceOp.MAX)
                 d = float(m[0])
             return {"value": total_rows_step * steps / d, "unit": "datapoints/s", "h2d_bytes_per_step": int(st.h2d_bytes),
-                    "d2h_bytes_per_step": int(st.d2h_bytes), "ms_per_step": d / steps * 1e3, "steps": steps}
+                    "d2h_bytes_per_step": int(st.d2h_bytes), "ms_per_step": d / steps * 1e3, "steps": steps,
+                    "scan_kernel_ms": st.scan_kernel_ms, "device_ms": st.device_ms}
 
         e2e_steps = max(3, min(args.steps, 10))
         from bydb_b200.capi import Q_HOST_ZERO_COPY
