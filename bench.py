@@ -15,8 +15,8 @@ over the synthetic measure of BASELINE.json configs[1]:
 ``--impl reference`` times that CPU port alone (all host threads) and prints the same JSON shape.
 
 N > 1 (torchrun): every rank owns one part of the same shape (weak scaling, series-disjoint), runs the
-scan into a partial table on its GPU, the tables are combined by NCCL all-reduce (SUM and MAX ranges)
-and rank 0 finalises.  No data-path collective other than that reduce.
+scan into a partial table on its GPU, the tiny tables are exchanged with ONE NCCL all-gather and rank 0
+combines them in rank order (deterministic) and finalises.  No other data-path collective.
 """
 from __future__ import annotations
 
@@ -222,18 +222,21 @@ def main():
             return r
     else:
         lay = ctx.partials_layout(q)
-        table = torch.zeros(lay["total_bytes"] // 8, dtype=torch.float64, device="cuda")
-        tf64 = table
-        from importlib import import_module
-        multi = import_module("bydb_b200.multi")
+        words = lay["total_bytes"] // 8
+        table = torch.zeros(words, dtype=torch.float64, device="cuda")
+        gathered = torch.zeros(world * words, dtype=torch.float64, device="cuda")
         stream = torch.cuda.current_stream().cuda_stream
 
         def step():
+            # map: every rank scans its own parts into a partial table on its GPU
             st = ctx.scan_partials(q, table.data_ptr(), lay["total_bytes"], stream)
             stats_acc.append(st)
-            multi.allreduce_partial_table(tf64, lay, dist)   # <= 4 tiny NCCL all-reduces (SUM / MAX ranges)
+            # reduce: ONE NCCL collective (all-gather of the tiny tables over NVLink), then a deterministic
+            # rank-ordered combine + finalisation on rank 0's GPU
+            dist.all_gather_into_tensor(gathered, table)
             if rank == 0:
-                return ctx.reduce_finalize(q, table.data_ptr(), lay["total_bytes"], stream)
+                ctx.partials_combine(q, gathered.data_ptr(), world, lay["total_bytes"], stream)
+                return ctx.reduce_finalize(q, gathered.data_ptr(), lay["total_bytes"], stream)
             torch.cuda.current_stream().synchronize()
             return None
 
@@ -254,7 +257,7 @@ def main():
     rows_step = stats_acc[-1].rows_scanned
     scan_ms = float(np.mean([s.scan_kernel_ms for s in stats_acc]))
     dev_ms = float(np.mean([s.device_ms for s in stats_acc]))
-    launches = int(sum(s.kernel_launches for s in stats_acc)) + (args.steps if world > 1 and rank == 0 else 0)
+    launches = int(sum(s.kernel_launches for s in stats_acc)) + (3 * args.steps if world > 1 and rank == 0 else 0)
     page_bytes = stats_acc[-1].page_bytes
     if world > 1:
         tt = torch.tensor([dt, float(rows_step)], dtype=torch.float64, device="cuda")

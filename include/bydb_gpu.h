@@ -198,6 +198,9 @@ int bydb_partials_layout(const bydb_query *q, bydb_partials_layout_t *out);
  * enqueued on `stream` (a cudaStream_t passed as void*; NULL = the library's own stream, synchronised
  * before return). */
 int bydb_scan_partials(bydb_ctx *ctx, const bydb_query *q, void *d_partials, uint64_t bytes, void *stream, bydb_stats *stats);
+/* Combine n_tables partial tables laid out back to back in DEVICE memory (e.g. the output of ONE all-gather of the
+ * per-rank tables) into the first one, in rank order: sums add, max ranges take the maximum.  Deterministic. */
+int bydb_partials_combine(bydb_ctx *ctx, const bydb_query *q, void *d_tables, uint32_t n_tables, uint64_t bytes_each, void *stream);
 /* Finalize a (reduced) partial table: MEAN finalisation, output typing, Top-N; copies the result to host. */
 int bydb_reduce_finalize(bydb_ctx *ctx, const bydb_query *q, const void *d_partials, uint64_t bytes, void *stream, bydb_result *out);
 

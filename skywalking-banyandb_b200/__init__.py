@@ -21,7 +21,7 @@ from .capi import (  # noqa: F401
     VT_BINARY, VT_FLOAT64, VT_INT64, VT_STR, BydbError, Context, Pred, Query, Result, Stats,
     library_path, load_library,
 )
-from .operator import (  # noqa: F401
+from .scan_operator import (  # noqa: F401
     AggCount, AggFunc, AggMax, AggMean, AggMin, AggSpec, AggSum, BatchSchema, ColumnDef, ColumnType,
     ColumnRole, GPUScanAgg, RecordBatch, ScanSpec, TopSpec,
 )

@@ -78,7 +78,7 @@ class _Layout(C.Structure):
 # every symbol include/bydb_gpu.h declares (tests/test_capi_symbols.py checks the list against the header)
 EXPORTS = ["bydb_init", "bydb_shutdown", "bydb_part_register", "bydb_part_release", "bydb_part_info",
            "bydb_scan_agg", "bydb_scan_agg_host", "bydb_result_free", "bydb_partials_layout",
-           "bydb_scan_partials", "bydb_reduce_finalize", "bydb_last_error", "bydb_version"]
+           "bydb_scan_partials", "bydb_partials_combine", "bydb_reduce_finalize", "bydb_last_error", "bydb_version"]
 
 _lib = None
 
@@ -109,6 +109,7 @@ def load_library():
     L.bydb_result_free.argtypes = [C.c_void_p, C.POINTER(_Result)]
     L.bydb_partials_layout.argtypes = [C.POINTER(_Query), C.POINTER(_Layout)]
     L.bydb_scan_partials.argtypes = [C.c_void_p, C.POINTER(_Query), C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(_Stats)]
+    L.bydb_partials_combine.argtypes = [C.c_void_p, C.POINTER(_Query), C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p]
     L.bydb_reduce_finalize.argtypes = [C.c_void_p, C.POINTER(_Query), C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(_Result)]
     _lib = L
     return L
@@ -343,6 +344,11 @@ class Context:
         st = _Stats()
         _check(self._L.bydb_scan_partials(self._h, C.byref(cq), d_ptr, nbytes, stream or None, C.byref(st)))
         return Stats.of(st)
+
+    def partials_combine(self, q: Query, d_ptr: int, n_tables: int, bytes_each: int, stream: int = 0) -> None:
+        keep: list = []
+        cq = _mk_query(q, keep)
+        _check(self._L.bydb_partials_combine(self._h, C.byref(cq), d_ptr, n_tables, bytes_each, stream or None))
 
     def reduce_finalize(self, q: Query, d_ptr: int, nbytes: int, stream: int = 0) -> Result:
         keep: list = []

@@ -914,6 +914,23 @@ int bydb_scan_partials(bydb_ctx *ctx, const bydb_query *q, void *d_partials, uin
     return rc;
 }
 
+int bydb_partials_combine(bydb_ctx *ctx, const bydb_query *q, void *d_tables, uint32_t n_tables, uint64_t bytes_each, void *stream) {
+    if (!ctx || !d_tables || n_tables == 0) return fail(BYDB_EINVAL, "NULL argument");
+    int rc = validate_query(q, false);
+    if (rc) return rc;
+    std::vector<std::string> fcols;
+    std::vector<int> agg_fcol;
+    distinct_fields(q, fcols, agg_fcol);
+    TableLayout tl(static_cast<size_t>(q->series_group ? q->n_groups : 1), fcols.size());
+    if (bytes_each != tl.total) return fail(BYDB_EINVAL, "partial tables must be exactly bydb_partials_layout().total_bytes each");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    launch_combine_tables(static_cast<uint64_t *>(d_tables), n_tables, tl.total / 8, tl.off_sum_f64 / 8, tl.off_max_f64 / 8, tl.off_max_f64 / 8,
+                          tl.off_sum_i64 / 8, tl.off_sum_i64 / 8, tl.off_max_i64 / 8, tl.off_max_i64 / 8, tl.total / 8,
+                          static_cast<cudaStream_t>(stream));
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 int bydb_reduce_finalize(bydb_ctx *ctx, const bydb_query *q, const void *d_partials, uint64_t bytes, void *stream, bydb_result *out) {
     if (!ctx || !d_partials || !out) return fail(BYDB_EINVAL, "NULL argument");
     memset(out, 0, sizeof *out);

@@ -2034,6 +2034,31 @@ __global__ void __launch_bounds__(1024) select_rows_kernel(const __grid_constant
     if (tid == 0) *p.sel_count = M + n_nulls;
 }
 
+
+// Multi-GPU reduce after ONE all-gather of the per-rank partial tables: every word of the table is
+// combined across ranks in rank order (deterministic float sums, unlike a ring all-reduce), which is
+// the liaison's reduceAccumulator.Combine (measure_plan_aggregation.go:96-124) done on the device.
+__global__ void combine_tables_kernel(uint64_t *t, uint32_t n, uint64_t words, uint64_t sf_lo, uint64_t sf_hi, uint64_t mf_lo, uint64_t mf_hi,
+                                      uint64_t si_lo, uint64_t si_hi, uint64_t mi_lo, uint64_t mi_hi) {
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= words) return;
+    uint64_t a = t[i];
+    for (uint32_t r = 1; r < n; ++r) {
+        const uint64_t b = t[static_cast<uint64_t>(r) * words + i];
+        if (i >= sf_lo && i < sf_hi) {
+            a = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(a)) + __longlong_as_double(static_cast<long long>(b))));
+        } else if (i >= mf_lo && i < mf_hi) {
+            const double x = __longlong_as_double(static_cast<long long>(a)), y = __longlong_as_double(static_cast<long long>(b));
+            a = static_cast<uint64_t>(__double_as_longlong(y > x ? y : x));
+        } else if (i >= si_lo && i < si_hi) {
+            a += b;  // wraps like Go's int64
+        } else if (i >= mi_lo && i < mi_hi) {
+            a = static_cast<uint64_t>(static_cast<int64_t>(b) > static_cast<int64_t>(a) ? b : a);
+        }
+    }
+    t[i] = a;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
@@ -2092,6 +2117,12 @@ void launch_series_reduce(const ReduceParams &p, cudaStream_t s) {
 void launch_group_reduce(const ReduceParams &p, cudaStream_t s) {
     if (p.n_groups <= 0) return;
     group_reduce_kernel<<<p.n_groups, 256, 0, s>>>(p);
+}
+void launch_combine_tables(uint64_t *tables, uint32_t n_tables, uint64_t words, uint64_t sum_f64_lo, uint64_t sum_f64_hi, uint64_t max_f64_lo,
+                           uint64_t max_f64_hi, uint64_t sum_i64_lo, uint64_t sum_i64_hi, uint64_t max_i64_lo, uint64_t max_i64_hi, cudaStream_t s) {
+    if (words == 0 || n_tables < 2) return;
+    combine_tables_kernel<<<static_cast<unsigned>((words + 255) / 256), 256, 0, s>>>(tables, n_tables, words, sum_f64_lo, sum_f64_hi, max_f64_lo, max_f64_hi,
+                                                                                  sum_i64_lo, sum_i64_hi, max_i64_lo, max_i64_hi);
 }
 void launch_select_rows(const SelectParams &p, cudaStream_t s) { select_rows_kernel<<<1, 1024, 0, s>>>(p); }
 void launch_finalize(const FinalizeParams &p, cudaStream_t s) {

@@ -153,6 +153,9 @@ struct SelectParams {
     uint32_t *sel_count;
 };
 void launch_select_rows(const SelectParams &p, cudaStream_t s);
+// combines n partial tables (each `words` 8-byte words, laid out back to back) into the first one, rank order
+void launch_combine_tables(uint64_t *tables, uint32_t n_tables, uint64_t words, uint64_t sum_f64_lo, uint64_t sum_f64_hi, uint64_t max_f64_lo,
+                           uint64_t max_f64_hi, uint64_t sum_i64_lo, uint64_t sum_i64_hi, uint64_t max_i64_lo, uint64_t max_i64_hi, cudaStream_t s);
 
 size_t scan_smem_bytes();
 void launch_plan_blocks(const ScanParams &p, cudaStream_t s);

@@ -11,6 +11,9 @@ which replaces the liaison's gather + reduceAccumulator.Combine
 (pkg/query/logical/measure/measure_plan_aggregation.go:96-124).  min is carried as max of the negation
 (float) / of the bitwise complement (int64) so that one MAX covers both.  Works on any backend
 (NCCL on GPUs; gloo in the CPU tests).
+
+bench.py uses the other reduce the C ABI offers: ONE all-gather of the tables followed by
+bydb_partials_combine (rank-ordered, hence deterministic float sums) and bydb_reduce_finalize.
 """
 from __future__ import annotations
 
