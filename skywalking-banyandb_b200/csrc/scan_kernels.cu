@@ -487,24 +487,32 @@ __device__ __forceinline__ void fast_lane_decode(const uint4 &wa, const uint4 &w
     for (int q8 = 0; q8 < 8; ++q8) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t b = (w0 >> (8 * j)) & 0xffu;
-            if (kFull || ((vm >> j) & 1u)) {
-                accv |= (b & 0x7fu) << sh;
+            // branch-free on purpose: every lane executes the same straight-line code and the
+            // per-terminator work is applied through masks (a divergent `if` costs more here)
+            const uint32_t b = (w0 >> (8 * j)) & 0x7fu;
+            if (kFull) {
+                accv |= b << sh;
                 sh += 7;
+            } else {
+                const uint32_t vmask = 0u - ((vm >> j) & 1u);
+                accv |= (b << sh) & vmask;
+                sh += 7u & vmask;
             }
-            if ((tm >> j) & 1u) {
-                P += static_cast<int32_t>(accv >> 1) ^ -static_cast<int32_t>(accv & 1u);
-                if (aw & 1u) {
-                    if (kNeed & kNeedSum) sumP += P;
-                    if (kNeed & kNeedMinMax) {
-                        minP = P < minP ? P : minP;
-                        maxP = P > maxP ? P : maxP;
-                    }
-                }
-                aw >>= 1;
-                accv = 0;
-                sh = 0;
+            const uint32_t t = (tm >> j) & 1u;
+            const uint32_t m = 0u - t;  // all ones at a terminator
+            const int32_t v = static_cast<int32_t>(accv >> 1) ^ -static_cast<int32_t>(accv & 1u);
+            P += v & static_cast<int32_t>(m);
+            const uint32_t am = m & (0u - (aw & 1u));  // terminator of an active row
+            if (kNeed & kNeedSum) sumP += P & static_cast<int32_t>(am);
+            if (kNeed & kNeedMinMax) {
+                const int32_t lo_c = static_cast<int32_t>((static_cast<uint32_t>(P) & am) | (0x7fffffffu & ~am));
+                const int32_t hi_c = static_cast<int32_t>((static_cast<uint32_t>(P) & am) | (0x80000000u & ~am));
+                minP = lo_c < minP ? lo_c : minP;
+                maxP = hi_c > maxP ? hi_c : maxP;
             }
+            aw >>= t;
+            accv &= ~m;
+            sh &= ~m;
         }
         w0 = w1;
         w1 = w2;
