@@ -59,7 +59,8 @@ struct Part {
 // One in-flight call: stream, events and a pinned staging buffer.
 struct ExecSlot {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    static constexpr int kMaxBatches = 8;  // pipelined cold path: one set of events / zero page per batch
+    cudaEvent_t ev[4 * kMaxBatches] = {};
     uint8_t *pinned = nullptr;
     size_t pinned_bytes = 0;
     uint8_t *zpage = nullptr;  // 256 B pinned: read-back of the per-query zero page (errors + counters)
@@ -110,7 +111,7 @@ struct SlotLease {
         if (cudaStreamCreateWithFlags(&slot->stream, cudaStreamNonBlocking) != cudaSuccess) return -1;
         for (auto &e : slot->ev)
             if (cudaEventCreate(&e) != cudaSuccess) return -1;
-        if (cudaMallocHost(reinterpret_cast<void **>(&slot->zpage), 256) != cudaSuccess) return -1;
+        if (cudaMallocHost(reinterpret_cast<void **>(&slot->zpage), 256 * ExecSlot::kMaxBatches) != cudaSuccess) return -1;
         return 0;
     }
     ~SlotLease() {
@@ -224,7 +225,7 @@ struct TableLayout {
 // zero_copy: the data files stay in (pinned, device-mapped) host memory and the kernels read the
 // pages they need straight over PCIe; only the block directory is uploaded.
 int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_files *files, std::shared_ptr<Part> &out, uint64_t *h2d,
-                              bool zero_copy = false, bool transient = false) {
+                              bool zero_copy = false, bool transient = false, size_t batch = 0, size_t n_batches = 1) {
     if (!files || files->n_files == 0 || !files->files) return fail(BYDB_EINVAL, "no files");
     std::vector<FileImage> imgs;
     for (uint32_t i = 0; i < files->n_files; ++i) {
@@ -238,7 +239,7 @@ int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_f
     std::string err;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);  // NameTable is shared
-        int rc = build_part_dir(imgs, ctx->names, part->dir, err);
+        int rc = build_part_dir(imgs, ctx->names, part->dir, err, batch, n_batches);
         if (rc) return fail(rc, "part " + std::to_string(part_id) + ": " + err);
     }
     // arena: each data file 256 B aligned with >= 256 B of slack after it (TMA over-read, bit windows)
@@ -349,7 +350,9 @@ struct Scratch {
 // Runs plan -> scan -> series_reduce -> group_reduce on `stream`, leaving the partial table at
 // `d_table` (device).  Synchronises the stream.  Fills stats.
 int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cudaStream_t stream, uint8_t *d_table, const TableLayout &tl,
-             bydb_stats *stats) {
+             bydb_stats *stats, int batch = 0, bool presized = false) {
+    cudaEvent_t *ev = slot.ev + 4 * batch;
+    uint8_t *zpage = slot.zpage + 256 * batch;
     const size_t F = plan.fcols.size();
     const size_t NS = q->n_series;
     const size_t NB = plan.total_blocks;
@@ -393,8 +396,9 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
     CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&sc.base), o, stream));
     uint8_t *d = sc.base;
     const size_t stage_bytes = NS * 8 + NS * 4 + (static_cast<size_t>(G) + 1) * 4;
-    if (slot.ensure_pinned(stage_bytes + 256)) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
-    uint8_t *h = slot.pinned;
+    const size_t stage_stride = align_up(stage_bytes + 256, 256);
+    if (!presized && slot.ensure_pinned(stage_stride * static_cast<size_t>(batch + 1))) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
+    uint8_t *h = slot.pinned + stage_stride * static_cast<size_t>(batch);
     if (NS) memcpy(h, q->series_ids, NS * 8);
     if (NS) memcpy(h + NS * 8, order.data(), NS * 4);
     memcpy(h + NS * 12, gstart.data(), (static_cast<size_t>(G) + 1) * 4);
@@ -488,7 +492,7 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
     rp.notmin_i64 = reinterpret_cast<int64_t *>(d_table + tl.off_notmin_i64);
     rp.coltype = reinterpret_cast<int64_t *>(d_table + tl.off_coltype);
 
-    CUDA_TRY(cudaEventRecord(slot.ev[0], stream));
+    CUDA_TRY(cudaEventRecord(ev[0], stream));
     launch_plan_blocks(sp, stream);
     // ---- version dedup: only when two parts of the query overlap in time at all (host-side precheck on
     //      the part directories); then the device finds the series that really overlap
@@ -510,10 +514,10 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
         sp.dd_counts = reinterpret_cast<unsigned long long *>(d + off_zero + 96);
         CUDA_TRY(cudaMemsetAsync(sp.dd_index, 0xff, NB * 4, stream));
         launch_detect_overlap(sp, stream);
-        CUDA_TRY(cudaMemcpyAsync(slot.zpage + 128, d + off_zero + 96, 16, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(zpage + 128, d + off_zero + 96, 16, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
-        const unsigned long long n_ddb = reinterpret_cast<unsigned long long *>(slot.zpage + 128)[0];
-        const unsigned long long n_ddr = reinterpret_cast<unsigned long long *>(slot.zpage + 128)[1];
+        const unsigned long long n_ddb = reinterpret_cast<unsigned long long *>(zpage + 128)[0];
+        const unsigned long long n_ddr = reinterpret_cast<unsigned long long *>(zpage + 128)[1];
         extra_launches += 1;
         if (stats) stats->d2h_bytes += 16;
         if (n_ddb > 0) {
@@ -528,14 +532,14 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
         }
         rp.dedup_done = 1;
     }
-    CUDA_TRY(cudaEventRecord(slot.ev[1], stream));
+    CUDA_TRY(cudaEventRecord(ev[1], stream));
     launch_scan_blocks(sp, ctx->sm_count * ctx->ctas_per_sm_fast, ctx->sm_count * ctx->ctas_per_sm, stream);
-    CUDA_TRY(cudaEventRecord(slot.ev[2], stream));
+    CUDA_TRY(cudaEventRecord(ev[2], stream));
     launch_series_reduce(rp, stream);
     launch_group_reduce(rp, stream);
-    CUDA_TRY(cudaEventRecord(slot.ev[3], stream));
+    CUDA_TRY(cudaEventRecord(ev[3], stream));
     // read back the zero page (errors + counters); the caller synchronises and then calls collect_scan
-    CUDA_TRY(cudaMemcpyAsync(slot.zpage, d + off_zero, 256, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(zpage, d + off_zero, 256, cudaMemcpyDeviceToHost, stream));
     if (stats) {
         stats->kernel_launches += (NB ? 1u : 0u) + 2u + (NS ? 1u : 0u) + 1u + extra_launches;
         stats->d2h_bytes += 256;
@@ -545,10 +549,11 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
 }
 
 // after the stream is synchronised: device errors + counters of the scan
-int collect_scan(ExecSlot &slot, bydb_stats *stats) {
-    const uint32_t *hz = reinterpret_cast<const uint32_t *>(slot.zpage);
+int collect_scan(ExecSlot &slot, bydb_stats *stats, int batch = 0) {
+    cudaEvent_t *ev = slot.ev + 4 * batch;
+    const uint32_t *hz = reinterpret_cast<const uint32_t *>(slot.zpage + 256 * batch);
     if (stats) {
-        const unsigned long long *hs = reinterpret_cast<const unsigned long long *>(slot.zpage + 16);
+        const unsigned long long *hs = reinterpret_cast<const unsigned long long *>(slot.zpage + 256 * batch + 16);
         stats->rows_scanned += hs[0];
         stats->rows_matched += hs[1];
         stats->page_bytes += hs[2];
@@ -556,9 +561,9 @@ int collect_scan(ExecSlot &slot, bydb_stats *stats) {
         stats->blocks_slow_lane += static_cast<uint32_t>(hs[4]);
         stats->slow_lane_reasons |= static_cast<uint32_t>(hs[5]);
         float ms = 0;
-        cudaEventElapsedTime(&ms, slot.ev[1], slot.ev[2]);
+        cudaEventElapsedTime(&ms, ev[1], ev[2]);
         stats->scan_kernel_ms += ms;
-        cudaEventElapsedTime(&ms, slot.ev[0], slot.ev[3]);
+        cudaEventElapsedTime(&ms, ev[0], ev[3]);
         stats->device_ms += ms;
     }
     if (hz[2] != 0) {
@@ -839,6 +844,67 @@ int bydb_scan_agg(bydb_ctx *ctx, const bydb_query *q, bydb_result *out) {
     return scan_agg_impl(ctx, q, nullptr, out, 0);
 }
 
+// Cold path, one zero-copy part: the block index is parsed in slices and the scan of slice k runs on the
+// GPU (pulling its pages over PCIe) while the host parses slice k+1; the per-slice partial tables are
+// combined on the device.  A series may straddle slices: partial tables merge exactly.
+static int scan_agg_host_pipelined(bydb_ctx *ctx, const bydb_part_files *files, const bydb_query *q, bydb_result *out) {
+    constexpr int K = 4;
+    SlotLease lease(ctx);
+    if (lease.init()) return fail(BYDB_EIO, "cannot create stream");
+    ExecSlot &slot = *lease.slot;
+    Plan base;
+    distinct_fields(q, base.fcols, base.agg_fcol);
+    if (base.fcols.size() > kMaxFcols) return fail(BYDB_EINVAL, "too many distinct aggregated fields (max 8)");
+    base.n_groups = q->series_group ? q->n_groups : 1;
+    base.n_series = q->n_series;
+    TableLayout tl(static_cast<size_t>(base.n_groups), base.fcols.size());
+    Scratch tables;
+    tables.stream = slot.stream;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&tables.base), tl.total * K, slot.stream));
+    {
+        const size_t G = static_cast<size_t>(base.n_groups), A = q->n_aggs, NS = q->n_series;
+        const size_t stage_stride = align_up(NS * 12 + (G + 1) * 4 + 256, 256);
+        if (slot.ensure_pinned(std::max(stage_stride * K, G * (12 + 16 * A) + 16 * A + 8192))) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
+    }
+    memset(&out->stats, 0, sizeof out->stats);
+    std::vector<std::shared_ptr<Part>> keep;
+    int rc = 0;
+    for (int k = 0; k < K && !rc; ++k) {
+        std::shared_ptr<Part> p;
+        uint64_t h2d = 0;
+        rc = register_part_locked_free(ctx, ~0ull - static_cast<uint64_t>(k), files, p, &h2d, true, true, static_cast<size_t>(k), K);
+        if (rc) break;
+        keep.push_back(p);
+        out->stats.h2d_bytes += h2d;
+        Plan plan = base;
+        plan.parts = {p};
+        plan.total_blocks = static_cast<uint32_t>(p->dir.blocks.size());
+        rc = run_scan(ctx, q, plan, slot, slot.stream, tables.base + tl.total * static_cast<size_t>(k), tl, &out->stats, k, true);
+    }
+    if (!rc) {
+        launch_combine_tables(reinterpret_cast<uint64_t *>(tables.base), K, tl.total / 8, tl.off_sum_f64 / 8, tl.off_max_f64 / 8, tl.off_max_f64 / 8,
+                              tl.off_sum_i64 / 8, tl.off_sum_i64 / 8, tl.off_max_i64 / 8, tl.off_max_i64 / 8, tl.total / 8, slot.stream);
+        out->stats.kernel_launches += 1;
+        // the pinned staging of the last slices may still be in flight: finalize copies into it only after the kernels
+        rc = finalize_to_host(ctx, q, base, slot, slot.stream, tables.base, tl, out);
+    } else {
+        cudaStreamSynchronize(slot.stream);
+    }
+    for (int k = 0; k < static_cast<int>(keep.size()); ++k) {
+        int rc2 = collect_scan(slot, &out->stats, k);
+        if (!rc && rc2) {
+            bydb_result_free(ctx, out);
+            rc = rc2;
+        }
+    }
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (auto &p : keep) ctx->hbm_used -= p->hbm_bytes;
+    }
+    if (!rc) out->stats.h2d_bytes += out->stats.page_bytes;  // pages were read in place over PCIe
+    return rc;
+}
+
 int bydb_scan_agg_host(bydb_ctx *ctx, uint32_t n_parts, const bydb_part_files *parts, const bydb_query *q, bydb_result *out) {
     if (!ctx || !out) return fail(BYDB_EINVAL, "ctx/out is NULL");
     memset(out, 0, sizeof *out);
@@ -846,6 +912,7 @@ int bydb_scan_agg_host(bydb_ctx *ctx, uint32_t n_parts, const bydb_part_files *p
     if (rc) return rc;
     if (n_parts == 0 || !parts || n_parts > kMaxParts) return fail(BYDB_EINVAL, "need 1..64 host parts");
     CUDA_TRY(cudaSetDevice(ctx->device));
+    if (n_parts == 1 && (q->flags & BYDB_Q_HOST_ZERO_COPY)) return scan_agg_host_pipelined(ctx, &parts[0], q, out);
     std::vector<std::shared_ptr<Part>> tmp;
     uint64_t h2d = 0;
     for (uint32_t i = 0; i < n_parts; ++i) {

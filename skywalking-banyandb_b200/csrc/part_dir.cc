@@ -316,7 +316,7 @@ int parse_primary_block(ParseCtx &cx, const uint8_t *data, size_t len, std::vect
 }
 }  // namespace
 
-int build_part_dir(const std::vector<FileImage> &files, NameTable &names, PartDir &out, std::string &err) {
+int build_part_dir(const std::vector<FileImage> &files, NameTable &names, PartDir &out, std::string &err, size_t batch, size_t n_batches) {
     const FileImage *meta = find_file(files, "meta.bin");
     const FileImage *primary = find_file(files, "primary.bin");
     const FileImage *tsf = find_file(files, "timestamps.bin");
@@ -360,6 +360,11 @@ int build_part_dir(const std::vector<FileImage> &files, NameTable &names, PartDi
             }
     }
     // primary blocks are independent zstd frames: decompress + parse them on a few threads
+    if (n_batches > 1) {
+        const size_t all = pbms.size();
+        const size_t a = all * batch / n_batches, b = all * (batch + 1) / n_batches;
+        pbms = std::vector<Pbm>(pbms.begin() + static_cast<long>(a), pbms.begin() + static_cast<long>(b));
+    }
     const size_t np = pbms.size();
     unsigned hw = std::thread::hardware_concurrency();
     const size_t nt = std::max<size_t>(1, std::min<size_t>({np, hw ? hw : 4, size_t{16}}));

@@ -64,7 +64,9 @@ struct PartDir {
 };
 
 // Parses meta.bin / primary.bin / *.tfm.  Returns 0 or a negative BYDB_* code; err gets a message.
-int build_part_dir(const std::vector<FileImage> &files, NameTable &names, PartDir &out, std::string &err);
+// batch / n_batches: parse only that slice of the primary blocks (the cold host path pipelines the parsing of one
+// slice with the scan of the previous one); the default parses the whole part.
+int build_part_dir(const std::vector<FileImage> &files, NameTable &names, PartDir &out, std::string &err, size_t batch = 0, size_t n_batches = 1);
 
 // zstd frame decompression through the system libzstd (dlopen, no header in the image).
 int zstd_decompress(const uint8_t *src, size_t n, std::vector<uint8_t> &dst, std::string &err);
