@@ -256,7 +256,7 @@ struct AggCons {
     int mode;
     __device__ __forceinline__ void operator()(uint32_t row, int64_t v) {
         bool a = row >= r0 && row <= r1;
-        if (mode == kRowsMask) a = (mask[row >> 5] >> (row & 31)) & 1u;
+        if (mode == kRowsMask) a = row < kMaskWords * 32 && ((mask[row >> 5] >> (row & 31)) & 1u);
         if (a) acc.add(v);
     }
 };
@@ -578,7 +578,8 @@ __device__ __forceinline__ uint32_t fast_active_window(const WarpSmem *sm, uint3
         const uint32_t b = (r1 + 1u) < (row0 + n) ? (r1 + 1u > row0 ? r1 + 1u - row0 : 0u) : n;
         return a < b ? (low_bits(b) & ~low_bits(a)) : 0u;
     }
-    const uint32_t wi = row0 >> 5;
+    // a corrupt page can hold more varints than the block has rows: never index past the mask
+    const uint32_t wi = min(row0 >> 5, static_cast<uint32_t>(kMaskWords));
     const uint64_t m64 = static_cast<uint64_t>(sm->mask[wi]) | (static_cast<uint64_t>(sm->mask[wi + 1]) << 32);
     return static_cast<uint32_t>(m64 >> (row0 & 31)) & low_bits(n);
 }
@@ -1512,7 +1513,10 @@ __global__ void detect_overlap_kernel(const __grid_constant__ ScanParams p) {
 
 struct StoreCons {
     int64_t *out;
-    __device__ __forceinline__ void operator()(uint32_t row, int64_t v) { out[row] = v; }
+    uint32_t limit;  // rows of the block: a corrupt page may decode more values
+    __device__ __forceinline__ void operator()(uint32_t row, int64_t v) {
+        if (row < limit) out[row] = v;
+    }
 };
 
 // decodes one int64 list body (timestamps or versions) into out[0..count)
@@ -1528,6 +1532,7 @@ __device__ __forceinline__ bool decode_list_to(WarpSmem *sm, uint32_t &seq, cons
     }
     StoreCons sc;
     sc.out = out;
+    sc.limit = count;
     bool ok;
     if (enc == 3) ok = decode_varint_page<false>(sm, seq, body, len, count, first, sc, lane);
     else if (enc == 4) ok = decode_varint_page<true>(sm, seq, body, len, count, first, sc, lane);

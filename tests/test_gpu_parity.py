@@ -424,3 +424,64 @@ def test_large_property_checks(bydb, gpu_ctx):
     assert abs(a.val_f64[0, 5] - exact) <= 1e-9 * exact
     assert abs(g.val_f64[:, 5].sum() - exact) <= 1e-9 * exact
     gpu_ctx.release_part(h)
+
+
+def test_c3_shape_grouped_sum_top(bydb, gpu_ctx):
+    # BASELINE config 3 scaled down: GROUP BY service_id (100 services x 10 series) sum(latency) -> Top 10 desc
+    rng = np.random.default_rng(0xC3)
+    n_series, n_pts = 1000, 3000
+    sids, ts, ver = grid(n_series, n_pts, sid0=17, sid_step=3)
+    lat = np.round(rng.gamma(2.0, 12.0, sids.size), 2)
+    part = build_part(sids, ts, ver, [("latency", O.VT_FLOAT64, lat, None)])
+    usid = np.unique(sids)
+    groups = (np.arange(usid.size) // 10).astype(np.int32)
+    aggs = [("latency", O.AGG_SUM), ("latency", O.AGG_COUNT)]
+    oq = O.Query([part], usid, aggs, groups=groups, n_groups=100, top_n=10, top_desc=True, threads=4)
+    got, want = run_both(bydb, gpu_ctx, [part], oq, _next_pid())
+    assert_parity(got, want, aggs, "C3 shape")
+    assert got.stats.blocks_slow_lane == 0
+
+
+@pytest.mark.timeout(120)
+def test_corrupt_pages_fail_or_answer_but_never_hang(bydb, gpu_ctx):
+    # flipped / truncated page bytes must surface as an error code (or a wrong-but-terminating answer), never a hang or a crash
+    rng = np.random.default_rng(404)
+    sids, ts, ver = grid(6, 3000)
+    lat = np.round(rng.normal(20, 4, sids.size), 2)
+    wide = rng.integers(-(1 << 40), 1 << 40, sids.size)
+    region = [b"r%d" % v for v in rng.integers(0, 5, sids.size)]
+    part = build_part(sids, ts, ver, [("latency", O.VT_FLOAT64, lat, None), ("wide", O.VT_INT64, wide, None)],
+                      [("default", [("region", O.VT_STR, region, None)])])
+    files = part.files()
+    q_aggs = [("latency", O.AGG_SUM), ("wide", O.AGG_MAX)]
+    outcomes = {"ok": 0, "error": 0}
+    for trial in range(24):
+        bad = dict(files)
+        target = ["fv.bin", "default.tf", "timestamps.bin"][trial % 3]
+        buf = bytearray(bad[target])
+        if trial % 4 == 3:
+            buf = buf[: max(16, len(buf) // 2)]                     # truncation -> registration must refuse
+        else:
+            for pos in rng.integers(0, len(buf), 6):
+                buf[int(pos)] ^= int(rng.integers(1, 256))          # bit rot inside the pages
+        bad[target] = bytes(buf)
+        try:
+            h = gpu_ctx.register_part(_next_pid(), bad)
+        except bydb.BydbError:
+            outcomes["error"] += 1
+            continue
+        try:
+            gpu_ctx.scan_agg(bydb.Query([h], np.unique(sids), q_aggs, preds=[bydb.Pred("default", "region", bydb.OP_EQ, b"r2")]))
+            outcomes["ok"] += 1
+        except bydb.BydbError as e:
+            assert e.code in (-22, -95, -5)
+            outcomes["error"] += 1
+        finally:
+            gpu_ctx.release_part(h)
+    assert outcomes["error"] > 0
+    # the context is still healthy afterwards
+    h = gpu_ctx.register_part(_next_pid(), files)
+    got = gpu_ctx.scan_agg(bydb.Query([h], np.unique(sids), q_aggs))
+    want = O.run_query(O.Query([part], np.unique(sids), q_aggs))
+    assert_parity(got, want, q_aggs, "after corruption trials")
+    gpu_ctx.release_part(h)
