@@ -168,6 +168,11 @@ int bydb_part_register(bydb_ctx *ctx, uint64_t part_id, const bydb_part_files *f
 int bydb_part_release(bydb_ctx *ctx, bydb_part_h part);
 /* resident bytes / block / row counts of a registered part */
 int bydb_part_info(bydb_ctx *ctx, bydb_part_h part, uint64_t *hbm_bytes, uint64_t *n_blocks, uint64_t *n_rows);
+/* Fallback pages of a registered part -- EncodeTypePlain numeric pages (null cells, floats that are not short
+ * decimals; banyand/measure/column.go:147-153,203-208) and zstd-compressed string blocks (pkg/encoding/bytes.go:
+ * 291-304): `unpacked` were rewritten into scan-friendly pages in HBM when the part was registered, `left` could
+ * not be (a query that touches one of those returns BYDB_ENOTSUP). */
+int bydb_part_fallback_pages(bydb_ctx *ctx, bydb_part_h part, uint64_t *unpacked, uint64_t *left);
 
 /* Scan -> filter -> aggregate over parts already resident in HBM. */
 int bydb_scan_agg(bydb_ctx *ctx, const bydb_query *q, bydb_result *out);

@@ -76,7 +76,7 @@ class _Layout(C.Structure):
 
 
 # every symbol include/bydb_gpu.h declares (tests/test_capi_symbols.py checks the list against the header)
-EXPORTS = ["bydb_init", "bydb_shutdown", "bydb_part_register", "bydb_part_release", "bydb_part_info",
+EXPORTS = ["bydb_init", "bydb_shutdown", "bydb_part_register", "bydb_part_release", "bydb_part_info", "bydb_part_fallback_pages",
            "bydb_scan_agg", "bydb_scan_agg_host", "bydb_result_free", "bydb_partials_layout",
            "bydb_scan_partials", "bydb_partials_combine", "bydb_reduce_finalize", "bydb_last_error", "bydb_version"]
 
@@ -104,6 +104,7 @@ def load_library():
     L.bydb_part_register.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(_PartFiles), C.POINTER(C.c_uint64)]
     L.bydb_part_release.argtypes = [C.c_void_p, C.c_uint64]
     L.bydb_part_info.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.bydb_part_fallback_pages.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.bydb_scan_agg.argtypes = [C.c_void_p, C.POINTER(_Query), C.POINTER(_Result)]
     L.bydb_scan_agg_host.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_PartFiles), C.POINTER(_Query), C.POINTER(_Result)]
     L.bydb_result_free.argtypes = [C.c_void_p, C.POINTER(_Result)]
@@ -304,7 +305,9 @@ class Context:
     def part_info(self, handle: int) -> Dict[str, int]:
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         _check(self._L.bydb_part_info(self._h, handle, C.byref(a), C.byref(b), C.byref(c)))
-        return dict(hbm_bytes=a.value, n_blocks=b.value, n_rows=c.value)
+        u, l = C.c_uint64(), C.c_uint64()
+        _check(self._L.bydb_part_fallback_pages(self._h, handle, C.byref(u), C.byref(l)))
+        return dict(hbm_bytes=a.value, n_blocks=b.value, n_rows=c.value, fallback_unpacked=u.value, fallback_left=l.value)
 
     # ---- queries
     def scan_agg(self, q: Query) -> Result:

@@ -21,6 +21,7 @@ using namespace bydb;
 namespace {
 
 thread_local std::string g_last_error;
+thread_local uint32_t g_last_dev_err = 0;  // DevErr of the last failed scan on this thread (drives the lazy unpack retry)
 int fail(int code, const std::string &msg) {
     g_last_error = msg;
     return code;
@@ -39,6 +40,8 @@ struct Part {
     PartDir dir;
     uint8_t *d_arena = nullptr;       // all file images, each 256 B aligned and padded
     uint8_t *d_dir = nullptr;         // DevBlock[] | DevCol[] | file pointer table
+    uint8_t *d_unpack = nullptr;      // fallback pages rewritten at admission (unpack_kernels.cu); file slot `n_files`
+    uint64_t unpacked_pages = 0, unpack_skipped = 0;
     const DevBlock *d_blocks = nullptr;
     const DevCol *d_cols = nullptr;
     const uint8_t *const *d_files = nullptr;
@@ -49,9 +52,11 @@ struct Part {
         if (pool_stream) {
             if (d_arena) cudaFreeAsync(d_arena, pool_stream);
             if (d_dir) cudaFreeAsync(d_dir, pool_stream);
+            if (d_unpack) cudaFreeAsync(d_unpack, pool_stream);
         } else {
             if (d_arena) cudaFree(d_arena);
             if (d_dir) cudaFree(d_dir);
+            if (d_unpack) cudaFree(d_unpack);
         }
     }
 };
@@ -224,8 +229,10 @@ struct TableLayout {
 
 // zero_copy: the data files stay in (pinned, device-mapped) host memory and the kernels read the
 // pages they need straight over PCIe; only the block directory is uploaded.
+int unpack_fallback_pages(bydb_ctx *ctx, Part &part, size_t n_files, cudaStream_t s);
+
 int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_files *files, std::shared_ptr<Part> &out, uint64_t *h2d,
-                              bool zero_copy = false, bool transient = false, size_t batch = 0, size_t n_batches = 1) {
+                              bool zero_copy = false, bool transient = false, size_t batch = 0, size_t n_batches = 1, bool unpack = false) {
     if (!files || files->n_files == 0 || !files->files) return fail(BYDB_EINVAL, "no files");
     std::vector<FileImage> imgs;
     for (uint32_t i = 0; i < files->n_files; ++i) {
@@ -270,7 +277,7 @@ int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_f
         arena = 0;
     }
     const size_t nb = part->dir.blocks.size(), nc = part->dir.cols.size(), nf = order.size();
-    const size_t dir_bytes = align_up(nb * sizeof(DevBlock), 256) + align_up(nc * sizeof(DevCol), 256) + align_up(nf * sizeof(void *), 256);
+    const size_t dir_bytes = align_up(nb * sizeof(DevBlock), 256) + align_up(nc * sizeof(DevCol), 256) + align_up((nf + 1) * sizeof(void *), 256);
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         if (ctx->hbm_budget && ctx->hbm_used + arena + dir_bytes > ctx->hbm_budget) return fail(BYDB_ENOMEM, "HBM budget exceeded");
@@ -334,7 +341,74 @@ int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_f
             for (size_t i = 0; i < nf; ++i) *h2d += order[i]->len;
         *h2d += dir_bytes;
     }
+    if (unpack) {
+        const int rc = unpack_fallback_pages(ctx, *part, nf, s);
+        if (rc) {
+            undo_budget();
+            return rc;
+        }
+    }
     out = part;
+    return 0;
+}
+
+// Rewrites the part's fallback pages (EncodeTypePlain numeric pages, zstd-compressed string blocks) into a side
+// arena in HBM so the scan kernels never meet zstd or per-cell byte strings; see unpack_kernels.cu.
+int unpack_fallback_pages(bydb_ctx *ctx, Part &part, size_t n_files, cudaStream_t s) {
+    const size_t nb = part.dir.blocks.size(), nc = part.dir.cols.size();
+    if (nb == 0 || nc == 0) return 0;
+    if (n_files >= 255) return 0;
+    struct Tmp {
+        uint8_t *p = nullptr;
+        cudaStream_t s = nullptr;
+        ~Tmp() {
+            if (p) cudaFreeAsync(p, s);
+        }
+    } jobs, scratch;
+    jobs.s = scratch.s = s;
+    const size_t jobs_off = 256;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&jobs.p), jobs_off + nc * sizeof(UnpackJob), s));
+    CUDA_TRY(cudaMemsetAsync(jobs.p, 0, jobs_off, s));
+    UnpackParams up{};
+    up.blocks = part.d_blocks;
+    up.cols = const_cast<DevCol *>(part.d_cols);
+    up.files = part.d_files;
+    up.n_blocks = static_cast<uint32_t>(nb);
+    up.arena_file_id = static_cast<uint32_t>(n_files);
+    up.counters = reinterpret_cast<unsigned long long *>(jobs.p);
+    up.jobs = reinterpret_cast<UnpackJob *>(jobs.p + jobs_off);
+    up.max_jobs = nc;
+    launch_classify_pages(up, s);
+    unsigned long long cnt[5] = {0, 0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(cnt, jobs.p, sizeof cnt, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    part.unpack_skipped = cnt[3];
+    if (cnt[0] == 0) return 0;
+    const size_t arena = align_up(cnt[1] + 256, 256);
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ctx->hbm_budget && ctx->hbm_used + arena > ctx->hbm_budget) return fail(BYDB_ENOMEM, "HBM budget exceeded while unpacking fallback pages");
+        ctx->hbm_used += arena;
+    }
+    part.hbm_bytes += arena;
+    cudaError_t e = part.pool_stream ? cudaMallocAsync(reinterpret_cast<void **>(&part.d_unpack), arena, s)
+                                     : cudaMalloc(reinterpret_cast<void **>(&part.d_unpack), arena);
+    if (e != cudaSuccess) return fail(BYDB_ENOMEM, "device allocation failed for the unpack arena");
+    const int n_warps = static_cast<int>(std::min<unsigned long long>(cnt[0], 4ull * static_cast<unsigned long long>(ctx->sm_count)));
+    const int n_warps4 = (n_warps + 3) / 4 * 4;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&scratch.p), static_cast<size_t>(n_warps4) * unpack_scratch_stride(), s));
+    // publish the arena as one more file of the part
+    const uint8_t *ap = part.d_unpack;
+    CUDA_TRY(cudaMemcpyAsync(const_cast<uint8_t **>(reinterpret_cast<const uint8_t *const *>(part.d_files)) + n_files, &ap, sizeof ap,
+                             cudaMemcpyHostToDevice, s));
+    up.n_jobs = cnt[0];
+    up.arena = part.d_unpack;
+    up.scratch = scratch.p;
+    launch_unpack_pages(up, n_warps4, s);
+    CUDA_TRY(cudaMemcpyAsync(cnt, jobs.p, sizeof cnt, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    part.unpacked_pages = cnt[4];
+    part.unpack_skipped = cnt[3];
     return 0;
 }
 
@@ -566,6 +640,7 @@ int collect_scan(ExecSlot &slot, bydb_stats *stats, int batch = 0) {
         cudaEventElapsedTime(&ms, ev[0], ev[3]);
         stats->device_ms += ms;
     }
+    g_last_dev_err = hz[2];
     if (hz[2] != 0) {
         char buf[96];
         snprintf(buf, sizeof buf, " (block/series #%u)", hz[3]);
@@ -798,7 +873,7 @@ int bydb_part_register(bydb_ctx *ctx, uint64_t part_id, const bydb_part_files *f
     }
     CUDA_TRY(cudaSetDevice(ctx->device));
     std::shared_ptr<Part> part;
-    int rc = register_part_locked_free(ctx, part_id, files, part, nullptr);
+    int rc = register_part_locked_free(ctx, part_id, files, part, nullptr, false, false, 0, 1, true);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
     bydb_part_h h = ctx->next_handle++;
@@ -833,6 +908,16 @@ int bydb_part_info(bydb_ctx *ctx, bydb_part_h h, uint64_t *hbm_bytes, uint64_t *
     if (hbm_bytes) *hbm_bytes = it->second->hbm_bytes;
     if (n_blocks) *n_blocks = it->second->dir.blocks.size();
     if (n_rows) *n_rows = it->second->dir.total_rows;
+    return 0;
+}
+
+int bydb_part_fallback_pages(bydb_ctx *ctx, bydb_part_h h, uint64_t *unpacked, uint64_t *left) {
+    if (!ctx) return fail(BYDB_EINVAL, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->parts.find(h);
+    if (it == ctx->parts.end()) return fail(BYDB_ENOENT, "unknown part handle");
+    if (unpacked) *unpacked = it->second->unpacked_pages;
+    if (left) *left = it->second->unpack_skipped;
     return 0;
 }
 
@@ -912,20 +997,35 @@ int bydb_scan_agg_host(bydb_ctx *ctx, uint32_t n_parts, const bydb_part_files *p
     if (rc) return rc;
     if (n_parts == 0 || !parts || n_parts > kMaxParts) return fail(BYDB_EINVAL, "need 1..64 host parts");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    if (n_parts == 1 && (q->flags & BYDB_Q_HOST_ZERO_COPY)) return scan_agg_host_pipelined(ctx, &parts[0], q, out);
-    std::vector<std::shared_ptr<Part>> tmp;
-    uint64_t h2d = 0;
-    for (uint32_t i = 0; i < n_parts; ++i) {
-        std::shared_ptr<Part> p;
-        rc = register_part_locked_free(ctx, ~0ull - i, &parts[i], p, &h2d, (q->flags & BYDB_Q_HOST_ZERO_COPY) != 0, true);
-        if (rc) break;
-        tmp.push_back(p);
+    // The cold path first scans the pages as they are; only when a block turns out to hold fallback pages
+    // (EncodeTypePlain numeric pages, zstd string blocks) are the parts unpacked on the device and scanned again.
+    auto wants_unpack = [](int code) {
+        return code == BYDB_ENOTSUP && (g_last_dev_err == kErrPlainPage || g_last_dev_err == kErrZstdDict || g_last_dev_err == kErrTagPlain);
+    };
+    g_last_dev_err = 0;
+    if (n_parts == 1 && (q->flags & BYDB_Q_HOST_ZERO_COPY)) {
+        rc = scan_agg_host_pipelined(ctx, &parts[0], q, out);
+        if (!wants_unpack(rc)) return rc;
     }
-    if (!rc) rc = scan_agg_impl(ctx, q, &tmp, out, h2d);
-    if (!rc && (q->flags & BYDB_Q_HOST_ZERO_COPY)) out->stats.h2d_bytes += out->stats.page_bytes;  // pages were read in place over PCIe
-    {
-        std::lock_guard<std::mutex> lk(ctx->mu);
-        for (auto &p : tmp) ctx->hbm_used -= p->hbm_bytes;
+    for (int attempt = rc ? 1 : 0; attempt < 2; ++attempt) {
+        std::vector<std::shared_ptr<Part>> tmp;
+        uint64_t h2d = 0;
+        rc = 0;
+        g_last_dev_err = 0;
+        memset(out, 0, sizeof *out);
+        for (uint32_t i = 0; i < n_parts; ++i) {
+            std::shared_ptr<Part> p;
+            rc = register_part_locked_free(ctx, ~0ull - i, &parts[i], p, &h2d, (q->flags & BYDB_Q_HOST_ZERO_COPY) != 0, true, 0, 1, attempt == 1);
+            if (rc) break;
+            tmp.push_back(p);
+        }
+        if (!rc) rc = scan_agg_impl(ctx, q, &tmp, out, h2d);
+        if (!rc && (q->flags & BYDB_Q_HOST_ZERO_COPY)) out->stats.h2d_bytes += out->stats.page_bytes;  // pages were read in place over PCIe
+        {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            for (auto &p : tmp) ctx->hbm_used -= p->hbm_bytes;
+        }
+        if (!wants_unpack(rc)) break;
     }
     return rc;
 }

@@ -723,6 +723,140 @@ __device__ __forceinline__ uint64_t load_be64_unaligned(const uint8_t *p) {
     return u;
 }
 
+// compressBlock header (bytes.go:291-350): type 0 = [len u8], kBlockRawLong = [len u32 LE] (a zstd frame inflated
+// at part admission, unpack_kernels.cu); a type-1 frame that was not inflated surfaces as `zstd_err`.
+// Leaves p at the payload and checks that `len` bytes are there.
+__device__ __forceinline__ uint32_t read_cblock_header(const uint8_t *&p, const uint8_t *end, uint32_t &len, uint32_t zstd_err) {
+    if (end - p < 2) return kErrCorrupt;
+    const uint8_t t = __ldg(p++);
+    if (t == 1) return zstd_err;
+    if (t == 0) {
+        len = __ldg(p++);
+    } else if (t == kBlockRawLong) {
+        if (end - p < 4) return kErrCorrupt;
+        len = __ldg(p) | (__ldg(p + 1) << 8) | (__ldg(p + 2) << 16) | (static_cast<uint32_t>(__ldg(p + 3)) << 24);
+        p += 4;
+    } else {
+        return kErrCorrupt;
+    }
+    if (static_cast<uint64_t>(end - p) < len) return kErrCorrupt;
+    return kErrNone;
+}
+
+// Plain (high-cardinality) string tag page -> mask: a bytes block of `count` cells (bytes.go:45-127), cell i is
+// lens[i]-1 bytes long, 0 = nil.  page points just after the 0x09 type byte.
+__device__ __noinline__ uint32_t apply_plain_pred(WarpSmem *sm, const DevPred &pr, const uint8_t *page, uint32_t size, uint32_t count, int lane) {
+    const uint8_t *p = page;
+    const uint8_t *end = page + size;
+    uint32_t llen = 0, dlen = 0;
+    uint32_t berr = read_cblock_header(p, end, llen, kErrTagPlain);
+    if (berr != kErrNone) return berr;
+    if (llen < 1) return kErrCorrupt;
+    const uint8_t wt = __ldg(p);
+    if (wt > 3) return kErrCorrupt;
+    const uint32_t width = 1u << wt;
+    if (llen != 1 + static_cast<uint64_t>(count) * width) return kErrCorrupt;
+    const uint8_t *lens = p + 1;
+    p += llen;
+    berr = read_cblock_header(p, end, dlen, kErrTagPlain);
+    if (berr != kErrNone) return berr;
+    const uint8_t *data = p;
+    if (p + dlen != end) return kErrCorrupt;  // bytes.go:121-123
+    uint64_t off_carry = 0;
+    bool bad = false;
+    for (uint32_t base = 0; base < count; base += 32) {
+        const uint32_t r = base + lane;
+        uint64_t L = 0;
+        if (r < count)
+            for (uint32_t i = 0; i < width; ++i) L = (L << 8) | __ldg(lens + static_cast<size_t>(r) * width + i);
+        const bool have = L > 0;
+        const uint64_t vlen = have ? L - 1 : 0;
+        uint64_t incl = vlen;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint64_t o = shfl_up_u64(incl, s);
+            if (lane >= s) incl += o;
+        }
+        const uint64_t off = off_carry + incl - vlen;
+        off_carry += shfl_u64(incl, 31);
+        bool pass = true;
+        if (r < count) {
+            int cmp = 0;
+            if (have && off + vlen > dlen) {
+                bad = true;
+            } else if (have) {
+                const uint32_t ml = vlen < pr.lit_len ? static_cast<uint32_t>(vlen) : pr.lit_len;
+                for (uint32_t i = 0; i < ml && cmp == 0; ++i) {
+                    const int a = __ldg(data + off + i), b = pr.lit[i];
+                    cmp = a < b ? -1 : (a > b ? 1 : 0);
+                }
+                if (cmp == 0) cmp = vlen < pr.lit_len ? -1 : (vlen > pr.lit_len ? 1 : 0);
+            }
+            pass = cmp_op(pr.op, have, cmp);
+        }
+        const uint32_t keep = __ballot_sync(0xffffffffu, pass);
+        if (lane == 0 && (base >> 5) < kMaskWords) sm->mask[base >> 5] &= keep;
+    }
+    if (__any_sync(0xffffffffu, bad) || off_carry != dlen) return kErrCorrupt;
+    return kErrNone;
+}
+
+// Raw-cell numeric page (kEncRawCells, written by unpack_kernels.cu from an EncodeTypePlain fallback page):
+// [0x40][has_nulls][6 pad][count x u64 LE][count x u8 valid].  Null cells are skipped (aggregation.go:292-294).
+// Floats are arbitrary doubles here (not short decimals), so they are folded in double: each lane its rows in
+// order, then a fixed xor tree -- deterministic, within 1e-9 relative of the reference's sequential sum.
+// The float result travels in the AggAcc as bit patterns: lo = sum, mn / mx = extremes.
+constexpr int kExpRawFloat = INT32_MIN;
+__device__ __noinline__ uint32_t agg_raw_page(const uint8_t *page, uint32_t size, bool is_float, int mode, uint32_t count, uint32_t r0, uint32_t r1,
+                                              const uint32_t *mask, AggAcc &out, int lane) {
+    if (size < 8 + 9ull * count || (reinterpret_cast<uintptr_t>(page) & 7)) return kErrCorrupt;
+    const bool nulls = __ldg(page + 1) != 0;
+    const unsigned long long *vals = reinterpret_cast<const unsigned long long *>(page + 8);
+    const uint8_t *valid = page + 8 + 8ull * count;
+    AggAcc acc;
+    acc.init();
+    double fs = 0.0, fmn = 1.7976931348623157e308, fmx = -1.7976931348623157e308;  // function.go MIN/MAX sentinels
+    const uint32_t lo = mode == kRowsMask ? 0 : r0, hi = mode == kRowsMask ? count - 1 : r1;
+    for (uint32_t r = lo + lane; r <= hi && r < count; r += 32) {
+        bool a = true;
+        if (mode == kRowsMask) a = r < kMaskWords * 32 && ((mask[r >> 5] >> (r & 31)) & 1u);
+        if (a && nulls) a = __ldg(valid + r) != 0;
+        if (!a) continue;
+        const unsigned long long u = __ldg(vals + r);
+        if (is_float) {
+            const double v = __longlong_as_double(static_cast<long long>(u));
+            fs += v;
+            fmn = v < fmn ? v : fmn;
+            fmx = v > fmx ? v : fmx;
+            acc.cnt++;
+        } else {
+            acc.add(static_cast<int64_t>(u));
+        }
+    }
+    if (is_float) {
+        uint32_t cnt = acc.cnt;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const double os = __longlong_as_double(static_cast<long long>(shfl_xor_u64(static_cast<uint64_t>(__double_as_longlong(fs)), m)));
+            const double omn = __longlong_as_double(static_cast<long long>(shfl_xor_u64(static_cast<uint64_t>(__double_as_longlong(fmn)), m)));
+            const double omx = __longlong_as_double(static_cast<long long>(shfl_xor_u64(static_cast<uint64_t>(__double_as_longlong(fmx)), m)));
+            // lanes pair up symmetrically: add in a fixed (lower lane first) order so both partners get the same bits
+            fs = (lane & m) ? os + fs : fs + os;
+            fmn = omn < fmn ? omn : fmn;
+            fmx = omx > fmx ? omx : fmx;
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, m);
+        }
+        acc.cnt = cnt;
+        acc.lo = static_cast<uint64_t>(__double_as_longlong(fs));
+        acc.mn = __double_as_longlong(fmn);
+        acc.mx = __double_as_longlong(fmx);
+    } else {
+        acc.warp_reduce();
+    }
+    out = acc;
+    return kErrNone;
+}
+
 // Dictionary tag page -> mask (pkg/encoding/dictionary.go:69-114, bytes.go:45-127, writer.go/reader.go).
 // page points just after the 0x0A type byte.  Returns a DevErr.
 __device__ __noinline__ uint32_t apply_dict_pred(WarpSmem *sm, const DevPred &pr, const uint8_t *page, uint32_t size, uint32_t count, int lane) {
@@ -731,12 +865,10 @@ __device__ __noinline__ uint32_t apply_dict_pred(WarpSmem *sm, const DevPred &pr
     uint64_t nvals;
     if (!read_varuint_seq(p, end, nvals) || nvals == 0 || nvals > 256) return kErrCorrupt;
     // lens block: compressBlock(encodeUint64List(len+1 | 0 for nil))
-    if (end - p < 2) return kErrCorrupt;
-    uint8_t t = __ldg(p++);
-    if (t == 1) return kErrZstdDict;
-    if (t != 0) return kErrCorrupt;
-    uint32_t llen = __ldg(p++);
-    if (static_cast<uint32_t>(end - p) < llen || llen < 1) return kErrCorrupt;
+    uint32_t llen = 0;
+    uint32_t berr = read_cblock_header(p, end, llen, kErrZstdDict);
+    if (berr != kErrNone) return berr;
+    if (llen < 1) return kErrCorrupt;
     const uint8_t wt = __ldg(p);
     if (wt > 3) return kErrCorrupt;
     const uint32_t width = 1u << wt;
@@ -744,12 +876,9 @@ __device__ __noinline__ uint32_t apply_dict_pred(WarpSmem *sm, const DevPred &pr
     const uint8_t *lens = p + 1;
     p += llen;
     // data block
-    if (end - p < 2) return kErrCorrupt;
-    t = __ldg(p++);
-    if (t == 1) return kErrZstdDict;
-    if (t != 0) return kErrCorrupt;
-    uint32_t dlen = __ldg(p++);
-    if (static_cast<uint32_t>(end - p) < dlen) return kErrCorrupt;
+    uint32_t dlen = 0;
+    berr = read_cblock_header(p, end, dlen, kErrZstdDict);
+    if (berr != kErrNone) return berr;
     const uint8_t *data = p;
     p += dlen;
     // ---- match set over the dictionary values
@@ -1110,7 +1239,12 @@ __device__ __forceinline__ uint32_t agg_field_page(WarpSmem *sm, uint32_t &seq, 
                                                    uint32_t count, uint32_t r0, uint32_t r1, AggAcc &out, int &exp_out, int lane) {
     if (size < 1) return kErrCorrupt;
     const uint32_t enc = __ldg(page);
-    if (enc == 9) return kErrPlainPage;  // EncodeTypePlain fallback page (column.go:147-153,203-208)
+    if (enc == kEncRawCells) {
+        if (kFastLane) return kDeferSlow;  // keeps the fast lane's register budget for the varint decoders
+        exp_out = is_float ? kExpRawFloat : 0;
+        return agg_raw_page(page, size, is_float, kMode, count, r0, r1, sm->mask, out, lane);
+    }
+    if (enc == 9) return kErrPlainPage;  // EncodeTypePlain fallback page that was not unpacked at admission
     const uint32_t hdr = is_float ? 11u : 9u;
     if (size < hdr) return kErrCorrupt;
     exp_out = 0;
@@ -1293,6 +1427,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
                     if (pr.value_type == BYDB_VT_INT64) {
                         if (col.value_type != BYDB_VT_INT64) {
                             err = kErrPredType;
+                        } else if (enc == kEncRawCells && kFastLane) {
+                            defer = true;
+                            defer_why |= 2u;
+                        } else if (enc == kEncRawCells) {
+                            if (col.size < 8 + 9ull * count || (reinterpret_cast<uintptr_t>(page) & 7)) {
+                                err = kErrCorrupt;
+                            } else {
+                                const bool nulls = __ldg(page + 1) != 0;
+                                const long long *vals = reinterpret_cast<const long long *>(page + 8);
+                                const uint8_t *valid = page + 8 + 8ull * count;
+                                for (uint32_t row = lane; row < count; row += 32) {
+                                    const bool have = !nulls || __ldg(valid + row) != 0;
+                                    const int64_t v = __ldg(vals + row);
+                                    const int c = v < pr.lit_i64 ? -1 : (v > pr.lit_i64 ? 1 : 0);
+                                    if (!cmp_op(pr.op, have, c)) atomicAnd(&sm->mask[row >> 5], ~(1u << (row & 31)));
+                                }
+                            }
                         } else if (enc == 9) {
                             err = kErrPlainPage;
                         } else if (col.size < 9) {
@@ -1332,7 +1483,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
                         }
                     } else {
                         if (col.value_type != BYDB_VT_STR && col.value_type != BYDB_VT_BINARY) err = kErrPredType;
-                        else if (enc == 9) err = kErrTagPlain;
+                        else if (enc == 9 && kFastLane) defer = true, defer_why |= 2u;
+                        else if (enc == 9) err = apply_plain_pred(sm, pr, page + 1, col.size - 1, count, lane);
                         else if (enc != 10) err = kErrBadEnc;
                         else err = apply_dict_pred(sm, pr, page + 1, col.size - 1, count, lane);
                         err = __reduce_max_sync(0xffffffffu, err);
@@ -1380,10 +1532,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
                     if (need == 0) {
                         // COUNT only: numeric pages hold no nulls (a null forces the Plain fallback page), so the
                         // count is the number of surviving rows and the page body is never read
-                        if (col.size < 1) e2 = kErrCorrupt;
-                        else if (__ldg(page) == 9) e2 = kErrPlainPage;
                         acc.cnt = rows;
                         page_bytes += 1;
+                        if (col.size < 2) {
+                            e2 = kErrCorrupt;
+                        } else if (__ldg(page) == 9) {
+                            e2 = kErrPlainPage;
+                        } else if (__ldg(page) == kEncRawCells && __ldg(page + 1) && kFastLane) {
+                            e2 = kDeferSlow;
+                        } else if (__ldg(page) == kEncRawCells && __ldg(page + 1)) {
+                            // a page with null cells: COUNT skips them (aggregation.go:292-294)
+                            const int mode = use_mask ? kRowsMask : kRowsRange;
+                            e2 = agg_raw_page(page, col.size, false, mode, count, r0, r1, sm->mask, acc, lane);
+                            acc.lo = 0;
+                            acc.hi = 0;
+                            page_bytes += count;
+                        }
                     } else {
                         page_bytes += col.size;
                         if (use_mask) e2 = agg_field_page<kRowsMask, kFastLane>(sm, seq, page, col.size, is_float, need, count, r0, r1, acc, exp, lane);
@@ -1399,7 +1563,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
                     if (err == kErrNone) err = e2;
                     if (err == kErrNone && !defer && acc.cnt > 0) {
                         bp.cnt = acc.cnt;
-                        if (is_float) {
+                        if (is_float && exp == kExpRawFloat) {
+                            bp.sum.f = __longlong_as_double(static_cast<long long>(acc.lo));
+                            bp.mn.f = __longlong_as_double(acc.mn);
+                            bp.mx.f = __longlong_as_double(acc.mx);
+                        } else if (is_float) {
                             // block sum in the exact decimal-integer domain, converted once
                             double s;
                             if (acc.hi == (static_cast<int64_t>(acc.lo) >> 63)) s = __ll2double_rn(static_cast<int64_t>(acc.lo));

@@ -157,6 +157,33 @@ void launch_select_rows(const SelectParams &p, cudaStream_t s);
 void launch_combine_tables(uint64_t *tables, uint32_t n_tables, uint64_t words, uint64_t sum_f64_lo, uint64_t sum_f64_hi, uint64_t max_f64_lo,
                            uint64_t max_f64_hi, uint64_t sum_i64_lo, uint64_t sum_i64_hi, uint64_t max_i64_lo, uint64_t max_i64_hi, cudaStream_t s);
 
+// ---- fallback-page normalisation at part admission (unpack_kernels.cu)
+constexpr uint8_t kEncRawCells = 0x40;   // numeric page rewritten as [0x40][has_nulls][6 pad][n x u64 LE][n x u8 valid]
+constexpr uint8_t kBlockRawLong = 2;     // compressBlock rewritten as [2][u32 LE len][bytes] (an inflated zstd frame)
+constexpr uint32_t kUnpackNumeric = 1, kUnpackString = 2;
+struct UnpackJob {
+    uint64_t out_off;   // into the unpack arena
+    uint32_t col;       // index into the part's DevCol table
+    uint32_t rows;
+    uint32_t out_cap;
+    uint32_t kind;
+};
+struct UnpackParams {
+    const DevBlock *blocks;
+    DevCol *cols;                   // rewritten in place for the pages that were unpacked
+    const uint8_t *const *files;
+    uint32_t n_blocks;
+    uint32_t arena_file_id;         // slot of the unpack arena in the part's file table
+    UnpackJob *jobs;
+    unsigned long long max_jobs, n_jobs;
+    unsigned long long *counters;   // [0] jobs found [1] arena bytes [2] cursor [3] pages left as they are [4] pages unpacked
+    uint8_t *arena;
+    uint8_t *scratch;               // n_warps * unpack_scratch_stride()
+};
+size_t unpack_scratch_stride();
+void launch_classify_pages(const UnpackParams &p, cudaStream_t s);
+void launch_unpack_pages(const UnpackParams &p, int n_warps, cudaStream_t s);
+
 size_t scan_smem_bytes();
 void launch_plan_blocks(const ScanParams &p, cudaStream_t s);
 void launch_scan_blocks(const ScanParams &p, int grid_fast, int grid_slow, cudaStream_t s);

@@ -256,17 +256,109 @@ def test_empty_and_missing(bydb, gpu_ctx):
         assert_parity(got, want, aggs, "empty/missing")
 
 
-def test_unsupported_pages_fail_loudly_not_silently(bydb, gpu_ctx):
-    # null cells force the EncodeTypePlain fallback page (column.go:147-153): the device path must refuse
-    sids, ts, ver = grid(2, 300)
-    nulls = np.zeros(sids.size, dtype=np.uint8)
-    nulls[5] = 1
-    part = build_part(sids, ts, ver, [("calls", O.VT_INT64, np.arange(sids.size), nulls)])
+def _fallback_part(rng, n_series=5, n_pts=8193 + 700):
+    """Every fallback shape of banyand/measure/column.go in one part: null cells (147-153, 192-195), floats that are
+    not short decimals (203-208), few distinct values (dictionary inside the Plain page) and many (plain bytes block
+    whose >= 128 B blocks are zstd frames, pkg/encoding/bytes.go:291-304)."""
+    sids, ts, ver = grid(n_series, n_pts)
+    n = sids.size
+    calls = rng.integers(-10**12, 10**12, n)
+    calls_null = (rng.random(n) < 0.1).astype(np.uint8)
+    lat = rng.random(n) * 1e3 + rng.random(n) * 1e-7            # 16-17 significant digits, mixed exponents
+    lat_null = (rng.random(n) < 0.05).astype(np.uint8)
+    raw = rng.standard_normal(n) * 1e6                           # no nulls, just not decimal
+    few = rng.choice(np.array([0.1 + 0.2, np.pi, -1e-300, 5e300, 2.0 / 3.0]), n)
+    few_null = (rng.random(n) < 0.3).astype(np.uint8)
+    few[sids == sids[0]] = np.e                                  # one value + nulls in the first series' blocks
+    code = rng.integers(0, 50, n)
+    code_null = (rng.random(n) < 0.05).astype(np.uint8)
+    svc = [b"service-name-%03d" % v for v in rng.integers(0, 60, n)]          # 60 x 16 B values: zstd data block
+    wide = [b"w%04d" % v for v in rng.integers(0, 200, n)]                     # 200 values: zstd lens + data blocks
+    trace = [None if i % 97 == 0 else b"trace-%08d" % (i * 7919 % 100003) for i in range(n)]   # > 256 values: plain page
+    part = build_part(sids, ts, ver,
+                      [("calls", O.VT_INT64, calls, calls_null), ("latency", O.VT_FLOAT64, lat, lat_null),
+                       ("raw", O.VT_FLOAT64, raw, None), ("few", O.VT_FLOAT64, few, few_null)],
+                      [("default", [("code", O.VT_INT64, code, code_null), ("svc", O.VT_STR, svc, None), ("wide", O.VT_STR, wide, None),
+                                    ("trace", O.VT_STR, trace, None)])])
+    return part, sids, ts
+
+
+FALLBACK_AGGS = [("calls", O.AGG_SUM), ("calls", O.AGG_COUNT), ("calls", O.AGG_MIN), ("calls", O.AGG_MAX), ("calls", O.AGG_MEAN),
+                 ("latency", O.AGG_SUM), ("latency", O.AGG_COUNT), ("latency", O.AGG_MIN), ("latency", O.AGG_MAX), ("latency", O.AGG_MEAN),
+                 ("raw", O.AGG_SUM), ("raw", O.AGG_MIN), ("raw", O.AGG_MAX), ("few", O.AGG_COUNT), ("few", O.AGG_MAX), ("few", O.AGG_MIN)]
+
+
+def _assert_parity_abs(got, want, aggs, ctx):
+    """assert_parity, except that float sums of mixed-sign data are compared against the magnitude of the terms."""
+    sum_like = [a for a, (f, fn) in enumerate(aggs) if want.is_float[a] and fn in (O.AGG_SUM, O.AGG_MEAN)]
+    keep = [a for a in range(len(aggs)) if a not in sum_like]
+    sub = lambda r, idx: type("R", (), dict(group_id=r.group_id, rows=r.rows, is_float=r.is_float[idx], val_i64=r.val_i64[:, idx],
+                                            val_f64=r.val_f64[:, idx]))
+    assert_parity(sub(got, keep), sub(want, keep), [aggs[a] for a in keep], ctx)
+    for a in sum_like:
+        g, w = got.val_f64[:, a], want.val_f64[:, a]
+        assert (np.abs(g - w) <= 1e-9 * np.maximum(np.abs(w), 1e6)).all(), f"{ctx}: float agg {a} {aggs[a]}: {g} vs {w}"
+
+
+def test_fallback_numeric_pages_nulls_and_non_decimal_floats(bydb, gpu_ctx):
+    rng = np.random.default_rng(41)
+    part, sids, ts = _fallback_part(rng)
+    usid = np.unique(sids)
     h = gpu_ctx.register_part(_next_pid(), part.files())
-    with pytest.raises(bydb.BydbError) as ei:
-        gpu_ctx.scan_agg(bydb.Query([h], np.unique(sids), [("calls", O.AGG_SUM)]))
-    assert ei.value.code == -95
+    info = gpu_ctx.part_info(h)
+    assert info["fallback_unpacked"] >= 4 * 2 * usid.size and info["fallback_left"] == 0, info
     gpu_ctx.release_part(h)
+    groups = (np.arange(usid.size) % 2).astype(np.int32)
+    for kw in (dict(), dict(tmin=T0 + 100 * STEP, tmax=T0 + 8500 * STEP), dict(groups=groups, n_groups=2),
+               dict(preds=[O.Pred("default", "code", O.OP_LT, 25)]),
+               dict(preds=[O.Pred("default", "code", O.OP_NE, 7)], tmin=T0 + 8000 * STEP, tmax=T0 + 8400 * STEP, groups=groups, n_groups=2)):
+        oq = O.Query([part], usid, FALLBACK_AGGS, **kw)
+        got, want = run_both(bydb, gpu_ctx, [part], oq, _next_pid())
+        _assert_parity_abs(got, want, FALLBACK_AGGS, f"fallback/{sorted(kw)}")
+    # Top-N over a float sum of raw cells, and a group whose only column is all-null in range
+    oq = O.Query([part], usid, [("raw", O.AGG_MAX), ("few", O.AGG_COUNT)], groups=np.arange(usid.size, dtype=np.int32), n_groups=usid.size,
+                 top_n=3, top_agg=0, top_desc=True)
+    got, want = run_both(bydb, gpu_ctx, [part], oq, _next_pid())
+    assert_parity(got, want, oq.aggs, "fallback/top")
+
+
+def test_fallback_string_pages_zstd_dictionary_and_plain(bydb, gpu_ctx):
+    rng = np.random.default_rng(43)
+    part, sids, ts = _fallback_part(rng, n_series=4)
+    usid = np.unique(sids)
+    aggs = [("calls", O.AGG_COUNT), ("raw", O.AGG_MAX), ("latency", O.AGG_MIN)]
+    for preds in ([O.Pred("default", "svc", O.OP_EQ, b"service-name-017")], [O.Pred("default", "svc", O.OP_GE, b"service-name-040")],
+                  [O.Pred("default", "wide", O.OP_NE, b"w0100")], [O.Pred("default", "wide", O.OP_LT, b"w0050"), O.Pred("default", "svc", O.OP_GT, b"service-name-010")],
+                  [O.Pred("default", "trace", O.OP_EQ, b"trace-%08d" % (5 * 7919 % 100003))], [O.Pred("default", "trace", O.OP_GT, b"trace-00050000")],
+                  [O.Pred("default", "trace", O.OP_NE, b"trace-00000000")], [O.Pred("default", "trace", O.OP_LE, b"trace-0001")],
+                  [O.Pred("default", "trace", O.OP_LT, b"trace-00070000"), O.Pred("default", "code", O.OP_GE, 10)]):
+        oq = O.Query([part], usid, aggs, groups=(np.arange(usid.size) % 2).astype(np.int32), n_groups=2, preds=preds)
+        got, want = run_both(bydb, gpu_ctx, [part], oq, _next_pid())
+        assert_parity(got, want, aggs, f"fallback-str/{[(p.tag, p.op, p.value) for p in preds]}")
+
+
+def test_fallback_pages_on_the_cold_host_path(bydb, gpu_ctx):
+    # bydb_scan_agg_host scans the pages as they are and only unpacks (then rescans) when it meets a fallback page
+    import torch
+    rng = np.random.default_rng(47)
+    part, sids, ts = _fallback_part(rng, n_series=3, n_pts=9000)
+    usid = np.unique(sids)
+    aggs = [("latency", O.AGG_MEAN), ("calls", O.AGG_MAX), ("few", O.AGG_COUNT)]
+    oq = O.Query([part], usid, aggs, preds=[O.Pred("default", "svc", O.OP_LE, b"service-name-030")])
+    want = O.run_query(oq)
+    files = {k: np.frombuffer(v, dtype=np.uint8) for k, v in part.files().items()}
+    q = bydb.Query([], usid, aggs, preds=[bydb.Pred("default", "svc", O.OP_LE, b"service-name-030")])
+    got = gpu_ctx.scan_agg_host([files], q)
+    _assert_parity_abs(got, want, aggs, "fallback/host staged")
+    keep, pinned = [], {}
+    for k, v in files.items():
+        t = torch.empty(v.size + 256, dtype=torch.uint8, pin_memory=True)
+        t[:v.size].copy_(torch.from_numpy(v.copy()))
+        keep.append(t)
+        pinned[k] = t[:v.size].numpy()
+    q.flags = 1
+    got = gpu_ctx.scan_agg_host([pinned], q)
+    _assert_parity_abs(got, want, aggs, "fallback/host zero-copy")
 
 
 def test_version_dedup_across_overlapping_parts(bydb, gpu_ctx):
