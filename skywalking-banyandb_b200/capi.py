@@ -253,6 +253,24 @@ def _mk_query(q: Query, keep: list) -> _Query:
     return cq
 
 
+class PreparedQuery:
+    """A Query marshalled once into the C struct (with everything it points at kept alive): repeated calls skip
+    the per-call ctypes work.  Context methods take a Query or a PreparedQuery."""
+
+    def __init__(self, q: Query):
+        self.query = q
+        self._keep: list = []
+        self.c = _mk_query(q, self._keep)
+
+
+def _cq(q):
+    """-> (ctypes struct, keepalive) for a Query or a PreparedQuery."""
+    if isinstance(q, PreparedQuery):
+        return q.c, q
+    keep: list = []
+    return _mk_query(q, keep), keep
+
+
 def _read_result(r: _Result) -> Result:
     n, a = r.n_rows, r.n_aggs
 
@@ -310,9 +328,11 @@ class Context:
         return dict(hbm_bytes=a.value, n_blocks=b.value, n_rows=c.value, fallback_unpacked=u.value, fallback_left=l.value)
 
     # ---- queries
-    def scan_agg(self, q: Query) -> Result:
-        keep: list = []
-        cq = _mk_query(q, keep)
+    def prepare(self, q: Query) -> PreparedQuery:
+        return PreparedQuery(q)
+
+    def scan_agg(self, q) -> Result:
+        cq, keep = _cq(q)
         r = _Result()
         _check(self._L.bydb_scan_agg(self._h, C.byref(cq), C.byref(r)))
         try:
@@ -341,21 +361,23 @@ class Context:
         _check(self._L.bydb_partials_layout(C.byref(cq), C.byref(lay)))
         return {k: getattr(lay, k) for k, _ in _Layout._fields_}
 
-    def scan_partials(self, q: Query, d_ptr: int, nbytes: int, stream: int = 0) -> Stats:
-        keep: list = []
-        cq = _mk_query(q, keep)
+    def scan_partials(self, q, d_ptr: int, nbytes: int, stream: int = 0, want_stats: bool = True) -> Optional[Stats]:
+        """want_stats=False is the asynchronous form: returns as soon as the scan is enqueued on `stream`; failures
+        surface in reduce_finalize (they travel in the table)."""
+        cq, keep = _cq(q)
+        if not want_stats:
+            _check(self._L.bydb_scan_partials(self._h, C.byref(cq), d_ptr, nbytes, stream or None, None))
+            return None
         st = _Stats()
         _check(self._L.bydb_scan_partials(self._h, C.byref(cq), d_ptr, nbytes, stream or None, C.byref(st)))
         return Stats.of(st)
 
-    def partials_combine(self, q: Query, d_ptr: int, n_tables: int, bytes_each: int, stream: int = 0) -> None:
-        keep: list = []
-        cq = _mk_query(q, keep)
+    def partials_combine(self, q, d_ptr: int, n_tables: int, bytes_each: int, stream: int = 0) -> None:
+        cq, keep = _cq(q)
         _check(self._L.bydb_partials_combine(self._h, C.byref(cq), d_ptr, n_tables, bytes_each, stream or None))
 
-    def reduce_finalize(self, q: Query, d_ptr: int, nbytes: int, stream: int = 0) -> Result:
-        keep: list = []
-        cq = _mk_query(q, keep)
+    def reduce_finalize(self, q, d_ptr: int, nbytes: int, stream: int = 0) -> Result:
+        cq, keep = _cq(q)
         r = _Result()
         _check(self._L.bydb_reduce_finalize(self._h, C.byref(cq), d_ptr, nbytes, stream or None, C.byref(r)))
         try:

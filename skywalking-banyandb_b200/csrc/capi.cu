@@ -69,6 +69,12 @@ struct ExecSlot {
     uint8_t *pinned = nullptr;
     size_t pinned_bytes = 0;
     uint8_t *zpage = nullptr;  // 256 B pinned: read-back of the per-query zero page (errors + counters)
+    cudaEvent_t busy = nullptr;  // recorded by a call that returned before its work finished (asynchronous scan_partials)
+    bool busy_pending = false;
+    void wait_idle() {
+        if (busy_pending) cudaEventSynchronize(busy);
+        busy_pending = false;
+    }
     int ensure_pinned(size_t n) {
         if (n <= pinned_bytes) return 0;
         if (pinned) cudaFreeHost(pinned);
@@ -111,12 +117,16 @@ struct SlotLease {
         }
     }
     int init() {
-        if (slot) return 0;
+        if (slot) {
+            slot->wait_idle();  // its pinned staging may still feed an asynchronous call's copies
+            return 0;
+        }
         slot.reset(new ExecSlot());
         if (cudaStreamCreateWithFlags(&slot->stream, cudaStreamNonBlocking) != cudaSuccess) return -1;
         for (auto &e : slot->ev)
             if (cudaEventCreate(&e) != cudaSuccess) return -1;
         if (cudaMallocHost(reinterpret_cast<void **>(&slot->zpage), 256 * ExecSlot::kMaxBatches) != cudaSuccess) return -1;
+        if (cudaEventCreateWithFlags(&slot->busy, cudaEventDisableTiming) != cudaSuccess) return -1;
         return 0;
     }
     ~SlotLease() {
@@ -650,7 +660,7 @@ int collect_scan(ExecSlot &slot, bydb_stats *stats, int batch = 0) {
 }
 
 int finalize_to_host(bydb_ctx *ctx, const bydb_query *q, const Plan &plan, ExecSlot &slot, cudaStream_t stream, const uint8_t *d_table,
-                     const TableLayout &tl, bydb_result *out) {
+                     const TableLayout &tl, bydb_result *out, bool check_inband_status = false) {
     const size_t F = plan.fcols.size();
     const int32_t G = plan.n_groups;
     const size_t A = q->n_aggs;
@@ -693,6 +703,7 @@ int finalize_to_host(bydb_ctx *ctx, const bydb_query *q, const Plan &plan, ExecS
     fp.out_i64 = reinterpret_cast<int64_t *>(d + o_vi);
     fp.out_f64 = reinterpret_cast<double *>(d + o_vf);
     fp.out_is_float = d + o_isf;
+    fp.err_out = reinterpret_cast<uint32_t *>(d + o_cnt + 8);
     launch_finalize(fp, stream);
     // output rows are chosen and ordered on the device (stable compaction, or Top-N)
     SelectParams sp;
@@ -725,6 +736,12 @@ int finalize_to_host(bydb_ctx *ctx, const bydb_query *q, const Plan &plan, ExecS
     CUDA_TRY(cudaGetLastError());
     out->stats.d2h_bytes += out_bytes;
     out->stats.kernel_launches += 2;
+    if (check_inband_status) {
+        // the table came from bydb_scan_partials (possibly asynchronous, possibly another rank's): its status is in the table
+        const uint32_t e = *reinterpret_cast<const uint32_t *>(h + (o_cnt - o_out) + 8);
+        g_last_dev_err = e;
+        if (e != 0) return fail(dev_err_code(e), std::string(dev_err_text(e)) + " (status carried in a partial table)");
+    }
     const size_t R = std::min<size_t>(*reinterpret_cast<const uint32_t *>(h + (o_cnt - o_out)), cap);
     auto owner = new ResultOwner();
     const int32_t *sg = reinterpret_cast<const int32_t *>(h + (o_sg - o_out));
@@ -1068,10 +1085,17 @@ int bydb_scan_partials(bydb_ctx *ctx, const bydb_query *q, void *d_partials, uin
     CUDA_TRY(cudaSetDevice(ctx->device));
     SlotLease lease(ctx);
     if (lease.init()) return fail(BYDB_EIO, "cannot create stream");
-    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : lease.slot->stream;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);  // NULL = the legacy default stream, like every partial-table call
     bydb_stats local;
     memset(&local, 0, sizeof local);
     rc = run_scan(ctx, q, plan, *lease.slot, s, static_cast<uint8_t *>(d_partials), tl, &local);
+    if (!rc && !stats) {
+        // asynchronous form: nothing is read back here.  A device-side failure travels in the table (coltype words)
+        // and surfaces in bydb_reduce_finalize on whichever rank finalises.
+        CUDA_TRY(cudaEventRecord(lease.slot->busy, s));
+        lease.slot->busy_pending = true;
+        return 0;
+    }
     if (!rc) {
         CUDA_TRY(cudaStreamSynchronize(s));
         CUDA_TRY(cudaGetLastError());
@@ -1111,8 +1135,8 @@ int bydb_reduce_finalize(bydb_ctx *ctx, const bydb_query *q, const void *d_parti
     CUDA_TRY(cudaSetDevice(ctx->device));
     SlotLease lease(ctx);
     if (lease.init()) return fail(BYDB_EIO, "cannot create stream");
-    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : lease.slot->stream;
-    return finalize_to_host(ctx, q, plan, *lease.slot, s, static_cast<const uint8_t *>(d_partials), tl, out);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);  // NULL = the legacy default stream, like every partial-table call
+    return finalize_to_host(ctx, q, plan, *lease.slot, s, static_cast<const uint8_t *>(d_partials), tl, out, true);
 }
 
 }  // extern "C"

@@ -1953,7 +1953,9 @@ __global__ void __launch_bounds__(256) group_reduce_kernel(const __grid_constant
             p.sum_i64[o] = (have && !is_float) ? t.sum.i : 0;
             p.max_i64[o] = (have && !is_float) ? t.mx.i : INT64_MIN;
             p.notmin_i64[o] = (have && !is_float) ? ~t.mn.i : INT64_MIN;
-            if (g == 0) p.coltype[c] = p.col_type[c];
+            // the scan's status rides in the table (bits 8..): an asynchronous bydb_scan_partials has no other way
+            // to tell the rank that finalises that one of its blocks failed
+            if (g == 0) p.coltype[c] = static_cast<int64_t>(p.col_type[c]) | (static_cast<int64_t>(p.err[0]) << 8);
         }
     }
 }
@@ -1963,14 +1965,20 @@ __global__ void finalize_kernel(const __grid_constant__ FinalizeParams p) {
     const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g == 0) {
         for (uint32_t a = 0; a < p.n_aggs; ++a)
-            p.out_is_float[a] = (p.agg_func[a] != BYDB_AGG_COUNT && p.coltype[p.agg_fcol[a]] == BYDB_VT_FLOAT64) ? 1 : 0;
+            p.out_is_float[a] = (p.agg_func[a] != BYDB_AGG_COUNT && (p.coltype[p.agg_fcol[a]] & 0xff) == BYDB_VT_FLOAT64) ? 1 : 0;
+        uint32_t e = 0;
+        for (uint32_t c = 0; c < p.n_fcols; ++c) {
+            const uint32_t ec = static_cast<uint32_t>(p.coltype[c] >> 8);
+            e = ec > e ? ec : e;
+        }
+        if (p.err_out) *p.err_out = e;
     }
     if (g >= p.n_groups) return;
     for (uint32_t a = 0; a < p.n_aggs; ++a) {
         const uint32_t c = p.agg_fcol[a];
         const size_t o = static_cast<size_t>(g) * p.n_fcols + c;
         const size_t oo = static_cast<size_t>(g) * p.n_aggs + a;
-        const int64_t typ = p.coltype[c];
+        const int64_t typ = p.coltype[c] & 0xff;
         const int64_t cnt = p.cnt[o];
         int64_t vi = 0;
         double vf = 0.0;

@@ -132,6 +132,7 @@ struct FinalizeParams {
     int64_t *out_i64;             // [n_groups * n_aggs]
     double *out_f64;              // [n_groups * n_aggs]
     uint8_t *out_is_float;        // [n_aggs]
+    uint32_t *err_out;            // DevErr carried in the table's coltype words (0 = none); may be NULL
 };
 
 // output row selection on the device: stable compaction of the groups that appeared, or Top-N

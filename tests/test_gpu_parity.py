@@ -577,3 +577,52 @@ def test_corrupt_pages_fail_or_answer_but_never_hang(bydb, gpu_ctx):
     want = O.run_query(O.Query([part], np.unique(sids), q_aggs))
     assert_parity(got, want, q_aggs, "after corruption trials")
     gpu_ctx.release_part(h)
+
+
+def test_partial_tables_async_scan_combine_finalize(bydb, gpu_ctx):
+    # the multi-GPU reduce on one device: two "ranks" = two series-disjoint parts, each scanned into its own partial table
+    # (one synchronously with statistics, one asynchronously), rank-ordered combine, finalisation.  Same answer as one query.
+    import torch
+    rng = np.random.default_rng(61)
+    parts, all_sids = [], []
+    for r in range(2):
+        sids, ts, ver = grid(40, 700, sid0=1 + 1000 * r)
+        lat = np.round(rng.gamma(2.0, 15.0, sids.size), 2)
+        calls = rng.integers(-500, 500, sids.size)
+        region = [b"r%d" % v for v in rng.integers(0, 4, sids.size)]
+        parts.append(build_part(sids, ts, ver, [("latency", O.VT_FLOAT64, lat, None), ("calls", O.VT_INT64, calls, None)],
+                                [("default", [("region", O.VT_STR, region, None)])]))
+        all_sids.append(np.unique(sids))
+    usid = np.concatenate(all_sids)
+    groups = (np.arange(usid.size) % 7).astype(np.int32)
+    aggs = [("latency", O.AGG_MEAN), ("latency", O.AGG_MIN), ("calls", O.AGG_SUM), ("calls", O.AGG_MAX), ("calls", O.AGG_COUNT)]
+    preds = [O.Pred("default", "region", O.OP_NE, b"r1")]
+    want = O.run_query(O.Query(parts, usid, aggs, groups=groups, n_groups=7, preds=preds, tmin=T0 + 10 * STEP, tmax=T0 + 650 * STEP))
+    handles = [gpu_ctx.register_part(_next_pid(), p.files()) for p in parts]
+    stream = torch.cuda.current_stream().cuda_stream
+    try:
+        def q_of(hs, preds_):
+            return bydb.Query(hs, usid, aggs, series_group=groups, n_groups=7, tmin=T0 + 10 * STEP, tmax=T0 + 650 * STEP,
+                              preds=[bydb.Pred(p.family, p.tag, p.op, p.value) for p in preds_])
+        lay = gpu_ctx.partials_layout(q_of([handles[0]], preds))
+        words = lay["total_bytes"] // 8
+        tables = torch.zeros(2 * words, dtype=torch.float64, device="cuda")
+        st = gpu_ctx.scan_partials(q_of([handles[0]], preds), tables.data_ptr(), lay["total_bytes"], stream)
+        assert st.rows_scanned > 0
+        pq1 = gpu_ctx.prepare(q_of([handles[1]], preds))
+        assert gpu_ctx.scan_partials(pq1, tables.data_ptr() + lay["total_bytes"], lay["total_bytes"], stream, want_stats=False) is None
+        qf = q_of([], preds)
+        gpu_ctx.partials_combine(qf, tables.data_ptr(), 2, lay["total_bytes"], stream)
+        got = gpu_ctx.reduce_finalize(qf, tables.data_ptr(), lay["total_bytes"], stream)
+        assert_parity(got, want, aggs, "partials/async")
+        # a device-side failure of an asynchronous scan travels in the table and fails the finalisation
+        bad = [O.Pred("default", "region", O.OP_EQ, 5)]            # int64 literal against a string tag
+        assert gpu_ctx.scan_partials(q_of([handles[1]], bad), tables.data_ptr(), lay["total_bytes"], stream, want_stats=False) is None
+        with pytest.raises(bydb.BydbError) as ei:
+            gpu_ctx.reduce_finalize(q_of([], bad), tables.data_ptr(), lay["total_bytes"], stream)
+        assert ei.value.code == -22
+        with pytest.raises(bydb.BydbError):                          # the synchronous form reports it itself
+            gpu_ctx.scan_partials(q_of([handles[1]], bad), tables.data_ptr(), lay["total_bytes"], stream)
+    finally:
+        for h in handles:
+            gpu_ctx.release_part(h)
