@@ -60,6 +60,16 @@ def load_pkg():
     return ge.load_package()
 
 
+def traffic_from_profile():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one scan_blocks launch of this query, from the committed
+    ncu --set full capture (profiles/traffic.json names it); None when there is none."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def make_part(pkg, n_series, n_points, sid0, seed):
     from importlib import import_module
     S = import_module("bydb_b200.synth")
@@ -203,7 +213,11 @@ def main():
     sid0 = 1 + rank * n_series
     img = make_part(pkg, n_series, n_points, sid0, 0xB200 + rank)
     files = img.files()
+    t_reg = time.perf_counter()
     h = ctx.register_part(1 + rank, files)
+    admission = {"register_ms": (time.perf_counter() - t_reg) * 1e3, **ctx.part_info(h),
+                 "note": "one-time per part: upload to HBM, host parse of the block index, device unpack of the fallback pages "
+                         "(the `uniform` field is full-precision float64 = zstd-compressed EncodeTypePlain pages)"}
     # the query names every series of the job: ranks only hold their own (series-disjoint parts)
     sids = np.arange(1, world * n_series + 1, dtype=np.uint64)
     q = query_of(pkg, [h], sids, n_points)
@@ -355,11 +369,30 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": int(rows_step * B_ALG), "kernel_ms": scan_ms,
                 "encoded_page_bytes_per_launch": int(page_bytes), "encoded_GBps": page_bytes / (scan_ms * 1e-3) / 1e9,
-                "traffic": None, "kernel_timing": kernel_timing}
+                "traffic": traffic_from_profile(), "kernel_timing": kernel_timing}
     out = {"metric": "measure datapoints scanned+aggregated/sec", "value": value, "unit": "datapoints/s", "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": cfg, "datapoints_per_step": total_rows_step, "device_ms_per_step": dev_ms,
            "scan_kernel_ms": scan_ms, "blocks_slow_lane": int(stats_acc[-1].blocks_slow_lane), "slow_lane_reasons": int(stats_acc[-1].slow_lane_reasons), "roofline": roofline, "clocks": clocks, "gpu_launches": launches, "e2e": e2e}
+    out["part_admission"] = admission
+    if world == 1:
+        # the fallback (zstd) field is reported separately -- same predicate and range over `uniform`
+        qf = pkg.Query(parts=[h], series_ids=sids, aggs=[("uniform", pkg.AGG_MEAN), ("uniform", pkg.AGG_MAX)], tmin=q.tmin, tmax=q.tmax,
+                       preds=[pkg.Pred("default", "region", pkg.OP_EQ, b"r3")])
+        pqf = ctx.prepare(qf)
+        for _ in range(3):
+            rf = ctx.scan_agg(pqf)
+        barrier()
+        t0 = time.perf_counter()
+        nf = max(3, min(args.steps, 10))
+        for _ in range(nf):
+            rf = ctx.scan_agg(pqf)
+        barrier()
+        df = (time.perf_counter() - t0) / nf
+        out["fallback_field_query"] = {"query": "mean(uniform), max(uniform), same range and predicate", "ms_per_step": df * 1e3,
+                                       "value": rf.stats.rows_scanned / df, "unit": "datapoints/s", "scan_kernel_ms": rf.stats.scan_kernel_ms,
+                                       "blocks_slow_lane": int(rf.stats.blocks_slow_lane), "mean": float(rf.val_f64[0, 0]), "max": float(rf.val_f64[0, 1]),
+                                       "note": "raw-cell pages written at admission (unpack_kernels.cu), scanned by the general lane"}
     if world > 1:
         out["host_phase_ms_per_step_rank0"] = {k: v / args.steps * 1e3 for k, v in phase_timed.items()}
     if last is not None:

@@ -15,7 +15,7 @@ echo "== bench (reference arm)"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>>$OUT/${TAG}_bench.err | tee $OUT/${TAG}_bench_ref.json
 if [ "$2" != "noprof" ]; then
 echo "== ncu launch list"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/${TAG}_launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > $OUT/${TAG}_ncu_launches.log 2>&1
 tail -3 $OUT/${TAG}_ncu_launches.log
 echo "== ncu full capture of scan_blocks_kernel"
