@@ -404,7 +404,7 @@ int unpack_fallback_pages(bydb_ctx *ctx, Part &part, size_t n_files, cudaStream_
     cudaError_t e = part.pool_stream ? cudaMallocAsync(reinterpret_cast<void **>(&part.d_unpack), arena, s)
                                      : cudaMalloc(reinterpret_cast<void **>(&part.d_unpack), arena);
     if (e != cudaSuccess) return fail(BYDB_ENOMEM, "device allocation failed for the unpack arena");
-    const int n_warps = static_cast<int>(std::min<unsigned long long>(cnt[0], 4ull * static_cast<unsigned long long>(ctx->sm_count)));
+    const int n_warps = static_cast<int>(std::min<unsigned long long>(cnt[0], 8ull * static_cast<unsigned long long>(ctx->sm_count)));
     const int n_warps4 = (n_warps + 3) / 4 * 4;
     CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&scratch.p), static_cast<size_t>(n_warps4) * unpack_scratch_stride(), s));
     // publish the arena as one more file of the part

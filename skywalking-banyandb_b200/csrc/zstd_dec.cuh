@@ -81,23 +81,111 @@ struct FwdBits {  // forward, LSB first (FSE table descriptions)
     BYDB_HD const uint8_t *byte_pos() const { return p - (nb >> 3); }  // first unread whole byte
 };
 
+// (BYDB_ZSTD_ALIGNED_IO compiles the device flavour of the two helpers below for the host, so the CPU tests cover it.)
+// little-endian 64-bit load from any address.  Device: two aligned loads and a funnel shift (reads up to 15 bytes past
+// p+8 inside the same pair of aligned words -- every buffer handed to the decoder carries >= 16 bytes of readable slack);
+// host: a plain unaligned load.
+BYDB_HD inline uint64_t load64_le(const uint8_t *p) {
+#if defined(__CUDA_ARCH__) || defined(BYDB_ZSTD_ALIGNED_IO)
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint64_t *w = reinterpret_cast<const uint64_t *>(a & ~static_cast<uintptr_t>(7));
+    const int sh = static_cast<int>(a & 7) * 8;
+    const uint64_t lo = w[0];
+    if (sh == 0) return lo;
+    return (lo >> sh) | (w[1] << (64 - sh));
+#else
+    uint64_t v;
+    __builtin_memcpy(&v, p, 8);
+    return v;
+#endif
+}
+
+// copies n bytes, regions must not overlap; device version moves 8 bytes at a time through aligned words
+BYDB_HD inline void copy_bytes(uint8_t *d, const uint8_t *s, int64_t n) {
+#if defined(__CUDA_ARCH__) || defined(BYDB_ZSTD_ALIGNED_IO)
+    while (n > 0 && (reinterpret_cast<uintptr_t>(d) & 7)) {
+        *d++ = *s++;
+        --n;
+    }
+    if (n >= 8) {
+        const int sh = static_cast<int>(reinterpret_cast<uintptr_t>(s) & 7) * 8;
+        const uint64_t *sp = reinterpret_cast<const uint64_t *>(s - (sh >> 3));
+        uint64_t *dp = reinterpret_cast<uint64_t *>(d);
+        const int64_t words = n >> 3;
+        if (sh == 0) {
+            for (int64_t i = 0; i < words; ++i) dp[i] = sp[i];
+        } else {
+            uint64_t lo = sp[0];
+            for (int64_t i = 0; i < words; ++i) {
+                const uint64_t hi = sp[i + 1];
+                dp[i] = (lo >> sh) | (hi << (64 - sh));
+                lo = hi;
+            }
+        }
+        d += words << 3;
+        s += words << 3;
+        n &= 7;
+    }
+    while (n > 0) {
+        *d++ = *s++;
+        --n;
+    }
+#else
+    __builtin_memcpy(d, s, static_cast<size_t>(n));
+#endif
+}
+
+// LZ77 match copy: dst[i] = dst[i - offset], forward, may overlap itself
+BYDB_HD inline void copy_match(uint8_t *d, int64_t offset, int64_t n) {
+    if (offset >= 16) {
+        while (n > 0) {  // pieces of at most `offset` bytes never overlap their source
+            const int64_t c = n < offset ? n : offset;
+            copy_bytes(d, d - offset, c);
+            d += c;
+            n -= c;
+        }
+    } else {
+        for (int64_t k = 0; k < n; ++k) d[k] = d[k - offset];
+    }
+}
+
 struct BackBits {  // backward: starts at the last byte, below its highest set bit
     const uint8_t *start;
+    int64_t len;
     int64_t bitpos;  // number of unread bits
-    BYDB_HD int init(const uint8_t *s, int64_t len) {
+    uint64_t win;    // stream bits [wbit, wbit + 64)
+    int64_t wbit;
+    BYDB_HD int init(const uint8_t *s, int64_t n) {
         start = s;
-        if (len <= 0) return kErrTrunc;
-        uint8_t last = s[len - 1];
+        len = n;
+        win = 0;
+        wbit = static_cast<int64_t>(1) << 60;  // no window yet
+        if (n <= 0) return kErrTrunc;
+        uint8_t last = s[n - 1];
         if (last == 0) return kErrCorrupt;
         int hb = 7;
         while (!((last >> hb) & 1)) --hb;
-        bitpos = (len - 1) * 8 + hb;
+        bitpos = (n - 1) * 8 + hb;
         return kOk;
     }
     // reads n bits (n <= 32); bits below the start of the stream read as zero (allowed at the end)
     BYDB_HD uint32_t read(int n) {
         if (n == 0) return 0;
+        const int64_t old = bitpos;
         bitpos -= n;
+        const uint64_t mask = (1ull << n) - 1ull;
+        if (bitpos >= wbit) return static_cast<uint32_t>((win >> (bitpos - wbit)) & mask);  // window top >= old by construction
+        if (bitpos >= 0 && len >= 8) {
+            // slide the window so that its top byte is the one holding bit old-1: at least 57 fresh bits
+            int64_t wb = ((old + 7) >> 3) - 8;
+            if (wb < 0) wb = 0;
+            win = load64_le(start + wb);
+            wbit = wb << 3;
+            return static_cast<uint32_t>((win >> (bitpos - wbit)) & mask);
+        }
+        return read_slow(n);
+    }
+    BYDB_HD uint32_t read_slow(int n) {  // bitpos already moved
         uint64_t v = 0;
         int64_t bp = bitpos;
         int got = 0;
@@ -332,15 +420,62 @@ BYDB_HD inline int huf_decode_stream(const Workspace *ws, const uint8_t *src, in
     int rc = bb.init(src, len);
     if (rc) return rc;
     const int log = ws->huf_log;
+    const uint32_t smask = (1u << log) - 1;
     uint32_t state = bb.read(log);
     for (int64_t i = 0; i < n; ++i) {
         const uint16_t e = ws->huf[state];
         dst[i] = static_cast<uint8_t>(e & 0xff);
         const int nb = e >> 8;
-        state = ((state << nb) & ((1u << log) - 1)) | bb.read(nb);
+        state = ((state << nb) & smask) | bb.read(nb);
     }
     // all bits must be consumed: after the last symbol the reader sits `log` bits before the stream start
     if (bb.bitpos != -static_cast<int64_t>(log)) return kErrCorrupt;
+    return kOk;
+}
+
+// the four streams of a literals section decoded in lock step: four independent dependency chains in one thread
+// (table look-up -> bit count -> next state) hide each other's latency -- that is what the format's 4 streams are for
+BYDB_HD inline int huf_decode_4streams(const Workspace *ws, const uint8_t *s0, int64_t l0, const uint8_t *s1, int64_t l1, const uint8_t *s2, int64_t l2,
+                                       const uint8_t *s3, int64_t l3, uint8_t *dst, int64_t per, int64_t last) {
+    BackBits b0, b1, b2, b3;
+    int rc = b0.init(s0, l0);
+    if (!rc) rc = b1.init(s1, l1);
+    if (!rc) rc = b2.init(s2, l2);
+    if (!rc) rc = b3.init(s3, l3);
+    if (rc) return rc;
+    const int log = ws->huf_log;
+    const uint32_t smask = (1u << log) - 1;
+    const uint16_t *tab = ws->huf;
+    uint32_t t0 = b0.read(log), t1 = b1.read(log), t2 = b2.read(log), t3 = b3.read(log);
+    uint8_t *d0 = dst, *d1 = dst + per, *d2 = dst + 2 * per, *d3 = dst + 3 * per;
+    const int64_t common = last < per ? last : per;
+    for (int64_t i = 0; i < common; ++i) {
+        const uint16_t e0 = tab[t0], e1 = tab[t1], e2 = tab[t2], e3 = tab[t3];
+        d0[i] = static_cast<uint8_t>(e0);
+        d1[i] = static_cast<uint8_t>(e1);
+        d2[i] = static_cast<uint8_t>(e2);
+        d3[i] = static_cast<uint8_t>(e3);
+        t0 = ((t0 << (e0 >> 8)) & smask) | b0.read(e0 >> 8);
+        t1 = ((t1 << (e1 >> 8)) & smask) | b1.read(e1 >> 8);
+        t2 = ((t2 << (e2 >> 8)) & smask) | b2.read(e2 >> 8);
+        t3 = ((t3 << (e3 >> 8)) & smask) | b3.read(e3 >> 8);
+    }
+    for (int64_t i = common; i < per; ++i) {  // the last stream is the short one
+        const uint16_t e0 = tab[t0], e1 = tab[t1], e2 = tab[t2];
+        d0[i] = static_cast<uint8_t>(e0);
+        d1[i] = static_cast<uint8_t>(e1);
+        d2[i] = static_cast<uint8_t>(e2);
+        t0 = ((t0 << (e0 >> 8)) & smask) | b0.read(e0 >> 8);
+        t1 = ((t1 << (e1 >> 8)) & smask) | b1.read(e1 >> 8);
+        t2 = ((t2 << (e2 >> 8)) & smask) | b2.read(e2 >> 8);
+    }
+    for (int64_t i = common; i < last; ++i) {  // (not reachable for conforming frames: last <= per)
+        const uint16_t e3 = tab[t3];
+        d3[i] = static_cast<uint8_t>(e3);
+        t3 = ((t3 << (e3 >> 8)) & smask) | b3.read(e3 >> 8);
+    }
+    const int64_t endpos = -static_cast<int64_t>(log);
+    if (b0.bitpos != endpos || b1.bitpos != endpos || b2.bitpos != endpos || b3.bitpos != endpos) return kErrCorrupt;
     return kOk;
 }
 
@@ -445,10 +580,8 @@ BYDB_HD inline int64_t decode_block(Workspace *ws, const uint8_t *src, int64_t l
             const int64_t per = (regen + 3) / 4;
             const int64_t last = regen - 3 * per;
             if (last < 0) return kErrCorrupt;
-            int rc = huf_decode_stream(ws, ls, s1, lit, per);
-            if (!rc) rc = huf_decode_stream(ws, ls + s1, s2, lit + per, per);
-            if (!rc) rc = huf_decode_stream(ws, ls + s1 + s2, s3, lit + 2 * per, per);
-            if (!rc) rc = huf_decode_stream(ws, ls + s1 + s2 + s3, s4, lit + 3 * per, last);
+            if (s1 < 1 || s2 < 1 || s3 < 1) return kErrCorrupt;
+            const int rc = huf_decode_4streams(ws, ls, s1, ls + s1, s2, ls + s1 + s2, s3, ls + s1 + s2 + s3, s4, lit, per, last);
             if (rc) return rc;
         }
         literals = lit;
@@ -542,18 +675,18 @@ BYDB_HD inline int64_t decode_block(Workspace *ws, const uint8_t *src, int64_t l
             // execute
             if (lpos + llen > regen) return kErrCorrupt;
             if (dpos + llen + mlen > dcap) return kErrDstFull;
-            for (int64_t k = 0; k < llen; ++k) dst[dpos + k] = literals[lpos + k];
+            copy_bytes(dst + dpos, literals + lpos, llen);
             dpos += llen;
             lpos += llen;
             if (static_cast<int64_t>(offset) > dpos) return kErrCorrupt;
-            for (int64_t k = 0; k < mlen; ++k) dst[dpos + k] = dst[dpos + k - static_cast<int64_t>(offset)];
+            copy_match(dst + dpos, static_cast<int64_t>(offset), mlen);
             dpos += mlen;
         }
         if (bb.bitpos != 0) return kErrCorrupt;
     }
     const int64_t rest = regen - lpos;
     if (dpos + rest > dcap) return kErrDstFull;
-    for (int64_t k = 0; k < rest; ++k) dst[dpos + k] = literals[lpos + k];
+    copy_bytes(dst + dpos, literals + lpos, rest);
     return dpos + rest;
 }
 
@@ -601,7 +734,7 @@ BYDB_HD inline int64_t decode_frame(Workspace *ws, const uint8_t *src, int64_t l
         if (type == 0) {
             if (len < pos + bsize) return kErrTrunc;
             if (dpos + bsize > dcap) return kErrDstFull;
-            for (int64_t k = 0; k < bsize; ++k) dst[dpos + k] = src[pos + k];
+            copy_bytes(dst + dpos, src + pos, bsize);
             dpos += bsize;
             pos += bsize;
         } else if (type == 1) {

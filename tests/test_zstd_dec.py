@@ -14,12 +14,13 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def shim(tmp_path_factory):
+@pytest.fixture(scope="module", params=["host-io", "device-io"])
+def shim(tmp_path_factory, request):
     if shutil.which("g++") is None:
         pytest.skip("no g++")
-    out = tmp_path_factory.mktemp("zstd") / "zstd_shim.so"
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "skywalking-banyandb_b200", "csrc"),
+    out = tmp_path_factory.mktemp("zstd") / ("zstd_shim_%s.so" % request.param)
+    flags = ["-DBYDB_ZSTD_ALIGNED_IO"] if request.param == "device-io" else []
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", *flags, "-I", os.path.join(ROOT, "skywalking-banyandb_b200", "csrc"),
                            "-o", str(out), os.path.join(ROOT, "tests", "native", "zstd_dec_shim.cc")])
     lib = C.CDLL(str(out))
     lib.zstd_dec_host.restype = C.c_longlong
