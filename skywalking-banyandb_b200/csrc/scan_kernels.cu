@@ -123,7 +123,8 @@ __device__ __forceinline__ void stream_release(const PageStream &s, WarpSmem *sm
 // helpers
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t msb4(uint32_t x) {  // gathers the 4 byte-MSBs of x into bits 0..3
-    return (((x >> 7) & 0x01010101u) * 0x01020408u) >> 24 & 0xfu;
+    // bit 8j+7 times 2^(21-7j) lands on bit 28+j; no two partial products share a bit, so nothing carries
+    return ((x & 0x80808080u) * 0x00204081u) >> 28;
 }
 __device__ __forceinline__ int64_t zigzag64(uint64_t u) { return static_cast<int64_t>(u >> 1) ^ -static_cast<int64_t>(u & 1); }
 
@@ -476,43 +477,59 @@ constexpr uint32_t kFastChunkBytes = 32 * kFastLaneBytes;  // 1 KB per warp iter
 
 __device__ __forceinline__ uint32_t low_bits(uint32_t n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
 
-template <bool kFull, int kNeed>
-__device__ __forceinline__ void fast_lane_decode(const uint4 &wa, const uint4 &wb, uint32_t valid, uint32_t term, uint32_t aw, uint32_t &accv,
-                                                 uint32_t &sh, int32_t &P, int32_t &sumP, int32_t &minP, int32_t &maxP) {
+// 32-bit multiply-add that stays a multiply-add: IMAD runs on the FMA pipe, which this integer kernel otherwise
+// leaves idle while LOP3/SHF/SEL/IADD3 saturate the ALU pipe (ncu r01h: alu 82 %, fma 17 %).  Written as inline PTX
+// so that neither the front end nor ptxas turns a multiply by a 0/1 flag back into logic ops.
+__device__ __forceinline__ uint32_t imad_u32(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int32_t imad_s32(int32_t a, int32_t b, int32_t c) {
+    int32_t d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// Interior chunk (all 32 bytes valid): the per-byte state machine with its selects, masks and shifts rewritten as
+// multiply-adds by 0/1 flags so that the work splits about evenly between the ALU and the FMA pipe.
+//   accv += b * mul                (mul = 128^k inside a varint, back to 1 after its terminator)
+//   v     = h - s * accv           (zig-zag: accv = 2h + s)
+//   P    += v * t ; sumP += P * (t & active)
+// kMasked: the chunk holds bytes outside the page (first / last chunk): `reset` = term | ~valid restarts the varint
+// state at those bytes too, their payload is zeroed by the caller, and only real terminators (term) count as rows.
+template <int kNeed, bool kMasked>
+__device__ __forceinline__ void fast_lane_decode_imad(const uint4 &wa, const uint4 &wb, uint32_t term, uint32_t reset, uint32_t aw, uint32_t &accv,
+                                                      uint32_t &sh, int32_t &P, int32_t &sumP, int32_t &minP, int32_t &maxP) {
     // 8 words x 4 bytes: the word loop stays rolled so that the body (the hottest code of the whole
-    // path) is ~70 instructions and stays resident in the instruction caches of every scheduler
+    // path) stays resident in the instruction caches of every scheduler
     uint32_t w0 = wa.x, w1 = wa.y, w2 = wa.z, w3 = wa.w, w4 = wb.x, w5 = wb.y, w6 = wb.z, w7 = wb.w;
-    uint32_t vm = valid, tm = term;
-#pragma unroll 1
+    uint32_t tm = term, rm = reset;
+    uint32_t mul = 1u << sh;
+#pragma unroll 2
     for (int q8 = 0; q8 < 8; ++q8) {
+        const uint32_t p = w0 & 0x7f7f7f7fu;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            // branch-free on purpose: every lane executes the same straight-line code and the
-            // per-terminator work is applied through masks (a divergent `if` costs more here)
-            const uint32_t b = (w0 >> (8 * j)) & 0x7fu;
-            if (kFull) {
-                accv |= b << sh;
-                sh += 7;
-            } else {
-                const uint32_t vmask = 0u - ((vm >> j) & 1u);
-                accv |= (b << sh) & vmask;
-                sh += 7u & vmask;
-            }
+            const uint32_t b = j == 3 ? (p >> 24) : (j == 0 ? (p & 0xffu) : __byte_perm(p, 0u, 0x4440u + j));
             const uint32_t t = (tm >> j) & 1u;
-            const uint32_t m = 0u - t;  // all ones at a terminator
-            const int32_t v = static_cast<int32_t>(accv >> 1) ^ -static_cast<int32_t>(accv & 1u);
-            P += v & static_cast<int32_t>(m);
-            const uint32_t am = m & (0u - (aw & 1u));  // terminator of an active row
-            if (kNeed & kNeedSum) sumP += P & static_cast<int32_t>(am);
+            const uint32_t nr = (kMasked ? ((rm >> j) & 1u) : t) ^ 1u;
+            accv = imad_u32(b, mul, accv);
+            const uint32_t h = accv >> 1, s = accv & 1u;
+            const int32_t v = imad_s32(static_cast<int32_t>(s), static_cast<int32_t>(0u - accv), static_cast<int32_t>(h));
+            P = imad_s32(v, static_cast<int32_t>(t), P);
+            const uint32_t at = aw & t;  // terminator of an active row
+            if (kNeed & kNeedSum) sumP = imad_s32(P, static_cast<int32_t>(at), sumP);
             if (kNeed & kNeedMinMax) {
-                const int32_t lo_c = static_cast<int32_t>((static_cast<uint32_t>(P) & am) | (0x7fffffffu & ~am));
-                const int32_t hi_c = static_cast<int32_t>((static_cast<uint32_t>(P) & am) | (0x80000000u & ~am));
+                // candidate = P at an active terminator, the neutral element otherwise
+                const int32_t lo_c = static_cast<int32_t>(imad_u32(at, static_cast<uint32_t>(P) - 0x7fffffffu, 0x7fffffffu));
+                const int32_t hi_c = static_cast<int32_t>(imad_u32(at, static_cast<uint32_t>(P) - 0x80000000u, 0x80000000u));
                 minP = lo_c < minP ? lo_c : minP;
                 maxP = hi_c > maxP ? hi_c : maxP;
             }
             aw >>= t;
-            accv &= ~m;
-            sh &= ~m;
+            accv = imad_u32(accv, nr, 0u);
+            mul = imad_u32(mul, imad_u32(nr, 128u, 0u), nr ^ 1u);
         }
         w0 = w1;
         w1 = w2;
@@ -521,8 +538,24 @@ __device__ __forceinline__ void fast_lane_decode(const uint4 &wa, const uint4 &w
         w4 = w5;
         w5 = w6;
         w6 = w7;
-        vm >>= 4;
         tm >>= 4;
+        if (kMasked) rm >>= 4;
+    }
+    sh = 31u - static_cast<uint32_t>(__clz(mul));
+}
+
+// 4 bits -> 4 byte masks (bit j -> 0xff in byte j): bit j times 2^(7j) lands on bit 8j, nothing else does
+__device__ __forceinline__ uint32_t expand4(uint32_t n) { return (((n & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu; }
+
+template <bool kFull, int kNeed>
+__device__ __forceinline__ void fast_lane_decode(const uint4 &wa, const uint4 &wb, uint32_t valid, uint32_t term, uint32_t aw, uint32_t &accv,
+                                                 uint32_t &sh, int32_t &P, int32_t &sumP, int32_t &minP, int32_t &maxP) {
+    if (kFull) {
+        fast_lane_decode_imad<kNeed, false>(wa, wb, term, term, aw, accv, sh, P, sumP, minP, maxP);
+    } else {
+        const uint4 ma = make_uint4(wa.x & expand4(valid), wa.y & expand4(valid >> 4), wa.z & expand4(valid >> 8), wa.w & expand4(valid >> 12));
+        const uint4 mb = make_uint4(wb.x & expand4(valid >> 16), wb.y & expand4(valid >> 20), wb.z & expand4(valid >> 24), wb.w & expand4(valid >> 28));
+        fast_lane_decode_imad<kNeed, true>(ma, mb, term, term | ~valid, aw, accv, sh, P, sumP, minP, maxP);
     }
 }
 
@@ -555,8 +588,15 @@ __device__ __forceinline__ void fast_chunk_load(FastChunk &fc, const PageStream 
     lo_i = lo_i < 0 ? 0 : (lo_i > 32 ? 32 : lo_i);
     hi_i = hi_i < 0 ? 0 : (hi_i > 32 ? 32 : hi_i);
     fc.valid = low_bits(hi_i) & ~low_bits(lo_i);
-    const uint32_t msb = msb4(fc.wa.x) | (msb4(fc.wa.y) << 4) | (msb4(fc.wa.z) << 8) | (msb4(fc.wa.w) << 12) | (msb4(fc.wb.x) << 16) |
-                         (msb4(fc.wb.y) << 20) | (msb4(fc.wb.z) << 24) | (msb4(fc.wb.w) << 28);
+    // nibbles gathered with multiply-adds (FMA pipe) instead of shift+or pairs (ALU pipe)
+    uint32_t msb = msb4(fc.wa.x);
+    msb = imad_u32(msb4(fc.wa.y), 1u << 4, msb);
+    msb = imad_u32(msb4(fc.wa.z), 1u << 8, msb);
+    msb = imad_u32(msb4(fc.wa.w), 1u << 12, msb);
+    msb = imad_u32(msb4(fc.wb.x), 1u << 16, msb);
+    msb = imad_u32(msb4(fc.wb.y), 1u << 20, msb);
+    msb = imad_u32(msb4(fc.wb.z), 1u << 24, msb);
+    msb = imad_u32(msb4(fc.wb.w), 1u << 28, msb);
     fc.term = fc.valid & ~msb;
     const uint32_t cont = fc.valid & msb;
     fc.n = __popc(fc.term);
@@ -857,6 +897,18 @@ __device__ __noinline__ uint32_t agg_raw_page(const uint8_t *page, uint32_t size
     return kErrNone;
 }
 
+// A <= 32-bit big-endian bit field at bit offset `bo` of a byte stream (writer.go:25-96): two aligned 32-bit loads
+// and a funnel shift instead of eight byte loads.  Touches at most 7 bytes past the field.
+__device__ __forceinline__ uint32_t read_bits_be(const uint8_t *base, uint64_t bo, uint32_t wbits, uint64_t vmask) {
+    const uint8_t *p = base + (bo >> 3);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~static_cast<uintptr_t>(3));
+    const uint32_t w0 = __byte_perm(__ldg(w), 0u, 0x0123u), w1 = __byte_perm(__ldg(w + 1), 0u, 0x0123u);  // to big endian
+    const uint64_t x = (static_cast<uint64_t>(w0) << 32) | w1;
+    const uint32_t off = static_cast<uint32_t>(a & 3) * 8u + static_cast<uint32_t>(bo & 7);
+    return static_cast<uint32_t>((x >> (64u - off - wbits)) & vmask);
+}
+
 // Dictionary tag page -> mask (pkg/encoding/dictionary.go:69-114, bytes.go:45-127, writer.go/reader.go).
 // page points just after the 0x0A type byte.  Returns a DevErr.
 __device__ __noinline__ uint32_t apply_dict_pred(WarpSmem *sm, const DevPred &pr, const uint8_t *page, uint32_t size, uint32_t count, int lane) {
@@ -939,12 +991,9 @@ __device__ __noinline__ uint32_t apply_dict_pred(WarpSmem *sm, const DevPred &pr
         uint32_t value = 0, cnt = 0;
         if (ri < nruns) {
             // reads up to 7 bytes past the last needed byte: file images are padded in HBM
-            uint64_t bo = static_cast<uint64_t>(2 * ri) * wbits;
-            uint64_t x = load_be64_unaligned(bits + (bo >> 3));
-            value = static_cast<uint32_t>((x >> (64 - (bo & 7) - wbits)) & vmask);
-            bo += wbits;
-            x = load_be64_unaligned(bits + (bo >> 3));
-            cnt = static_cast<uint32_t>((x >> (64 - (bo & 7) - wbits)) & vmask);
+            const uint64_t bo = static_cast<uint64_t>(2 * ri) * wbits;
+            value = read_bits_be(bits, bo, wbits, vmask);
+            cnt = read_bits_be(bits, bo + wbits, wbits, vmask);
         }
         uint32_t incl = cnt;
 #pragma unroll
