@@ -218,8 +218,9 @@ def main():
     admission = {"register_ms": (time.perf_counter() - t_reg) * 1e3, **ctx.part_info(h),
                  "note": "one-time per part: upload to HBM, host parse of the block index, device unpack of the fallback pages "
                          "(the `uniform` field is full-precision float64 = zstd-compressed EncodeTypePlain pages)"}
-    # the query names every series of the job: ranks only hold their own (series-disjoint parts)
-    sids = np.arange(1, world * n_series + 1, dtype=np.uint64)
+    # every rank resolves the series of ITS shard (a data node's index lookup returns local series only); the scalar /
+    # group layout of the partial table is the same on all ranks, so the tables combine
+    sids = np.arange(sid0, sid0 + n_series, dtype=np.uint64)
     q = query_of(pkg, [h], sids, n_points)
 
     def barrier():
@@ -398,7 +399,7 @@ def main():
     if last is not None:
         out["result"] = {"mean_latency": float(last.val_f64[0, 0]), "max_walk": float(last.val_f64[0, 1]), "rows_matched": int(last.rows[0])}
     if world == 1 and not args.no_cpu:
-        rate, nser, r, cdt = cpu_port_rate(files, sids[:n_series], n_points, cores, args.cpu_seconds)
+        rate, nser, r, cdt = cpu_port_rate(files, sids, n_points, cores, args.cpu_seconds)
         out["cpu_baseline"] = {"value": rate, "unit": "datapoints/s", "cores": cores, "kind": "port",
                                "sample": f"{nser} of {n_series} series of the same part ({r.rows_scanned} datapoints, {cdt:.1f} s); "
                                          "C port of the reference Go path: decode on a thread pool, single-threaded merge+fold"}

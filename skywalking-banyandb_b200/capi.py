@@ -84,7 +84,8 @@ _lib = None
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libbydbgpu.so")
+    # BYDB_GPU_LIB: a differently built libbydbgpu.so (kernel-variant experiments); still the CUDA library, never a fallback
+    return os.environ.get("BYDB_GPU_LIB") or os.path.join(_HERE, "libbydbgpu.so")
 
 
 def load_library():

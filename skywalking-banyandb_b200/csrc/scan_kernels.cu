@@ -496,6 +496,13 @@ __device__ __forceinline__ int32_t imad_s32(int32_t a, int32_t b, int32_t c) {
 //   accv += b * mul                (mul = 128^k inside a varint, back to 1 after its terminator)
 //   v     = h - s * accv           (zig-zag: accv = 2h + s)
 //   P    += v * t ; sumP += P * (t & active)
+#ifndef BYDB_UNROLL
+#define BYDB_UNROLL 2
+#endif
+#define BYDB_PRAGMA_(x) _Pragma(#x)
+#define BYDB_PRAGMA(x) BYDB_PRAGMA_(x)
+#define BYDB_UNROLL_WORDS BYDB_PRAGMA(unroll BYDB_UNROLL)
+
 // kMasked: the chunk holds bytes outside the page (first / last chunk): `reset` = term | ~valid restarts the varint
 // state at those bytes too, their payload is zeroed by the caller, and only real terminators (term) count as rows.
 template <int kNeed, bool kMasked>
@@ -506,7 +513,7 @@ __device__ __forceinline__ void fast_lane_decode_imad(const uint4 &wa, const uin
     uint32_t w0 = wa.x, w1 = wa.y, w2 = wa.z, w3 = wa.w, w4 = wb.x, w5 = wb.y, w6 = wb.z, w7 = wb.w;
     uint32_t tm = term, rm = reset;
     uint32_t mul = 1u << sh;
-#pragma unroll 2
+    BYDB_UNROLL_WORDS
     for (int q8 = 0; q8 < 8; ++q8) {
         const uint32_t p = w0 & 0x7f7f7f7fu;
 #pragma unroll

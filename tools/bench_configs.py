@@ -60,7 +60,7 @@ def main():
     t_reg = time.perf_counter() - t0
     info = ctx.part_info(h)
     del img
-    sids = np.arange(1, args.series + 1, dtype=np.uint64)
+    sids = np.arange(sid0, sid0 + n_mine, dtype=np.uint64)       # a rank resolves the series of its own shard
     groups = ((sids - 1) % args.services).astype(np.int32)          # service_id of a series: comes from the index, not the part
     q = pkg.Query(parts=[h], series_ids=sids, aggs=[("latency", pkg.AGG_SUM), ("latency", pkg.AGG_COUNT)], series_group=groups,
                   n_groups=args.services, top_n=100, top_agg=0, top_desc=True)
