@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -950,7 +951,13 @@ int bydb_scan_agg(bydb_ctx *ctx, const bydb_query *q, bydb_result *out) {
 // GPU (pulling its pages over PCIe) while the host parses slice k+1; the per-slice partial tables are
 // combined on the device.  A series may straddle slices: partial tables merge exactly.
 static int scan_agg_host_pipelined(bydb_ctx *ctx, const bydb_part_files *files, const bydb_query *q, bydb_result *out) {
-    constexpr int K = 4;
+    // slices of the block index: more slices shorten the un-overlapped parse of the first one, fewer amortise the
+    // per-slice launches; BYDB_COLD_SLICES (2..8) overrides the default for experiments
+    static const int K = [] {
+        const char *e = getenv("BYDB_COLD_SLICES");
+        const int k = e ? atoi(e) : 4;
+        return k < 2 ? 2 : (k > ExecSlot::kMaxBatches ? ExecSlot::kMaxBatches : k);
+    }();
     SlotLease lease(ctx);
     if (lease.init()) return fail(BYDB_EIO, "cannot create stream");
     ExecSlot &slot = *lease.slot;
