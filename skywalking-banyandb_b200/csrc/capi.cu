@@ -5,7 +5,13 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <chrono>
+#include <condition_variable>
 #include <cstdlib>
+#include <deque>
+#include <functional>
+#include <thread>
+#include <future>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -90,6 +96,52 @@ struct ExecSlot {
 
 }  // namespace
 
+// A few persistent host threads for the cold path's block-index parsing: creating a dozen threads per query costs
+// more (~0.5 ms, serialised on the calling thread) than parsing the first primary block.
+class WorkPool {
+  public:
+    ~WorkPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    void submit(std::function<void()> fn) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (th_.empty()) {
+                unsigned hw = std::thread::hardware_concurrency();
+                const unsigned n = std::max(2u, std::min(16u, hw ? hw : 4u));
+                for (unsigned i = 0; i < n; ++i) th_.emplace_back([this] { run(); });
+            }
+            q_.push_back(std::move(fn));
+        }
+        cv_.notify_one();
+    }
+
+  private:
+    void run() {
+        for (;;) {
+            std::function<void()> fn;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;  // stop_ and drained
+                fn = std::move(q_.front());
+                q_.pop_front();
+            }
+            fn();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+    std::vector<std::thread> th_;
+    bool stop_ = false;
+};
+
 struct bydb_ctx {
     int device = 0;
     int sm_count = 0;
@@ -103,6 +155,7 @@ struct bydb_ctx {
     std::unordered_map<uint64_t, bydb_part_h> by_id;
     bydb_part_h next_handle = 1;
     std::vector<std::unique_ptr<ExecSlot>> free_slots;
+    WorkPool pool;
 };
 
 namespace {
@@ -243,7 +296,8 @@ struct TableLayout {
 int unpack_fallback_pages(bydb_ctx *ctx, Part &part, size_t n_files, cudaStream_t s);
 
 int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_files *files, std::shared_ptr<Part> &out, uint64_t *h2d,
-                              bool zero_copy = false, bool transient = false, size_t batch = 0, size_t n_batches = 1, bool unpack = false) {
+                              bool zero_copy = false, bool transient = false, size_t batch = 0, size_t n_batches = 1, bool unpack = false,
+                              PartDir *parsed = nullptr) {
     if (!files || files->n_files == 0 || !files->files) return fail(BYDB_EINVAL, "no files");
     std::vector<FileImage> imgs;
     for (uint32_t i = 0; i < files->n_files; ++i) {
@@ -255,8 +309,9 @@ int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_f
     part->id = part_id;
     part->device = ctx->device;
     std::string err;
-    {
-        std::lock_guard<std::mutex> lk(ctx->mu);  // NameTable is shared
+    if (parsed) {
+        part->dir = std::move(*parsed);  // the caller parsed this slice of the block index already (cold path, in the background)
+    } else {
         int rc = build_part_dir(imgs, ctx->names, part->dir, err, batch, n_batches);
         if (rc) return fail(rc, "part " + std::to_string(part_id) + ": " + err);
     }
@@ -651,7 +706,7 @@ int collect_scan(ExecSlot &slot, bydb_stats *stats, int batch = 0) {
         cudaEventElapsedTime(&ms, ev[0], ev[3]);
         stats->device_ms += ms;
     }
-    g_last_dev_err = hz[2];
+    if (hz[2] != 0) g_last_dev_err = hz[2];  // reset by the API entry points; a later clean slice must not hide it
     if (hz[2] != 0) {
         char buf[96];
         snprintf(buf, sizeof buf, " (block/series #%u)", hz[3]);
@@ -951,13 +1006,7 @@ int bydb_scan_agg(bydb_ctx *ctx, const bydb_query *q, bydb_result *out) {
 // GPU (pulling its pages over PCIe) while the host parses slice k+1; the per-slice partial tables are
 // combined on the device.  A series may straddle slices: partial tables merge exactly.
 static int scan_agg_host_pipelined(bydb_ctx *ctx, const bydb_part_files *files, const bydb_query *q, bydb_result *out) {
-    // slices of the block index: more slices shorten the un-overlapped parse of the first one, fewer amortise the
-    // per-slice launches; BYDB_COLD_SLICES (2..8) overrides the default for experiments
-    static const int K = [] {
-        const char *e = getenv("BYDB_COLD_SLICES");
-        const int k = e ? atoi(e) : 4;
-        return k < 2 ? 2 : (k > ExecSlot::kMaxBatches ? ExecSlot::kMaxBatches : k);
-    }();
+    constexpr int K = ExecSlot::kMaxBatches;  // most slices (scan launches) per call
     SlotLease lease(ctx);
     if (lease.init()) return fail(BYDB_EIO, "cannot create stream");
     ExecSlot &slot = *lease.slot;
@@ -967,6 +1016,18 @@ static int scan_agg_host_pipelined(bydb_ctx *ctx, const bydb_part_files *files, 
     base.n_groups = q->series_group ? q->n_groups : 1;
     base.n_series = q->n_series;
     TableLayout tl(static_cast<size_t>(base.n_groups), base.fcols.size());
+    std::vector<FileImage> imgs;
+    for (uint32_t i = 0; i < files->n_files; ++i) {
+        const bydb_file &f = files->files[i];
+        if (!f.name || (!f.data && f.len)) return fail(BYDB_EINVAL, "file without name/data");
+        imgs.push_back(FileImage{f.name, f.data, f.len});
+    }
+    size_t n_primary = 0;
+    {
+        std::string err;
+        const int rc0 = count_primary_blocks(imgs, &n_primary, err);
+        if (rc0) return fail(rc0, err);
+    }
     Scratch tables;
     tables.stream = slot.stream;
     CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&tables.base), tl.total * K, slot.stream));
@@ -976,26 +1037,78 @@ static int scan_agg_host_pipelined(bydb_ctx *ctx, const bydb_part_files *files, 
         if (slot.ensure_pinned(std::max(stage_stride * K, G * (12 + 16 * A) + 16 * A + 8192))) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
     }
     memset(&out->stats, 0, sizeof out->stats);
+    // The block index is parsed in the background from the start, one task per group of primary blocks (they are
+    // independent zstd frames).  The main thread takes the pieces in order: whatever is parsed by the time the GPU can
+    // take more work becomes the next slice -- first slice = the first piece (shortest wait before the first launch),
+    // later slices grow with what the parsers delivered meanwhile, the last allowed slice takes the rest.
+    struct Parsed {
+        PartDir dir;
+        std::string err;
+        int rc = 0;
+    };
+    const size_t T = std::max<size_t>(1, std::min<size_t>(n_primary, 32));
+    static const bool trace = getenv("BYDB_TRACE") != nullptr;  // host-side timeline of the cold path on stderr
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); };
+    std::vector<std::future<Parsed>> parses;
+    for (size_t t = 0; t < T; ++t) {
+        auto task = std::make_shared<std::packaged_task<Parsed()>>([ctx, &imgs, t, T] {
+            Parsed r;
+            r.rc = build_part_dir(imgs, ctx->names, r.dir, r.err, t, T);
+            return r;
+        });
+        parses.push_back(task->get_future());
+        ctx->pool.submit([task] { (*task)(); });
+    }
     std::vector<std::shared_ptr<Part>> keep;
-    int rc = 0;
-    for (int k = 0; k < K && !rc; ++k) {
+    int rc = 0, n_slices = 0;
+    size_t next = 0;
+    while (next < T) {
+        std::vector<PartDir> pieces;
+        auto take = [&] {
+            Parsed pr = parses[next++].get();
+            if (pr.rc && !rc) rc = fail(pr.rc, "block index: " + pr.err);
+            pieces.push_back(std::move(pr.dir));
+        };
+        take();
+        if (rc || n_slices == K - 1) {
+            while (next < T) take();  // the last slice takes the rest; after a failure every task is still joined
+        } else {
+            while (next < T && parses[next].wait_for(std::chrono::seconds(0)) == std::future_status::ready) take();
+        }
+        if (rc) break;
+        PartDir merged;
+        {
+            std::string err;
+            const int mrc = merge_part_dirs(pieces, merged, err);
+            if (mrc) {
+                rc = fail(mrc, err);
+                continue;
+            }
+        }
+        const int k = n_slices++;
+        if (trace) fprintf(stderr, "[bydb cold] slice %d = pieces ..%zu of %zu, parsed at %.0f us (%zu blocks)\n", k, next, T, since(), merged.blocks.size());
         std::shared_ptr<Part> p;
         uint64_t h2d = 0;
-        rc = register_part_locked_free(ctx, ~0ull - static_cast<uint64_t>(k), files, p, &h2d, true, true, static_cast<size_t>(k), K);
-        if (rc) break;
+        rc = register_part_locked_free(ctx, ~0ull - static_cast<uint64_t>(k), files, p, &h2d, true, true, 0, 1, false, &merged);
+        if (rc) continue;
         keep.push_back(p);
         out->stats.h2d_bytes += h2d;
         Plan plan = base;
         plan.parts = {p};
         plan.total_blocks = static_cast<uint32_t>(p->dir.blocks.size());
         rc = run_scan(ctx, q, plan, slot, slot.stream, tables.base + tl.total * static_cast<size_t>(k), tl, &out->stats, k, true);
+        if (trace) fprintf(stderr, "[bydb cold] slice %d enqueued at %.0f us\n", k, since());
     }
-    if (!rc) {
-        launch_combine_tables(reinterpret_cast<uint64_t *>(tables.base), K, tl.total / 8, tl.off_sum_f64 / 8, tl.off_max_f64 / 8, tl.off_max_f64 / 8,
-                              tl.off_sum_i64 / 8, tl.off_sum_i64 / 8, tl.off_max_i64 / 8, tl.off_max_i64 / 8, tl.total / 8, slot.stream);
+    while (next < T) (void)parses[next++].get();
+    if (!rc && n_slices > 0) {
+        launch_combine_tables(reinterpret_cast<uint64_t *>(tables.base), static_cast<uint32_t>(n_slices), tl.total / 8, tl.off_sum_f64 / 8,
+                              tl.off_max_f64 / 8, tl.off_max_f64 / 8, tl.off_sum_i64 / 8, tl.off_sum_i64 / 8, tl.off_max_i64 / 8, tl.off_max_i64 / 8,
+                              tl.total / 8, slot.stream);
         out->stats.kernel_launches += 1;
         // the pinned staging of the last slices may still be in flight: finalize copies into it only after the kernels
         rc = finalize_to_host(ctx, q, base, slot, slot.stream, tables.base, tl, out);
+        if (trace) fprintf(stderr, "[bydb cold] finalized at %.0f us\n", since());
     } else {
         cudaStreamSynchronize(slot.stream);
     }

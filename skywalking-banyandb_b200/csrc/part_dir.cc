@@ -13,6 +13,7 @@
 namespace bydb {
 
 uint16_t NameTable::intern(const std::string &s) {
+    std::lock_guard<std::mutex> lk(mu_);
     auto it = ids_.find(s);
     if (it != ids_.end()) return it->second;
     uint16_t id = static_cast<uint16_t>(ids_.size() + 1);
@@ -20,6 +21,7 @@ uint16_t NameTable::intern(const std::string &s) {
     return id;
 }
 uint16_t NameTable::find(const std::string &s) const {
+    std::lock_guard<std::mutex> lk(mu_);
     auto it = ids_.find(s);
     return it == ids_.end() ? 0 : it->second;
 }
@@ -431,6 +433,80 @@ int build_part_dir(const std::vector<FileImage> &files, NameTable &names, PartDi
             out.blocks.push_back(b);
         }
         out.cols.insert(out.cols.end(), tc[t].begin(), tc[t].end());
+    }
+    return 0;
+}
+
+int count_primary_blocks(const std::vector<FileImage> &files, size_t *n, std::string &err) {
+    const FileImage *meta = find_file(files, "meta.bin");
+    if (!meta) {
+        err = "part needs meta.bin";
+        return BYDB_ENOENT;
+    }
+    std::vector<uint8_t> raw;
+    int rc = zstd_decompress(meta->data, meta->len, raw, err);
+    if (rc) return rc;
+    if (raw.size() % 40 != 0) {
+        err = "meta.bin: length is not a multiple of 40";
+        return BYDB_EINVAL;
+    }
+    *n = raw.size() / 40;
+    return 0;
+}
+
+int merge_part_dirs(std::vector<PartDir> &pieces, PartDir &out, std::string &err) {
+    out = PartDir();
+    out.files = {"timestamps.bin", "fv.bin"};
+    out.min_ts = INT64_MAX;
+    out.max_ts = INT64_MIN;
+    size_t nb = 0, nc = 0;
+    for (const auto &p : pieces) {
+        nb += p.blocks.size();
+        nc += p.cols.size();
+    }
+    out.blocks.reserve(nb);
+    out.cols.reserve(nc);
+    for (auto &p : pieces) {
+        // file tables are built in discovery order per piece: map this piece's ids onto the merged table
+        std::vector<uint8_t> remap(p.files.size(), 0);
+        for (size_t i = 0; i < p.files.size(); ++i) {
+            size_t k = 0;
+            while (k < out.files.size() && out.files[k] != p.files[i]) ++k;
+            if (k == out.files.size()) {
+                if (out.files.size() >= 255) {
+                    err = "too many tag family files";
+                    return BYDB_EINVAL;
+                }
+                out.files.push_back(p.files[i]);
+            }
+            remap[i] = static_cast<uint8_t>(k);
+        }
+        const uint32_t shift = static_cast<uint32_t>(out.cols.size());
+        for (DevBlock b : p.blocks) {
+            b.col_begin += shift;
+            if (!out.blocks.empty()) {
+                const DevBlock &pre = out.blocks.back();
+                if (b.sid < pre.sid || (b.sid == pre.sid && b.ts_min < pre.ts_min)) {
+                    err = "blockMetadata out of order";
+                    return BYDB_EINVAL;
+                }
+            }
+            out.blocks.push_back(b);
+        }
+        for (DevCol c : p.cols) {
+            c.file_id = c.file_id < remap.size() ? remap[c.file_id] : 0;
+            out.cols.push_back(c);
+        }
+        out.total_rows += p.total_rows;
+        out.max_block_rows = std::max(out.max_block_rows, p.max_block_rows);
+        if (!p.blocks.empty()) {
+            out.min_ts = std::min(out.min_ts, p.min_ts);
+            out.max_ts = std::max(out.max_ts, p.max_ts);
+        }
+    }
+    if (out.blocks.empty()) {
+        out.min_ts = 0;
+        out.max_ts = 0;
     }
     return 0;
 }

@@ -8,6 +8,7 @@
 #pragma once
 
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -39,12 +40,13 @@ struct DevCol {
 };
 static_assert(sizeof(DevCol) == 16, "DevCol layout");
 
-class NameTable {
+class NameTable {  // thread-safe: block-index slices of one part are parsed concurrently on the cold path
   public:
     // returns a stable id (>=1); 0 is "unknown"
     uint16_t intern(const std::string &s);
     uint16_t find(const std::string &s) const;
   private:
+    mutable std::mutex mu_;
     std::unordered_map<std::string, uint16_t> ids_;
 };
 
@@ -67,6 +69,11 @@ struct PartDir {
 // batch / n_batches: parse only that slice of the primary blocks (the cold host path pipelines the parsing of one
 // slice with the scan of the previous one); the default parses the whole part.
 int build_part_dir(const std::vector<FileImage> &files, NameTable &names, PartDir &out, std::string &err, size_t batch = 0, size_t n_batches = 1);
+
+// number of primary blocks (independent zstd frames of primary.bin) of the part
+int count_primary_blocks(const std::vector<FileImage> &files, size_t *n, std::string &err);
+// concatenates consecutive slices of one part's directory (file ids remapped onto one table)
+int merge_part_dirs(std::vector<PartDir> &pieces, PartDir &out, std::string &err);
 
 // zstd frame decompression through the system libzstd (dlopen, no header in the image).
 int zstd_decompress(const uint8_t *src, size_t n, std::vector<uint8_t> &dst, std::string &err);
