@@ -23,5 +23,5 @@ from .capi import (  # noqa: F401
 )
 from .scan_operator import (  # noqa: F401
     AggCount, AggFunc, AggMax, AggMean, AggMin, AggSpec, AggSum, BatchSchema, ColumnDef, ColumnType,
-    ColumnRole, GPUScanAgg, RecordBatch, ScanSpec, TopSpec,
+    ColumnRole, GPUScanAgg, LimitSpec, RecordBatch, ScanSpec, TopSpec,
 )

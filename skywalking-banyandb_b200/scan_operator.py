@@ -93,6 +93,13 @@ class TopSpec:
 
 
 @dataclass
+class LimitSpec:
+    """BatchLimit (pkg/query/vectorized/measure/limit.go:27-73): the rows [Offset, Offset+Limit) of the output stream."""
+    Offset: int = 0
+    Limit: int = 100   # the planner's default when the request sets none (pkg/query/logical/measure/measure_analyzer.go:31)
+
+
+@dataclass
 class ScanSpec:
     """What measure.Query resolved before the scan (banyand/measure/query.go:88-312)."""
     parts: Sequence[int]                       # part handles (snapshot.getParts, query.go:216)
@@ -108,7 +115,7 @@ class GPUScanAgg:
     """PullOperator: (batch) / None at EOF / raises BydbError (sticky) -- operator.go:41-48."""
 
     def __init__(self, ctx: capi.Context, input_schema: BatchSchema, key_indices: Sequence[int], aggs: Sequence[AggSpec],
-                 scan: ScanSpec, batch_size: int = 1024, top: Optional[TopSpec] = None):
+                 scan: ScanSpec, batch_size: int = 1024, top: Optional[TopSpec] = None, limit: Optional[LimitSpec] = None):
         self._ctx = ctx
         self._in = input_schema
         self._keys = list(key_indices)
@@ -116,6 +123,8 @@ class GPUScanAgg:
         self._scan = scan
         self._batch = max(1, int(batch_size))
         self._top = top
+        self._limit = limit
+        self._row_end = 0
         self._tag_idx = [i for i, c in enumerate(input_schema.Columns) if c.Role == ColumnRole.RoleTag] or list(self._keys)
         for a in self._aggs:
             col = input_schema.Columns[a.InputCol]
@@ -158,9 +167,9 @@ class GPUScanAgg:
                 self._err = e
                 raise
         r = self._result
-        if self._cursor >= len(r.group_id):
+        if self._cursor >= self._row_end:
             return None
-        lo, hi = self._cursor, min(self._cursor + self._batch, len(r.group_id))
+        lo, hi = self._cursor, min(self._cursor + self._batch, self._row_end)
         self._cursor = hi
         cols: List[object] = []
         for ti in self._tag_idx:
@@ -205,4 +214,10 @@ class GPUScanAgg:
             self._group_first_series = [0] if len(sids) else []
         self._result = self._ctx.scan_agg(q)
         self.stats = self._result.stats
-        self._cursor = 0
+        # offset / limit window over the (Top-ordered) output rows, limit.go:56-73
+        n = len(self._result.group_id)
+        if self._limit is None:
+            self._cursor, self._row_end = 0, n
+        else:
+            self._cursor = min(max(int(self._limit.Offset), 0), n)
+            self._row_end = min(self._cursor + max(int(self._limit.Limit), 0), n)

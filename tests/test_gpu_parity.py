@@ -488,6 +488,22 @@ def test_operator_gpuscanagg_matches_batch_aggregation_contract(bydb, gpu_ctx):
         m = np.array([sid_svc[int(s)] == name for s in sids])
         tot, n = int(calls[m].sum()), int(m.sum())
         assert out[name] == (tot, n, max(tot // n, 1))
+    # BatchLimit windows over the same output stream (limit_test.go:52-129): first N, rows N..N+M, offset beyond the data
+    def names_of(limit):
+        o = V.GPUScanAgg(gpu_ctx, schema, [0], [V.AggSpec("sum_v", V.AggSum, 1)],
+                         V.ScanSpec(parts=[h], series_ids=usid, series_tags={("default", "service_id"): svc}), batch_size=2, limit=limit)
+        o.Init()
+        got_names = []
+        while (bt := o.NextBatch()) is not None:
+            assert 0 < bt.Len <= 2
+            got_names += list(bt.Columns[0])
+        o.Close()
+        return got_names
+    assert names_of(V.LimitSpec(0, 3)) == first_seen[:3]
+    assert names_of(V.LimitSpec(2, 4)) == first_seen[2:6]
+    assert names_of(V.LimitSpec(5, 100)) == first_seen[5:]
+    assert names_of(V.LimitSpec(50, 10)) == []
+    assert names_of(V.LimitSpec(1, 0)) == []
     gpu_ctx.release_part(h)
 
 
