@@ -57,3 +57,65 @@ def run_both(bydb, ctx, parts, oq: O.Query, part_id0=1000):
             ctx.release_part(h)
     want = O.run_query(oq)
     return got, want
+
+
+# ------------------------------------------------------------------ the reference's end-to-end cases (tests/golden/e2e_cases.json)
+import json as _json
+import os as _os
+
+_E2E = _json.load(open(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "e2e_cases.json")))
+E2E_CASES = sorted(_E2E)
+_AGG = {"SUM": O.AGG_SUM, "COUNT": O.AGG_COUNT, "MIN": O.AGG_MIN, "MAX": O.AGG_MAX, "MEAN": O.AGG_MEAN}
+_OPS = {"BINARY_OP_EQ": O.OP_EQ, "BINARY_OP_NE": O.OP_NE, "BINARY_OP_LT": O.OP_LT, "BINARY_OP_LE": O.OP_LE, "BINARY_OP_GT": O.OP_GT,
+        "BINARY_OP_GE": O.OP_GE}
+
+
+def load_e2e_case(name):
+    """-> (oracle part, oracle query, group names by dense id, want rows, ordered?) for one case of the reference's
+    test/cases/measure suite.  Series = distinct entity tuples (ids in order of first appearance), timestamps one
+    interval apart in data order (test/cases/measure/data/data.go:238-252), every tag also stored as a tag column."""
+    c = _E2E[name]
+    tags, ent = c["tags"], c["entity"]
+    series = {}
+    for r in c["rows"]:
+        series.setdefault(tuple(r["tags"][tags.index(t)] for t in ent), len(series) + 1)
+    n = len(c["rows"])
+    sid = np.array([series[tuple(r["tags"][tags.index(t)] for t in ent)] for r in c["rows"]], dtype=np.uint64)
+    ts = T0 + np.arange(n, dtype=np.int64) * STEP
+    order = np.lexsort((ts, sid))
+    rows = [c["rows"][i] for i in order]
+    fields = []
+    for fi, f in enumerate(c["fields"]):
+        vals = [r["fields"][fi] for r in rows]
+        fields.append((f["name"], O.VT_FLOAT64 if f["type"] == "float" else O.VT_INT64,
+                       np.array(vals, dtype=np.float64 if f["type"] == "float" else np.int64), None))
+    tag_cols = [(t, O.VT_STR, [r["tags"][ti].encode() for r in rows], None) for ti, t in enumerate(tags)]
+    part = build_part(sid[order], ts[order], np.ones(n, np.int64), fields, [(c["family"], tag_cols)])
+    q = c["query"]
+    gi = tags.index(q["group_by"])
+    usid = np.unique(sid)
+    names, gid_of_series = [], []
+    for s in usid.tolist():
+        vals = {r["tags"][gi] for r, rs in zip(c["rows"], sid.tolist()) if rs == s}
+        assert len(vals) == 1, "group-by tag must be constant per series for the series->group table"
+        v = vals.pop()
+        if v not in names:
+            names.append(v)
+        gid_of_series.append(names.index(v))
+    preds = []
+    if q["criteria"]:
+        preds.append(O.Pred(c["family"], q["criteria"]["tag"], _OPS[q["criteria"]["op"]], q["criteria"]["value"].encode()))
+    oq = O.Query([part], usid, [(q["field"], _AGG[q["agg"]])], groups=np.array(gid_of_series, dtype=np.int32), n_groups=len(names), preds=preds,
+                 top_n=q["top"]["n"] if q["top"] else 0, top_agg=0, top_desc=q["top"]["desc"] if q["top"] else True)
+    return part, oq, names, c["want"], bool(q["top"])
+
+
+def check_e2e_rows(res, names, want, ordered, ctx=""):
+    got = [(names[g], float(res.val_f64[i, 0]) if res.is_float[0] else int(res.val_i64[i, 0])) for i, g in enumerate(res.group_id.tolist())]
+    exp = [(w["group"], w["value"]) for w in want]
+    if not ordered:
+        got, exp = sorted(got), sorted(exp)
+    assert [g for g, _ in got] == [g for g, _ in exp], f"{ctx}: groups {got} vs {exp}"
+    for (g, a), (_, b) in zip(got, exp):
+        # the row path's COUNT of a float field is a float (SURVEY 8a, a14); the vectorized path this library mirrors returns int64
+        assert abs(float(a) - float(b)) <= 1e-9 * max(abs(float(b)), 1e-300), f"{ctx}: {g}: {a} vs {b}"

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from tests.helpers import STEP, T0, assert_parity, build_part, grid, run_both
+from tests.helpers import E2E_CASES, STEP, T0, assert_parity, build_part, check_e2e_rows, grid, load_e2e_case, run_both
 
 pytestmark = pytest.mark.gpu
 
@@ -642,3 +642,12 @@ def test_partial_tables_async_scan_combine_finalize(bydb, gpu_ctx):
     finally:
         for h in handles:
             gpu_ctx.release_part(h)
+
+
+@pytest.mark.parametrize("name", E2E_CASES)
+def test_reference_e2e_cases_on_the_device(bydb, gpu_ctx, name):
+    # the reference's own end-to-end cases (test/cases/measure/data, tests/golden/e2e_cases.json): expected rows of the want/*.yaml
+    part, oq, names, want, ordered = load_e2e_case(name)
+    got, oracle_res = run_both(bydb, gpu_ctx, [part], oq, _next_pid())
+    check_e2e_rows(got, names, want, ordered, name)
+    assert_parity(got, oracle_res, oq.aggs, f"e2e/{name}")
