@@ -109,6 +109,9 @@ class ScanSpec:
     tmin: int = -(1 << 63)
     tmax: int = (1 << 63) - 1
     preds: Sequence[capi.Pred] = field(default_factory=list)
+    order_desc: bool = False
+    # ^ orderBy sort of the request: the scan visits the series list backwards, so groups are numbered (and non-key
+    #   projected tags take their first-seen value) from the far end -- aggregation.go:211-213 on a reversed stream
 
 
 class GPUScanAgg:
@@ -195,7 +198,7 @@ class GPUScanAgg:
         group_of: Dict[tuple, int] = {}
         gids = np.zeros(len(sids), dtype=np.int32)
         self._group_first_series = []
-        for i in range(len(sids)):
+        for i in (range(len(sids) - 1, -1, -1) if sc.order_desc else range(len(sids))):
             k = tuple(kv[i] for kv in keyvals)
             g = group_of.get(k)
             if g is None:
@@ -211,7 +214,7 @@ class GPUScanAgg:
                        top_n=self._top.N if self._top else 0, top_agg=self._top.AggIndex if self._top else 0,
                        top_desc=self._top.Desc if self._top else True)
         if not self._keys:
-            self._group_first_series = [0] if len(sids) else []
+            self._group_first_series = ([len(sids) - 1] if sc.order_desc else [0]) if len(sids) else []
         self._result = self._ctx.scan_agg(q)
         self.stats = self._result.stats
         # offset / limit window over the (Top-ordered) output rows, limit.go:56-73

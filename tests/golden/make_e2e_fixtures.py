@@ -27,6 +27,18 @@ CASES = {
     "group_sum": "service_cpm_minute_data.json",
     "group_sum_with_filter": "service_cpm_minute_data.json",
     "top": "service_cpm_minute_data.json",
+    # generated feature combinations of the same suite: order-by direction x top x filter; they also project a non-key
+    # tag (entity_id), which carries the first-seen value of the group in scan order
+    "gen_feat_count_group_order_desc_8": "service_cpm_minute_data.json",
+    "gen_feat_max_group_order_desc_6": "service_cpm_minute_data.json",
+    "gen_feat_mean_group_2": "service_cpm_minute_data.json",
+    "gen_feat_mean_group_order_asc_5": "service_cpm_minute_data.json",
+    "gen_feat_mean_top_asc_group_order_asc_4": "service_cpm_minute_data.json",
+    "gen_feat_mean_top_asc_group_order_desc_filter_1": "service_cpm_minute_data.json",
+    "gen_feat_mean_top_desc_group_order_asc_0": "service_cpm_minute_data.json",
+    "gen_feat_mean_top_desc_group_order_desc_3": "service_cpm_minute_data.json",
+    "gen_feat_min_group_order_desc_7": "service_cpm_minute_data.json",
+    "gen_feat_sum_group_order_desc_9": "service_cpm_minute_data.json",
 }
 
 
@@ -65,9 +77,10 @@ def main():
             top = {"n": int(q["top"]["number"]), "desc": q["top"]["fieldValueSort"] == "SORT_DESC"}
         wrows = []
         for dp in want.get("dataPoints", []):
-            key = scalar(dp["tagFamilies"][0]["tags"][0]["value"])["value"]
+            wtags = {t["key"]: scalar(t["value"])["value"] for t in dp["tagFamilies"][0]["tags"]}
+            key = wtags[gb["tagProjection"]["tagFamilies"][0]["tags"][0]]
             val = scalar(dp["fields"][0]["value"])
-            wrows.append({"group": key, "value": val["value"], "type": val["type"]})
+            wrows.append({"group": key, "value": val["value"], "type": val["type"], "tags": wtags})
         out[case] = {
             "source": {"input": f"test/cases/measure/data/input/{case}.yaml", "want": f"test/cases/measure/data/want/{case}.yaml",
                        "data": f"test/cases/measure/data/testdata/{data_file}", "schema": f"pkg/test/measure/testdata/measures/{q['name']}.json"},
@@ -75,7 +88,9 @@ def main():
             "fields": [{"name": n, "type": "float" if t == "FIELD_TYPE_FLOAT" else "int"} for n, t in fields],
             "rows": rows,
             "query": {"group_by": gb["tagProjection"]["tagFamilies"][0]["tags"][0], "agg": q["agg"]["function"].replace("AGGREGATION_FUNCTION_", ""),
-                      "field": q["agg"]["fieldName"], "top": top, "criteria": crit},
+                      "field": q["agg"]["fieldName"], "top": top, "criteria": crit,
+                      "order": (q.get("orderBy") or {}).get("sort"),
+                      "projected_tags": q["tagProjection"]["tagFamilies"][0]["tags"]},
             "want": wrows,
         }
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "e2e_cases.json")

@@ -651,3 +651,44 @@ def test_reference_e2e_cases_on_the_device(bydb, gpu_ctx, name):
     got, oracle_res = run_both(bydb, gpu_ctx, [part], oq, _next_pid())
     check_e2e_rows(got, names, want, ordered, name)
     assert_parity(got, oracle_res, oq.aggs, f"e2e/{name}")
+
+
+@pytest.mark.parametrize("name", [c for c in E2E_CASES if c.startswith("gen_feat_") or c.startswith("float_top") or c == "top"])
+def test_reference_e2e_cases_through_the_operator(bydb, gpu_ctx, name):
+    # the same cases through the PullOperator mirror: row order (group first-appearance under the request's order-by, or Top order),
+    # the non-key projected tag's first-seen value, values -- exactly the rows of the reference's want/*.yaml
+    import json, os
+    case = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "e2e_cases.json")))[name]
+    part, oq, names, want, ordered = load_e2e_case(name)
+    V = bydb
+    h = gpu_ctx.register_part(_next_pid(), part.files())
+    try:
+        tags, q = case["tags"], case["query"]
+        proj = q["projected_tags"]
+        is_float = next(f["type"] for f in case["fields"] if f["name"] == q["field"]) == "float"
+        schema = V.BatchSchema([V.ColumnDef(t, V.ColumnRole.RoleTag, V.ColumnType.ColumnTypeString, case["family"]) for t in proj] +
+                               [V.ColumnDef(q["field"], V.ColumnRole.RoleField, V.ColumnType.ColumnTypeFloat64 if is_float else V.ColumnType.ColumnTypeInt64)])
+        # per-series tag values in series order (= first appearance in the data, which is time order)
+        ent_rows = {}
+        for r in case["rows"]:
+            ent_rows.setdefault(tuple(r["tags"][tags.index(t)] for t in case["entity"]), r)
+        series_rows = list(ent_rows.values())
+        series_tags = {(case["family"], t): [r["tags"][tags.index(t)] for r in series_rows] for t in proj}
+        func = {"SUM": V.AggSum, "COUNT": V.AggCount, "MIN": V.AggMin, "MAX": V.AggMax, "MEAN": V.AggMean}[q["agg"]]
+        preds = [V.Pred(p.family, p.tag, p.op, p.value) for p in oq.preds]
+        op = V.GPUScanAgg(gpu_ctx, schema, [proj.index(q["group_by"])], [V.AggSpec(q["field"], func, len(proj))],
+                          V.ScanSpec(parts=[h], series_ids=np.asarray(oq.sids, dtype=np.uint64), series_tags=series_tags, preds=preds,
+                                     order_desc=q["order"] == "SORT_DESC"),
+                          batch_size=2, top=V.TopSpec(q["top"]["n"], 0, q["top"]["desc"]) if q["top"] else None)
+        op.Init()
+        rows = []
+        while (b := op.NextBatch()) is not None:
+            for i in range(b.Len):
+                rows.append(({t: b.Columns[k][i] for k, t in enumerate(proj)}, b.Columns[len(proj)][i]))
+        op.Close()
+        assert len(rows) == len(want), (rows, want)
+        for (gt, gv), w in zip(rows, want):
+            assert gt == {t: w["tags"][t] for t in proj}, f"{name}: tags {gt} vs {w['tags']}"
+            assert abs(float(gv) - float(w["value"])) <= 1e-9 * max(abs(float(w["value"])), 1e-300), f"{name}: {gv} vs {w['value']}"
+    finally:
+        gpu_ctx.release_part(h)
