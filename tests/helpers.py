@@ -119,3 +119,49 @@ def check_e2e_rows(res, names, want, ordered, ctx=""):
     for (g, a), (_, b) in zip(got, exp):
         # the row path's COUNT of a float field is a float; the vectorized path this library mirrors returns int64
         assert abs(float(a) - float(b)) <= 1e-9 * max(abs(float(b)), 1e-300), f"{ctx}: {g}: {a} vs {b}"
+
+
+# ------------------------------------------------------------------ the fixtures of banyand/measure/query_test.go (tstable_test.go:333-487)
+def query_test_fixture(which):
+    """dpsTS1 / dpsTS11 / dpsTS2 reduced to what the hot path reads: series 1..3 at one timestamp with versions, an int64 and a
+    float64 field (series 2 carries no field, series 3 only the int field -> null cells), and the int64 tag."""
+    spec = {
+        "dpsTS1": dict(ts=1, versions=[1, 2, 3], intField=[1110, None, 1110], floatField=[1221233.343, None, None], intTag=[10, None, None]),
+        "dpsTS11": dict(ts=1, versions=[0, 1, 2], intField=[3330, None, 4440], floatField=[3663699.029, None, None], intTag=[30, None, None]),
+        "dpsTS2": dict(ts=2, versions=[4, 5, 6], intField=[3330, None, 4440], floatField=[3663699.029, None, None], intTag=[30, None, None]),
+    }[which]
+    sids = np.array([1, 2, 3], dtype=np.uint64)
+    ts = np.full(3, spec["ts"], dtype=np.int64)
+    ver = np.array(spec["versions"], dtype=np.int64)
+
+    def col(vals, dtype):
+        nulls = np.array([v is None for v in vals], dtype=np.uint8)
+        return np.array([0 if v is None else v for v in vals], dtype=dtype), nulls
+    iv, inull = col(spec["intField"], np.int64)
+    fv, fnull = col(spec["floatField"], np.float64)
+    tv, tnull = col(spec["intTag"], np.int64)
+    return build_part(sids, ts, ver, [("intField", O.VT_INT64, iv, inull), ("floatField", O.VT_FLOAT64, fv, fnull)],
+                      [("singleTag", [("intTag", O.VT_INT64, tv, tnull)])])
+
+
+# expected per-series aggregates of the cases of TestQueryResult (query_test.go:48-1364), derived from the rows its `want` keeps:
+# (parts, {sid: (rows, sum(intField), count(intField), max(floatField) or None)}, kept versions per sid)
+QUERY_TEST_CASES = {
+    "duplicated data": (["dpsTS1", "dpsTS1"], {1: (1, 1110, 1, 1221233.343), 2: (1, 0, 0, None), 3: (1, 1110, 1, None)}, {1: [1], 2: [2], 3: [3]}),
+    "different version 1": (["dpsTS1", "dpsTS11"], {1: (1, 1110, 1, 1221233.343), 2: (1, 0, 0, None), 3: (1, 1110, 1, None)}, {1: [1], 2: [2], 3: [3]}),
+    "different version 2": (["dpsTS11", "dpsTS1"], {1: (1, 1110, 1, 1221233.343), 2: (1, 0, 0, None), 3: (1, 1110, 1, None)}, {1: [1], 2: [2], 3: [3]}),
+    "multiple data 1": (["dpsTS1", "dpsTS2"], {1: (2, 4440, 2, 3663699.029), 2: (2, 0, 0, None), 3: (2, 5550, 2, None)}, {1: [1, 4], 2: [2, 5], 3: [3, 6]}),
+    "multiple data 2": (["dpsTS2", "dpsTS1"], {1: (2, 4440, 2, 3663699.029), 2: (2, 0, 0, None), 3: (2, 5550, 2, None)}, {1: [1, 4], 2: [2, 5], 3: [3, 6]}),
+}
+QUERY_TEST_AGGS = [("intField", O.AGG_SUM), ("intField", O.AGG_COUNT), ("floatField", O.AGG_MAX), ("floatField", O.AGG_COUNT)]
+
+
+def check_query_test_case(res, expect, ctx=""):
+    assert res.group_id.tolist() == [0, 1, 2], ctx
+    for g, sid in enumerate((1, 2, 3)):
+        rows, isum, icnt, fmax = expect[sid]
+        assert int(res.rows[g]) == rows, f"{ctx}: rows of series {sid}"
+        assert int(res.val_i64[g, 0]) == isum and int(res.val_i64[g, 1]) == icnt, f"{ctx}: intField of series {sid}"
+        assert int(res.val_i64[g, 3]) == (0 if fmax is None else rows), f"{ctx}: count(floatField) of series {sid}"
+        if fmax is not None:
+            assert float(res.val_f64[g, 2]) == fmax, f"{ctx}: max(floatField) of series {sid}"

@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from tests.helpers import E2E_CASES, STEP, T0, assert_parity, build_part, check_e2e_rows, grid, load_e2e_case, run_both
+from tests.helpers import (E2E_CASES, QUERY_TEST_AGGS, QUERY_TEST_CASES, STEP, T0, assert_parity, build_part, check_e2e_rows,
+                           check_query_test_case, grid, load_e2e_case, query_test_fixture, run_both)
 
 pytestmark = pytest.mark.gpu
 
@@ -692,3 +693,19 @@ def test_reference_e2e_cases_through_the_operator(bydb, gpu_ctx, name):
             assert abs(float(gv) - float(w["value"])) <= 1e-9 * max(abs(float(w["value"])), 1e-300), f"{name}: {gv} vs {w['value']}"
     finally:
         gpu_ctx.release_part(h)
+
+
+@pytest.mark.parametrize("case", sorted(QUERY_TEST_CASES))
+def test_reference_query_test_fixtures_on_the_device(bydb, gpu_ctx, case):
+    # banyand/measure/query_test.go TestQueryResult on dpsTS1 / dpsTS11 / dpsTS2: cross-part version dedup in either part order,
+    # series without a field (all-null fallback pages), per-series aggregates of the surviving rows
+    names, expect, _ = QUERY_TEST_CASES[case]
+    parts = [query_test_fixture(n) for n in names]
+    oq = O.Query(parts, [1, 2, 3], QUERY_TEST_AGGS, groups=np.arange(3, dtype=np.int32), n_groups=3, tmin=1, tmax=2)
+    got, want = run_both(bydb, gpu_ctx, parts, oq, _next_pid())
+    check_query_test_case(got, expect, case)
+    assert_parity(got, want, QUERY_TEST_AGGS, f"query_test/{case}")
+    # the int64 tag with null cells as a row predicate on top of the dedup (series 1 only carries it)
+    oq.preds = [O.Pred("singleTag", "intTag", O.OP_GE, 10)]
+    got, want = run_both(bydb, gpu_ctx, parts, oq, _next_pid())
+    assert_parity(got, want, QUERY_TEST_AGGS, f"query_test/{case}/pred")

@@ -197,3 +197,17 @@ def test_part_reopen_from_files():
     q = lambda p: O.run_query(O.Query([p], np.unique(sids), [("latency", O.AGG_SUM), ("calls", O.AGG_MAX)]))
     assert q(part).val_f64.tolist() == q(again).val_f64.tolist()
     assert again.meta()["total_count"] == sids.size
+
+
+@pytest.mark.parametrize("case", sorted(__import__("tests.helpers", fromlist=["x"]).QUERY_TEST_CASES))
+def test_reference_query_test_fixtures(case):
+    # banyand/measure/query_test.go TestQueryResult on dpsTS1 / dpsTS11 / dpsTS2 (tstable_test.go:333-487): which rows survive the
+    # cross-part merge (highest version per (series, timestamp), either part order) and what they aggregate to
+    from tests.helpers import QUERY_TEST_AGGS, QUERY_TEST_CASES, check_query_test_case, query_test_fixture
+    names, expect, versions = QUERY_TEST_CASES[case]
+    parts = [query_test_fixture(n) for n in names]
+    q = O.Query(parts, [1, 2, 3], QUERY_TEST_AGGS, groups=np.arange(3, dtype=np.int32), n_groups=3, tmin=1, tmax=2)
+    check_query_test_case(O.run_query(q), expect, case)
+    rows = O.scan_rows(q)
+    for sid, vs in versions.items():
+        assert rows["version"][rows["sid"] == sid].tolist() == vs, f"{case}: versions kept for series {sid}"
