@@ -17,6 +17,8 @@ def pytest_configure(config):
 
 def _load_pkg():
     import __graft_entry__ as ge
+    if not os.path.exists(os.path.join(ge.PKG_DIR, "libbydbgpu.so")):
+        ge.build()  # a fresh checkout has no built artefacts (they are git-ignored): compile the CUDA library first
     return ge.load_package()
 
 
