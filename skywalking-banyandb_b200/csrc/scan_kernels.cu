@@ -584,7 +584,39 @@ struct FastChunk {
     uint32_t valid, term, n;
     bool wide;
 };
+#ifdef BYDB_EXP_INTERIOR
+// EXPERIMENT (off by default, `make variant EXTRA=-DBYDB_EXP_INTERIOR`): chunks that lie completely inside the page skip
+// the validity arithmetic of the front end (warp-uniform branch).
+__device__ __forceinline__ void fast_chunk_load_interior(FastChunk &fc, const uint8_t *buf, uint32_t c, uint32_t carry_sh, int lane) {
+    const uint32_t o = c * kFastChunkBytes + lane * kFastLaneBytes;
+    fc.wa = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes));
+    fc.wb = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes) + 16);
+    fc.valid = 0xffffffffu;
+    uint32_t msb = msb4(fc.wa.x);
+    msb = imad_u32(msb4(fc.wa.y), 1u << 4, msb);
+    msb = imad_u32(msb4(fc.wa.z), 1u << 8, msb);
+    msb = imad_u32(msb4(fc.wa.w), 1u << 12, msb);
+    msb = imad_u32(msb4(fc.wb.x), 1u << 16, msb);
+    msb = imad_u32(msb4(fc.wb.y), 1u << 20, msb);
+    msb = imad_u32(msb4(fc.wb.z), 1u << 24, msb);
+    msb = imad_u32(msb4(fc.wb.w), 1u << 28, msb);
+    fc.term = ~msb;
+    fc.n = __popc(fc.term);
+    const uint32_t lead = fc.term ? static_cast<uint32_t>(__ffs(fc.term) - 1) : 32u;
+    const uint32_t trail = fc.term ? static_cast<uint32_t>(__clz(fc.term)) : 32u;
+    uint32_t trail_prev = __shfl_up_sync(0xffffffffu, trail, 1);
+    if (lane == 0) trail_prev = carry_sh / 7;
+    fc.wide = __any_sync(0xffffffffu, (msb & (msb >> 1) & (msb >> 2)) != 0 || (trail_prev + lead) > 2);
+}
+#endif
+
 __device__ __forceinline__ void fast_chunk_load(FastChunk &fc, const PageStream &st, const uint8_t *buf, uint32_t c, uint32_t carry_sh, int lane) {
+#ifdef BYDB_EXP_INTERIOR
+    if (c * kFastChunkBytes >= st.pstart && (c + 1) * kFastChunkBytes <= st.pend) {
+        fast_chunk_load_interior(fc, buf, c, carry_sh, lane);
+        return;
+    }
+#endif
     const uint32_t o = c * kFastChunkBytes + lane * kFastLaneBytes;
     fc.wa = make_uint4(0, 0, 0, 0);
     fc.wb = make_uint4(0, 0, 0, 0);

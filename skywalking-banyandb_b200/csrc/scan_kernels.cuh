@@ -11,8 +11,14 @@
 namespace bydb {
 
 constexpr int kWarpsPerCta = 8;          // 256 threads; every warp is an independent block worker
-constexpr int kStageBytes = 2048;        // one TMA bulk copy (cp.async.bulk) per stage
-constexpr int kStages = 2;               // per-warp ring: decode stage k while stage k+1 lands
+#ifndef BYDB_STAGE_BYTES
+#define BYDB_STAGE_BYTES 2048            // experiment knobs (make variant EXTRA="-DBYDB_STAGE_BYTES=4096 -DBYDB_STAGES=3")
+#endif
+#ifndef BYDB_STAGES
+#define BYDB_STAGES 2
+#endif
+constexpr int kStageBytes = BYDB_STAGE_BYTES;  // one TMA bulk copy (cp.async.bulk) per stage
+constexpr int kStages = BYDB_STAGES;           // per-warp ring: decode stage k while stage k+1 lands
 constexpr int kChunkBytes = 512;         // 32 lanes x 16 B per decode iteration
 constexpr int kMaskWords = 264;          // row bitmask: 8448 rows (memPart blocks hold <= 8193 rows)
 constexpr int kMaxFcols = 8;             // distinct aggregated fields per query
