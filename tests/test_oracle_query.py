@@ -211,3 +211,25 @@ def test_reference_query_test_fixtures(case):
     rows = O.scan_rows(q)
     for sid, vs in versions.items():
         assert rows["version"][rows["sid"] == sid].tolist() == vs, f"{case}: versions kept for series {sid}"
+
+
+@pytest.mark.parametrize("vals,n,asc,want", [
+    ([5, 2, 8, 1, 7, 3], 3, True, [1, 2, 3]),      # top_test.go:71-88  TestBatchTop_AscendingHeap_KeepsLowestN
+    ([5, 2, 8, 1, 7, 3], 3, False, [8, 7, 5]),     # top_test.go:90-104 TestBatchTop_DescendingHeap_KeepsHighestN
+    ([3, 1, 2], 5, True, [1, 2, 3]),               # top_test.go:106-123 TestBatchTop_FewerInputThanN_ReturnsAll_InOrder
+])
+def test_top_known_answers_top_test_go(vals, n, asc, want):
+    sids = np.arange(1, len(vals) + 1, dtype=np.uint64)
+    part = _build(sids, np.full(len(vals), T0, np.int64), np.ones(len(vals), np.int64), f_int=np.array(vals))
+    r = O.run_query(O.Query([part], sids, [("calls", O.AGG_SUM)], groups=np.arange(len(vals), dtype=np.int32), n_groups=len(vals),
+                            top_n=n, top_desc=not asc))
+    assert r.val_i64[:, 0].tolist() == want
+
+
+def test_top_tie_breaker_stable_top_test_go():
+    # top_test.go:125-158 TestBatchTop_TieBreaker_Stable: all values equal, only the first two rows are retained
+    sids = np.arange(1, 5, dtype=np.uint64)
+    part = _build(sids, np.full(4, T0, np.int64), np.ones(4, np.int64), f_int=np.full(4, 5))
+    for desc in (False, True):
+        r = O.run_query(O.Query([part], sids, [("calls", O.AGG_SUM)], groups=np.arange(4, dtype=np.int32), n_groups=4, top_n=2, top_desc=desc))
+        assert r.group_id.tolist() == [0, 1]
