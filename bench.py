@@ -134,8 +134,9 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_rate(files, sids_all, n_points, threads, target_seconds):
-    """Datapoints/s of the oracle (reference-shaped: decode pool + single-threaded merge/fold) on a bounded sample."""
+def cpu_port_rate(files, sids_all, n_points, threads, target_seconds, per_thread_partials=False):
+    """Datapoints/s of the oracle on a bounded sample.  Default = reference-shaped (decode pool + single-threaded
+    merge/fold, like mergeBatch/Consume); per_thread_partials = the optimistic all-core variant of SURVEY.md 8(d)."""
     from oracle import oracle as O
     part = O.Part.open({k: bytes(v) for k, v in files.items()})
     tmin = T0 + (n_points // 4) * STEP
@@ -143,7 +144,7 @@ def cpu_port_rate(files, sids_all, n_points, threads, target_seconds):
 
     def run(nser):
         q = O.Query([part], sids_all[:nser], [("latency", O.AGG_MEAN), ("walk", O.AGG_MAX)], tmin=tmin, tmax=tmax,
-                    preds=[O.Pred("default", "region", O.OP_EQ, b"r3")], threads=threads)
+                    preds=[O.Pred("default", "region", O.OP_EQ, b"r3")], threads=threads, per_thread_partials=per_thread_partials)
         t = time.perf_counter()
         r = O.run_query(q)
         return time.perf_counter() - t, r
@@ -406,6 +407,12 @@ def main():
         out["cpu_baseline"] = {"value": rate, "unit": "datapoints/s", "cores": cores, "kind": "port",
                                "sample": f"{nser} of {n_series} series of the same part ({r.rows_scanned} datapoints, {cdt:.1f} s); "
                                          "C port of the reference Go path: decode on a thread pool, single-threaded merge+fold"}
+        try:  # the optimistic variant (every core folds its own partials), so the GPU is not compared against a strawman
+            rate2, nser2, _, cdt2 = cpu_port_rate(files, sids, n_points, cores, min(args.cpu_seconds, 6.0), per_thread_partials=True)
+            out["cpu_baseline"]["all_core_partials_variant"] = {"value": rate2, "unit": "datapoints/s", "cores": cores,
+                                                                "sample": f"{nser2} of {n_series} series, {cdt2:.1f} s; per-thread partial aggregates"}
+        except Exception as ex:
+            out["cpu_baseline"]["all_core_partials_variant"] = {"error": str(ex)[:120]}
         if last is not None and nser == n_series:
             out["cpu_baseline"]["agrees_with_gpu"] = bool(abs(r.val_f64[0, 0] - last.val_f64[0, 0]) <= 1e-9 * abs(r.val_f64[0, 0])
                                                           and r.val_f64[0, 1] == last.val_f64[0, 1])
