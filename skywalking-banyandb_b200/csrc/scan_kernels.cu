@@ -505,7 +505,8 @@ __device__ __forceinline__ int32_t imad_s32(int32_t a, int32_t b, int32_t c) {
 
 // kMasked: the chunk holds bytes outside the page (first / last chunk): `reset` = term | ~valid restarts the varint
 // state at those bytes too, their payload is zeroed by the caller, and only real terminators (term) count as rows.
-template <int kNeed, bool kMasked>
+// kAllRows (only instantiated by the BYDB_EXP_ALLROWS experiment): every row of the block is active, no window arithmetic.
+template <int kNeed, bool kMasked, bool kAllRows = false>
 __device__ __forceinline__ void fast_lane_decode_imad(const uint4 &wa, const uint4 &wb, uint32_t term, uint32_t reset, uint32_t aw, uint32_t &accv,
                                                       uint32_t &sh, int32_t &P, int32_t &sumP, int32_t &minP, int32_t &maxP) {
     // 8 words x 4 bytes: the word loop stays rolled so that the body (the hottest code of the whole
@@ -525,7 +526,7 @@ __device__ __forceinline__ void fast_lane_decode_imad(const uint4 &wa, const uin
             const uint32_t h = accv >> 1, s = accv & 1u;
             const int32_t v = imad_s32(static_cast<int32_t>(s), static_cast<int32_t>(0u - accv), static_cast<int32_t>(h));
             P = imad_s32(v, static_cast<int32_t>(t), P);
-            const uint32_t at = aw & t;  // terminator of an active row
+            const uint32_t at = kAllRows ? t : (aw & t);  // terminator of an active row
             if (kNeed & kNeedSum) sumP = imad_s32(P, static_cast<int32_t>(at), sumP);
             if (kNeed & kNeedMinMax) {
                 // candidate = P at an active terminator, the neutral element otherwise
@@ -534,7 +535,7 @@ __device__ __forceinline__ void fast_lane_decode_imad(const uint4 &wa, const uin
                 minP = lo_c < minP ? lo_c : minP;
                 maxP = hi_c > maxP ? hi_c : maxP;
             }
-            aw >>= t;
+            if (!kAllRows) aw >>= t;
             accv = imad_u32(accv, nr, 0u);
             mul = imad_u32(mul, imad_u32(nr, 128u, 0u), nr ^ 1u);
         }
@@ -812,7 +813,14 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const u
         // ---- decode: local prefix P, folded over the active rows
         uint32_t accv = 0, sh = 0;
         int32_t P = 0, sumP = 0, minP = INT32_MAX, maxP = INT32_MIN;
-        if (__all_sync(0xffffffffu, fc.valid == 0xffffffffu)) fast_lane_decode<true, kNeed>(fc.wa, fc.wb, fc.valid, fc.term, aw, accv, sh, P, sumP, minP, maxP);
+        const bool full_chunk = __all_sync(0xffffffffu, fc.valid == 0xffffffffu);
+#ifdef BYDB_EXP_ALLROWS
+        // EXPERIMENT (off by default): a query without row predicate over a block fully inside the time range needs no
+        // active-row window in the byte loop (BASELINE config 3: group-by sum over every row)
+        if (kMode == kRowsAll && full_chunk) fast_lane_decode_imad<kNeed, false, true>(fc.wa, fc.wb, fc.term, fc.term, aw, accv, sh, P, sumP, minP, maxP);
+        else
+#endif
+        if (full_chunk) fast_lane_decode<true, kNeed>(fc.wa, fc.wb, fc.valid, fc.term, aw, accv, sh, P, sumP, minP, maxP);
         else fast_lane_decode<false, kNeed>(fc.wa, fc.wb, fc.valid, fc.term, aw, accv, sh, P, sumP, minP, maxP);
         // ---- head correction by the previous lane's unfinished tail
         uint32_t prev_acc = __shfl_up_sync(0xffffffffu, accv, 1);
