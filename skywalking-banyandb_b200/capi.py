@@ -278,6 +278,8 @@ def _read_result(r: _Result) -> Result:
     def arr(ptr, count, dtype):
         if count == 0:
             return np.zeros(0, dtype=dtype)
+        if count <= 256:   # typical aggregate results are a handful of rows: slicing the pointer beats wrapping it (~2 us per array)
+            return np.array(ptr[:count], dtype=dtype)
         return np.ctypeslib.as_array(ptr, (count,)).copy()
 
     return Result(group_id=arr(r.group_id, n, np.int32), rows=arr(r.rows, n, np.int64),
