@@ -6,7 +6,9 @@ set -e
 cd "$(dirname "$0")/../skywalking-banyandb_b200"
 mkdir -p variants
 build() { echo "== $1: $2"; make -s variant OUT=variants/$1.so EXTRA="$2"; grep -A3 "scan_blocks_kernelILb1" build_variant.log | grep -E "registers|spill" || true; }
+build earlystop "-DBYDB_EXP_EARLYSTOP"
 build dual "-DBYDB_EXP_DUAL"
+build dual_earlystop "-DBYDB_EXP_DUAL -DBYDB_EXP_EARLYSTOP"
 build dual_allrows "-DBYDB_EXP_DUAL -DBYDB_EXP_ALLROWS"
 build interior "-DBYDB_EXP_INTERIOR"
 build dual_interior "-DBYDB_EXP_DUAL -DBYDB_EXP_INTERIOR"

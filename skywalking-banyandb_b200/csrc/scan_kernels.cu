@@ -865,6 +865,19 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const u
         }
         V0 += static_cast<int64_t>(__shfl_sync(0xffffffffu, s_in, 31));
         row_base += n_tot;
+#ifdef BYDB_EXP_EARLYSTOP
+        // EXPERIMENT (off by default): rows after r1 are never active (the time range is folded into the mask too), and
+        // nothing later in the page feeds an active row, so the rest of the page is neither fetched nor decoded.  The
+        // stages already in flight are drained exactly like on the wide-varint bail-out.  (The tail is then not
+        // validated against the block's row count.)
+        if (kMode != kRowsAll && row_base > r1 && c + 1 < nchunks) {
+            stream_drain(st, sm, k);
+            seq = st.seq0 + min(st.nstages, k + static_cast<uint32_t>(kStages));
+            __syncwarp();
+            acc_io = acc;
+            return 0;
+        }
+#endif
         if ((c % kChunksPerStage) == kChunksPerStage - 1 || c == nchunks - 1) stream_release(st, sm, k, lane);
     }
     acc_io = acc;
