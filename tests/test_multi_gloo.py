@@ -86,8 +86,27 @@ def _worker(rank, world, port, out):
     layout = {k: getattr(lay, k) for k, _ in _Layout._fields_}
     oq = O.Query([part], all_sids, [], groups=groups, n_groups=4, tmin=gq.tmin, tmax=gq.tmax)
     tab = torch.from_numpy(_fill_table(layout, oq, 4, ["latency", "calls"], [O.VT_FLOAT64, O.VT_INT64]))
+    mine = tab.clone()
     n = multi.allreduce_partial_table(tab, layout, dist)
     assert n == 4
+    # the other reduce (the one bench.py runs over NCCL): ONE all-gather of the tables, then the rank-ordered combine that
+    # bydb_partials_combine performs on the device -- restated here in numpy: SUM ranges add in rank order, MAX ranges take the max
+    gathered = torch.empty(world * mine.numel(), dtype=torch.float64)
+    dist.all_gather_into_tensor(gathered, mine)
+    tabs = gathered.numpy().reshape(world, -1)
+    comb = tabs[0].copy()
+    ci = comb.view(np.int64)
+    for r in range(1, world):
+        ti = tabs[r].view(np.int64)
+        a, k = layout["off_sum_f64"] // 8, layout["n_sum_f64"]
+        comb[a:a + k] += tabs[r][a:a + k]
+        a, k = layout["off_max_f64"] // 8, layout["n_max_f64"]
+        comb[a:a + k] = np.maximum(comb[a:a + k], tabs[r][a:a + k])
+        a, k = layout["off_sum_i64"] // 8, layout["n_sum_i64"]
+        ci[a:a + k] += ti[a:a + k]
+        a, k = layout["off_max_i64"] // 8, layout["n_max_i64"]
+        ci[a:a + k] = np.maximum(ci[a:a + k], ti[a:a + k])
+    assert comb.view(np.int64).tolist() == tab.numpy().view(np.int64).tolist(), "all-gather + combine must equal the all-reduce result"
     if rank == 0:
         np.save(out, tab.numpy())
     dist.destroy_process_group()
