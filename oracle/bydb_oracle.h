@@ -115,6 +115,7 @@ void ob_bitw_bool(ob_bitw *w, int b);
 void ob_bitw_bits(ob_bitw *w, uint64_t u, int nbits);
 void ob_bitw_byte(ob_bitw *w, uint8_t b);
 void ob_bitw_flush(ob_bitw *w);
+int ob_bit_reader_script(const uint8_t *data, size_t n, const int *ops, size_t n_ops, uint64_t *out); /* reader.go test hook */
 
 /* ---- zstd (pkg/compress/zstd/zstd.go:49-57) via dlopen(libzstd.so.1) ---- */
 int ob_zstd_compress(ob_buf *dst, const void *src, size_t n, int level);

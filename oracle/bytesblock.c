@@ -308,6 +308,26 @@ static int bitr_bits(bitr *r, int nbits, uint64_t *out) {
     return 0;
 }
 
+/* test hook for pkg/encoding/reader_test.go: runs a script of reads over `data`.
+ * ops[i]: 0 = ReadBool, -1 = ReadByte, n > 0 = ReadBits(n); out[i] receives the value. Returns 0 or -1. */
+int ob_bit_reader_script(const uint8_t *data, size_t n, const int *ops, size_t n_ops, uint64_t *out) {
+    bitr r = {data, n, 0, 0, 0};
+    for (size_t i = 0; i < n_ops; i++) {
+        if (ops[i] == 0) {
+            int bit;
+            if (bitr_bool(&r, &bit)) return -1;
+            out[i] = (uint64_t)bit;
+        } else if (ops[i] < 0) {
+            uint8_t b;
+            if (bitr_byte(&r, &b)) return -1;
+            out[i] = b;
+        } else if (bitr_bits(&r, ops[i], &out[i])) {
+            return -1;
+        }
+    }
+    return 0;
+}
+
 /* dictionary.go:199-219 bitPackingEncoder.encode + :253-261 encodeBitPacking */
 void ob_bitpack_encode(ob_buf *dst, const uint32_t *src, size_t n) {
     ob_bitw w;

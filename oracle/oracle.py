@@ -325,6 +325,17 @@ class BitWriter:
         return self._buf.bytes()
 
 
+def bit_reader_script(data: bytes, ops: Sequence[int]) -> List[int]:
+    """pkg/encoding/reader.go Reader over `data`: ops 0 = ReadBool, -1 = ReadByte, n > 0 = ReadBits(n)."""
+    arr = (C.c_int * len(ops))(*ops)
+    out = (C.c_uint64 * len(ops))()
+    L = lib()
+    L.ob_bit_reader_script.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.c_size_t, C.POINTER(C.c_uint64)]
+    if L.ob_bit_reader_script(data, len(data), arr, len(ops), out) != 0:
+        raise RuntimeError("bit reader ran out of data")
+    return list(out)
+
+
 def zstd_compress(data: bytes, level: int = 1) -> bytes:
     b = _Buf()
     if lib().ob_zstd_compress(C.byref(b), data, len(data), level) != 0:

@@ -180,6 +180,13 @@ def test_bit_writer_golden():
     assert w.bytes() == bytes([0xC1, 0x7F, 0xAC, 0x89, 0x24, 0x78, 0x01, 0x02, 0xF8, 0x08, 0xF0, 0xFF, 0x80])
 
 
+# ---- pkg/encoding/reader_test.go:27-45 bit reader known answers
+def test_bit_reader_golden():
+    data = bytes([3, 255, 0xCC, 0x1A, 0xBC, 0xDE, 0x80])
+    got = O.bit_reader_script(data, [-1, 8, 4, 8, 20, 0, 0])
+    assert got == [3, 255, 0xC, 0xC1, 0xABCDE, 1, 0]
+
+
 # ---- pkg/encoding/bytes_test.go:48-208: nil vs empty, large (zstd) blocks
 def test_bytes_block_nil_vs_empty():
     items = [None, b"", b"a", None, b"hello world", b""]
