@@ -467,7 +467,10 @@ int ob_float_to_decimal(double f, int64_t *mant, int16_t *exp) {
         if (a < 9007199254740992.0 && a >= 1e-15) {
             for (int k = 1; k <= 15; k++) {
                 double t = a * p10[k];
-                if (t >= 9007199254740992.0) break;
+                /* only mantissas of <= 15 digits: there the doubles around t are < 1 apart after scaling, so at most ONE
+                 * integer m maps back to f.  With 16-17 digits several neighbours round-trip and the shortest-digits rule
+                 * (strconv 'e', -1: the candidate closest to the exact value) must decide -- that is the general search. */
+                if (t >= 1e15) break;
                 double m0 = nearbyint(t);
                 for (int dm = -1; dm <= 1; dm++) {
                     double m = m0 + dm;

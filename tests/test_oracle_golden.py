@@ -322,3 +322,26 @@ def test_fast_and_general_shortest_decimal_agree():
             got_slow.append(None)
     O.force_slow_float(False)
     assert got_fast == got_slow
+
+
+def test_shortest_decimal_matches_an_independent_shortest_repr():
+    # float.go:128-190 relies on strconv.AppendFloat(f, 'e', -1, 64): the shortest digits that round-trip and, among several
+    # candidates of that length, the one closest to the exact value.  Python's repr() implements the same contract (David Gay),
+    # so mantissa/exponent must agree for doubles of every digit count -- 16-digit values are where two candidates round-trip.
+    from decimal import Decimal
+    rng = np.random.default_rng(77)
+    vals = np.concatenate([rng.standard_normal(3000) * 10.0 ** rng.integers(-6, 9, 3000), rng.random(1000) * 1e5,
+                           np.round(rng.random(1000) * 1e4, 3), np.array([70828.40467154187, -88378.67643533742, 0.1 + 0.2, 1 / 3])])
+    for slow in (False, True):
+        O.force_slow_float(slow)
+        try:
+            for v in vals.tolist():
+                sign, digits, e = Decimal(repr(v)).as_tuple()
+                m = int("".join(map(str, digits)))
+                while m and m % 10 == 0:
+                    m //= 10
+                    e += 1
+                ints, exp = O.float64_to_decimal_list([v])
+                assert (int(ints[0]), exp) == ((-m if sign else m), e), (v, slow)
+        finally:
+            O.force_slow_float(False)

@@ -126,3 +126,30 @@ def test_synth_is_deterministic_across_thread_counts(bydb):
     a = S.synth_part(20, 3000, fields, region_values=4, region_run=8, threads=1)
     b = S.synth_part(20, 3000, fields, region_values=4, region_run=8, threads=5)
     _same_files(a.files(), b.files())
+
+
+def test_writers_agree_on_random_shapes(bydb):
+    # small blocks of full-precision floats stay decimal pages (one exponent fits), which makes the shortest-digits rule of
+    # float.go:128-190 visible in the bytes: the two independent writers must still emit identical files
+    from importlib import import_module
+    S = import_module("bydb_b200.synth")
+    for seed in (11, 15, 19, 28, 36, 38, 5, 6):
+        rng = np.random.default_rng(1000 + seed)
+        ns, npts = int(rng.integers(1, 6)), int(rng.choice([1, 2, 100, 8193, 9000]))
+        sids, ts, ver = grid(ns, npts, sid0=int(rng.integers(1, 100)), sid_step=int(rng.integers(1, 7)))
+        if rng.random() < 0.5:
+            ts = (T0 + np.tile(np.cumsum(rng.integers(1, 1000, npts)), ns) * 1000).astype(np.int64)
+        n = sids.size
+        digs = int(rng.integers(0, 5))
+        k = rng.integers(-10 ** int(rng.integers(1, 9)), 10 ** int(rng.integers(1, 9)), n).astype(np.int64)
+        f2 = rng.standard_normal(n) * 10.0 ** int(rng.integers(-5, 8))
+        i1 = rng.integers(-2 ** int(rng.integers(1, 62)), 2 ** int(rng.integers(1, 62)), n)
+        nv = int(rng.choice([1, 3, 40, 200, 300]))
+        ridx = rng.integers(0, nv, n).astype(np.uint32)
+        rvals = [b"value-%04d-%s" % (i, b"x" * int(rng.integers(0, 12))) for i in range(nv)]
+        img = S.write_part(sids, ts, ver, [("f1", O.VT_FLOAT64, k, digs), ("f2", O.VT_FLOAT64, f2), ("i1", O.VT_INT64, i1)],
+                           "default", [("tag", O.VT_STR, ridx, rvals)], threads=int(rng.integers(1, 4)))
+        b = O.PartBuilder()
+        b.append(sids, ts, ver, [("f1", O.VT_FLOAT64, k / (10.0 ** digs), None), ("f2", O.VT_FLOAT64, f2, None), ("i1", O.VT_INT64, i1, None)],
+                 [("default", [("tag", O.VT_STR, [rvals[i] for i in ridx], None)])])
+        _same_files(img.files(), b.finish().files())
