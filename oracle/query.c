@@ -554,7 +554,13 @@ static void merge_series(folder *fo, cursor **cs, size_t k, int32_t gid) {
                 continue;
             }
             int64_t a = c->ts[c->idx], b = best->ts[best->idx];
-            if (a < b || (a == b && c->ver[c->idx] > best->ver[best->idx])) best = c;
+            /* equal (timestamp, version) in several parts: the reference's heap leaves the winner to container/heap's
+             * internal order (Less is false both ways, query.go:912-942; the first one popped is kept, :995-1004), i.e. it
+             * is unspecified -- real writes never produce it with different values.  Oracle and device both define it:
+             * the row of the earlier part of the query wins. */
+            if (a < b || (a == b && (c->ver[c->idx] > best->ver[best->idx] ||
+                                     (c->ver[c->idx] == best->ver[best->idx] && c->part < best->part))))
+                best = c;
         }
         if (!best) break;
         int64_t t = best->ts[best->idx];

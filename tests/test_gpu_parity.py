@@ -709,3 +709,17 @@ def test_reference_query_test_fixtures_on_the_device(bydb, gpu_ctx, case):
     oq.preds = [O.Pred("singleTag", "intTag", O.OP_GE, 10)]
     got, want = run_both(bydb, gpu_ctx, parts, oq, _next_pid())
     assert_parity(got, want, QUERY_TEST_AGGS, f"query_test/{case}/pred")
+
+
+def test_equal_version_duplicates_keep_the_earlier_part(bydb, gpu_ctx):
+    # same (series, timestamp, version) in two parts with different values: unspecified in the reference (heap order), defined
+    # here as "the earlier part of the query wins" -- oracle and device must agree for both part orders
+    ts_a = T0 + np.array([5, 6, 7], dtype=np.int64) * STEP
+    ts_b = T0 + np.array([1, 5, 6, 9], dtype=np.int64) * STEP
+    pa = build_part(np.full(3, 4, np.uint64), ts_a, np.array([2, 2, 1], np.int64), [("calls", O.VT_INT64, np.array([10, 20, 30]), None)])
+    pb = build_part(np.full(4, 4, np.uint64), ts_b, np.array([2, 2, 3, 2], np.int64), [("calls", O.VT_INT64, np.array([100, 200, 300, 400]), None)])
+    aggs = [("calls", O.AGG_SUM), ("calls", O.AGG_COUNT), ("calls", O.AGG_MIN)]
+    for parts, want in (([pa, pb], 840), ([pb, pa], 1030)):
+        got, ora = run_both(bydb, gpu_ctx, parts, O.Query(parts, [4], aggs), _next_pid())
+        assert_parity(got, ora, aggs, "equal-version duplicates")
+        assert int(got.val_i64[0, 0]) == want and int(got.val_i64[0, 1]) == 5

@@ -233,3 +233,15 @@ def test_top_tie_breaker_stable_top_test_go():
     for desc in (False, True):
         r = O.run_query(O.Query([part], sids, [("calls", O.AGG_SUM)], groups=np.arange(4, dtype=np.int32), n_groups=4, top_n=2, top_desc=desc))
         assert r.group_id.tolist() == [0, 1]
+
+
+def test_equal_version_duplicates_keep_the_earlier_part():
+    # the reference leaves equal (series, timestamp, version) rows of different parts to the heap's internal order
+    # (query.go:912-942, 995-1004); oracle and device define it: the earlier part of the query wins, whatever the blocks' spans
+    ts_a = T0 + np.array([5, 6, 7], dtype=np.int64) * STEP            # part A's block starts later ...
+    ts_b = T0 + np.array([1, 5, 6, 9], dtype=np.int64) * STEP         # ... than part B's block
+    pa = _build(np.full(3, 4, np.uint64), ts_a, np.array([2, 2, 1], np.int64), f_int=np.array([10, 20, 30]))
+    pb = _build(np.full(4, 4, np.uint64), ts_b, np.array([2, 2, 3, 2], np.int64), f_int=np.array([100, 200, 300, 400]))
+    for parts, want in (([pa, pb], 100 + 10 + 300 + 30 + 400), ([pb, pa], 100 + 200 + 300 + 30 + 400)):
+        r = O.run_query(O.Query(parts, [4], [("calls", O.AGG_SUM), ("calls", O.AGG_COUNT)]))
+        assert r.val_i64[0].tolist() == [want, 5]
