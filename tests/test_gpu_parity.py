@@ -723,3 +723,25 @@ def test_equal_version_duplicates_keep_the_earlier_part(bydb, gpu_ctx):
         got, ora = run_both(bydb, gpu_ctx, parts, O.Query(parts, [4], aggs), _next_pid())
         assert_parity(got, ora, aggs, "equal-version duplicates")
         assert int(got.val_i64[0, 0]) == want and int(got.val_i64[0, 1]) == 5
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("BYDB_SWEEP"), reason="randomised device-vs-oracle sweep: enable with BYDB_SWEEP=1 "
+                    "(written at the end of round 1 without GPU time left to run it once; to be made unconditional after its first green run)")
+@pytest.mark.parametrize("seed", range(24))
+def test_random_sweep_device_vs_oracle(bydb, gpu_ctx, seed):
+    # the generator of tests/test_oracle_model_sweep.py (1-3 overlapping parts, versions incl. equal ones, nil cells, int/str
+    # predicates, groups, all five functions): device vs oracle; float sums against the magnitude of the terms
+    from tests.test_oracle_model_sweep import AGGS, case_query, random_case
+    parts, _, kw = random_case(seed)
+    oq = case_query(parts, kw)
+    got, want = run_both(bydb, gpu_ctx, parts, oq, _next_pid())
+    assert got.group_id.tolist() == want.group_id.tolist() and got.rows.tolist() == want.rows.tolist()
+    assert got.is_float.tolist() == want.is_float.tolist()
+    for a, (_, fn) in enumerate(AGGS):
+        if not want.is_float[a]:
+            assert got.val_i64[:, a].tolist() == want.val_i64[:, a].tolist(), (seed, a)
+        elif fn in (O.AGG_MIN, O.AGG_MAX):
+            assert got.val_f64[:, a].view(np.uint64).tolist() == want.val_f64[:, a].view(np.uint64).tolist(), (seed, a)
+        else:
+            scale = np.maximum(np.abs(want.val_f64[:, a]), 1e5)      # |terms| reach 1e4 x 9000 rows in the mixed-exponent variant
+            assert (np.abs(got.val_f64[:, a] - want.val_f64[:, a]) <= 1e-9 * scale).all(), (seed, a)

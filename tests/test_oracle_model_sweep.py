@@ -14,8 +14,8 @@ AGGS = [("i", O.AGG_SUM), ("i", O.AGG_COUNT), ("i", O.AGG_MIN), ("i", O.AGG_MAX)
         ("f", O.AGG_SUM), ("f", O.AGG_COUNT), ("f", O.AGG_MIN), ("f", O.AGG_MAX), ("f", O.AGG_MEAN)]
 
 
-@pytest.mark.parametrize("seed", range(12))
-def test_oracle_equals_brute_force_model(seed):
+def random_case(seed):
+    """-> (parts, best-row dict, query kwargs): shared with the device sweep in test_gpu_parity.py"""
     rng = np.random.default_rng(9000 + seed)
     nparts, nser = int(rng.integers(1, 4)), int(rng.integers(1, 7))
     best, parts = {}, []
@@ -54,8 +54,19 @@ def test_oracle_equals_brute_force_model(seed):
         preds.append(("code", int(rng.choice(list(OPS))), int(rng.integers(0, 5))))
     G = int(rng.integers(1, 4))
     groups = [int(rng.integers(0, G)) for _ in range(nser)]
-    res = O.run_query(O.Query(parts, list(range(1, nser + 1)), AGGS, groups=np.array(groups, dtype=np.int32), n_groups=G, tmin=tmin, tmax=tmax,
-                              preds=[O.Pred("default", t, op, v) for t, op, v in preds], threads=int(rng.integers(1, 4))))
+    return parts, best, dict(nser=nser, groups=groups, G=G, tmin=tmin, tmax=tmax, preds=preds, threads=int(rng.integers(1, 4)))
+
+
+def case_query(parts, kw):
+    return O.Query(parts, list(range(1, kw["nser"] + 1)), AGGS, groups=np.array(kw["groups"], dtype=np.int32), n_groups=kw["G"], tmin=kw["tmin"],
+                   tmax=kw["tmax"], preds=[O.Pred("default", t, op, v) for t, op, v in kw["preds"]], threads=kw["threads"])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_oracle_equals_brute_force_model(seed):
+    parts, best, kw = random_case(seed)
+    groups, tmin, tmax, preds = kw["groups"], kw["tmin"], kw["tmax"], kw["preds"]
+    res = O.run_query(case_query(parts, kw))
     exp = {}
     for (s, t), (_, row) in sorted(best.items()):
         if t < tmin or t > tmax:
