@@ -1,0 +1,120 @@
+// Host build of the per-lane fast decoders (skywalking-banyandb_b200/csrc/lane_decode.cuh) against a byte-at-a-time reference:
+//   * fast_lane_decode<true>   interior chunk (all 32 bytes valid), every kNeed variant
+//   * fast_lane_decode<false>  chunk with bytes outside the page (first / last chunk), random valid windows
+//   * fast_lane_decode_dual    the two-chain experiment (BYDB_EXP_DUAL) -- must equal the single chain bit for bit
+//   * head_delta               the cross-lane / cross-half correction identity
+// Built and run by tests/test_lane_decode_native.py with g++ (the CUDA toolkit headers only provide uint4).
+#include <cstdint>
+#include <cstdio>
+#include <random>
+#include <vector>
+
+#include "lane_decode.cuh"
+
+using namespace bydb;
+
+struct Ref {
+    uint32_t accv = 0, sh = 0;
+    int32_t P = 0, sumP = 0, minP = INT32_MAX, maxP = INT32_MIN;
+};
+static int32_t zz(uint32_t u) { return static_cast<int32_t>(u >> 1) ^ -static_cast<int32_t>(u & 1u); }
+
+// the semantics the kernel documents: only valid bytes exist; invalid bytes restart the varint state
+static Ref reference(const uint8_t *b, uint32_t valid, uint32_t aw) {
+    Ref r;
+    for (int i = 0; i < 32; ++i) {
+        if (!((valid >> i) & 1u)) {
+            r.accv = 0;
+            r.sh = 0;
+            continue;
+        }
+        r.accv |= static_cast<uint32_t>(b[i] & 0x7f) << r.sh;
+        r.sh += 7;
+        if (b[i] < 0x80) {
+            r.P += zz(r.accv);
+            if (aw & 1u) {
+                r.sumP += r.P;
+                r.minP = r.P < r.minP ? r.P : r.minP;
+                r.maxP = r.P > r.maxP ? r.P : r.maxP;
+            }
+            aw >>= 1;
+            r.accv = 0;
+            r.sh = 0;
+        }
+    }
+    return r;
+}
+
+template <bool kFull, int kNeed>
+static bool check(const uint8_t *b, uint32_t valid, uint32_t aw, bool dual) {
+    uint4 wa, wb;
+    uint32_t w[8];
+    for (int k = 0; k < 8; ++k) w[k] = b[4 * k] | (b[4 * k + 1] << 8) | (b[4 * k + 2] << 16) | (static_cast<uint32_t>(b[4 * k + 3]) << 24);
+    wa = {w[0], w[1], w[2], w[3]};
+    wb = {w[4], w[5], w[6], w[7]};
+    uint32_t msb = 0;
+    for (int k = 0; k < 8; ++k) msb |= msb4(w[k]) << (4 * k);
+    const uint32_t term = valid & ~msb;
+    uint32_t accv = 0, sh = 0;
+    int32_t P = 0, sumP = 0, minP = INT32_MAX, maxP = INT32_MIN;
+    if (dual) fast_lane_decode_dual<kNeed>(wa, wb, term, aw, accv, sh, P, sumP, minP, maxP);
+    else fast_lane_decode<kFull, kNeed>(wa, wb, valid, term, aw, accv, sh, P, sumP, minP, maxP);
+    const Ref r = reference(b, valid, aw);
+    bool ok = accv == r.accv && sh == r.sh && P == r.P;
+    if (kNeed & kNeedSum) ok = ok && sumP == r.sumP;
+    if (kNeed & kNeedMinMax) ok = ok && minP == r.minP && maxP == r.maxP;
+    if (!ok)
+        std::printf("FAIL full=%d need=%d dual=%d valid=%08x aw=%08x: got (%u,%u,%d,%d,%d,%d) want (%u,%u,%d,%d,%d,%d)\n", kFull, kNeed, dual, valid, aw,
+                    accv, sh, P, sumP, minP, maxP, r.accv, r.sh, r.P, r.sumP, r.minP, r.maxP);
+    return ok;
+}
+
+int main() {
+    std::mt19937_64 rng(20260922);
+    long n = 0;
+    for (int it = 0; it < 200000; ++it) {
+        // a stream of narrow (1..3 byte) varints, window cut at a random offset
+        std::vector<uint8_t> s;
+        while (s.size() < 48) {
+            const int L = 1 + static_cast<int>(rng() % 3);
+            uint32_t u = static_cast<uint32_t>(rng()) & ((1u << (7 * L)) - 1u);
+            if (L > 1 && (u >> (7 * (L - 1))) == 0) u |= 1u << (7 * (L - 1));  // canonical length
+            for (int k = 0; k < L; ++k) s.push_back(static_cast<uint8_t>(((u >> (7 * k)) & 0x7f) | (k < L - 1 ? 0x80 : 0)));
+        }
+        const uint8_t *b = s.data() + rng() % 4;
+        const uint32_t aw = (rng() % 4 == 0) ? 0xffffffffu : (rng() % 5 == 0 ? 0u : static_cast<uint32_t>(rng()));
+        bool ok = check<true, kNeedSum>(b, 0xffffffffu, aw, false) && check<true, kNeedMinMax>(b, 0xffffffffu, aw, false) &&
+                  check<true, kNeedSum | kNeedMinMax>(b, 0xffffffffu, aw, false);
+        ok = ok && check<true, kNeedSum>(b, 0xffffffffu, aw, true) && check<true, kNeedMinMax>(b, 0xffffffffu, aw, true) &&
+             check<true, kNeedSum | kNeedMinMax>(b, 0xffffffffu, aw, true);
+        // first / last chunk of a page: a contiguous valid window [lo, hi)
+        const uint32_t lo = rng() % 33, hi = lo + rng() % (33 - lo);
+        const uint32_t valid = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~(lo >= 32 ? 0xffffffffu : ((1u << lo) - 1u));
+        ok = ok && check<false, kNeedSum>(b, valid, aw, false) && check<false, kNeedSum | kNeedMinMax>(b, valid, aw, false);
+        if (!ok) return 1;
+        n += 8;
+    }
+    // head_delta: value split between a previous tail (prev_acc, prev_sh) and the first 1..2 bytes of this lane
+    for (int it = 0; it < 100000; ++it) {
+        const int L = 2 + static_cast<int>(rng() % 2), cut = 1 + static_cast<int>(rng() % (L - 1));
+        const uint32_t u = static_cast<uint32_t>(rng()) & ((1u << (7 * L)) - 1u);
+        uint8_t bytes[3];
+        for (int k = 0; k < L; ++k) bytes[k] = static_cast<uint8_t>(((u >> (7 * k)) & 0x7f) | (k < L - 1 ? 0x80 : 0));
+        uint32_t prev_acc = 0;
+        for (int k = 0; k < cut; ++k) prev_acc |= static_cast<uint32_t>(bytes[k] & 0x7f) << (7 * k);
+        uint32_t w0 = 0, hx = 0;
+        for (int k = cut; k < L; ++k) {
+            w0 |= static_cast<uint32_t>(bytes[k]) << (8 * (k - cut));
+            hx |= static_cast<uint32_t>(bytes[k] & 0x7f) << (7 * (k - cut));
+        }
+        w0 |= static_cast<uint32_t>(rng()) << (8 * (L - cut));  // whatever follows in the word
+        const uint32_t term = 1u << (L - cut - 1);
+        if (head_delta(w0, term | (static_cast<uint32_t>(rng()) << (L - cut)), prev_acc, 7u * cut) != zz(u) - zz(hx)) {
+            std::printf("FAIL head_delta u=%u L=%d cut=%d\n", u, L, cut);
+            return 1;
+        }
+        (void)term;
+    }
+    std::printf("OK %ld lane decodes\n", n);
+    return 0;
+}
