@@ -165,3 +165,15 @@ def check_query_test_case(res, expect, ctx=""):
         assert int(res.val_i64[g, 3]) == (0 if fmax is None else rows), f"{ctx}: count(floatField) of series {sid}"
         if fmax is not None:
             assert float(res.val_f64[g, 2]) == fmax, f"{ctx}: max(floatField) of series {sid}"
+
+
+# ------------------------------------------------------------------ banyand/measure/part_iter_test.go Test_partIter_nextBlock
+def part_iter_fixture():
+    """`dps` of part_test.go:130-133 reduced to what block selection reads: series 1,1,2,2,3,3 at timestamps 1,2,8,10,100,220."""
+    sids = np.array([1, 1, 2, 2, 3, 3], dtype=np.uint64)
+    ts = np.array([1, 2, 8, 10, 100, 220], dtype=np.int64)
+    return build_part(sids, ts, np.arange(1, 7, dtype=np.int64), [("intField", O.VT_INT64, np.arange(6) * 10, None)])
+
+
+# (query series, expected series of the selected blocks) over [1, 220] -- every block holds 2 rows (part_iter_test.go:43-110)
+PART_ITER_CASES = [([1, 2, 3], [1, 2, 3]), ([], []), ([1], [1]), ([1, 3], [1, 3]), ([4], []), ([4, 5, 6], []), ([1, 4], [1])]

@@ -745,3 +745,14 @@ def test_random_sweep_device_vs_oracle(bydb, gpu_ctx, seed):
         else:
             scale = np.maximum(np.abs(want.val_f64[:, a]), 1e5)      # |terms| reach 1e4 x 9000 rows in the mixed-exponent variant
             assert (np.abs(got.val_f64[:, a] - want.val_f64[:, a]) <= 1e-9 * scale).all(), (seed, a)
+
+
+def test_block_selection_part_iter_test_go(bydb, gpu_ctx):
+    # banyand/measure/part_iter_test.go Test_partIter_nextBlock on `dps`: the blocks plan_blocks selects for each series list
+    from tests.helpers import PART_ITER_CASES, part_iter_fixture
+    part = part_iter_fixture()
+    for sids, want_sids in PART_ITER_CASES:
+        oq = O.Query([part], sids, [("intField", O.AGG_COUNT)], groups=np.arange(len(sids), dtype=np.int32), n_groups=max(len(sids), 1), tmin=1, tmax=220)
+        got, want = run_both(bydb, gpu_ctx, [part], oq, _next_pid())
+        assert_parity(got, want, oq.aggs, f"part_iter/{sids}")
+        assert got.stats.blocks_scanned == len(want_sids) and got.stats.rows_scanned == 2 * len(want_sids)

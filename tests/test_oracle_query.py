@@ -245,3 +245,14 @@ def test_equal_version_duplicates_keep_the_earlier_part():
     for parts, want in (([pa, pb], 100 + 10 + 300 + 30 + 400), ([pb, pa], 100 + 200 + 300 + 30 + 400)):
         r = O.run_query(O.Query(parts, [4], [("calls", O.AGG_SUM), ("calls", O.AGG_COUNT)]))
         assert r.val_i64[0].tolist() == [want, 5]
+
+
+def test_block_selection_part_iter_test_go():
+    # banyand/measure/part_iter_test.go:35-163 Test_partIter_nextBlock: which blocks a sorted series list selects
+    from tests.helpers import PART_ITER_CASES, part_iter_fixture
+    part = part_iter_fixture()
+    for sids, want in PART_ITER_CASES:
+        r = O.run_query(O.Query([part], sids, [("intField", O.AGG_COUNT)], groups=np.arange(len(sids), dtype=np.int32), n_groups=max(len(sids), 1),
+                                tmin=1, tmax=220))
+        assert r.blocks_scanned == len(want) and r.rows_scanned == 2 * len(want)
+        assert [sids[g] for g in r.group_id.tolist()] == want and r.rows.tolist() == [2] * len(want)
