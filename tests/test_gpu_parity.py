@@ -711,6 +711,8 @@ def test_reference_query_test_fixtures_on_the_device(bydb, gpu_ctx, case):
     assert_parity(got, want, QUERY_TEST_AGGS, f"query_test/{case}/pred")
 
 
+@pytest.mark.skipif(not __import__("os").environ.get("BYDB_SWEEP"), reason="written after the GPU budget of round 1 was spent: enable with BYDB_SWEEP=1, "
+                    "to be made unconditional after the first green run on a GPU")
 def test_equal_version_duplicates_keep_the_earlier_part(bydb, gpu_ctx):
     # same (series, timestamp, version) in two parts with different values: unspecified in the reference (heap order), defined
     # here as "the earlier part of the query wins" -- oracle and device must agree for both part orders
@@ -747,6 +749,8 @@ def test_random_sweep_device_vs_oracle(bydb, gpu_ctx, seed):
             assert (np.abs(got.val_f64[:, a] - want.val_f64[:, a]) <= 1e-9 * scale).all(), (seed, a)
 
 
+@pytest.mark.skipif(not __import__("os").environ.get("BYDB_SWEEP"), reason="written after the GPU budget of round 1 was spent: enable with BYDB_SWEEP=1, "
+                    "to be made unconditional after the first green run on a GPU")
 def test_block_selection_part_iter_test_go(bydb, gpu_ctx):
     # banyand/measure/part_iter_test.go Test_partIter_nextBlock on `dps`: the blocks plan_blocks selects for each series list
     from tests.helpers import PART_ITER_CASES, part_iter_fixture
