@@ -10,8 +10,12 @@
  * Parity pinning: the Go reference cannot be built here (no Go toolchain, no
  * vendored modules), so the oracle is pinned against every known-answer vector
  * the reference's own tests hold for this path (tests/test_oracle_golden.py
- * transcribes them) -- it is NOT pinned against
- * outputs of the running reference.  zstd frames (third-party
+ * transcribes them), against the expected rows of its
+ * end-to-end measure cases (tests/golden/e2e_cases.json, generated from
+ * test/cases/measure/data), against the merge / block-selection fixtures of
+ * banyand/measure/{query,part_iter}_test.go, and cross-checked by a randomised
+ * brute-force model and a second, independent part writer -- it is NOT pinned
+ * against outputs of the running reference.  zstd frames (third-party
  * github.com/klauspost/compress v1.18.5, go.mod:171) are "parity unpinned" at
  * the compressed-byte level and pinned at the decompressed level by RFC 8878
  * conformance (system libzstd 1.5.5 via dlopen).
