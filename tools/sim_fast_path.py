@@ -19,8 +19,9 @@ def enc(vals):
     return bytes(out)
 
 
-def sim(body, pstart, count, first, active):
-    """returns (rc, sum, mn, mx, cnt) like the kernel; active: bool per row"""
+def sim(body, pstart, count, first, active, r1=None):
+    """returns (rc, sum, mn, mx, cnt) like the kernel; active: bool per row.
+    r1: last row that can be active -> the BYDB_EXP_EARLYSTOP variant stops after the first chunk that passed it."""
     LB = 32  # bytes per lane (kFastLaneBytes)
     total = ((pstart + len(body)) + 15) & ~15
     buf = bytes(pstart) + body + bytes(total - pstart - len(body))
@@ -111,6 +112,8 @@ def sim(body, pstart, count, first, active):
                 mn = a if mn is None else min(mn, a); mx = b if mx is None else max(mx, b)
                 cnt += L['cntA']
         V0 += lanes[31]['s_in']; row_base += lanes[31]['n_in']
+        if r1 is not None and row_base > r1 and c + 1 < nchunks:
+            return (0, S, mn, mx, cnt)            # early stop: nothing after r1 is active, the tail is not decoded
     ok = row_base == count and carry_sh == 0
     return (0 if ok else 2, S, mn, mx, cnt)
 
@@ -136,6 +139,12 @@ def main():
         assert cnt == len(av) and S == sum(av), (trial, cnt, len(av))
         if av:
             assert mn == min(av) and mx == max(av), trial
+        # the early-stop experiment: rows after a random r1 are inactive; stopping at the first chunk past r1 changes nothing
+        r1 = int(rng.integers(0, n))
+        act2 = [a and i <= r1 for i, a in enumerate(active)]
+        full = sim(body, pstart, n, first, act2)
+        early = sim(body, pstart, n, first, act2, r1=r1)
+        assert early[0] == 0 and early[1:] == full[1:], (trial, r1)
     print("fast path simulation ok")
 
 
