@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--points", type=int, default=100_000)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="also time the prepared-query path (one captured CUDA graph per step)")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
@@ -398,6 +399,25 @@ def main():
                                        "value": rf.stats.rows_scanned / df, "unit": "datapoints/s", "scan_kernel_ms": rf.stats.scan_kernel_ms,
                                        "blocks_slow_lane": int(rf.stats.blocks_slow_lane), "mean": float(rf.val_f64[0, 0]), "max": float(rf.val_f64[0, 1]),
                                        "note": "raw-cell pages written at admission (unpack_kernels.cu), scanned by the general lane"}
+    if world == 1 and args.graph:
+        # the same query through bydb_query_prepare / bydb_scan_agg_prepared: step 1 ordinary, step 2 capture, then replays
+        gq = ctx.prepare_graph(q)
+        try:
+            for _ in range(max(args.warmup, 3) + 2):
+                rg = gq.run()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                rg = gq.run()
+            barrier()
+            dg = (time.perf_counter() - t0) / args.steps
+            out["prepared_graph"] = {"ms_per_step": dg * 1e3, "value": rg.stats.rows_scanned / dg, "unit": "datapoints/s", "device_ms": rg.stats.device_ms,
+                                     "same_result": bool(last is not None and rg.val_f64.tolist() == last.val_f64.tolist() and rg.rows.tolist() == last.rows.tolist()),
+                                     "note": "bydb_scan_agg_prepared: the whole step replayed as one CUDA graph (one launch + one synchronisation)"}
+        except Exception as ex:
+            out["prepared_graph"] = {"error": str(ex)[:200]}
+        finally:
+            gq.close()
     if world > 1:
         out["host_phase_ms_per_step_rank0"] = {k: v / args.steps * 1e3 for k, v in phase_timed.items()}
     if last is not None:

@@ -183,6 +183,19 @@ int bydb_scan_agg_host(bydb_ctx *ctx, uint32_t n_parts, const bydb_part_files *p
 
 void bydb_result_free(bydb_ctx *ctx, bydb_result *r);
 
+/* Prepared queries.  A query that is executed many times (dashboard refresh, alert rule) is copied and planned once;
+ * from its third execution on, the whole step -- staging copy, block selection, scan, reduce, finalisation, row
+ * selection, read-back -- is replayed as ONE captured CUDA graph: one launch and one synchronisation per call instead of
+ * ~20 runtime calls.  Every execution still scans the parts (nothing is cached but the launch sequence).  Results and
+ * errors are those of bydb_scan_agg; stats.scan_kernel_ms is 0 on replays (per-kernel events do not exist inside a
+ * graph), stats.device_ms is the whole graph.  Queries whose parts overlap in time (version dedup needs a host
+ * decision) transparently keep the ordinary path.  One execution at a time per prepared query; different prepared
+ * queries run concurrently.  The parts named by the query must stay registered while it exists. */
+typedef struct bydb_prepared bydb_prepared;
+int bydb_query_prepare(bydb_ctx *ctx, const bydb_query *q, bydb_prepared **out);
+int bydb_scan_agg_prepared(bydb_ctx *ctx, bydb_prepared *pq, bydb_result *out);
+void bydb_query_release(bydb_ctx *ctx, bydb_prepared *pq);
+
 /* ---- multi-GPU map/reduce: per-rank partial tables, one collective, one finalize ----
  * Layout of a partial table for (n_groups G, n_fields F = distinct aggregated fields):
  *   double  sum_f64[G*F]; double max_f64[G*F]; double negmin_f64[G*F];

@@ -77,7 +77,8 @@ class _Layout(C.Structure):
 
 # every symbol include/bydb_gpu.h declares (tests/test_capi_symbols.py checks the list against the header)
 EXPORTS = ["bydb_init", "bydb_shutdown", "bydb_part_register", "bydb_part_release", "bydb_part_info", "bydb_part_fallback_pages",
-           "bydb_scan_agg", "bydb_scan_agg_host", "bydb_result_free", "bydb_partials_layout",
+           "bydb_scan_agg", "bydb_scan_agg_host", "bydb_result_free", "bydb_query_prepare", "bydb_scan_agg_prepared",
+           "bydb_query_release", "bydb_partials_layout",
            "bydb_scan_partials", "bydb_partials_combine", "bydb_reduce_finalize", "bydb_last_error", "bydb_version"]
 
 _lib = None
@@ -109,6 +110,10 @@ def load_library():
     L.bydb_scan_agg.argtypes = [C.c_void_p, C.POINTER(_Query), C.POINTER(_Result)]
     L.bydb_scan_agg_host.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_PartFiles), C.POINTER(_Query), C.POINTER(_Result)]
     L.bydb_result_free.argtypes = [C.c_void_p, C.POINTER(_Result)]
+    L.bydb_query_prepare.argtypes = [C.c_void_p, C.POINTER(_Query), C.POINTER(C.c_void_p)]
+    L.bydb_scan_agg_prepared.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Result)]
+    L.bydb_query_release.argtypes = [C.c_void_p, C.c_void_p]
+    L.bydb_query_release.restype = None
     L.bydb_partials_layout.argtypes = [C.POINTER(_Query), C.POINTER(_Layout)]
     L.bydb_scan_partials.argtypes = [C.c_void_p, C.POINTER(_Query), C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(_Stats)]
     L.bydb_partials_combine.argtypes = [C.c_void_p, C.POINTER(_Query), C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p]
@@ -288,6 +293,26 @@ def _read_result(r: _Result) -> Result:
                   val_f64=arr(r.val_f64, n * a, np.float64).reshape(n, a), stats=Stats.of(r.stats))
 
 
+class GraphQuery:
+    """A query held by the library (deep copy) whose step is replayed as one CUDA graph from its third run on."""
+
+    def __init__(self, ctx: "Context", handle):
+        self._ctx, self._h = ctx, handle
+
+    def run(self) -> Result:
+        r = _Result()
+        _check(self._ctx._L.bydb_scan_agg_prepared(self._ctx._h, self._h, C.byref(r)))
+        try:
+            return _read_result(r)
+        finally:
+            self._ctx._L.bydb_result_free(self._ctx._h, C.byref(r))
+
+    def close(self):
+        if self._h:
+            self._ctx._L.bydb_query_release(self._ctx._h, self._h)
+            self._h = None
+
+
 class Context:
     """bydb_ctx: one device, its streams and the HBM part cache."""
 
@@ -342,6 +367,14 @@ class Context:
             return _read_result(r)
         finally:
             self._L.bydb_result_free(self._h, C.byref(r))
+
+    # ---- prepared queries replayed as one captured CUDA graph (bydb_query_prepare / bydb_scan_agg_prepared)
+    def prepare_graph(self, q: Query) -> "GraphQuery":
+        keep: list = []
+        cq = _mk_query(q, keep)
+        h = C.c_void_p()
+        _check(self._L.bydb_query_prepare(self._h, C.byref(cq), C.byref(h)))
+        return GraphQuery(self, h)
 
     def scan_agg_host(self, parts: Sequence[Dict[str, Union[bytes, np.ndarray]]], q: Query) -> Result:
         keep: list = []

@@ -873,6 +873,212 @@ int scan_agg_impl(bydb_ctx *ctx, const bydb_query *q, const std::vector<std::sha
     return rc;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Prepared queries: the whole step (staging copy, plan, scan, reduce, finalize, row selection, read-back) captured once
+// into a CUDA graph and replayed.  A query executed many times (dashboards, alert rules) then costs one graph launch and
+// one synchronisation instead of ~20 runtime calls.  Everything here is additive: bydb_scan_agg is untouched.
+// ------------------------------------------------------------------------------------------------
+struct FinalLayout {
+    size_t o_out = 0, o_cnt = 0, o_isf = 0, o_sg = 0, o_sr = 0, o_si = 0, o_sf = 0, out_bytes = 0, cap = 0, A = 0;
+};
+
+// finalize_to_host up to (and including) the read-back copy, without the synchronisation and the parsing; the result
+// lands at slot.pinned + host_off so that the staging area of run_scan (at the start of slot.pinned) stays intact
+int finalize_enqueue(const bydb_query *q, const Plan &plan, ExecSlot &slot, cudaStream_t stream, const uint8_t *d_table, const TableLayout &tl,
+                     size_t host_off, FinalLayout &fl, Scratch &sc) {
+    const size_t F = plan.fcols.size();
+    const int32_t G = plan.n_groups;
+    const size_t A = q->n_aggs;
+    const size_t cap = q->top_n > 0 ? std::min<size_t>(static_cast<size_t>(q->top_n), static_cast<size_t>(G)) : static_cast<size_t>(G);
+    if (q->top_n > kMaxDeviceTopN) return fail(BYDB_ENOTSUP, "top_n larger than 2048 is not supported on the device path");
+    size_t o = 0;
+    auto carve = [&](size_t bytes) {
+        size_t at = o;
+        o = align_up(o + bytes, 256);
+        return at;
+    };
+    const size_t o_vi = carve(static_cast<size_t>(G) * A * 8), o_vf = carve(static_cast<size_t>(G) * A * 8), o_keys = carve(static_cast<size_t>(G) * 8),
+                 o_kst = carve(static_cast<size_t>(G));
+    fl.o_out = o;
+    fl.o_cnt = carve(16);
+    fl.o_isf = carve(A);
+    fl.o_sg = carve(cap * 4);
+    fl.o_sr = carve(cap * 8);
+    fl.o_si = carve(cap * A * 8);
+    fl.o_sf = carve(cap * A * 8);
+    fl.out_bytes = o - fl.o_out;
+    fl.cap = cap;
+    fl.A = A;
+    sc.stream = stream;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&sc.base), o, stream));
+    uint8_t *d = sc.base;
+    FinalizeParams fp;
+    memset(&fp, 0, sizeof fp);
+    fp.n_groups = G;
+    fp.n_fcols = static_cast<uint32_t>(F);
+    fp.n_aggs = static_cast<uint32_t>(A);
+    for (size_t a = 0; a < A; ++a) {
+        fp.agg_fcol[a] = plan.agg_fcol[a];
+        fp.agg_func[a] = q->aggs[a].func;
+    }
+    fp.sum_f64 = reinterpret_cast<const double *>(d_table + tl.off_sum_f64);
+    fp.max_f64 = reinterpret_cast<const double *>(d_table + tl.off_max_f64);
+    fp.negmin_f64 = reinterpret_cast<const double *>(d_table + tl.off_negmin_f64);
+    fp.sum_i64 = reinterpret_cast<const int64_t *>(d_table + tl.off_sum_i64);
+    fp.cnt = reinterpret_cast<const int64_t *>(d_table + tl.off_cnt);
+    fp.rows = reinterpret_cast<const int64_t *>(d_table + tl.off_rows);
+    fp.max_i64 = reinterpret_cast<const int64_t *>(d_table + tl.off_max_i64);
+    fp.notmin_i64 = reinterpret_cast<const int64_t *>(d_table + tl.off_notmin_i64);
+    fp.coltype = reinterpret_cast<const int64_t *>(d_table + tl.off_coltype);
+    fp.out_i64 = reinterpret_cast<int64_t *>(d + o_vi);
+    fp.out_f64 = reinterpret_cast<double *>(d + o_vf);
+    fp.out_is_float = d + fl.o_isf;
+    fp.err_out = reinterpret_cast<uint32_t *>(d + fl.o_cnt + 8);
+    launch_finalize(fp, stream);
+    SelectParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.n_groups = G;
+    sp.n_fcols = static_cast<uint32_t>(F);
+    sp.n_aggs = static_cast<uint32_t>(A);
+    sp.top_n = q->top_n;
+    sp.top_agg = q->top_n > 0 ? q->top_agg : 0;
+    sp.top_desc = q->top_desc;
+    sp.top_fcol = plan.agg_fcol[sp.top_agg];
+    sp.top_is_count = q->aggs[sp.top_agg].func == BYDB_AGG_COUNT;
+    sp.rows = fp.rows;
+    sp.cnt = fp.cnt;
+    sp.val_i64 = fp.out_i64;
+    sp.val_f64 = fp.out_f64;
+    sp.is_float = fp.out_is_float;
+    sp.keys = reinterpret_cast<uint64_t *>(d + o_keys);
+    sp.kstate = d + o_kst;
+    sp.sel_count = reinterpret_cast<uint32_t *>(d + fl.o_cnt);
+    sp.sel_group = reinterpret_cast<int32_t *>(d + fl.o_sg);
+    sp.sel_rows = reinterpret_cast<int64_t *>(d + fl.o_sr);
+    sp.sel_i64 = reinterpret_cast<int64_t *>(d + fl.o_si);
+    sp.sel_f64 = reinterpret_cast<double *>(d + fl.o_sf);
+    launch_select_rows(sp, stream);
+    CUDA_TRY(cudaMemcpyAsync(slot.pinned + host_off, d + fl.o_out, fl.out_bytes, cudaMemcpyDeviceToHost, stream));
+    return 0;
+}
+
+void finalize_parse(const uint8_t *h, const FinalLayout &fl, bydb_result *out) {
+    const size_t A = fl.A;
+    const size_t R = std::min<size_t>(*reinterpret_cast<const uint32_t *>(h + (fl.o_cnt - fl.o_out)), fl.cap);
+    auto owner = new ResultOwner();
+    const int32_t *sg = reinterpret_cast<const int32_t *>(h + (fl.o_sg - fl.o_out));
+    const int64_t *sr = reinterpret_cast<const int64_t *>(h + (fl.o_sr - fl.o_out));
+    const int64_t *si = reinterpret_cast<const int64_t *>(h + (fl.o_si - fl.o_out));
+    const double *sf = reinterpret_cast<const double *>(h + (fl.o_sf - fl.o_out));
+    owner->group_id.assign(sg, sg + R);
+    owner->rows.assign(sr, sr + R);
+    owner->is_float.assign(h + (fl.o_isf - fl.o_out), h + (fl.o_isf - fl.o_out) + A);
+    owner->val_i64.assign(si, si + R * A);
+    owner->val_f64.assign(sf, sf + R * A);
+    out->n_rows = static_cast<int32_t>(R);
+    out->n_aggs = static_cast<int32_t>(A);
+    out->group_id = owner->group_id.data();
+    out->rows = owner->rows.data();
+    out->is_float = owner->is_float.data();
+    out->val_i64 = owner->val_i64.data();
+    out->val_f64 = owner->val_f64.data();
+    out->owner = owner;
+}
+
+}  // namespace
+
+struct bydb_prepared {
+    // deep copy of the query: the caller's arrays only live for the duration of bydb_query_prepare
+    std::vector<bydb_part_h> parts;
+    std::vector<uint64_t> sids;
+    std::vector<int32_t> groups;
+    std::vector<std::string> agg_names, pred_family, pred_tag;
+    std::vector<std::vector<uint8_t>> pred_lit;
+    std::vector<bydb_agg> aggs;
+    std::vector<bydb_pred> preds;
+    bydb_query q{};
+    std::mutex mu;                     // one execution at a time per prepared query
+    std::unique_ptr<ExecSlot> slot;    // dedicated stream + pinned staging: their addresses are baked into the graph
+    cudaGraphExec_t exec = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    FinalLayout fl;
+    size_t host_off = 0;
+    bydb_stats captured{};             // host-side counters of one step (launch counts, byte counts)
+    uint64_t runs = 0;
+    bool capturable = true;
+};
+
+namespace {
+
+void prepared_destroy(bydb_prepared *p) {
+    if (!p) return;
+    if (p->exec) cudaGraphExecDestroy(p->exec);
+    if (p->t0) cudaEventDestroy(p->t0);
+    if (p->t1) cudaEventDestroy(p->t1);
+    if (p->slot) {
+        if (p->slot->stream) cudaStreamDestroy(p->slot->stream);
+        for (auto &e : p->slot->ev)
+            if (e) cudaEventDestroy(e);
+        if (p->slot->busy) cudaEventDestroy(p->slot->busy);
+        if (p->slot->pinned) cudaFreeHost(p->slot->pinned);
+        if (p->slot->zpage) cudaFreeHost(p->slot->zpage);
+    }
+    delete p;
+}
+
+// captures one step into p->exec; returns 0, or a code after leaving the stream out of capture mode
+int prepared_capture(bydb_ctx *ctx, bydb_prepared *p) {
+    Plan plan;
+    int rc = make_plan(ctx, &p->q, nullptr, plan);
+    if (rc) return rc;
+    // the version-dedup precheck of run_scan synchronises: parts that overlap in time keep the uncaptured path
+    for (size_t a = 0; a < plan.parts.size(); ++a)
+        for (size_t b = a + 1; b < plan.parts.size(); ++b) {
+            const PartDir &x = plan.parts[a]->dir, &y = plan.parts[b]->dir;
+            if (x.blocks.empty() || y.blocks.empty()) continue;
+            if (std::max(std::max(x.min_ts, y.min_ts), p->q.tmin) <= std::min(std::min(x.max_ts, y.max_ts), p->q.tmax)) {
+                p->capturable = false;
+                return 0;
+            }
+        }
+    ExecSlot &slot = *p->slot;
+    TableLayout tl(static_cast<size_t>(plan.n_groups), plan.fcols.size());
+    const size_t G = static_cast<size_t>(plan.n_groups), A = p->q.n_aggs, NS = p->q.n_series;
+    const size_t stage = align_up(NS * 12 + (G + 1) * 4 + 512, 256);
+    p->host_off = stage;  // results land behind the staging area, which must survive from replay to replay
+    if (slot.ensure_pinned(stage + G * (12 + 16 * A) + 16 * A + 16384)) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
+    memset(&p->captured, 0, sizeof p->captured);
+    cudaError_t e = cudaStreamBeginCapture(slot.stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return fail(BYDB_EIO, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e));
+    {
+        Scratch table, fin;
+        table.stream = slot.stream;
+        rc = cudaMallocAsync(reinterpret_cast<void **>(&table.base), tl.total, slot.stream) == cudaSuccess ? 0 : fail(BYDB_ENOMEM, "cudaMallocAsync (capture)");
+        if (!rc) rc = run_scan(ctx, &p->q, plan, slot, slot.stream, table.base, tl, &p->captured, 0, true);
+        if (!rc) rc = finalize_enqueue(&p->q, plan, slot, slot.stream, table.base, tl, p->host_off, p->fl, fin);
+        // table / fin are released here: inside the capture, i.e. as free nodes of the graph
+    }
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(slot.stream, &graph);
+    if (rc || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        p->capturable = false;  // fall back to the uncaptured path for good
+        return rc ? rc : 0;
+    }
+    e = cudaGraphInstantiate(&p->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        p->exec = nullptr;
+        p->capturable = false;
+    }
+    p->captured.kernel_launches += 2;  // finalize + select_rows
+    p->captured.d2h_bytes += p->fl.out_bytes;
+    return 0;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -1257,6 +1463,105 @@ int bydb_reduce_finalize(bydb_ctx *ctx, const bydb_query *q, const void *d_parti
     if (lease.init()) return fail(BYDB_EIO, "cannot create stream");
     cudaStream_t s = static_cast<cudaStream_t>(stream);  // NULL = the legacy default stream, like every partial-table call
     return finalize_to_host(ctx, q, plan, *lease.slot, s, static_cast<const uint8_t *>(d_partials), tl, out, true);
+}
+
+
+int bydb_query_prepare(bydb_ctx *ctx, const bydb_query *q, bydb_prepared **out) {
+    if (!ctx || !out) return fail(BYDB_EINVAL, "ctx/out is NULL");
+    *out = nullptr;
+    int rc = validate_query(q, true);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    auto p = new bydb_prepared();
+    p->parts.assign(q->parts, q->parts + q->n_parts);
+    p->sids.assign(q->series_ids, q->series_ids + q->n_series);
+    if (q->series_group) p->groups.assign(q->series_group, q->series_group + q->n_series);
+    p->aggs.assign(q->aggs, q->aggs + q->n_aggs);
+    p->agg_names.resize(q->n_aggs);
+    for (uint32_t a = 0; a < q->n_aggs; ++a) p->agg_names[a] = q->aggs[a].field;
+    for (uint32_t a = 0; a < q->n_aggs; ++a) p->aggs[a].field = p->agg_names[a].c_str();
+    p->preds.assign(q->preds, q->preds + q->n_preds);
+    p->pred_family.resize(q->n_preds);
+    p->pred_tag.resize(q->n_preds);
+    p->pred_lit.resize(q->n_preds);
+    for (uint32_t i = 0; i < q->n_preds; ++i) {
+        p->pred_family[i] = q->preds[i].family;
+        p->pred_tag[i] = q->preds[i].tag;
+        if (q->preds[i].lit && q->preds[i].lit_len) p->pred_lit[i].assign(q->preds[i].lit, q->preds[i].lit + q->preds[i].lit_len);
+    }
+    for (uint32_t i = 0; i < q->n_preds; ++i) {
+        p->preds[i].family = p->pred_family[i].c_str();
+        p->preds[i].tag = p->pred_tag[i].c_str();
+        p->preds[i].lit = p->pred_lit[i].empty() ? nullptr : p->pred_lit[i].data();
+    }
+    p->q = *q;
+    p->q.parts = p->parts.data();
+    p->q.series_ids = p->sids.data();
+    p->q.series_group = q->series_group ? p->groups.data() : nullptr;
+    p->q.aggs = p->aggs.data();
+    p->q.preds = p->preds.data();
+    // a dedicated slot: stream, events, pinned staging
+    p->slot.reset(new ExecSlot());
+    bool ok = cudaStreamCreateWithFlags(&p->slot->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto &e : p->slot->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    ok = ok && cudaMallocHost(reinterpret_cast<void **>(&p->slot->zpage), 256 * ExecSlot::kMaxBatches) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&p->slot->busy, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreate(&p->t0) == cudaSuccess && cudaEventCreate(&p->t1) == cudaSuccess;
+    if (!ok) {
+        prepared_destroy(p);
+        return fail(BYDB_EIO, "cannot create the stream / events of a prepared query");
+    }
+    *out = p;
+    return 0;
+}
+
+void bydb_query_release(bydb_ctx *ctx, bydb_prepared *p) {
+    if (ctx) cudaSetDevice(ctx->device);
+    prepared_destroy(p);
+}
+
+int bydb_scan_agg_prepared(bydb_ctx *ctx, bydb_prepared *p, bydb_result *out) {
+    if (!ctx || !p || !out) return fail(BYDB_EINVAL, "NULL argument");
+    memset(out, 0, sizeof *out);
+    std::lock_guard<std::mutex> lk(p->mu);
+    g_last_dev_err = 0;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    // the first execution runs the ordinary path (it also performs the one-time kernel attribute setup); the second one
+    // captures; from then on the graph is replayed
+    const uint64_t run = p->runs++;
+    if (run == 0 || !p->capturable) return scan_agg_impl(ctx, &p->q, nullptr, out, 0);
+    if (!p->exec) {
+        const int rc = prepared_capture(ctx, p);
+        if (rc) return rc;
+        if (!p->exec) return scan_agg_impl(ctx, &p->q, nullptr, out, 0);
+    }
+    ExecSlot &slot = *p->slot;
+    CUDA_TRY(cudaEventRecord(p->t0, slot.stream));
+    CUDA_TRY(cudaGraphLaunch(p->exec, slot.stream));
+    CUDA_TRY(cudaEventRecord(p->t1, slot.stream));
+    CUDA_TRY(cudaStreamSynchronize(slot.stream));
+    CUDA_TRY(cudaGetLastError());
+    out->stats = p->captured;
+    const uint32_t *hz = reinterpret_cast<const uint32_t *>(slot.zpage);
+    const unsigned long long *hs = reinterpret_cast<const unsigned long long *>(slot.zpage + 16);
+    out->stats.rows_scanned = hs[0];
+    out->stats.rows_matched = hs[1];
+    out->stats.page_bytes = hs[2];
+    out->stats.blocks_scanned = hs[3];
+    out->stats.blocks_slow_lane = static_cast<uint32_t>(hs[4]);
+    out->stats.slow_lane_reasons = static_cast<uint32_t>(hs[5]);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p->t0, p->t1);
+    out->stats.device_ms = ms;
+    out->stats.scan_kernel_ms = 0;  // per-kernel events are not available inside a graph replay
+    if (hz[2] != 0) {
+        g_last_dev_err = hz[2];
+        char buf[96];
+        snprintf(buf, sizeof buf, " (block/series #%u)", hz[3]);
+        return fail(dev_err_code(hz[2]), std::string(dev_err_text(hz[2])) + buf);
+    }
+    finalize_parse(slot.pinned + p->host_off, p->fl, out);
+    return 0;
 }
 
 }  // extern "C"

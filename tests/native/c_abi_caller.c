@@ -22,6 +22,10 @@ int main(void) {
     int (*f_part)(bydb_ctx *, const bydb_query *, void *, uint64_t, void *, bydb_stats *) = bydb_scan_partials;
     int (*f_comb)(bydb_ctx *, const bydb_query *, void *, uint32_t, uint64_t, void *) = bydb_partials_combine;
     int (*f_fin)(bydb_ctx *, const bydb_query *, const void *, uint64_t, void *, bydb_result *) = bydb_reduce_finalize;
+    int (*f_prep)(bydb_ctx *, const bydb_query *, bydb_prepared **) = bydb_query_prepare;
+    int (*f_run)(bydb_ctx *, bydb_prepared *, bydb_result *) = bydb_scan_agg_prepared;
+    void (*f_qrel)(bydb_ctx *, bydb_prepared *) = bydb_query_release;
+    (void)f_prep; (void)f_run; (void)f_qrel;
     (void)f_shutdown; (void)f_reg; (void)f_rel; (void)f_info; (void)f_fb; (void)f_scan; (void)f_host; (void)f_free; (void)f_part; (void)f_comb; (void)f_fin;
 
     printf("version %s\n", bydb_version());
