@@ -345,3 +345,20 @@ def test_shortest_decimal_matches_an_independent_shortest_repr():
                 assert (int(ints[0]), exp) == ((-m if sign else m), e), (v, slow)
         finally:
             O.force_slow_float(False)
+
+
+# ---- pkg/encoding/dictionary_test.go:73-157 + bytes_test.go:65-128 edge cases (nil vs empty vs content, duplicates)
+EDGE_CASES = [
+    [None], [b""], [b"a"], [None, b""], [b"", b"hello"], [None, None, None], [b"", b"", b""],
+    [None, b"", b"test", None, b"value"], [b"", b"a", b"", b"a"], [None, b"b", None, b"b"],
+]
+
+
+@pytest.mark.parametrize("items", EDGE_CASES)
+def test_dictionary_and_bytes_block_edge_cases(items):
+    enc = O.dictionary_encode(items)
+    assert enc is not None and O.dictionary_decode(enc, len(items)) == items
+    assert O.bytes_block_decode(O.bytes_block_encode(items), len(items)) == items
+    # the same cells as a string column page (column.go:222-234 -> dictionary) and back
+    page = O.column_encode(O.VT_STR, items)
+    assert page[0] == O.ENC_DICTIONARY and O.column_decode(O.VT_STR, page, len(items)) == items
