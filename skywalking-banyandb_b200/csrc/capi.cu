@@ -33,6 +33,20 @@ int fail(int code, const std::string &msg) {
     g_last_error = msg;
     return code;
 }
+// No exception may cross the C ABI ("never abort"): allocation failures and anything a hostile part provokes in the
+// standard library become error codes.
+template <class F>
+int guarded(F &&f) {
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        return fail(BYDB_ENOMEM, "out of host memory");
+    } catch (const std::exception &e) {
+        return fail(BYDB_EINVAL, std::string("internal error: ") + e.what());
+    } catch (...) {
+        return fail(BYDB_EIO, "internal error: unknown exception");
+    }
+}
 #define CUDA_TRY(expr)                                                                          \
     do {                                                                                        \
         cudaError_t _e = (expr);                                                                \
@@ -255,6 +269,8 @@ int validate_query(const bydb_query *q, bool need_parts) {
     }
     if (q->top_n < 0 || (q->top_n > 0 && (q->top_agg < 0 || static_cast<uint32_t>(q->top_agg) >= q->n_aggs)))
         return fail(BYDB_EINVAL, "bad top_n / top_agg");
+    // checked before anything is enqueued: a refusal after run_scan would leave work in flight on a pooled stream
+    if (q->top_n > kMaxDeviceTopN) return fail(BYDB_ENOTSUP, "top_n larger than 2048 is not supported on the device path");
     return 0;
 }
 
@@ -493,6 +509,7 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
              bydb_stats *stats, int batch = 0, bool presized = false) {
     cudaEvent_t *ev = slot.ev + 4 * batch;
     uint8_t *zpage = slot.zpage + 256 * batch;
+    memset(zpage, 0, 256);  // a failure before the read-back is enqueued must not leave a previous call's status behind
     const size_t F = plan.fcols.size();
     const size_t NS = q->n_series;
     const size_t NB = plan.total_blocks;
@@ -862,9 +879,18 @@ int scan_agg_impl(bydb_ctx *ctx, const bydb_query *q, const std::vector<std::sha
         if (slot.ensure_pinned(NS * 12 + (G + 1) * 4 + G * (12 + 16 * A) + 16 * A + 8192)) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
     }
     rc = run_scan(ctx, q, plan, slot, slot.stream, table.base, tl, &out->stats);
-    if (rc) return rc;
     // finalisation is enqueued behind the scan; one synchronisation covers both
-    rc = finalize_to_host(ctx, q, plan, slot, slot.stream, table.base, tl, out);
+    if (!rc) rc = finalize_to_host(ctx, q, plan, slot, slot.stream, table.base, tl, out);
+    if (rc) {
+        // a failure after something was enqueued: the slot (and, on the host path, the transient parts the kernels read)
+        // go back to their pools when this returns, so nothing may still be in flight
+        cudaStreamSynchronize(slot.stream);
+        const std::string keep = g_last_error;
+        (void)collect_scan(slot, nullptr);  // a device-side error of the scan, if any, still drives the lazy-unpack retry
+        g_last_error = keep;
+        bydb_result_free(ctx, out);
+        return rc;
+    }
     int rc2 = collect_scan(slot, &out->stats);
     if (rc2) {
         bydb_result_free(ctx, out);
@@ -1004,6 +1030,7 @@ struct bydb_prepared {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     FinalLayout fl;
     size_t host_off = 0;
+    std::vector<std::shared_ptr<Part>> held;  // the parts whose device pointers are baked into the graph stay alive with it
     bydb_stats captured{};             // host-side counters of one step (launch counts, byte counts)
     uint64_t runs = 0;
     bool capturable = true;
@@ -1076,6 +1103,7 @@ int prepared_capture(bydb_ctx *ctx, bydb_prepared *p) {
     }
     p->captured.kernel_launches += 2;  // finalize + select_rows
     p->captured.d2h_bytes += p->fl.out_bytes;
+    p->held = plan.parts;
     return 0;
 }
 
@@ -1088,6 +1116,7 @@ const char *bydb_last_error(void) { return g_last_error.c_str(); }
 const char *bydb_version(void) { return "bydb-b200 0.1 (sm_100a)"; }
 
 int bydb_init(const bydb_cfg *cfg, bydb_ctx **out) {
+    return guarded([&]() -> int {
     if (!out) return fail(BYDB_EINVAL, "out is NULL");
     *out = nullptr;
     int dev = cfg ? cfg->device : 0;
@@ -1122,6 +1151,7 @@ int bydb_init(const bydb_cfg *cfg, bydb_ctx **out) {
     ctx->ctas_per_sm_fast = std::max(1, std::min(want, occ_fast));
     *out = ctx;
     return 0;
+    });
 }
 
 void bydb_shutdown(bydb_ctx *ctx) {
@@ -1132,6 +1162,7 @@ void bydb_shutdown(bydb_ctx *ctx) {
         if (s->stream) cudaStreamDestroy(s->stream);
         for (auto &e : s->ev)
             if (e) cudaEventDestroy(e);
+        if (s->busy) cudaEventDestroy(s->busy);
         if (s->pinned) cudaFreeHost(s->pinned);
         if (s->zpage) cudaFreeHost(s->zpage);
     }
@@ -1141,6 +1172,7 @@ void bydb_shutdown(bydb_ctx *ctx) {
 }
 
 int bydb_part_register(bydb_ctx *ctx, uint64_t part_id, const bydb_part_files *files, bydb_part_h *out) {
+    return guarded([&]() -> int {
     if (!ctx || !out) return fail(BYDB_EINVAL, "ctx/out is NULL");
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1155,14 +1187,23 @@ int bydb_part_register(bydb_ctx *ctx, uint64_t part_id, const bydb_part_files *f
     int rc = register_part_locked_free(ctx, part_id, files, part, nullptr, false, false, 0, 1, true);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    auto again = ctx->by_id.find(part_id);
+    if (again != ctx->by_id.end()) {
+        // another thread registered the same part meanwhile: keep its copy, drop ours (idempotent per part_id)
+        ctx->hbm_used -= part->hbm_bytes;
+        *out = again->second;
+        return 0;
+    }
     bydb_part_h h = ctx->next_handle++;
     ctx->parts[h] = part;
     ctx->by_id[part_id] = h;
     *out = h;
     return 0;
+    });
 }
 
 int bydb_part_release(bydb_ctx *ctx, bydb_part_h h) {
+    return guarded([&]() -> int {
     if (!ctx) return fail(BYDB_EINVAL, "ctx is NULL");
     std::shared_ptr<Part> victim;
     {
@@ -1177,9 +1218,11 @@ int bydb_part_release(bydb_ctx *ctx, bydb_part_h h) {
     cudaSetDevice(ctx->device);
     victim.reset();  // frees HBM once no in-flight query holds the part
     return 0;
+    });
 }
 
 int bydb_part_info(bydb_ctx *ctx, bydb_part_h h, uint64_t *hbm_bytes, uint64_t *n_blocks, uint64_t *n_rows) {
+    return guarded([&]() -> int {
     if (!ctx) return fail(BYDB_EINVAL, "ctx is NULL");
     std::lock_guard<std::mutex> lk(ctx->mu);
     auto it = ctx->parts.find(h);
@@ -1188,9 +1231,11 @@ int bydb_part_info(bydb_ctx *ctx, bydb_part_h h, uint64_t *hbm_bytes, uint64_t *
     if (n_blocks) *n_blocks = it->second->dir.blocks.size();
     if (n_rows) *n_rows = it->second->dir.total_rows;
     return 0;
+    });
 }
 
 int bydb_part_fallback_pages(bydb_ctx *ctx, bydb_part_h h, uint64_t *unpacked, uint64_t *left) {
+    return guarded([&]() -> int {
     if (!ctx) return fail(BYDB_EINVAL, "ctx is NULL");
     std::lock_guard<std::mutex> lk(ctx->mu);
     auto it = ctx->parts.find(h);
@@ -1198,14 +1243,17 @@ int bydb_part_fallback_pages(bydb_ctx *ctx, bydb_part_h h, uint64_t *unpacked, u
     if (unpacked) *unpacked = it->second->unpacked_pages;
     if (left) *left = it->second->unpack_skipped;
     return 0;
+    });
 }
 
 int bydb_scan_agg(bydb_ctx *ctx, const bydb_query *q, bydb_result *out) {
+    return guarded([&]() -> int {
     if (!ctx || !out) return fail(BYDB_EINVAL, "ctx/out is NULL");
     memset(out, 0, sizeof *out);
     int rc = validate_query(q, true);
     if (rc) return rc;
     return scan_agg_impl(ctx, q, nullptr, out, 0);
+    });
 }
 
 // Cold path, one zero-copy part: the block index is parsed in slices and the scan of slice k runs on the
@@ -1314,6 +1362,7 @@ static int scan_agg_host_pipelined(bydb_ctx *ctx, const bydb_part_files *files, 
         out->stats.kernel_launches += 1;
         // the pinned staging of the last slices may still be in flight: finalize copies into it only after the kernels
         rc = finalize_to_host(ctx, q, base, slot, slot.stream, tables.base, tl, out);
+        if (rc) cudaStreamSynchronize(slot.stream);  // nothing of this call may be in flight when the slot and the parts go back
         if (trace) fprintf(stderr, "[bydb cold] finalized at %.0f us\n", since());
     } else {
         cudaStreamSynchronize(slot.stream);
@@ -1334,6 +1383,7 @@ static int scan_agg_host_pipelined(bydb_ctx *ctx, const bydb_part_files *files, 
 }
 
 int bydb_scan_agg_host(bydb_ctx *ctx, uint32_t n_parts, const bydb_part_files *parts, const bydb_query *q, bydb_result *out) {
+    return guarded([&]() -> int {
     if (!ctx || !out) return fail(BYDB_EINVAL, "ctx/out is NULL");
     memset(out, 0, sizeof *out);
     int rc = validate_query(q, false);
@@ -1371,6 +1421,7 @@ int bydb_scan_agg_host(bydb_ctx *ctx, uint32_t n_parts, const bydb_part_files *p
         if (!wants_unpack(rc)) break;
     }
     return rc;
+    });
 }
 
 void bydb_result_free(bydb_ctx *, bydb_result *r) {
@@ -1380,6 +1431,7 @@ void bydb_result_free(bydb_ctx *, bydb_result *r) {
 }
 
 int bydb_partials_layout(const bydb_query *q, bydb_partials_layout_t *out) {
+    return guarded([&]() -> int {
     if (!q || !out) return fail(BYDB_EINVAL, "NULL argument");
     int rc = validate_query(q, false);
     if (rc) return rc;
@@ -1397,9 +1449,11 @@ int bydb_partials_layout(const bydb_query *q, bydb_partials_layout_t *out) {
     out->off_max_i64 = tl.off_max_i64;
     out->n_max_i64 = 2 * tl.GF + tl.F;
     return 0;
+    });
 }
 
 int bydb_scan_partials(bydb_ctx *ctx, const bydb_query *q, void *d_partials, uint64_t bytes, void *stream, bydb_stats *stats) {
+    return guarded([&]() -> int {
     if (!ctx || !d_partials) return fail(BYDB_EINVAL, "ctx/d_partials is NULL");
     int rc = validate_query(q, true);
     if (rc) return rc;
@@ -1429,9 +1483,11 @@ int bydb_scan_partials(bydb_ctx *ctx, const bydb_query *q, void *d_partials, uin
     }
     if (stats) *stats = local;
     return rc;
+    });
 }
 
 int bydb_partials_combine(bydb_ctx *ctx, const bydb_query *q, void *d_tables, uint32_t n_tables, uint64_t bytes_each, void *stream) {
+    return guarded([&]() -> int {
     if (!ctx || !d_tables || n_tables == 0) return fail(BYDB_EINVAL, "NULL argument");
     int rc = validate_query(q, false);
     if (rc) return rc;
@@ -1446,9 +1502,11 @@ int bydb_partials_combine(bydb_ctx *ctx, const bydb_query *q, void *d_tables, ui
                           static_cast<cudaStream_t>(stream));
     CUDA_TRY(cudaGetLastError());
     return 0;
+    });
 }
 
 int bydb_reduce_finalize(bydb_ctx *ctx, const bydb_query *q, const void *d_partials, uint64_t bytes, void *stream, bydb_result *out) {
+    return guarded([&]() -> int {
     if (!ctx || !d_partials || !out) return fail(BYDB_EINVAL, "NULL argument");
     memset(out, 0, sizeof *out);
     int rc = validate_query(q, false);
@@ -1463,10 +1521,12 @@ int bydb_reduce_finalize(bydb_ctx *ctx, const bydb_query *q, const void *d_parti
     if (lease.init()) return fail(BYDB_EIO, "cannot create stream");
     cudaStream_t s = static_cast<cudaStream_t>(stream);  // NULL = the legacy default stream, like every partial-table call
     return finalize_to_host(ctx, q, plan, *lease.slot, s, static_cast<const uint8_t *>(d_partials), tl, out, true);
+    });
 }
 
 
 int bydb_query_prepare(bydb_ctx *ctx, const bydb_query *q, bydb_prepared **out) {
+    return guarded([&]() -> int {
     if (!ctx || !out) return fail(BYDB_EINVAL, "ctx/out is NULL");
     *out = nullptr;
     int rc = validate_query(q, true);
@@ -1513,6 +1573,7 @@ int bydb_query_prepare(bydb_ctx *ctx, const bydb_query *q, bydb_prepared **out) 
     }
     *out = p;
     return 0;
+    });
 }
 
 void bydb_query_release(bydb_ctx *ctx, bydb_prepared *p) {
@@ -1521,6 +1582,7 @@ void bydb_query_release(bydb_ctx *ctx, bydb_prepared *p) {
 }
 
 int bydb_scan_agg_prepared(bydb_ctx *ctx, bydb_prepared *p, bydb_result *out) {
+    return guarded([&]() -> int {
     if (!ctx || !p || !out) return fail(BYDB_EINVAL, "NULL argument");
     memset(out, 0, sizeof *out);
     std::lock_guard<std::mutex> lk(p->mu);
@@ -1530,6 +1592,30 @@ int bydb_scan_agg_prepared(bydb_ctx *ctx, bydb_prepared *p, bydb_result *out) {
     // captures; from then on the graph is replayed
     const uint64_t run = p->runs++;
     if (run == 0 || !p->capturable) return scan_agg_impl(ctx, &p->q, nullptr, out, 0);
+    if (!p->exec) {
+        const int rc = prepared_capture(ctx, p);
+        if (rc) return rc;
+        if (!p->exec) return scan_agg_impl(ctx, &p->q, nullptr, out, 0);
+    }
+    {
+        // the graph reads the parts through the device pointers captured with it: every handle must still name the very
+        // part object that was captured (a released part makes the call fail like bydb_scan_agg would, a re-registered one
+        // drops the graph and captures again)
+        std::lock_guard<std::mutex> lk2(ctx->mu);
+        bool same = p->held.size() == p->parts.size();
+        bool missing = false;
+        for (size_t i = 0; i < p->parts.size(); ++i) {
+            auto it = ctx->parts.find(p->parts[i]);
+            if (it == ctx->parts.end()) missing = true;
+            else if (same && it->second != p->held[i]) same = false;
+        }
+        if (missing || !same) {
+            cudaGraphExecDestroy(p->exec);
+            p->exec = nullptr;
+            p->held.clear();
+            if (missing) return fail(BYDB_ENOENT, "unknown part handle");
+        }
+    }
     if (!p->exec) {
         const int rc = prepared_capture(ctx, p);
         if (rc) return rc;
@@ -1562,6 +1648,7 @@ int bydb_scan_agg_prepared(bydb_ctx *ctx, bydb_prepared *p, bydb_result *out) {
     }
     finalize_parse(slot.pinned + p->host_off, p->fl, out);
     return 0;
+    });
 }
 
 }  // extern "C"

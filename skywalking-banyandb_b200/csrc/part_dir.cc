@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <exception>
 #include <mutex>
 #include <thread>
 
@@ -63,6 +64,13 @@ int zstd_decompress(const uint8_t *src, size_t n, std::vector<uint8_t> &dst, std
         err = "not a zstd frame";
         return BYDB_EINVAL;
     }
+    // a frame of the block index is a primary block (flushed above 128 KiB raw, block_writer.go:247-250) or meta.bin
+    // (40 B per primary block): a declared size beyond this bound is a corrupt header, not something to allocate
+    const unsigned long long kMaxFrame = std::max<unsigned long long>(64ull << 20, static_cast<unsigned long long>(n) * 1024ull);
+    if (fcs != static_cast<unsigned long long>(-1) && fcs > kMaxFrame) {
+        err = "zstd frame declares an implausible content size";
+        return BYDB_EINVAL;
+    }
     size_t cap = fcs == static_cast<unsigned long long>(-1) ? n * 32 + 4096 : static_cast<size_t>(fcs);
     for (int attempt = 0; attempt < 8; ++attempt) {
         dst.resize(cap ? cap : 1);
@@ -73,6 +81,7 @@ int zstd_decompress(const uint8_t *src, size_t n, std::vector<uint8_t> &dst, std
         }
         if (fcs != static_cast<unsigned long long>(-1)) break;
         cap *= 8;
+        if (cap > kMaxFrame) break;
     }
     err = "zstd decompress failed";
     return BYDB_EINVAL;
@@ -80,6 +89,9 @@ int zstd_decompress(const uint8_t *src, size_t n, std::vector<uint8_t> &dst, std
 
 // ------------------------------------------------------------------ byte cursor
 namespace {
+// [off, off+size) inside a file of `len` bytes, without wrapping in uint64 (a crafted offset must not pass)
+inline bool in_file(uint64_t off, uint64_t size, uint64_t len) { return off <= len && size <= len - off; }
+
 struct Cur {
     const uint8_t *p, *end;
     bool bad = false;
@@ -188,7 +200,7 @@ int parse_primary_block(ParseCtx &cx, const uint8_t *data, size_t len, std::vect
         uint64_t ver_off = c.varu();
         b.ver_first = static_cast<int64_t>(c.u64be());
         b.ver_enc = c.u8();
-        if (c.bad || count == 0 || count > 0x7fffffffu || ts_size > 0xffffffffu || ver_off > ts_size || b.ts_off + ts_size > cx.tsf->len) {
+        if (c.bad || count == 0 || count > 0x7fffffffu || ts_size > 0xffffffffu || ver_off > ts_size || !in_file(b.ts_off, ts_size, cx.tsf->len)) {
             err = "corrupt blockMetadata (timestamps)";
             return BYDB_EINVAL;
         }
@@ -258,7 +270,7 @@ int parse_primary_block(ParseCtx &cx, const uint8_t *data, size_t len, std::vect
             col.value_type = c.u8();
             col.off = c.varu();
             uint64_t size = c.varu();
-            if (c.bad || size > 0xffffffffu || col.off + size > cx.fvf->len) {
+            if (c.bad || size > 0xffffffffu || !in_file(col.off, size, cx.fvf->len)) {
                 err = "corrupt field columnMetadata";
                 return BYDB_EINVAL;
             }
@@ -274,7 +286,7 @@ int parse_primary_block(ParseCtx &cx, const uint8_t *data, size_t len, std::vect
         size_t tag_pos = 0;
         for (uint64_t fi = 0; fi < nfam; ++fi) {
             const ParseCtx::FamSlot &fs = cx.fam_cache[fams[fi].slot];
-            if (!fs.tfm || !fs.tf || fs.file_id < 0 || fams[fi].off + fams[fi].size > fs.tfm->len) {
+            if (!fs.tfm || !fs.tf || fs.file_id < 0 || !in_file(fams[fi].off, fams[fi].size, fs.tfm->len)) {
                 err = "tag family '" + fs.name + "': missing or truncated .tf/.tfm";
                 return BYDB_EINVAL;
             }
@@ -292,7 +304,7 @@ int parse_primary_block(ParseCtx &cx, const uint8_t *data, size_t len, std::vect
                 col.value_type = t.u8();
                 col.off = t.varu();
                 uint64_t size = t.varu();
-                if (t.bad || size > 0xffffffffu || col.off + size > fs.tf->len) {
+                if (t.bad || size > 0xffffffffu || !in_file(col.off, size, fs.tf->len)) {
                     err = "corrupt tag columnMetadata";
                     return BYDB_EINVAL;
                 }
@@ -350,7 +362,7 @@ int build_part_dir(const std::vector<FileImage> &files, NameTable &names, PartDi
             p.mx = static_cast<int64_t>(c.u64be());
             p.off = c.u64be();
             p.size = c.u64be();
-            if (p.off + p.size > primary->len) {
+            if (!in_file(p.off, p.size, primary->len)) {
                 err = "primary block outside primary.bin";
                 return BYDB_EINVAL;
             }
@@ -376,6 +388,7 @@ int build_part_dir(const std::vector<FileImage> &files, NameTable &names, PartDi
     std::vector<std::string> terr(nt);
     std::mutex names_mu;
     auto work = [&](size_t t) {
+      try {
         ParseCtx cx;
         cx.files = &files;
         cx.tsf = tsf;
@@ -388,6 +401,10 @@ int build_part_dir(const std::vector<FileImage> &files, NameTable &names, PartDi
             trc[t] = zstd_decompress(primary->data + pbms[i].off, static_cast<size_t>(pbms[i].size), blk, terr[t]);
             if (trc[t] == 0) trc[t] = parse_primary_block(cx, blk.data(), blk.size(), tb[t], tc[t], terr[t]);
         }
+      } catch (const std::exception &e) {  // bad_alloc / length_error on a hostile part: an error code, never std::terminate
+        trc[t] = BYDB_ENOMEM;
+        terr[t] = std::string("block index: ") + e.what();
+      }
     };
     if (nt == 1) {
         work(0);

@@ -18,6 +18,7 @@
 #include "scan_kernels.cuh"
 #include "lane_decode.cuh"
 
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 
@@ -2255,13 +2256,18 @@ void launch_plan_blocks(const ScanParams &p, cudaStream_t s) {
     plan_blocks_kernel<<<(p.total_blocks + threads - 1) / threads, threads, 0, s>>>(p);
 }
 
-static bool g_scan_attr_set = false;
+// cudaFuncSetAttribute applies to the CURRENT device: one flag per device ordinal (several contexts, one per GPU, may
+// live in one process), atomics because every entry point is thread-safe
+static std::atomic<bool> g_attr_set[64];
 static void scan_set_attrs() {
-    if (g_scan_attr_set) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && g_attr_set[dev].load(std::memory_order_acquire)) return;
     const int smem = static_cast<int>(scan_smem_bytes());
     cudaFuncSetAttribute(scan_blocks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(scan_blocks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    g_scan_attr_set = true;
+    cudaFuncSetAttribute(dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (dev >= 0 && dev < 64) g_attr_set[dev].store(true, std::memory_order_release);
 }
 // fast lane over the planned blocks, then the slow lane over whatever the fast lane deferred
 void launch_scan_blocks(const ScanParams &p, int grid_fast, int grid_slow, cudaStream_t s) {
@@ -2288,11 +2294,7 @@ void launch_detect_overlap(const ScanParams &p, cudaStream_t s) {
 void launch_dedup(const ScanParams &p, int grid, cudaStream_t s) {
     if (p.n_dd_blocks == 0) return;
     const size_t smem = scan_smem_bytes();
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        attr = true;
-    }
+    scan_set_attrs();
     dedup_kernel<<<grid, kWarpsPerCta * 32, smem, s>>>(p, 0);
     dedup_kernel<<<grid, kWarpsPerCta * 32, smem, s>>>(p, 1);
 }

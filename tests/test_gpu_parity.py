@@ -13,6 +13,12 @@ ALL5 = [O.AGG_SUM, O.AGG_COUNT, O.AGG_MIN, O.AGG_MAX, O.AGG_MEAN]
 _pid = [10]
 
 
+def _seed_of(kind: str) -> int:
+    """A fixed seed per test-case name (crc32: the same in every process, unlike hash(str))."""
+    import zlib
+    return zlib.crc32(kind.encode()) & 0xFFFF
+
+
 def _next_pid(n=1):
     _pid[0] += 100
     return _pid[0]
@@ -54,7 +60,7 @@ def test_groups_time_range_dict_pred_all_functions(bydb, gpu_ctx):
 @pytest.mark.parametrize("kind", ["const", "delta_const", "delta_small", "delta_wide", "dod_monotone", "dod_counter_resets",
                                   "full_range", "negative", "two_byte", "one_byte"])
 def test_int64_encodings(bydb, gpu_ctx, kind):
-    rng = np.random.default_rng(hash(kind) & 0xFFFF)
+    rng = np.random.default_rng(_seed_of(kind))
     n_series, n_pts = 9, 8193 + 700   # 8193-row first block (measure.go:41-46 quirk) + a short tail block
     sids, ts, ver = grid(n_series, n_pts)
     n = sids.size
@@ -95,7 +101,7 @@ def test_int64_encodings(bydb, gpu_ctx, kind):
 
 @pytest.mark.parametrize("kind", ["two_decimals", "ints_as_float", "mixed_exponents", "tiny", "huge_scale", "negative_mix", "random_walk_3dp"])
 def test_float64_decimal_pages(bydb, gpu_ctx, kind):
-    rng = np.random.default_rng(hash(kind) & 0xFFFF)
+    rng = np.random.default_rng(_seed_of(kind))
     n_series, n_pts = 6, 5000
     sids, ts, ver = grid(n_series, n_pts)
     n = sids.size
@@ -124,7 +130,7 @@ def test_float64_decimal_pages(bydb, gpu_ctx, kind):
 
 @pytest.mark.parametrize("kind", ["irregular", "accelerating", "single_row_blocks"])
 def test_timestamp_encodings_and_ranges(bydb, gpu_ctx, kind):
-    rng = np.random.default_rng(hash(kind) & 0xFFFF)
+    rng = np.random.default_rng(_seed_of(kind))
     n_series = 5
     rows = []
     for s in range(n_series):
@@ -711,8 +717,6 @@ def test_reference_query_test_fixtures_on_the_device(bydb, gpu_ctx, case):
     assert_parity(got, want, QUERY_TEST_AGGS, f"query_test/{case}/pred")
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("BYDB_SWEEP"), reason="written after the GPU budget of round 1 was spent: enable with BYDB_SWEEP=1, "
-                    "to be made unconditional after the first green run on a GPU")
 def test_equal_version_duplicates_keep_the_earlier_part(bydb, gpu_ctx):
     # same (series, timestamp, version) in two parts with different values: unspecified in the reference (heap order), defined
     # here as "the earlier part of the query wins" -- oracle and device must agree for both part orders
@@ -727,8 +731,6 @@ def test_equal_version_duplicates_keep_the_earlier_part(bydb, gpu_ctx):
         assert int(got.val_i64[0, 0]) == want and int(got.val_i64[0, 1]) == 5
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("BYDB_SWEEP"), reason="randomised device-vs-oracle sweep: enable with BYDB_SWEEP=1 "
-                    "(written at the end of round 1 without GPU time left to run it once; to be made unconditional after its first green run)")
 @pytest.mark.parametrize("seed", range(24))
 def test_random_sweep_device_vs_oracle(bydb, gpu_ctx, seed):
     # the generator of tests/test_oracle_model_sweep.py (1-3 overlapping parts, versions incl. equal ones, nil cells, int/str
@@ -749,8 +751,6 @@ def test_random_sweep_device_vs_oracle(bydb, gpu_ctx, seed):
             assert (np.abs(got.val_f64[:, a] - want.val_f64[:, a]) <= 1e-9 * scale).all(), (seed, a)
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("BYDB_SWEEP"), reason="written after the GPU budget of round 1 was spent: enable with BYDB_SWEEP=1, "
-                    "to be made unconditional after the first green run on a GPU")
 def test_block_selection_part_iter_test_go(bydb, gpu_ctx):
     # banyand/measure/part_iter_test.go Test_partIter_nextBlock on `dps`: the blocks plan_blocks selects for each series list
     from tests.helpers import PART_ITER_CASES, part_iter_fixture
@@ -762,8 +762,6 @@ def test_block_selection_part_iter_test_go(bydb, gpu_ctx):
         assert got.stats.blocks_scanned == len(want_sids) and got.stats.rows_scanned == 2 * len(want_sids)
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("BYDB_SWEEP"), reason="written after the GPU budget of round 1 was spent: enable with BYDB_SWEEP=1, "
-                    "to be made unconditional after the first green run on a GPU")
 def test_concurrent_callers_share_one_context(bydb, gpu_ctx):
     # the cgo contract: many goroutines call into one bydb_ctx concurrently -> one stream / staging slot per call.
     # 8 threads x 25 queries of three shapes (resident scan, Top-N, cold host path) must all return the sequential answers.
@@ -808,8 +806,6 @@ def test_concurrent_callers_share_one_context(bydb, gpu_ctx):
     assert not errors, errors[:3]
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("BYDB_SWEEP"), reason="written after the GPU budget of round 1 was spent: enable with BYDB_SWEEP=1, "
-                    "to be made unconditional after the first green run on a GPU")
 def test_prepared_query_graph_replay_equals_scan_agg(bydb, gpu_ctx):
     # bydb_query_prepare / bydb_scan_agg_prepared: run 1 = ordinary path, run 2 = capture, runs 3.. = graph replays; every run must
     # return exactly what bydb_scan_agg returns, for a masked scalar query, a grouped Top-N and a fallback-page query

@@ -26,8 +26,6 @@ def test_operator_contract_without_a_device(tmp_path, bydb):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("BYDB_SWEEP"), reason="written after the GPU budget of round 1 was spent: enable with BYDB_SWEEP=1, "
-                    "to be made unconditional after the first green run on a GPU")
 def test_operator_full_flow_on_the_device(tmp_path, bydb):
     out = subprocess.run([str(_build(tmp_path, bydb))], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "OK full" in out.stdout, out.stdout + out.stderr
