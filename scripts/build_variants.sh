@@ -13,5 +13,7 @@ build dual_allrows "-DBYDB_EXP_DUAL -DBYDB_EXP_ALLROWS"
 build interior "-DBYDB_EXP_INTERIOR"
 build dual_interior "-DBYDB_EXP_DUAL -DBYDB_EXP_INTERIOR"
 build stages3 "-DBYDB_STAGES=3"
+build allrows "-DBYDB_EXP_ALLROWS"
+build es_int_all "-DBYDB_EXP_EARLYSTOP -DBYDB_EXP_INTERIOR -DBYDB_EXP_ALLROWS"
 rm -f build_variant.log
 ls -la variants

@@ -68,10 +68,21 @@ struct __align__(128) WarpSmem {
     uint32_t mask[kMaskWords + 2];  // +2: the fast path reads a 64-bit window at the last word
     uint32_t match[8];  // dictionary match set of the predicate being applied
     uint32_t fault;     // set when a TMA wait timed out
-    uint32_t pad;
+    uint32_t seq;       // warp-monotonic count of the TMA stages issued so far (mbarrier phase bookkeeping)
+    // result slot of the out-of-line page decoders: handing an accumulator over by reference would put it (and the
+    // caller's live registers) into local memory; shared memory costs one broadcast load per field instead
+    unsigned long long res_lo;
+    long long res_hi, res_mn, res_mx;
+    uint32_t res_cnt;
+    // argument slot of the same calls (more than a handful of arguments would be marshalled through local memory)
+    uint32_t a_len;
+    const uint8_t *a_body;
+    long long a_first;
+    uint32_t a_count, a_r0, a_r1, pad;
 };
 
 size_t scan_smem_bytes() { return sizeof(WarpSmem) * kWarpsPerCta; }
+
 
 struct PageStream {
     const uint8_t *abase;  // 16 B aligned global address at or below the first body byte
@@ -88,17 +99,17 @@ __device__ __forceinline__ void stream_issue(const PageStream &s, WarpSmem *sm, 
     mbar_expect_tx(&sm->bar[slot], bytes);
     tma_load_1d(sm->stage[slot], s.abase + off, bytes, &sm->bar[slot]);
 }
-__device__ __forceinline__ void stream_open(PageStream &s, WarpSmem *sm, uint32_t &seq, const uint8_t *body, uint32_t len, int lane) {
+__device__ __forceinline__ void stream_open(PageStream &s, WarpSmem *sm, const uint8_t *body, uint32_t len, int lane) {
     uintptr_t a = reinterpret_cast<uintptr_t>(body);
     s.abase = reinterpret_cast<const uint8_t *>(a & ~static_cast<uintptr_t>(15));
     s.pstart = static_cast<uint32_t>(a & 15);
     s.pend = s.pstart + len;
     s.total = (s.pend + 15u) & ~15u;
     s.nstages = (s.total + kStageBytes - 1) / kStageBytes;
-    s.seq0 = seq;
-    seq += s.nstages;
-    __syncwarp();  // every lane is done reading the stages of the previous page
+    s.seq0 = sm->seq;
+    __syncwarp();  // every lane is done reading the stages of the previous page (and sm->seq)
     if (lane == 0) {
+        sm->seq = s.seq0 + s.nstages;
         uint32_t n = min(s.nstages, static_cast<uint32_t>(kStages));
         for (uint32_t k = 0; k < n; ++k) stream_issue(s, sm, k);
     }
@@ -247,6 +258,26 @@ struct AggAcc {
     }
 };
 
+// the out-of-line fast decoders leave their (warp-reduced) result in the warp's shared-memory slot
+__device__ __forceinline__ void publish_acc(WarpSmem *sm, AggAcc &acc, int lane) {
+    acc.warp_reduce();
+    if (lane == 0) {
+        sm->res_lo = acc.lo;
+        sm->res_hi = acc.hi;
+        sm->res_mn = acc.mn;
+        sm->res_mx = acc.mx;
+        sm->res_cnt = acc.cnt;
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void fetch_acc(const WarpSmem *sm, AggAcc &acc) {
+    acc.lo = sm->res_lo;
+    acc.hi = sm->res_hi;
+    acc.mn = sm->res_mn;
+    acc.mx = sm->res_mx;
+    acc.cnt = sm->res_cnt;
+}
+
 // general-path consumer: the row mode is a runtime value to keep one instantiation of the decoder
 struct AggCons {
     AggAcc acc;
@@ -305,7 +336,7 @@ struct CmpCons {
 // int64 arithmetic wraps mod 2^64 like Go's, so the result is bit-exact.
 // ------------------------------------------------------------------------------------------------
 template <bool kDod, class Cons>
-__device__ __noinline__ bool decode_varint_page(WarpSmem *sm, uint32_t &seq, const uint8_t *body, uint32_t len, uint32_t count,
+__device__ __noinline__ bool decode_varint_page(WarpSmem *sm, const uint8_t *body, uint32_t len, uint32_t count,
                                                  int64_t first, Cons &cons_io, int lane) {
     Cons cons = cons_io;  // register copy: the by-reference object of a noinline call lives in local memory
     if (lane == 0) cons(0u, first);
@@ -314,7 +345,7 @@ __device__ __noinline__ bool decode_varint_page(WarpSmem *sm, uint32_t &seq, con
         return count == 1;
     }
     PageStream st;
-    stream_open(st, sm, seq, body, len, lane);
+    stream_open(st, sm, body, len, lane);
     const uint32_t nchunks = (st.total + kChunkBytes - 1) / kChunkBytes;
     constexpr uint32_t kChunksPerStage = kStageBytes / kChunkBytes;
     int64_t V0 = first;  // value of the row before this chunk's first varint (warp-uniform)
@@ -555,9 +586,12 @@ __device__ __forceinline__ uint32_t fast_active_window(const WarpSmem *sm, uint3
 }
 
 template <int kMode, int kNeed>
-__device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const uint8_t *body, uint32_t len, uint32_t count, int64_t first,
-                                            uint32_t r0, uint32_t r1, AggAcc &acc_io, int lane) {
-    AggAcc acc = acc_io;  // register copy (see decode_varint_page)
+__device__ __noinline__ int delta_page_fast(WarpSmem *sm, int lane) {
+    const uint8_t *body = sm->a_body;
+    const uint32_t len = sm->a_len, count = sm->a_count, r0 = sm->a_r0, r1 = sm->a_r1;
+    const int64_t first = sm->a_first;
+    AggAcc acc;
+    acc.init();
     if (lane == 0) {
         bool a = true;
         if (kMode == kRowsRange) a = r0 == 0;
@@ -565,11 +599,11 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const u
         if (a) acc.add(first);
     }
     if (len == 0) {
-        acc_io = acc;
+        publish_acc(sm, acc, lane);
         return count == 1 ? 0 : 2;
     }
     PageStream st;
-    stream_open(st, sm, seq, body, len, lane);
+    stream_open(st, sm, body, len, lane);
     const uint32_t nchunks = (st.total + kFastChunkBytes - 1) / kFastChunkBytes;
     constexpr uint32_t kChunksPerStage = kStageBytes / kFastChunkBytes;
     int64_t V0 = first;
@@ -585,7 +619,7 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const u
             // give the unissued stage numbers back: the mbarrier phases only advance for stages that
             // were really issued, and the next page must continue from exactly that count
             stream_drain(st, sm, k);
-            seq = st.seq0 + min(st.nstages, k + static_cast<uint32_t>(kStages));
+            if (lane == 0) sm->seq = st.seq0 + min(st.nstages, k + static_cast<uint32_t>(kStages));
             __syncwarp();
             return 1;
         }
@@ -668,15 +702,15 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, uint32_t &seq, const u
         // validated against the block's row count.)
         if (kMode != kRowsAll && row_base > r1 && c + 1 < nchunks) {
             stream_drain(st, sm, k);
-            seq = st.seq0 + min(st.nstages, k + static_cast<uint32_t>(kStages));
+            if (lane == 0) sm->seq = st.seq0 + min(st.nstages, k + static_cast<uint32_t>(kStages));
             __syncwarp();
-            acc_io = acc;
+            publish_acc(sm, acc, lane);
             return 0;
         }
 #endif
         if ((c % kChunksPerStage) == kChunksPerStage - 1 || c == nchunks - 1) stream_release(st, sm, k, lane);
     }
-    acc_io = acc;
+    publish_acc(sm, acc, lane);
     return (row_base == count && carry_sh == 0) ? 0 : 2;
 }
 
@@ -1086,9 +1120,13 @@ __device__ __forceinline__ bool find_col(const DevPartRef &part, const DevBlock 
 // Returns like delta_page_fast.
 // ------------------------------------------------------------------------------------------------
 template <int kMode, int kNeed>
-__device__ __noinline__ int dod_page_fast(WarpSmem *sm, uint32_t &seq, const uint8_t *body, uint32_t len, uint32_t count, int64_t first,
-                                          uint32_t r0, uint32_t r1, AggAcc &acc_io, int lane) {
-    AggAcc acc = acc_io;
+__device__ __noinline__ int dod_page_fast(WarpSmem *sm, int lane) {
+    const uint8_t *body = sm->a_body;
+    uint32_t len = sm->a_len;
+    const uint32_t count = sm->a_count, r0 = sm->a_r0, r1 = sm->a_r1;
+    const int64_t first = sm->a_first;
+    AggAcc acc;
+    acc.init();
     auto active0 = [&](uint32_t row) -> bool {
         if (kMode == kRowsRange) return row >= r0 && row <= r1;
         if (kMode == kRowsMask) return (sm->mask[row >> 5] >> (row & 31)) & 1u;
@@ -1105,11 +1143,11 @@ __device__ __noinline__ int dod_page_fast(WarpSmem *sm, uint32_t &seq, const uin
     body += used;
     len -= used;
     if (len == 0) {
-        acc_io = acc;
+        publish_acc(sm, acc, lane);
         return count == 2 ? 0 : 2;
     }
     PageStream st;
-    stream_open(st, sm, seq, body, len, lane);
+    stream_open(st, sm, body, len, lane);
     const uint32_t nchunks = (st.total + kFastChunkBytes - 1) / kFastChunkBytes;
     constexpr uint32_t kChunksPerStage = kStageBytes / kFastChunkBytes;
     int64_t V0 = first + d1;  // value of the row before this chunk's first varint
@@ -1124,7 +1162,7 @@ __device__ __noinline__ int dod_page_fast(WarpSmem *sm, uint32_t &seq, const uin
         fast_chunk_load(fc, st, buf, c, carry_sh, lane);
         if (fc.wide) {
             stream_drain(st, sm, k);
-            seq = st.seq0 + min(st.nstages, k + static_cast<uint32_t>(kStages));
+            if (lane == 0) sm->seq = st.seq0 + min(st.nstages, k + static_cast<uint32_t>(kStages));
             __syncwarp();
             return 1;
         }
@@ -1226,7 +1264,7 @@ __device__ __noinline__ int dod_page_fast(WarpSmem *sm, uint32_t &seq, const uin
         row_base += n_tot;
         if ((c % kChunksPerStage) == kChunksPerStage - 1 || c == nchunks - 1) stream_release(st, sm, k, lane);
     }
-    acc_io = acc;
+    publish_acc(sm, acc, lane);
     return (row_base == count && carry_sh == 0) ? 0 : 2;
 }
 
@@ -1234,7 +1272,7 @@ __device__ __noinline__ int dod_page_fast(WarpSmem *sm, uint32_t &seq, const uin
 constexpr uint32_t kDeferSlow = 0xffffffffu;
 
 template <int kMode, bool kFastLane>
-__device__ __forceinline__ uint32_t agg_field_page(WarpSmem *sm, uint32_t &seq, const uint8_t *page, uint32_t size, bool is_float, uint32_t need,
+__device__ __forceinline__ uint32_t agg_field_page(WarpSmem *sm, const uint8_t *page, uint32_t size, bool is_float, uint32_t need,
                                                    uint32_t count, uint32_t r0, uint32_t r1, AggAcc &out, int &exp_out, int lane) {
     if (size < 1) return kErrCorrupt;
     const uint32_t enc = __ldg(page);
@@ -1265,20 +1303,26 @@ __device__ __forceinline__ uint32_t agg_field_page(WarpSmem *sm, uint32_t &seq, 
     }
     if (enc != 3 && enc != 4) return kErrBadEnc;
     {
-        AggAcc fa;
-        fa.init();
-        int rc;
-        if (enc == 3) {
-            if (need == kNeedSum) rc = delta_page_fast<kMode, kNeedSum>(sm, seq, body, blen, count, first, r0, r1, fa, lane);
-            else if (need == kNeedMinMax) rc = delta_page_fast<kMode, kNeedMinMax>(sm, seq, body, blen, count, first, r0, r1, fa, lane);
-            else rc = delta_page_fast<kMode, kNeedSum | kNeedMinMax>(sm, seq, body, blen, count, first, r0, r1, fa, lane);
-        } else {
-            rc = dod_page_fast<kMode, kNeedSum | kNeedMinMax>(sm, seq, body, blen, count, first, r0, r1, fa, lane);
+        int rc;  // warp-uniform: every exit of the fast decoders is taken by the whole warp
+        __syncwarp();
+        if (lane == 0) {
+            sm->a_body = body;
+            sm->a_len = blen;
+            sm->a_count = count;
+            sm->a_first = first;
+            sm->a_r0 = r0;
+            sm->a_r1 = r1;
         }
-        rc = __reduce_max_sync(0xffffffffu, static_cast<unsigned>(rc));
+        __syncwarp();
+        if (enc == 3) {
+            if (need == kNeedSum) rc = delta_page_fast<kMode, kNeedSum>(sm, lane);
+            else if (need == kNeedMinMax) rc = delta_page_fast<kMode, kNeedMinMax>(sm, lane);
+            else rc = delta_page_fast<kMode, kNeedSum | kNeedMinMax>(sm, lane);
+        } else {
+            rc = dod_page_fast<kMode, kNeedSum | kNeedMinMax>(sm, lane);
+        }
         if (rc == 0) {
-            fa.warp_reduce();
-            out = fa;
+            fetch_acc(sm, out);
             return kErrNone;
         }
         if (rc == 2) return kErrCorrupt;
@@ -1294,8 +1338,8 @@ __device__ __forceinline__ uint32_t agg_field_page(WarpSmem *sm, uint32_t &seq, 
         cons.mask = sm->mask;
         cons.mode = kMode;
         bool ok;
-        if (enc == 3) ok = decode_varint_page<false>(sm, seq, body, blen, count, first, cons, lane);
-        else ok = decode_varint_page<true>(sm, seq, body, blen, count, first, cons, lane);
+        if (enc == 3) ok = decode_varint_page<false>(sm, body, blen, count, first, cons, lane);
+        else ok = decode_varint_page<true>(sm, body, blen, count, first, cons, lane);
         ok = __all_sync(0xffffffffu, ok);
         if (!ok) return kErrCorrupt;
         cons.acc.warp_reduce();
@@ -1312,11 +1356,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
     WarpSmem *sm = reinterpret_cast<WarpSmem *>(smem_raw) + warp;
     if (lane == 0) {
         sm->fault = 0;
+        sm->seq = 0;
         for (int s = 0; s < kStages; ++s) mbar_init(&sm->bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    uint32_t seq = 0;
     // fast lane: the planned work list; slow lane: the blocks the fast lane deferred
     const uint32_t nwork = kFastLane ? *p.work_count : *p.slow_count;
     const uint32_t *list = kFastLane ? p.worklist : p.slow_list;
@@ -1374,8 +1418,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
                 tc.lt = 0;
                 tc.le = 0;
                 bool ok;
-                if (blk.ts_enc == 3) ok = decode_varint_page<false>(sm, seq, tsp, blk.ver_off, count, blk.ts_min, tc, lane);
-                else ok = decode_varint_page<true>(sm, seq, tsp, blk.ver_off, count, blk.ts_min, tc, lane);
+                if (blk.ts_enc == 3) ok = decode_varint_page<false>(sm, tsp, blk.ver_off, count, blk.ts_min, tc, lane);
+                else ok = decode_varint_page<true>(sm, tsp, blk.ver_off, count, blk.ts_min, tc, lane);
                 if (!__all_sync(0xffffffffu, ok)) err = kErrCorrupt;
                 uint32_t lt = tc.lt, le = tc.le;
 #pragma unroll
@@ -1473,8 +1517,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
                                 cc.mask = sm->mask;
                                 cc.limit = count;
                                 bool ok;
-                                if (enc == 3) ok = decode_varint_page<false>(sm, seq, body, blen, count, first, cc, lane);
-                                else ok = decode_varint_page<true>(sm, seq, body, blen, count, first, cc, lane);
+                                if (enc == 3) ok = decode_varint_page<false>(sm, body, blen, count, first, cc, lane);
+                                else ok = decode_varint_page<true>(sm, body, blen, count, first, cc, lane);
                                 if (!__all_sync(0xffffffffu, ok)) err = kErrCorrupt;
                             } else {
                                 err = kErrBadEnc;
@@ -1537,22 +1581,24 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
                             e2 = kErrCorrupt;
                         } else if (__ldg(page) == 9) {
                             e2 = kErrPlainPage;
-                        } else if (__ldg(page) == kEncRawCells && __ldg(page + 1) && kFastLane) {
-                            e2 = kDeferSlow;
                         } else if (__ldg(page) == kEncRawCells && __ldg(page + 1)) {
                             // a page with null cells: COUNT skips them (aggregation.go:292-294)
-                            const int mode = use_mask ? kRowsMask : kRowsRange;
-                            e2 = agg_raw_page(page, col.size, false, mode, count, r0, r1, sm->mask, acc, lane);
-                            acc.lo = 0;
-                            acc.hi = 0;
-                            page_bytes += count;
+                            if (kFastLane) {  // compile-time: the fast lane never instantiates the raw-cell reader
+                                e2 = kDeferSlow;
+                            } else {
+                                const int mode = use_mask ? kRowsMask : kRowsRange;
+                                e2 = agg_raw_page(page, col.size, false, mode, count, r0, r1, sm->mask, acc, lane);
+                                acc.lo = 0;
+                                acc.hi = 0;
+                                page_bytes += count;
+                            }
                         }
                     } else {
                         page_bytes += col.size;
-                        if (use_mask) e2 = agg_field_page<kRowsMask, kFastLane>(sm, seq, page, col.size, is_float, need, count, r0, r1, acc, exp, lane);
+                        if (use_mask) e2 = agg_field_page<kRowsMask, kFastLane>(sm, page, col.size, is_float, need, count, r0, r1, acc, exp, lane);
                         else if (r0 == 0 && r1 == count - 1)
-                            e2 = agg_field_page<kRowsAll, kFastLane>(sm, seq, page, col.size, is_float, need, count, r0, r1, acc, exp, lane);
-                        else e2 = agg_field_page<kRowsRange, kFastLane>(sm, seq, page, col.size, is_float, need, count, r0, r1, acc, exp, lane);
+                            e2 = agg_field_page<kRowsAll, kFastLane>(sm, page, col.size, is_float, need, count, r0, r1, acc, exp, lane);
+                        else e2 = agg_field_page<kRowsRange, kFastLane>(sm, page, col.size, is_float, need, count, r0, r1, acc, exp, lane);
                     }
                     if (e2 == kDeferSlow) {
                         defer = true;
@@ -1687,7 +1733,7 @@ struct StoreCons {
 };
 
 // decodes one int64 list body (timestamps or versions) into out[0..count)
-__device__ __forceinline__ bool decode_list_to(WarpSmem *sm, uint32_t &seq, const uint8_t *body, uint32_t len, uint32_t enc, int64_t first, uint32_t count,
+__device__ __forceinline__ bool decode_list_to(WarpSmem *sm, const uint8_t *body, uint32_t len, uint32_t enc, int64_t first, uint32_t count,
                                                int64_t *out, int lane) {
     if (enc == 1 || enc == 2) {
         int64_t d = 0;
@@ -1701,8 +1747,8 @@ __device__ __forceinline__ bool decode_list_to(WarpSmem *sm, uint32_t &seq, cons
     sc.out = out;
     sc.limit = count;
     bool ok;
-    if (enc == 3) ok = decode_varint_page<false>(sm, seq, body, len, count, first, sc, lane);
-    else if (enc == 4) ok = decode_varint_page<true>(sm, seq, body, len, count, first, sc, lane);
+    if (enc == 3) ok = decode_varint_page<false>(sm, body, len, count, first, sc, lane);
+    else if (enc == 4) ok = decode_varint_page<true>(sm, body, len, count, first, sc, lane);
     else ok = false;
     return __all_sync(0xffffffffu, ok);
 }
@@ -1714,11 +1760,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) dedup_kernel(const __gri
     WarpSmem *sm = reinterpret_cast<WarpSmem *>(smem_raw) + warp;
     if (lane == 0) {
         sm->fault = 0;
+        sm->seq = 0;
         for (int s = 0; s < kStages; ++s) mbar_init(&sm->bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    uint32_t seq = 0;
     const uint32_t gw = blockIdx.x * kWarpsPerCta + warp, nw = gridDim.x * kWarpsPerCta;
     for (uint32_t k = gw; k < p.n_dd_blocks; k += nw) {
         const uint32_t g = p.dd_list[k];
@@ -1729,8 +1775,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) dedup_kernel(const __gri
         const unsigned long long off = p.dd_row_off[g];
         if (phase == 0) {
             const uint8_t *tsp = part.files[0] + blk.ts_off;
-            bool ok = decode_list_to(sm, seq, tsp, blk.ver_off, blk.ts_enc, blk.ts_min, blk.count, p.dd_ts + off, lane);
-            ok = ok && decode_list_to(sm, seq, tsp + blk.ver_off, blk.ts_size - blk.ver_off, blk.ver_enc, blk.ver_first, blk.count, p.dd_ver + off, lane);
+            bool ok = decode_list_to(sm, tsp, blk.ver_off, blk.ts_enc, blk.ts_min, blk.count, p.dd_ts + off, lane);
+            ok = ok && decode_list_to(sm, tsp + blk.ver_off, blk.ts_size - blk.ver_off, blk.ver_enc, blk.ver_first, blk.count, p.dd_ver + off, lane);
             if (!ok || blk.count > kMaskWords * 32) set_err(p, !ok ? kErrCorrupt : kErrBigBlock, g, lane);
             continue;
         }

@@ -43,7 +43,7 @@ def main():
     import torch
     torch.cuda.set_device(0)
     pkg0 = B.load_pkg()
-    img = B.make_part(pkg0, args.series, args.points, 1, 0xB200)
+    img = B.make_part(pkg0, args.series, args.points, 1)
     files = img.files()
     sids = np.arange(1, args.series + 1, dtype=np.uint64)
     reference = {}
@@ -55,7 +55,7 @@ def main():
         pkg = fresh_package(path)
         ctx = pkg.Context(device=0)
         h = ctx.register_part(1, files)
-        q1 = B.query_of(pkg, [h], sids, args.points)
+        q1 = B.c2_query(pkg, [h], sids, args.points)
         q2 = pkg.Query(parts=[h], series_ids=sids, aggs=[("latency", pkg.AGG_SUM), ("latency", pkg.AGG_COUNT)])
         for qname, q in (("masked", q1), ("allrows", q2)):
             pq = ctx.prepare(q)
