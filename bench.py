@@ -234,8 +234,8 @@ def reference_arm(args, cores):
     steps, warmup = max(args.steps, 1), args.warmup
     # bounded sample: the oracle's writer spends ~13 us per full-precision `uniform` cell, so the sample is sized for the
     # writer (a few tens of seconds on the pool), not for the query
-    n_sample = max(8, min(args.series, 4 * cores))
-    n_parts = max(1, min(32, n_sample // 4))
+    n_sample = max(8, min(args.series, 2 * cores))
+    n_parts = max(1, min(128, n_sample // 2))
     t0 = time.perf_counter()
     parts = oracle_written_parts(O, n_sample, n_points, n_parts, cores)
     t_build = time.perf_counter() - t0
@@ -360,19 +360,33 @@ def main():
             stats_acc.append(r.stats)
             return r
     else:
+        # the reduce lives behind the C ABI: peer mailboxes over NVLink (bydb_comm_*).  torch.distributed only carries the
+        # 128-byte mailbox handles once, at set-up -- it is not on the data path
         lay = ctx.partials_layout(q)
+        mine_h = torch.frombuffer(bytearray(ctx.comm_export(int(lay["total_bytes"]), world)), dtype=torch.uint8).cuda()
+        all_h = torch.empty(world * 128, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(all_h, mine_h)
+        raw = bytes(all_h.cpu().numpy().tobytes())
+        ctx.comm_connect(rank, world, [raw[i * 128:(i + 1) * 128] for i in range(world)])
+
+        def step(want_stats=True):
+            # ONE collective call per rank: scan -> the partial table lands in rank 0's mailbox (P2P stores) -> rank 0 waits for
+            # the arrival flags on the device, combines in rank order, finalises MEAN / Top-N and reads the rows back
+            r = ctx.scan_reduce(pq, root=0)
+            stats_acc.append(r.stats)
+            return r if rank == 0 else None
+
+    if world > 1:
         words = lay["total_bytes"] // 8
         table = torch.zeros(words, dtype=torch.float64, device="cuda")
         gathered = torch.zeros(world * words, dtype=torch.float64, device="cuda")
         stream = torch.cuda.current_stream().cuda_stream
 
-        def step(want_stats=False):
-            # map: every rank scans its shard into a partial table on its GPU (asynchronous: scan, collective and finalisation are
-            # enqueued back to back; the only host wait of the step is rank 0's result read-back)
+        def nccl_step(want_stats=False):
+            # the library-collective variant, measured beside the mailbox reduce: every rank scans its shard into a partial table
+            # on its GPU (asynchronous), ONE NCCL all-gather ships the tables, rank 0 combines in rank order and finalises
             ta = time.perf_counter()
-            st = ctx.scan_partials(pq, table.data_ptr(), lay["total_bytes"], stream, want_stats=want_stats)
-            if st is not None:
-                stats_acc.append(st)
+            ctx.scan_partials(pq, table.data_ptr(), lay["total_bytes"], stream, want_stats=False)
             tb = time.perf_counter()
             dist.all_gather_into_tensor(gathered, table)
             tc = time.perf_counter()
@@ -412,19 +426,11 @@ def main():
     if rank == 0:
         sampler.start()
     dt, last = timed(step, args.steps)
-    phase_timed = dict(phase)
     kernel_timing = "cuda events inside the timed steps"
-    if world > 1:
-        # the timed steps are asynchronous and carry no statistics: per-kernel device times (CUDA events inside
-        # bydb_scan_partials) come from the same steps run once more with statistics on, outside the timed region
-        for _ in range(args.steps):
-            step(want_stats=True)
-        barrier()
-        kernel_timing = "cuda events in a second pass of the same steps (the timed steps are asynchronous, no statistics read-back)"
     rows_step = stats_acc[-1].rows_scanned
     scan_ms = float(np.mean([s.scan_kernel_ms for s in stats_acc]))
     dev_ms = float(np.mean([s.device_ms for s in stats_acc]))
-    launches = int(sum(s.kernel_launches for s in stats_acc[:args.steps])) + (3 * args.steps if world > 1 and rank == 0 else 0)
+    launches = int(sum(s.kernel_launches for s in stats_acc[:args.steps]))
     page_bytes = stats_acc[-1].page_bytes
     slow_blocks, slow_why = int(stats_acc[-1].blocks_slow_lane), int(stats_acc[-1].slow_lane_reasons)
     total_rows_step = float(rows_step)
@@ -445,6 +451,16 @@ def main():
         d2, _ = timed(lambda: step(), ns)
         extra["sustained"] = {"steps": ns, "ms_per_step": d2 / ns * 1e3, "value": total_rows_step * ns / d2, "unit": "datapoints/s"}
         stats_acc[:] = stats_acc[:args.steps]
+        if world > 1:
+            for _ in range(warm):
+                nccl_step()
+            for k in phase:
+                phase[k] = 0.0
+            dn, _ = timed(nccl_step, args.steps)
+            extra["nccl_allgather_variant"] = {"steps": args.steps, "ms_per_step": dn / args.steps * 1e3, "value": total_rows_step * args.steps / dn, "unit": "datapoints/s",
+                                               "host_phase_ms_per_step_rank0": {k: v / args.steps * 1e3 for k, v in phase.items()},
+                                               "note": "bydb_scan_partials (asynchronous) -> one NCCL all-gather of the partial tables -> bydb_partials_combine + "
+                                                       "bydb_reduce_finalize on rank 0"}
         if world == 1:
             # the same query through bydb_query_prepare / bydb_scan_agg_prepared: run 1 ordinary, run 2 captures, then graph replays
             try:
@@ -500,13 +516,16 @@ def main():
             st = [None]
 
             def one():
-                r = ctx.scan_agg_host([bufs], qh)
+                r = ctx.scan_agg_host([bufs], qh) if world == 1 else ctx.scan_reduce_host([bufs], qh, root=0)
                 st[0] = r.stats
-                return r
+                return r if rank == 0 else None
             one()
             d, r = timed(one, steps)
             s = st[0]
-            return {"value": total_rows_step * steps / d, "unit": "datapoints/s", "h2d_bytes_per_step": int(s.h2d_bytes), "d2h_bytes_per_step": int(s.d2h_bytes),
+            hb = torch.tensor([float(s.h2d_bytes), float(s.d2h_bytes)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(hb, op=dist.ReduceOp.SUM)
+            return {"value": total_rows_step * steps / d, "unit": "datapoints/s", "h2d_bytes_per_step": int(hb[0]), "d2h_bytes_per_step": int(hb[1]),
                     "ms_per_step": d / steps * 1e3, "steps": steps, "scan_kernel_ms": s.scan_kernel_ms, "device_ms": s.device_ms}, r
 
         e2e_steps = max(3, min(args.steps, 5))
@@ -515,11 +534,16 @@ def main():
         e2e["note"] = ("bydb_scan_agg_host(BYDB_Q_HOST_ZERO_COPY): the part's file images stay in the caller's pinned host memory; every step parses "
                        "the block index, uploads the block directory and the kernels pull exactly the pages the query touches over PCIe "
                        "(h2d = directory + page bytes), result copied back"
-                       + ("; per rank, no cross-rank reduce in this leg" if world > 1 else ""))
+                       + ("; bydb_scan_reduce_host on every rank: host images in on all ranks, the partial tables meet in rank 0's mailbox, one "
+                          "result out on rank 0 -- the collective is inside the timed call" if world > 1 else ""))
         e2e["pin_copy_s_outside_timed_region"] = t_pin
         if last is not None and r_e2e is not None:
-            e2e["same_result_as_resident"] = bool(r_e2e.val_f64.tolist() == last.val_f64.tolist() and r_e2e.group_id.tolist() == last.group_id.tolist())
+            # the cold path scans in slices and combines their tables: float sums may differ from the resident run in the last bits
+            e2e["same_result_as_resident"] = bool(r_e2e.group_id.tolist() == last.group_id.tolist() and r_e2e.val_i64.tolist() == last.val_i64.tolist()
+                                                  and np.allclose(r_e2e.val_f64, last.val_f64, rtol=1e-12, atol=0))
         try:
+            if world > 1:
+                raise RuntimeError("single-GPU leg")
             staged, _ = e2e_leg(0, 2, files)
             staged["pinned_by_caller"] = False
             staged["note"] = ("bydb_scan_agg_host without the zero-copy flag on PAGEABLE images: every file of the part is copied to HBM "
@@ -560,7 +584,7 @@ def main():
            "gpu_launches": launches, "e2e": e2e, "part_admission": admission}
     out.update(extra)
     if world > 1:
-        out["host_phase_ms_per_step_rank0"] = {k: v / args.steps * 1e3 for k, v in phase_timed.items()}
+        out["reduce"] = "bydb_scan_reduce: peer mailboxes over NVLink behind the C ABI (no library collective on the data path)"
     if last is not None:
         out["result"] = {"rows": int(last.group_id.size), "top3": [[int(g), float(s), int(c)] for g, s, c in zip(last.group_id[:3], last.val_f64[:3, 0], last.val_i64[:3, 1])],
                          "top_sorted_desc": bool((np.diff(last.val_f64[:, 0]) <= 0).all()), "total_count_top100": int(last.val_i64[:, 1].sum())}

@@ -226,6 +226,31 @@ int bydb_partials_combine(bydb_ctx *ctx, const bydb_query *q, void *d_tables, ui
 /* Finalize a (reduced) partial table: MEAN finalisation, output typing, Top-N; copies the result to host. */
 int bydb_reduce_finalize(bydb_ctx *ctx, const bydb_query *q, const void *d_partials, uint64_t bytes, void *stream, bydb_result *out);
 
+/* ---- multi-GPU reduce behind the C ABI: one process (or thread) per GPU, no torch, no NCCL ----
+ * Replaces the liaison gather + reduceAccumulator.Combine (pkg/query/logical/measure/measure_plan_aggregation.go:96-124,
+ * measure_plan_distributed.go:254-328) inside one node: every rank owns a MAILBOX in its GPU's memory; in a collective
+ * bydb_scan_reduce each rank's reduce kernel writes its partial table straight into its slot of the ROOT's mailbox (peer
+ * memory: the stores travel over NVLink / NVSwitch) and raises an arrival flag there; the root waits for the flags on the
+ * device, combines the slots in rank order (deterministic float sums) and finalises.  No data-path library collective.
+ *
+ *   1. every rank:  bydb_comm_export(ctx, max_table_bytes, max_ranks, &h)     -- allocates the mailbox, h is 128 opaque bytes
+ *   2. the caller exchanges the handles by any channel it has (gRPC between data nodes, a pipe, torch all_gather in tests)
+ *   3. every rank:  bydb_comm_connect(ctx, rank, nranks, handles)             -- opens the peers' mailboxes (CUDA IPC between
+ *                   processes, plain peer access between contexts of one process)
+ *   4. every rank, in the same order:  bydb_scan_reduce(ctx, &q, root, &out)  -- q names THIS rank's parts and series; group
+ *                   layout, aggregations and Top-N must be the same on all ranks.  The root gets the result; the others get
+ *                   n_rows = 0 and their own scan statistics.  A rank that fails to arrive makes the root return BYDB_EIO
+ *                   after a bounded wait; a device-side scan error of any rank travels in its table and fails the root's call.
+ * max_table_bytes: the largest bydb_partials_layout().total_bytes of the queries to come. */
+typedef struct { uint8_t bytes[128]; } bydb_comm_handle;
+int bydb_comm_export(bydb_ctx *ctx, uint64_t max_table_bytes, int32_t max_ranks, bydb_comm_handle *out);
+int bydb_comm_connect(bydb_ctx *ctx, int32_t rank, int32_t nranks, const bydb_comm_handle *all);
+int bydb_scan_reduce(bydb_ctx *ctx, const bydb_query *q, int32_t root, bydb_result *out);
+/* The same collective with every rank's parts given as HOST file images (cold distributed query, end to end): admitted for
+ * the duration of the call (with BYDB_Q_HOST_ZERO_COPY only the block directory is uploaded and the scan pulls the pages it
+ * touches over PCIe), scanned into the root's mailbox, dropped.  q->parts / q->n_parts are ignored. */
+int bydb_scan_reduce_host(bydb_ctx *ctx, uint32_t n_parts, const bydb_part_files *parts, const bydb_query *q, int32_t root, bydb_result *out);
+
 const char *bydb_last_error(void);
 const char *bydb_version(void);
 

@@ -64,7 +64,18 @@ struct RecordBatch {
     int Len = 0;  // Selection is always nil: rows are materialised
 };
 
-enum class AggFunc { AggSum = 1, AggCount = 2, AggMin = 3, AggMax = 4, AggMean = 5 };  // values of BYDB_AGG_*
+enum class AggFunc { AggSum = 0, AggCount = 1, AggMin = 2, AggMax = 3, AggMean = 4 };  // aggregation.go:47-55 (iota order)
+// -> modelv1.AggregationFunction (BYDB_AGG_*), the numbering the C ABI takes
+inline int32_t to_model_agg(AggFunc f) {
+    switch (f) {
+        case AggFunc::AggSum: return BYDB_AGG_SUM;
+        case AggFunc::AggCount: return BYDB_AGG_COUNT;
+        case AggFunc::AggMin: return BYDB_AGG_MIN;
+        case AggFunc::AggMax: return BYDB_AGG_MAX;
+        case AggFunc::AggMean: return BYDB_AGG_MEAN;
+    }
+    return 0;
+}
 
 struct AggSpec {
     std::string Output;  // name of the output column
@@ -261,7 +272,7 @@ class GPUScanAgg final : public PullOperator {
         std::vector<bydb_agg> cagg(aggs_.size());
         for (size_t a = 0; a < aggs_.size(); ++a) {
             cagg[a].field = in_.Columns[static_cast<size_t>(aggs_[a].InputCol)].Name.c_str();
-            cagg[a].func = static_cast<int32_t>(aggs_[a].Func);
+            cagg[a].func = to_model_agg(aggs_[a].Func);
             cagg[a].reserved = 0;
         }
         std::vector<bydb_pred> cpred(scan_.Preds.size());

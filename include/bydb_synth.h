@@ -85,7 +85,8 @@ typedef struct {
     const bydb_synth_field *fields;
     uint32_t region_values;  /* 0 = no tag; else string tag "default"/"region" with values "r0".."r<N-1>" */
     uint32_t region_run;     /* mean run length of equal tag values; 0 = constant per series            */
-    uint32_t code_tag;       /* 1 = also an int64 tag "default"/"code" in {0,100,..,500}                */
+    uint32_t code_tag;       /* bit 0: also an int64 tag "default"/"code" in {0,100,..,500}; bit 1: also a second
+                                string tag "default"/"zone" with values "z0".."z4" in runs of mean length 64    */
     uint32_t threads;        /* 0 = hardware concurrency                                                */
     uint64_t seed;
 } bydb_synth_spec;

@@ -79,7 +79,8 @@ class _Layout(C.Structure):
 EXPORTS = ["bydb_init", "bydb_shutdown", "bydb_part_register", "bydb_part_release", "bydb_part_info", "bydb_part_fallback_pages",
            "bydb_scan_agg", "bydb_scan_agg_host", "bydb_result_free", "bydb_query_prepare", "bydb_scan_agg_prepared",
            "bydb_query_release", "bydb_partials_layout",
-           "bydb_scan_partials", "bydb_partials_combine", "bydb_reduce_finalize", "bydb_last_error", "bydb_version"]
+           "bydb_scan_partials", "bydb_partials_combine", "bydb_reduce_finalize", "bydb_comm_export", "bydb_comm_connect",
+           "bydb_scan_reduce", "bydb_scan_reduce_host", "bydb_last_error", "bydb_version"]
 
 _lib = None
 
@@ -118,6 +119,10 @@ def load_library():
     L.bydb_scan_partials.argtypes = [C.c_void_p, C.POINTER(_Query), C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(_Stats)]
     L.bydb_partials_combine.argtypes = [C.c_void_p, C.POINTER(_Query), C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p]
     L.bydb_reduce_finalize.argtypes = [C.c_void_p, C.POINTER(_Query), C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(_Result)]
+    L.bydb_comm_export.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p]
+    L.bydb_comm_connect.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.bydb_scan_reduce.argtypes = [C.c_void_p, C.POINTER(_Query), C.c_int32, C.POINTER(_Result)]
+    L.bydb_scan_reduce_host.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_PartFiles), C.POINTER(_Query), C.c_int32, C.POINTER(_Result)]
     _lib = L
     return L
 
@@ -407,6 +412,42 @@ class Context:
         st = _Stats()
         _check(self._L.bydb_scan_partials(self._h, C.byref(cq), d_ptr, nbytes, stream or None, C.byref(st)))
         return Stats.of(st)
+
+    # ---- multi-GPU reduce behind the C ABI (peer mailboxes over NVLink; no torch / NCCL on the data path)
+    def comm_export(self, max_table_bytes: int, max_ranks: int) -> bytes:
+        """-> this rank's 128-byte mailbox handle; exchange the handles of all ranks, then comm_connect."""
+        buf = C.create_string_buffer(128)
+        _check(self._L.bydb_comm_export(self._h, max_table_bytes, max_ranks, buf))
+        return buf.raw
+
+    def comm_connect(self, rank: int, nranks: int, handles: Sequence[bytes]) -> None:
+        assert len(handles) == nranks and all(len(h) == 128 for h in handles)
+        buf = C.create_string_buffer(b"".join(handles), 128 * nranks)
+        _check(self._L.bydb_comm_connect(self._h, rank, nranks, buf))
+
+    def scan_reduce(self, q, root: int = 0) -> Result:
+        """Collective: every rank scans its parts, the partial tables meet in the root's mailbox, the root finalises.
+        Non-root ranks get an empty result (n_rows = 0) with their own scan statistics."""
+        cq, keep = _cq(q)
+        r = _Result()
+        _check(self._L.bydb_scan_reduce(self._h, C.byref(cq), root, C.byref(r)))
+        try:
+            return _read_result(r)
+        finally:
+            self._L.bydb_result_free(self._h, C.byref(r))
+
+    def scan_reduce_host(self, parts: Sequence[Dict[str, Union[bytes, np.ndarray]]], q: Query, root: int = 0) -> Result:
+        keep: list = []
+        arr = (_PartFiles * len(parts))()
+        for i, files in enumerate(parts):
+            arr[i] = _part_files(files, keep)
+        cq = _mk_query(q, keep)
+        r = _Result()
+        _check(self._L.bydb_scan_reduce_host(self._h, len(parts), arr, C.byref(cq), root, C.byref(r)))
+        try:
+            return _read_result(r)
+        finally:
+            self._L.bydb_result_free(self._h, C.byref(r))
 
     def partials_combine(self, q, d_ptr: int, n_tables: int, bytes_each: int, stream: int = 0) -> None:
         cq, keep = _cq(q)

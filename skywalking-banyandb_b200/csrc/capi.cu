@@ -2,6 +2,7 @@
 // orchestration on CUDA streams.  Host logic only; every byte of page decoding happens in
 // scan_kernels.cu.  There is no CPU fallback here: unsupported encodings surface as BYDB_ENOTSUP.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -156,6 +157,23 @@ class WorkPool {
     bool stop_ = false;
 };
 
+// Peer mailboxes of the multi-GPU reduce (bydb_comm_*).  Layout of one rank's mailbox (device memory of that rank):
+//   [0, 4096)        control: arrival flags (u64 epoch per writer rank) at 0, status words (epoch << 32 | host-side error of
+//                    that rank's call) at 1024, `done` epoch at 2048, error word of this rank's wait kernels at 2056
+//   [4096, ...)      2 parities x nranks slots of slot_bytes each (partial tables written by the peers)
+constexpr int kCommMaxRanks = 64;
+constexpr size_t kCommCtl = 4096, kCommStatusOff = 1024, kCommDoneOff = 2048, kCommErrOff = 2056;
+struct Comm {
+    int rank = -1, nranks = 0;
+    uint8_t *mine = nullptr;            // this rank's mailbox (cudaMalloc)
+    size_t slot_bytes = 0, mailbox_bytes = 0;
+    std::vector<uint8_t *> peer;        // device-visible base of every rank's mailbox
+    std::vector<bool> ipc_opened;
+    std::vector<size_t> peer_slot_bytes;
+    uint64_t epoch = 0;
+    std::mutex mu;                      // collective calls are issued one at a time per context
+};
+
 struct bydb_ctx {
     int device = 0;
     int sm_count = 0;
@@ -170,6 +188,7 @@ struct bydb_ctx {
     bydb_part_h next_handle = 1;
     std::vector<std::unique_ptr<ExecSlot>> free_slots;
     WorkPool pool;
+    Comm comm;
 };
 
 namespace {
@@ -234,10 +253,11 @@ const char *dev_err_text(uint32_t code) {
         case kErrOverlap: return "a series lives in several parts with overlapping time spans and the dedup pass did not run (internal error)";
         case kErrPredType: return "predicate literal type does not match the stored tag column type";
         case kErrTmaTimeout: return "internal error: a TMA bulk copy did not complete";
+        case kErrPeerTimeout: return "multi-GPU reduce: a peer rank did not deliver its partial table in time";
     }
     return "unknown device error";
 }
-int dev_err_code(uint32_t code) { return (code == kErrCorrupt || code == kErrBadEnc || code == kErrTypeMix || code == kErrPredType) ? BYDB_EINVAL : (code == kErrTmaTimeout) ? BYDB_EIO : BYDB_ENOTSUP; }
+int dev_err_code(uint32_t code) { return (code == kErrCorrupt || code == kErrBadEnc || code == kErrTypeMix || code == kErrPredType) ? BYDB_EINVAL : (code == kErrTmaTimeout || code == kErrPeerTimeout) ? BYDB_EIO : BYDB_ENOTSUP; }
 
 int validate_query(const bydb_query *q, bool need_parts) {
     if (!q) return fail(BYDB_EINVAL, "query is NULL");
@@ -732,14 +752,19 @@ int collect_scan(ExecSlot &slot, bydb_stats *stats, int batch = 0) {
     return 0;
 }
 
-int finalize_to_host(bydb_ctx *ctx, const bydb_query *q, const Plan &plan, ExecSlot &slot, cudaStream_t stream, const uint8_t *d_table,
-                     const TableLayout &tl, bydb_result *out, bool check_inband_status = false) {
+struct FinalLayout {
+    size_t o_out = 0, o_cnt = 0, o_isf = 0, o_sg = 0, o_sr = 0, o_si = 0, o_sf = 0, out_bytes = 0, cap = 0, A = 0;
+    uint32_t launches = 0;
+};
+
+// finalize_to_host up to (and including) the read-back copy, without the synchronisation and the parsing; the result
+// lands at slot.pinned + host_off so that the staging area of run_scan (at the start of slot.pinned) stays intact
+int finalize_enqueue(const bydb_query *q, const Plan &plan, ExecSlot &slot, cudaStream_t stream, const uint8_t *d_table, const TableLayout &tl,
+                     size_t host_off, FinalLayout &fl, Scratch &sc) {
     const size_t F = plan.fcols.size();
     const int32_t G = plan.n_groups;
     const size_t A = q->n_aggs;
     const size_t cap = q->top_n > 0 ? std::min<size_t>(static_cast<size_t>(q->top_n), static_cast<size_t>(G)) : static_cast<size_t>(G);
-    if (q->top_n > kMaxDeviceTopN) return fail(BYDB_ENOTSUP, "top_n larger than 2048 is not supported on the device path");
-    // device scratch: finalized values [G x A] (i64, f64), typing [A], keys [G], key states [G]; then the selected rows
     size_t o = 0;
     auto carve = [&](size_t bytes) {
         size_t at = o;
@@ -748,10 +773,16 @@ int finalize_to_host(bydb_ctx *ctx, const bydb_query *q, const Plan &plan, ExecS
     };
     const size_t o_vi = carve(static_cast<size_t>(G) * A * 8), o_vf = carve(static_cast<size_t>(G) * A * 8), o_keys = carve(static_cast<size_t>(G) * 8),
                  o_kst = carve(static_cast<size_t>(G));
-    const size_t o_out = o;  // everything from here is copied back in one transfer
-    const size_t o_cnt = carve(16), o_isf = carve(A), o_sg = carve(cap * 4), o_sr = carve(cap * 8), o_si = carve(cap * A * 8), o_sf = carve(cap * A * 8);
-    const size_t out_bytes = o - o_out;
-    Scratch sc;
+    fl.o_out = o;
+    fl.o_cnt = carve(16);
+    fl.o_isf = carve(A);
+    fl.o_sg = carve(cap * 4);
+    fl.o_sr = carve(cap * 8);
+    fl.o_si = carve(cap * A * 8);
+    fl.o_sf = carve(cap * A * 8);
+    fl.out_bytes = o - fl.o_out;
+    fl.cap = cap;
+    fl.A = A;
     sc.stream = stream;
     CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&sc.base), o, stream));
     uint8_t *d = sc.base;
@@ -775,10 +806,8 @@ int finalize_to_host(bydb_ctx *ctx, const bydb_query *q, const Plan &plan, ExecS
     fp.coltype = reinterpret_cast<const int64_t *>(d_table + tl.off_coltype);
     fp.out_i64 = reinterpret_cast<int64_t *>(d + o_vi);
     fp.out_f64 = reinterpret_cast<double *>(d + o_vf);
-    fp.out_is_float = d + o_isf;
-    fp.err_out = reinterpret_cast<uint32_t *>(d + o_cnt + 8);
-    launch_finalize(fp, stream);
-    // output rows are chosen and ordered on the device (stable compaction, or Top-N)
+    fp.out_is_float = d + fl.o_isf;
+    fp.err_out = reinterpret_cast<uint32_t *>(d + fl.o_cnt + 8);
     SelectParams sp;
     memset(&sp, 0, sizeof sp);
     sp.n_groups = G;
@@ -796,34 +825,28 @@ int finalize_to_host(bydb_ctx *ctx, const bydb_query *q, const Plan &plan, ExecS
     sp.is_float = fp.out_is_float;
     sp.keys = reinterpret_cast<uint64_t *>(d + o_keys);
     sp.kstate = d + o_kst;
-    sp.sel_count = reinterpret_cast<uint32_t *>(d + o_cnt);
-    sp.sel_group = reinterpret_cast<int32_t *>(d + o_sg);
-    sp.sel_rows = reinterpret_cast<int64_t *>(d + o_sr);
-    sp.sel_i64 = reinterpret_cast<int64_t *>(d + o_si);
-    sp.sel_f64 = reinterpret_cast<double *>(d + o_sf);
-    launch_select_rows(sp, stream);
-    if (slot.ensure_pinned(out_bytes)) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
-    uint8_t *h = slot.pinned;
-    CUDA_TRY(cudaMemcpyAsync(h, d + o_out, out_bytes, cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaStreamSynchronize(stream));
-    CUDA_TRY(cudaGetLastError());
-    out->stats.d2h_bytes += out_bytes;
-    out->stats.kernel_launches += 2;
-    if (check_inband_status) {
-        // the table came from bydb_scan_partials (possibly asynchronous, possibly another rank's): its status is in the table
-        const uint32_t e = *reinterpret_cast<const uint32_t *>(h + (o_cnt - o_out) + 8);
-        g_last_dev_err = e;
-        if (e != 0) return fail(dev_err_code(e), std::string(dev_err_text(e)) + " (status carried in a partial table)");
-    }
-    const size_t R = std::min<size_t>(*reinterpret_cast<const uint32_t *>(h + (o_cnt - o_out)), cap);
+    sp.sel_count = reinterpret_cast<uint32_t *>(d + fl.o_cnt);
+    sp.sel_group = reinterpret_cast<int32_t *>(d + fl.o_sg);
+    sp.sel_rows = reinterpret_cast<int64_t *>(d + fl.o_sr);
+    sp.sel_i64 = reinterpret_cast<int64_t *>(d + fl.o_si);
+    sp.sel_f64 = reinterpret_cast<double *>(d + fl.o_sf);
+    fl.launches = launch_finalize_select(fp, sp, stream);
+    if (slot.ensure_pinned(host_off + fl.out_bytes)) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
+    CUDA_TRY(cudaMemcpyAsync(slot.pinned + host_off, d + fl.o_out, fl.out_bytes, cudaMemcpyDeviceToHost, stream));
+    return 0;
+}
+
+void finalize_parse(const uint8_t *h, const FinalLayout &fl, bydb_result *out) {
+    const size_t A = fl.A;
+    const size_t R = std::min<size_t>(*reinterpret_cast<const uint32_t *>(h + (fl.o_cnt - fl.o_out)), fl.cap);
     auto owner = new ResultOwner();
-    const int32_t *sg = reinterpret_cast<const int32_t *>(h + (o_sg - o_out));
-    const int64_t *sr = reinterpret_cast<const int64_t *>(h + (o_sr - o_out));
-    const int64_t *si = reinterpret_cast<const int64_t *>(h + (o_si - o_out));
-    const double *sf = reinterpret_cast<const double *>(h + (o_sf - o_out));
+    const int32_t *sg = reinterpret_cast<const int32_t *>(h + (fl.o_sg - fl.o_out));
+    const int64_t *sr = reinterpret_cast<const int64_t *>(h + (fl.o_sr - fl.o_out));
+    const int64_t *si = reinterpret_cast<const int64_t *>(h + (fl.o_si - fl.o_out));
+    const double *sf = reinterpret_cast<const double *>(h + (fl.o_sf - fl.o_out));
     owner->group_id.assign(sg, sg + R);
     owner->rows.assign(sr, sr + R);
-    owner->is_float.assign(h + (o_isf - o_out), h + (o_isf - o_out) + A);
+    owner->is_float.assign(h + (fl.o_isf - fl.o_out), h + (fl.o_isf - fl.o_out) + A);
     owner->val_i64.assign(si, si + R * A);
     owner->val_f64.assign(sf, sf + R * A);
     out->n_rows = static_cast<int32_t>(R);
@@ -834,6 +857,28 @@ int finalize_to_host(bydb_ctx *ctx, const bydb_query *q, const Plan &plan, ExecS
     out->val_i64 = owner->val_i64.data();
     out->val_f64 = owner->val_f64.data();
     out->owner = owner;
+}
+
+
+// finalisation + row selection + read-back of the result rows, synchronised and parsed
+int finalize_to_host(bydb_ctx *ctx, const bydb_query *q, const Plan &plan, ExecSlot &slot, cudaStream_t stream, const uint8_t *d_table,
+                     const TableLayout &tl, bydb_result *out, bool check_inband_status = false) {
+    (void)ctx;
+    FinalLayout fl;
+    Scratch sc;
+    int rc = finalize_enqueue(q, plan, slot, stream, d_table, tl, 0, fl, sc);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaGetLastError());
+    out->stats.d2h_bytes += fl.out_bytes;
+    out->stats.kernel_launches += fl.launches;
+    if (check_inband_status) {
+        // the table came from bydb_scan_partials / a peer's mailbox slot (possibly another rank's): its status is in the table
+        const uint32_t e = *reinterpret_cast<const uint32_t *>(slot.pinned + (fl.o_cnt - fl.o_out) + 8);
+        g_last_dev_err = e;
+        if (e != 0) return fail(dev_err_code(e), std::string(dev_err_text(e)) + " (status carried in a partial table)");
+    }
+    finalize_parse(slot.pinned, fl, out);
     return 0;
 }
 
@@ -905,113 +950,6 @@ int scan_agg_impl(bydb_ctx *ctx, const bydb_query *q, const std::vector<std::sha
 // into a CUDA graph and replayed.  A query executed many times (dashboards, alert rules) then costs one graph launch and
 // one synchronisation instead of ~20 runtime calls.  Everything here is additive: bydb_scan_agg is untouched.
 // ------------------------------------------------------------------------------------------------
-struct FinalLayout {
-    size_t o_out = 0, o_cnt = 0, o_isf = 0, o_sg = 0, o_sr = 0, o_si = 0, o_sf = 0, out_bytes = 0, cap = 0, A = 0;
-};
-
-// finalize_to_host up to (and including) the read-back copy, without the synchronisation and the parsing; the result
-// lands at slot.pinned + host_off so that the staging area of run_scan (at the start of slot.pinned) stays intact
-int finalize_enqueue(const bydb_query *q, const Plan &plan, ExecSlot &slot, cudaStream_t stream, const uint8_t *d_table, const TableLayout &tl,
-                     size_t host_off, FinalLayout &fl, Scratch &sc) {
-    const size_t F = plan.fcols.size();
-    const int32_t G = plan.n_groups;
-    const size_t A = q->n_aggs;
-    const size_t cap = q->top_n > 0 ? std::min<size_t>(static_cast<size_t>(q->top_n), static_cast<size_t>(G)) : static_cast<size_t>(G);
-    if (q->top_n > kMaxDeviceTopN) return fail(BYDB_ENOTSUP, "top_n larger than 2048 is not supported on the device path");
-    size_t o = 0;
-    auto carve = [&](size_t bytes) {
-        size_t at = o;
-        o = align_up(o + bytes, 256);
-        return at;
-    };
-    const size_t o_vi = carve(static_cast<size_t>(G) * A * 8), o_vf = carve(static_cast<size_t>(G) * A * 8), o_keys = carve(static_cast<size_t>(G) * 8),
-                 o_kst = carve(static_cast<size_t>(G));
-    fl.o_out = o;
-    fl.o_cnt = carve(16);
-    fl.o_isf = carve(A);
-    fl.o_sg = carve(cap * 4);
-    fl.o_sr = carve(cap * 8);
-    fl.o_si = carve(cap * A * 8);
-    fl.o_sf = carve(cap * A * 8);
-    fl.out_bytes = o - fl.o_out;
-    fl.cap = cap;
-    fl.A = A;
-    sc.stream = stream;
-    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&sc.base), o, stream));
-    uint8_t *d = sc.base;
-    FinalizeParams fp;
-    memset(&fp, 0, sizeof fp);
-    fp.n_groups = G;
-    fp.n_fcols = static_cast<uint32_t>(F);
-    fp.n_aggs = static_cast<uint32_t>(A);
-    for (size_t a = 0; a < A; ++a) {
-        fp.agg_fcol[a] = plan.agg_fcol[a];
-        fp.agg_func[a] = q->aggs[a].func;
-    }
-    fp.sum_f64 = reinterpret_cast<const double *>(d_table + tl.off_sum_f64);
-    fp.max_f64 = reinterpret_cast<const double *>(d_table + tl.off_max_f64);
-    fp.negmin_f64 = reinterpret_cast<const double *>(d_table + tl.off_negmin_f64);
-    fp.sum_i64 = reinterpret_cast<const int64_t *>(d_table + tl.off_sum_i64);
-    fp.cnt = reinterpret_cast<const int64_t *>(d_table + tl.off_cnt);
-    fp.rows = reinterpret_cast<const int64_t *>(d_table + tl.off_rows);
-    fp.max_i64 = reinterpret_cast<const int64_t *>(d_table + tl.off_max_i64);
-    fp.notmin_i64 = reinterpret_cast<const int64_t *>(d_table + tl.off_notmin_i64);
-    fp.coltype = reinterpret_cast<const int64_t *>(d_table + tl.off_coltype);
-    fp.out_i64 = reinterpret_cast<int64_t *>(d + o_vi);
-    fp.out_f64 = reinterpret_cast<double *>(d + o_vf);
-    fp.out_is_float = d + fl.o_isf;
-    fp.err_out = reinterpret_cast<uint32_t *>(d + fl.o_cnt + 8);
-    launch_finalize(fp, stream);
-    SelectParams sp;
-    memset(&sp, 0, sizeof sp);
-    sp.n_groups = G;
-    sp.n_fcols = static_cast<uint32_t>(F);
-    sp.n_aggs = static_cast<uint32_t>(A);
-    sp.top_n = q->top_n;
-    sp.top_agg = q->top_n > 0 ? q->top_agg : 0;
-    sp.top_desc = q->top_desc;
-    sp.top_fcol = plan.agg_fcol[sp.top_agg];
-    sp.top_is_count = q->aggs[sp.top_agg].func == BYDB_AGG_COUNT;
-    sp.rows = fp.rows;
-    sp.cnt = fp.cnt;
-    sp.val_i64 = fp.out_i64;
-    sp.val_f64 = fp.out_f64;
-    sp.is_float = fp.out_is_float;
-    sp.keys = reinterpret_cast<uint64_t *>(d + o_keys);
-    sp.kstate = d + o_kst;
-    sp.sel_count = reinterpret_cast<uint32_t *>(d + fl.o_cnt);
-    sp.sel_group = reinterpret_cast<int32_t *>(d + fl.o_sg);
-    sp.sel_rows = reinterpret_cast<int64_t *>(d + fl.o_sr);
-    sp.sel_i64 = reinterpret_cast<int64_t *>(d + fl.o_si);
-    sp.sel_f64 = reinterpret_cast<double *>(d + fl.o_sf);
-    launch_select_rows(sp, stream);
-    CUDA_TRY(cudaMemcpyAsync(slot.pinned + host_off, d + fl.o_out, fl.out_bytes, cudaMemcpyDeviceToHost, stream));
-    return 0;
-}
-
-void finalize_parse(const uint8_t *h, const FinalLayout &fl, bydb_result *out) {
-    const size_t A = fl.A;
-    const size_t R = std::min<size_t>(*reinterpret_cast<const uint32_t *>(h + (fl.o_cnt - fl.o_out)), fl.cap);
-    auto owner = new ResultOwner();
-    const int32_t *sg = reinterpret_cast<const int32_t *>(h + (fl.o_sg - fl.o_out));
-    const int64_t *sr = reinterpret_cast<const int64_t *>(h + (fl.o_sr - fl.o_out));
-    const int64_t *si = reinterpret_cast<const int64_t *>(h + (fl.o_si - fl.o_out));
-    const double *sf = reinterpret_cast<const double *>(h + (fl.o_sf - fl.o_out));
-    owner->group_id.assign(sg, sg + R);
-    owner->rows.assign(sr, sr + R);
-    owner->is_float.assign(h + (fl.o_isf - fl.o_out), h + (fl.o_isf - fl.o_out) + A);
-    owner->val_i64.assign(si, si + R * A);
-    owner->val_f64.assign(sf, sf + R * A);
-    out->n_rows = static_cast<int32_t>(R);
-    out->n_aggs = static_cast<int32_t>(A);
-    out->group_id = owner->group_id.data();
-    out->rows = owner->rows.data();
-    out->is_float = owner->is_float.data();
-    out->val_i64 = owner->val_i64.data();
-    out->val_f64 = owner->val_f64.data();
-    out->owner = owner;
-}
-
 }  // namespace
 
 struct bydb_prepared {
@@ -1101,7 +1039,7 @@ int prepared_capture(bydb_ctx *ctx, bydb_prepared *p) {
         p->exec = nullptr;
         p->capturable = false;
     }
-    p->captured.kernel_launches += 2;  // finalize + select_rows
+    p->captured.kernel_launches += p->fl.launches;  // finalize + select_rows (one fused launch for few groups)
     p->captured.d2h_bytes += p->fl.out_bytes;
     p->held = plan.parts;
     return 0;
@@ -1168,6 +1106,9 @@ void bydb_shutdown(bydb_ctx *ctx) {
     }
     ctx->free_slots.clear();
     ctx->parts.clear();
+    for (size_t r = 0; r < ctx->comm.peer.size(); ++r)
+        if (ctx->comm.ipc_opened[r] && ctx->comm.peer[r]) cudaIpcCloseMemHandle(ctx->comm.peer[r]);
+    if (ctx->comm.mine) cudaFree(ctx->comm.mine);
     delete ctx;
 }
 
@@ -1648,6 +1589,234 @@ int bydb_scan_agg_prepared(bydb_ctx *ctx, bydb_prepared *p, bydb_result *out) {
     }
     finalize_parse(slot.pinned + p->host_off, p->fl, out);
     return 0;
+    });
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU reduce behind the C ABI: peer mailboxes over NVLink (see scan_kernels.cu, comm_*_kernel)
+// ------------------------------------------------------------------------------------------------
+struct CommBlob {  // what travels inside a bydb_comm_handle
+    uint32_t magic, device;
+    uint64_t pid, raw_ptr, slot_bytes, mailbox_bytes;
+    cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(CommBlob) <= sizeof(bydb_comm_handle), "bydb_comm_handle too small");
+
+int bydb_comm_export(bydb_ctx *ctx, uint64_t max_table_bytes, int32_t max_ranks, bydb_comm_handle *out) {
+    return guarded([&]() -> int {
+    if (!ctx || !out) return fail(BYDB_EINVAL, "ctx/out is NULL");
+    if (max_ranks < 1 || max_ranks > kCommMaxRanks) return fail(BYDB_EINVAL, "max_ranks must be 1..64");
+    if (max_table_bytes == 0 || max_table_bytes > (1ull << 32)) return fail(BYDB_EINVAL, "bad max_table_bytes");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    Comm &cm = ctx->comm;
+    std::lock_guard<std::mutex> lk(cm.mu);
+    if (cm.mine) return fail(BYDB_EINVAL, "bydb_comm_export was already called on this context");
+    cm.slot_bytes = align_up(max_table_bytes, 256);
+    cm.mailbox_bytes = kCommCtl + 2 * static_cast<size_t>(max_ranks) * cm.slot_bytes;
+    {
+        std::lock_guard<std::mutex> lk2(ctx->mu);
+        if (ctx->hbm_budget && ctx->hbm_used + cm.mailbox_bytes > ctx->hbm_budget) return fail(BYDB_ENOMEM, "HBM budget exceeded (mailbox)");
+        ctx->hbm_used += cm.mailbox_bytes;
+    }
+    if (cudaMalloc(reinterpret_cast<void **>(&cm.mine), cm.mailbox_bytes) != cudaSuccess) {
+        cm.mine = nullptr;
+        return fail(BYDB_ENOMEM, "device allocation failed for the mailbox");
+    }
+    CUDA_TRY(cudaMemset(cm.mine, 0, cm.mailbox_bytes));
+    CommBlob b;
+    memset(&b, 0, sizeof b);
+    b.magic = 0xB1DBC011u;
+    b.device = static_cast<uint32_t>(ctx->device);
+    b.pid = static_cast<uint64_t>(getpid());
+    b.raw_ptr = reinterpret_cast<uint64_t>(cm.mine);
+    b.slot_bytes = cm.slot_bytes;
+    b.mailbox_bytes = cm.mailbox_bytes;
+    CUDA_TRY(cudaIpcGetMemHandle(&b.ipc, cm.mine));
+    memset(out, 0, sizeof *out);
+    memcpy(out, &b, sizeof b);
+    return 0;
+    });
+}
+
+int bydb_comm_connect(bydb_ctx *ctx, int32_t rank, int32_t nranks, const bydb_comm_handle *all) {
+    return guarded([&]() -> int {
+    if (!ctx || !all) return fail(BYDB_EINVAL, "ctx/handles is NULL");
+    if (nranks < 1 || nranks > kCommMaxRanks || rank < 0 || rank >= nranks) return fail(BYDB_EINVAL, "bad rank / nranks");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    Comm &cm = ctx->comm;
+    std::lock_guard<std::mutex> lk(cm.mu);
+    if (!cm.mine) return fail(BYDB_EINVAL, "call bydb_comm_export first");
+    if (cm.nranks) return fail(BYDB_EINVAL, "bydb_comm_connect was already called on this context");
+    std::vector<uint8_t *> peer(static_cast<size_t>(nranks), nullptr);
+    std::vector<bool> opened(static_cast<size_t>(nranks), false);
+    std::vector<size_t> slots(static_cast<size_t>(nranks), 0);
+    for (int r = 0; r < nranks; ++r) {
+        CommBlob b;
+        memcpy(&b, &all[r], sizeof b);
+        if (b.magic != 0xB1DBC011u) return fail(BYDB_EINVAL, "handle of rank " + std::to_string(r) + " is not a bydb_comm_handle");
+        if (kCommCtl + 2 * static_cast<uint64_t>(nranks) * b.slot_bytes > b.mailbox_bytes)
+            return fail(BYDB_EINVAL, "mailbox of rank " + std::to_string(r) + " was exported for fewer ranks");
+        slots[r] = b.slot_bytes;
+        if (r == rank) {
+            if (b.raw_ptr != reinterpret_cast<uint64_t>(cm.mine)) return fail(BYDB_EINVAL, "handles[rank] is not this context's own handle");
+            peer[r] = cm.mine;
+        } else if (b.pid == static_cast<uint64_t>(getpid())) {
+            // same process (several contexts, one per GPU, or tests): the pointer is valid as it is once peer access is on
+            if (static_cast<int>(b.device) != ctx->device) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, ctx->device, static_cast<int>(b.device));
+                if (!can) return fail(BYDB_ENOTSUP, "no peer access between device " + std::to_string(ctx->device) + " and " + std::to_string(b.device));
+                const cudaError_t e = cudaDeviceEnablePeerAccess(static_cast<int>(b.device), 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(BYDB_EIO, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            peer[r] = reinterpret_cast<uint8_t *>(b.raw_ptr);
+        } else {
+            void *p = nullptr;
+            const cudaError_t e = cudaIpcOpenMemHandle(&p, b.ipc, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                for (int k = 0; k < r; ++k)
+                    if (opened[k]) cudaIpcCloseMemHandle(peer[k]);
+                return fail(BYDB_EIO, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+            }
+            peer[r] = static_cast<uint8_t *>(p);
+            opened[r] = true;
+        }
+    }
+    cm.peer = std::move(peer);
+    cm.ipc_opened = std::move(opened);
+    cm.peer_slot_bytes = std::move(slots);
+    cm.rank = rank;
+    cm.nranks = nranks;
+    cm.epoch = 0;
+    return 0;
+    });
+}
+
+// given: the parts to scan instead of q->parts (the host-buffer form); pre_rc: a failure that already happened on this
+// rank (its transient parts could not be admitted) -- the rank still takes part in the collective and reports it
+static int scan_reduce_impl(bydb_ctx *ctx, const bydb_query *q, const std::vector<std::shared_ptr<Part>> *given, int pre_rc, uint64_t h2d_pre, int32_t root,
+                            bydb_result *out) {
+    {
+    const std::string pre_msg = pre_rc ? g_last_error : std::string();
+    Comm &cm = ctx->comm;
+    std::lock_guard<std::mutex> lk(cm.mu);
+    if (cm.nranks == 0) return fail(BYDB_EINVAL, "bydb_comm_connect was not called on this context");
+    if (root < 0 || root >= cm.nranks) return fail(BYDB_EINVAL, "bad root");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    SlotLease lease(ctx);
+    if (lease.init()) return fail(BYDB_EIO, "cannot create stream");
+    ExecSlot &es = *lease.slot;
+    cudaStream_t s = es.stream;
+    // From here on this rank ALWAYS raises its arrival flag (with a status word in front of it), whatever fails on the
+    // host side: the other ranks' calls must neither hang nor fall out of step (every rank counts the same epochs).
+    const uint64_t epoch = ++cm.epoch;
+    const size_t parity = static_cast<size_t>(epoch & 1u);
+    const size_t slot = cm.peer_slot_bytes[static_cast<size_t>(root)];
+    uint8_t *root_mb = cm.peer[static_cast<size_t>(root)];
+    uint8_t *slots0 = root_mb + kCommCtl + parity * static_cast<size_t>(cm.nranks) * slot;
+    uint8_t *my_slot = slots0 + static_cast<size_t>(cm.rank) * slot;
+    unsigned long long *flags = reinterpret_cast<unsigned long long *>(root_mb);
+    unsigned long long *status = reinterpret_cast<unsigned long long *>(root_mb + kCommStatusOff);
+    unsigned long long *done = reinterpret_cast<unsigned long long *>(root_mb + kCommDoneOff);
+    uint32_t *my_err = reinterpret_cast<uint32_t *>(cm.mine + kCommErrOff);
+    Plan plan;
+    int rc = pre_rc ? fail(pre_rc, pre_msg) : validate_query(q, given == nullptr);
+    if (!rc) rc = make_plan(ctx, q, given, plan);
+    TableLayout tl(static_cast<size_t>(rc ? 1 : plan.n_groups), rc ? 1 : plan.fcols.size());
+    if (!rc && tl.total > slot) rc = fail(BYDB_EINVAL, "partial table larger than the mailbox slots (bydb_comm_export max_table_bytes)");
+    if (!rc) {
+        const size_t G = static_cast<size_t>(plan.n_groups), A = q->n_aggs, NS = q->n_series;
+        if (es.ensure_pinned(NS * 12 + (G + 1) * 4 + G * (12 + 16 * A) + 16 * A + 8192)) rc = fail(BYDB_ENOMEM, "cudaMallocHost failed");
+    }
+    memset(&out->stats, 0, sizeof out->stats);
+    out->stats.h2d_bytes = h2d_pre;
+    // the slot's previous use (epoch - 2) must have been consumed by the root before it is overwritten
+    if (epoch > 2) launch_comm_wait(done, 1, epoch - 2, my_err, kErrPeerTimeout, s);
+    // map: this rank's group_reduce writes the table straight into the root's memory (P2P stores over NVLink)
+    if (!rc) rc = run_scan(ctx, q, plan, es, s, my_slot, tl, &out->stats);
+    const std::string my_msg = rc ? g_last_error : std::string();
+    const unsigned long long st_word = (epoch << 32) | static_cast<unsigned long long>(static_cast<uint32_t>(-rc));
+    cudaMemcpyAsync(status + cm.rank, &st_word, sizeof st_word, cudaMemcpyHostToDevice, s);  // pageable source: staged before the call returns
+    launch_comm_signal(flags + cm.rank, epoch, s);
+    unsigned long long peer_status[kCommMaxRanks] = {0};
+    bool finalized = false;
+    int frc = 0;
+    if (cm.rank == root) {
+        // reduce: wait for every rank's table, combine in rank order (deterministic float sums), finalise
+        launch_comm_wait(flags, static_cast<uint32_t>(cm.nranks), epoch, my_err, kErrPeerTimeout, s);
+        if (!rc) {
+            launch_combine_tables(reinterpret_cast<uint64_t *>(slots0), static_cast<uint32_t>(cm.nranks), tl.total / 8, tl.off_sum_f64 / 8, tl.off_max_f64 / 8,
+                                  tl.off_max_f64 / 8, tl.off_sum_i64 / 8, tl.off_sum_i64 / 8, tl.off_max_i64 / 8, tl.off_max_i64 / 8, tl.total / 8, s,
+                                  slot / 8);
+            out->stats.kernel_launches += 3;
+            frc = finalize_to_host(ctx, q, plan, es, s, slots0, tl, out, true);  // synchronises
+            finalized = frc == 0;
+        }
+        cudaStreamSynchronize(s);
+        cudaMemcpy(peer_status, status, sizeof(unsigned long long) * static_cast<size_t>(cm.nranks), cudaMemcpyDeviceToHost);
+        // the slots of this parity are free again: nothing reads them any more
+        cudaMemcpyAsync(done, &epoch, sizeof epoch, cudaMemcpyHostToDevice, s);
+    }
+    cudaStreamSynchronize(s);
+    uint32_t perr = 0;
+    if (cudaMemcpy(&perr, my_err, sizeof perr, cudaMemcpyDeviceToHost) == cudaSuccess && perr != 0) cudaMemset(my_err, 0, sizeof perr);
+    // ---- outcome, most specific first: this rank's own host-side failure, its device-side scan error, a peer's failure
+    if (rc) {
+        if (finalized) bydb_result_free(ctx, out);
+        return fail(rc, my_msg);
+    }
+    int crc = collect_scan(es, &out->stats);
+    if (!crc && perr) crc = fail(dev_err_code(perr), dev_err_text(perr));
+    if (!crc && cm.rank == root) {
+        for (int r = 0; r < cm.nranks && !crc; ++r) {
+            const unsigned long long w = peer_status[r];
+            if ((w >> 32) == (epoch & 0xffffffffull) && static_cast<uint32_t>(w) != 0)
+                crc = fail(-static_cast<int>(static_cast<uint32_t>(w)), "multi-GPU reduce: rank " + std::to_string(r) + " failed before its scan");
+        }
+        if (!crc) crc = frc;
+    }
+    if (crc && finalized) bydb_result_free(ctx, out);
+    return crc;
+    }
+}
+
+int bydb_scan_reduce(bydb_ctx *ctx, const bydb_query *q, int32_t root, bydb_result *out) {
+    return guarded([&]() -> int {
+    if (!ctx || !out) return fail(BYDB_EINVAL, "ctx/out is NULL");
+    memset(out, 0, sizeof *out);
+    return scan_reduce_impl(ctx, q, nullptr, 0, 0, root, out);
+    });
+}
+
+// The collective with HOST file images on every rank (the end-to-end form of a cold distributed query): each rank's parts
+// are admitted for the duration of the call (BYDB_Q_HOST_ZERO_COPY: directory upload only, pages pulled over PCIe by the
+// scan), scanned into the root's mailbox and dropped.  q->parts / q->n_parts are ignored.
+int bydb_scan_reduce_host(bydb_ctx *ctx, uint32_t n_parts, const bydb_part_files *parts, const bydb_query *q, int32_t root, bydb_result *out) {
+    return guarded([&]() -> int {
+    if (!ctx || !out) return fail(BYDB_EINVAL, "ctx/out is NULL");
+    memset(out, 0, sizeof *out);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    g_last_dev_err = 0;
+    std::vector<std::shared_ptr<Part>> tmp;
+    uint64_t h2d = 0;
+    int rc = validate_query(q, false);
+    if (!rc && (n_parts == 0 || !parts || n_parts > kMaxParts)) rc = fail(BYDB_EINVAL, "need 1..64 host parts");
+    const bool zc = !rc && (q->flags & BYDB_Q_HOST_ZERO_COPY) != 0;
+    for (uint32_t i = 0; i < n_parts && !rc; ++i) {
+        std::shared_ptr<Part> p;
+        // fallback pages are unpacked up front here: a collective cannot be re-run by one rank alone
+        rc = register_part_locked_free(ctx, ~0ull - i, &parts[i], p, &h2d, zc, true, 0, 1, !zc);
+        if (!rc) tmp.push_back(p);
+    }
+    rc = scan_reduce_impl(ctx, q, &tmp, rc, h2d, root, out);
+    if (!rc && zc) out->stats.h2d_bytes += out->stats.page_bytes;  // pages were read in place over PCIe
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (auto &p : tmp) ctx->hbm_used -= p->hbm_bytes;
+    }
+    return rc;
     });
 }
 

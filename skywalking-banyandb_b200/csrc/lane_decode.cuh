@@ -99,8 +99,7 @@ BYDB_LANE_FN int32_t imad_s32(int32_t a, int32_t b, int32_t c) {
 
 // kMasked: the chunk holds bytes outside the page (first / last chunk): `reset` = term | ~valid restarts the varint
 // state at those bytes too, their payload is zeroed by the caller, and only real terminators (term) count as rows.
-// kAllRows (only instantiated by the BYDB_EXP_ALLROWS experiment): every row of the block is active, no window arithmetic.
-template <int kNeed, bool kMasked, bool kAllRows = false>
+template <int kNeed, bool kMasked>
 BYDB_LANE_FN void fast_lane_decode_imad(const uint4 &wa, const uint4 &wb, uint32_t term, uint32_t reset, uint32_t aw, uint32_t &accv,
                                                       uint32_t &sh, int32_t &P, int32_t &sumP, int32_t &minP, int32_t &maxP) {
     // 8 words x 4 bytes: the word loop stays rolled so that the body (the hottest code of the whole
@@ -120,7 +119,7 @@ BYDB_LANE_FN void fast_lane_decode_imad(const uint4 &wa, const uint4 &wb, uint32
             const uint32_t h = accv >> 1, s = accv & 1u;
             const int32_t v = imad_s32(static_cast<int32_t>(s), static_cast<int32_t>(0u - accv), static_cast<int32_t>(h));
             P = imad_s32(v, static_cast<int32_t>(t), P);
-            const uint32_t at = kAllRows ? t : (aw & t);  // terminator of an active row
+            const uint32_t at = aw & t;  // terminator of an active row
             if (kNeed & kNeedSum) sumP = imad_s32(P, static_cast<int32_t>(at), sumP);
             if (kNeed & kNeedMinMax) {
                 // candidate = P at an active terminator, the neutral element otherwise
@@ -129,7 +128,7 @@ BYDB_LANE_FN void fast_lane_decode_imad(const uint4 &wa, const uint4 &wb, uint32
                 minP = lo_c < minP ? lo_c : minP;
                 maxP = hi_c > maxP ? hi_c : maxP;
             }
-            if (!kAllRows) aw >>= t;
+            aw >>= t;
             accv = imad_u32(accv, nr, 0u);
             mul = imad_u32(mul, imad_u32(nr, 128u, 0u), nr ^ 1u);
         }
@@ -146,94 +145,133 @@ BYDB_LANE_FN void fast_lane_decode_imad(const uint4 &wa, const uint4 &wb, uint32
     sh = 31u - static_cast<uint32_t>(lane_clz(mul));
 }
 
-// EXPERIMENT (off by default, `make variant EXTRA=-DBYDB_EXP_DUAL`): two independent dependency chains per lane.
-// The lane's 32 bytes are decoded as two 16-byte halves with separate state; the second half starts "fresh" and its
-// first value is corrected afterwards by what the first half's unfinished tail adds (the same identity that joins
-// neighbouring lanes, head_delta).  With P_A the first half's total, a value of the second half has the lane-local
-// prefix P_A + (its prefix inside the half), so
-//   sumP = sumP_A + cnt_B * P_A + sumP_B,  minP = min(minP_A, P_A + minP_B),  maxP likewise,  P = P_A + P_B,
-// and the lane's tail is the second half's.  Equivalence with the single chain was checked on 2e5 random windows
-// (tools/sim_dual_chain.py).  Doubles the ILP of the byte loop at the cost of one in-thread head correction.
 BYDB_LANE_FN int32_t head_delta(uint32_t w0, uint32_t term, uint32_t prev_acc, uint32_t prev_sh);
 
-template <int kNeed>
-BYDB_LANE_FN void imad_byte_step(uint32_t b, uint32_t t, uint32_t &accv, uint32_t &mul, int32_t &P, int32_t &sumP, int32_t &minP,
-                                               int32_t &maxP, uint32_t &aw) {
-    const uint32_t nr = t ^ 1u;
-    accv = imad_u32(b, mul, accv);
-    const uint32_t h = accv >> 1, s = accv & 1u;
-    const int32_t v = imad_s32(static_cast<int32_t>(s), static_cast<int32_t>(0u - accv), static_cast<int32_t>(h));
-    P = imad_s32(v, static_cast<int32_t>(t), P);
-    const uint32_t at = aw & t;
-    if (kNeed & kNeedSum) sumP = imad_s32(P, static_cast<int32_t>(at), sumP);
-    if (kNeed & kNeedMinMax) {
-        const int32_t lo_c = static_cast<int32_t>(imad_u32(at, static_cast<uint32_t>(P) - 0x7fffffffu, 0x7fffffffu));
-        const int32_t hi_c = static_cast<int32_t>(imad_u32(at, static_cast<uint32_t>(P) - 0x80000000u, 0x80000000u));
-        minP = lo_c < minP ? lo_c : minP;
-        maxP = hi_c > maxP ? hi_c : maxP;
+// ------------------------------------------------------------------------------------------------
+// SWAR sum decoder: every row active, SUM/MEAN/COUNT only (BASELINE config 3: group-by sum over all rows).
+//
+// For a page first, d_1 .. d_{n-1} the sum over all rows of value_r = first + sum_{j<=r} d_j is
+//     n*first + sum_j d_j * (n - j),
+// and a zig-zag varint is LINEAR in its payload bytes once its sign is known:
+//     d = sigma * ( (b0+1)>>1  +  64*b1  +  8192*b2 ),   sigma = 1 - 2*(b0 & 1)          (b_k = 7-bit payloads, <= 3 bytes)
+// so the whole page sum is  sum over BYTES of  (class scale) * sigma * payload * (n - 1 - #terminators before the byte):
+// no value is ever assembled, no prefix is carried along the bytes, and a varint that straddles two lanes (or two chunks)
+// needs no correction -- each of its bytes is accounted where it lies.  Per 4-byte word the lane builds, with byte
+// permutes (PRMT with sign replication) and bitwise selects,
+//     M1 / M2   0xff where the previous / second previous byte is a continuation  -> class of the byte (0, 1, 2)
+//     Sm        0xff where the byte belongs to a negative varint (bit 0 of the varint's first byte)
+//     rank1     1 + number of terminators before the byte inside the lane (a SWAR prefix sum by one multiply)
+// and feeds six 4-way byte dot products (IDP.4A): T_k += payload_k . (+-1), R_k += payload_k . (+-rank1).
+// The class-0 payload carries its own sign instead:  (b0 ^ Sm) as int8 = b0 (even, positive) or -(b0+1) = 2 * d's
+// class-0 part, so T0 / R0 hold twice their value (always even).  Lane result:
+//     T = T0/2 + 64*T1 + 8192*T2 = sum of the lane's byte contributions,  R' = same with weights rank+1,
+// page sum += (A + 1) * T - R'   with A = n - 1 - (terminators before the lane).
+// ------------------------------------------------------------------------------------------------
+BYDB_LANE_FN uint32_t lane_prmt(uint32_t a, uint32_t b, uint32_t sel) {  // PTX prmt.b32, default mode (bit 3 of a selector nibble = replicate the byte's msb)
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+#else
+    const uint64_t src = (static_cast<uint64_t>(b) << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t n = (sel >> (4 * i)) & 0xfu;
+        uint32_t byte = static_cast<uint32_t>((src >> (8 * (n & 7u))) & 0xffu);
+        if (n & 8u) byte = (byte & 0x80u) ? 0xffu : 0x00u;
+        r |= byte << (8 * i);
     }
-    aw >>= t;
-    accv = imad_u32(accv, nr, 0u);
-    mul = imad_u32(mul, imad_u32(nr, 128u, 0u), t);
+    return r;
+#endif
+}
+// 4-way byte dot products with 32-bit accumulate: a signed x b unsigned, a unsigned x b signed
+BYDB_LANE_FN int32_t dp4a_su(uint32_t a, uint32_t b, int32_t c) {
+#if defined(__CUDA_ARCH__)
+    int32_t d;
+    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#else
+    for (int i = 0; i < 4; ++i) c += static_cast<int32_t>(static_cast<int8_t>((a >> (8 * i)) & 0xff)) * static_cast<int32_t>((b >> (8 * i)) & 0xff);
+    return c;
+#endif
+}
+BYDB_LANE_FN int32_t dp4a_us(uint32_t a, uint32_t b, int32_t c) {
+#if defined(__CUDA_ARCH__)
+    int32_t d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#else
+    for (int i = 0; i < 4; ++i) c += static_cast<int32_t>((a >> (8 * i)) & 0xff) * static_cast<int32_t>(static_cast<int8_t>((b >> (8 * i)) & 0xff));
+    return c;
+#endif
 }
 
-template <int kNeed>
-BYDB_LANE_FN void fast_lane_decode_dual(const uint4 &wa, const uint4 &wb, uint32_t term, uint32_t aw, uint32_t &accv, uint32_t &sh,
-                                                      int32_t &P, int32_t &sumP, int32_t &minP, int32_t &maxP) {
-    uint32_t a0 = wa.x, a1 = wa.y, a2 = wa.z, a3 = wa.w, b0 = wb.x, b1 = wb.y, b2 = wb.z, b3 = wb.w;
-    const uint32_t termA = term & 0xffffu, termB = term >> 16;
-    const uint32_t nA = lane_popc(termA);
-    uint32_t tmA = termA, tmB = termB;
-    uint32_t awA = aw, awB = aw >> nA;  // nA <= 16; the first half only ever looks at its own nA low bits
-    const uint32_t cntB = lane_popc(awB & low_bits(lane_popc(termB)));
-    uint32_t accA = 0, mulA = 1, accB = 0, mulB = 1;
-    int32_t PA = 0, sumA = 0, mnA = INT32_MAX, mxA = INT32_MIN, PB = 0, sumB = 0, mnB = INT32_MAX, mxB = INT32_MIN;
-    const uint32_t headB = b0;
-#pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-        const uint32_t pa = a0 & 0x7f7f7f7fu, pb = b0 & 0x7f7f7f7fu;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t ba = j == 3 ? (pa >> 24) : (j == 0 ? (pa & 0xffu) : lane_byte_perm(pa, 0u, 0x4440u + j));
-            const uint32_t bb = j == 3 ? (pb >> 24) : (j == 0 ? (pb & 0xffu) : lane_byte_perm(pb, 0u, 0x4440u + j));
-            imad_byte_step<kNeed>(ba, (tmA >> j) & 1u, accA, mulA, PA, sumA, mnA, mxA, awA);
-            imad_byte_step<kNeed>(bb, (tmB >> j) & 1u, accB, mulB, PB, sumB, mnB, mxB, awB);
-        }
-        a0 = a1;
-        a1 = a2;
-        a2 = a3;
-        b0 = b1;
-        b1 = b2;
-        b2 = b3;
-        tmA >>= 4;
-        tmB >>= 4;
-    }
-    // the second half's first value continues the first half's unfinished tail
-    const uint32_t shA = 31u - static_cast<uint32_t>(lane_clz(mulA));
-    if (termB != 0 && shA != 0) {
-        const int32_t dlt = head_delta(headB, termB, accA, shA);
-        PB += dlt;
-        if (kNeed & kNeedSum) sumB += dlt * static_cast<int32_t>(cntB);
-        if ((kNeed & kNeedMinMax) && cntB) {
-            mnB += dlt;
-            mxB += dlt;
-        }
-    }
-    P = PA + PB;
-    if (kNeed & kNeedSum) sumP = sumA + static_cast<int32_t>(cntB) * PA + sumB;
-    if (kNeed & kNeedMinMax) {
-        minP = mnA;
-        maxP = mxA;
-        if (cntB) {
-            const int32_t lo = PA + mnB, hi = PA + mxB;
-            minP = lo < minP ? lo : minP;
-            maxP = hi > maxP ? hi : maxP;
-        }
-    }
-    accv = accB;
-    sh = 31u - static_cast<uint32_t>(lane_clz(mulB));
+BYDB_LANE_FN uint32_t mulhi_u32(uint32_t a, uint32_t b) {  // IMAD.HI: a right shift by a constant done on the FMA pipe
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+#else
+    return static_cast<uint32_t>((static_cast<uint64_t>(a) * b) >> 32);
+#endif
 }
 
+struct SwarLane {
+    int32_t T0, T1, T2, R0, R1, R2;
+    uint32_t wide;     // msb set in some byte <=> a varint of 4 or more bytes was seen
+    int32_t nterm;     // 1 + terminators seen so far in this lane
+    uint32_t prev_w;   // the word before the current one (the previous lane's last word for the first)
+};
+BYDB_LANE_FN void swar_begin(SwarLane &s, uint32_t prev_w) {
+    s.T0 = s.T1 = s.T2 = s.R0 = s.R1 = s.R2 = 0;
+    s.wide = 0;
+    s.nterm = 1;
+    s.prev_w = prev_w;
+}
+// kMasked: first / last chunk of a page -- vm is 0xff for the bytes of the word that belong to the page; the others
+// neither terminate, nor carry payload, nor continue anything.
+// Pipe balance (ncu r01: this integer kernel is bound by the ALU pipe, LOP3/PRMT/SHF, while the FMA pipe idles): everything
+// that can be a multiply-add is one -- the shifts by constants (IMAD / IMAD.HI), the in-word prefix sum, the running
+// terminator count (a dot product with 1s) and its broadcast.
+template <bool kMasked>
+BYDB_LANE_FN void swar_word(SwarLane &s, uint32_t w_in, uint32_t vm) {
+    const uint32_t w = kMasked ? (w_in & vm) : w_in;
+    const uint32_t pw = s.prev_w;
+    const uint32_t p = w & 0x7f7f7f7fu;
+    const uint32_t M1 = lane_prmt(w, pw, 0xA98Fu);   // byte i <- msb of byte i-1, replicated: 0xff = not the first byte of a varint
+    const uint32_t M2 = lane_prmt(w, pw, 0x98FEu);   // byte i <- msb of byte i-2
+    const uint32_t sb = imad_u32(w, 128u, 0u);       // bit 0 of every byte moved to its msb (the low bits are don't-care)
+    const uint32_t psb = imad_u32(pw, 128u, 0u);
+    const uint32_t S0 = lane_prmt(sb, 0u, 0xBA98u);  // sign of a varint that starts at this byte
+    const uint32_t S1 = lane_prmt(sb, psb, 0xA98Fu); // ... that started one / two bytes earlier
+    const uint32_t S2 = lane_prmt(sb, psb, 0x98FEu);
+    const uint32_t S12 = (M2 & S2) | (~M2 & S1);     // sign of the varint a class-1 / class-2 byte belongs to
+    const uint32_t x0 = (p ^ S0) & ~M1;              // class 0: int8 = 2 * (signed class-0 part); 0 elsewhere
+    const uint32_t p1 = p & M1 & ~M2;                // class 1 payloads
+    const uint32_t q2 = w & M1 & M2;                 // class 2 payloads; an msb here = a fourth byte follows (wide: the page bails out)
+    const uint32_t wT = S12 | 0x01010101u;           // +-1 (only read where p1 / q2 are non-zero, i.e. on class 1 / 2 bytes)
+    uint32_t t01 = ~mulhi_u32(w, 1u << 25) & 0x01010101u;  // 1 where the byte terminates a varint
+    if (kMasked) t01 &= vm;
+    const uint32_t base = imad_u32(static_cast<uint32_t>(s.nterm), 0x01010101u, 0u);
+    const uint32_t rinc = imad_u32(t01, 0x01010101u, base);    // inclusive terminator count + 1
+    const uint32_t rank1 = imad_u32(t01, 0xffffffffu, rinc);   // exclusive count + 1, in [1, 33]
+    s.nterm = dp4a_su(0x01010101u, t01, s.nterm);
+    const uint32_t wR = imad_u32(S12 & 0x01010101u, 1u, rank1 ^ S12);  // +-rank1 as int8 (rank1 >= 1: the +1 never carries)
+    s.T0 = dp4a_su(x0, 0x01010101u, s.T0);
+    s.R0 = dp4a_su(x0, rank1, s.R0);
+    s.T1 = dp4a_us(p1, wT, s.T1);
+    s.R1 = dp4a_us(p1, wR, s.R1);
+    s.T2 = dp4a_us(q2, wT, s.T2);
+    s.R2 = dp4a_us(q2, wR, s.R2);
+    s.wide |= q2;
+    s.prev_w = w;
+}
+// -> number of terminators of the lane; T and R' as defined above
+BYDB_LANE_FN uint32_t swar_end(const SwarLane &s, int32_t &T, int32_t &Rp) {
+    T = (s.T0 >> 1) + 64 * s.T1 + 8192 * s.T2;
+    Rp = (s.R0 >> 1) + 64 * s.R1 + 8192 * s.R2;
+    return static_cast<uint32_t>(s.nterm - 1);
+}
 
 // 4 bits -> 4 byte masks (bit j -> 0xff in byte j): bit j times 2^(7j) lands on bit 8j, nothing else does
 BYDB_LANE_FN uint32_t expand4(uint32_t n) { return (((n & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu; }
@@ -242,11 +280,7 @@ template <bool kFull, int kNeed>
 BYDB_LANE_FN void fast_lane_decode(const uint4 &wa, const uint4 &wb, uint32_t valid, uint32_t term, uint32_t aw, uint32_t &accv,
                                                  uint32_t &sh, int32_t &P, int32_t &sumP, int32_t &minP, int32_t &maxP) {
     if (kFull) {
-#ifdef BYDB_EXP_DUAL
-        fast_lane_decode_dual<kNeed>(wa, wb, term, aw, accv, sh, P, sumP, minP, maxP);
-#else
         fast_lane_decode_imad<kNeed, false>(wa, wb, term, term, aw, accv, sh, P, sumP, minP, maxP);
-#endif
     } else {
         const uint4 ma = make_uint4(wa.x & expand4(valid), wa.y & expand4(valid >> 4), wa.z & expand4(valid >> 8), wa.w & expand4(valid >> 12));
         const uint4 mb = make_uint4(wb.x & expand4(valid >> 16), wb.y & expand4(valid >> 20), wb.z & expand4(valid >> 24), wb.w & expand4(valid >> 28));

@@ -904,7 +904,8 @@ int bydb_synth_part(const bydb_synth_spec *spec, bydb_part_image **out) {
         sc.field_names.push_back(spec->fields[f].name);
         sc.field_types.push_back(spec->fields[f].kind >= BYDB_SYN_I_DELTA ? BYDB_VT_INT64 : BYDB_VT_FLOAT64);
     }
-    std::vector<std::string> region_values;
+    std::vector<std::string> region_values, zone_values;
+    const bool want_code = (spec->code_tag & 1u) != 0, want_zone = (spec->code_tag & 2u) != 0;
     if (spec->region_values > 0 || spec->code_tag) {
         sc.family = "default";
         if (spec->region_values > 0) {
@@ -912,7 +913,12 @@ int bydb_synth_part(const bydb_synth_spec *spec, bydb_part_image **out) {
             sc.tag_types.push_back(BYDB_VT_STR);
             for (uint32_t k = 0; k < spec->region_values; ++k) region_values.push_back("r" + std::to_string(k));
         }
-        if (spec->code_tag) {
+        if (want_zone) {  // a second dictionary tag (BASELINE config 5: two string predicates + one int64 predicate)
+            sc.tag_names.push_back("zone");
+            sc.tag_types.push_back(BYDB_VT_STR);
+            for (uint32_t k = 0; k < 5; ++k) zone_values.push_back("z" + std::to_string(k));
+        }
+        if (want_code) {
             sc.tag_names.push_back("code");
             sc.tag_types.push_back(BYDB_VT_INT64);
         }
@@ -930,7 +936,7 @@ int bydb_synth_part(const bydb_synth_spec *spec, bydb_part_image **out) {
             for (size_t j = 0; j < np; ++j) ts[j] = spec->t0 + static_cast<int64_t>(j) * spec->t_step;
             std::vector<std::vector<int64_t>> ibuf(spec->n_fields, std::vector<int64_t>(np));
             std::vector<std::vector<double>> dbuf(spec->n_fields);
-            std::vector<uint32_t> region(np);
+            std::vector<uint32_t> region(np), zone(np);
             std::vector<int64_t> code(np);
             const size_t a = ns * t / nt, b = ns * (t + 1) / nt;
             for (size_t s = a; s < b; ++s) {
@@ -1030,7 +1036,18 @@ int bydb_synth_part(const bydb_synth_spec *spec, bydb_part_image **out) {
                     all.t_idx.push_back(region.data());
                     all.t_values.push_back(&region_values);
                 }
-                if (spec->code_tag) {
+                if (want_zone) {
+                    size_t j = 0;
+                    while (j < np) {
+                        const uint32_t v = static_cast<uint32_t>(rng.below(5));
+                        const size_t run = 1 + rng.below(127);
+                        for (size_t e = std::min(np, j + run); j < e; ++j) zone[j] = v;
+                    }
+                    all.t_i64.push_back(nullptr);
+                    all.t_idx.push_back(zone.data());
+                    all.t_values.push_back(&zone_values);
+                }
+                if (want_code) {
                     for (size_t j = 0; j < np; ++j) code[j] = static_cast<int64_t>(rng.below(6)) * 100;
                     all.t_i64.push_back(code.data());
                     all.t_idx.push_back(nullptr);

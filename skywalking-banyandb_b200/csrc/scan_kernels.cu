@@ -21,6 +21,7 @@
 #include <atomic>
 #include <cfloat>
 #include <cmath>
+#include <cstring>
 
 #include "../../include/bydb_gpu.h"
 
@@ -78,7 +79,10 @@ struct __align__(128) WarpSmem {
     uint32_t a_len;
     const uint8_t *a_body;
     long long a_first;
-    uint32_t a_count, a_r0, a_r1, pad;
+    uint32_t a_count, a_r0, a_r1;
+    int res_exp;                 // decimal exponent of the page just aggregated (kExpRawFloat for raw float cells)
+    const uint8_t *a_page;       // arguments of agg_field_page
+    uint32_t a_size, a_flags;    // a_flags: bit 0 = float64 field, bits 1.. = kNeed*
 };
 
 size_t scan_smem_bytes() { return sizeof(WarpSmem) * kWarpsPerCta; }
@@ -261,6 +265,18 @@ struct AggAcc {
 // the out-of-line fast decoders leave their (warp-reduced) result in the warp's shared-memory slot
 __device__ __forceinline__ void publish_acc(WarpSmem *sm, AggAcc &acc, int lane) {
     acc.warp_reduce();
+    if (lane == 0) {
+        sm->res_lo = acc.lo;
+        sm->res_hi = acc.hi;
+        sm->res_mn = acc.mn;
+        sm->res_mx = acc.mx;
+        sm->res_cnt = acc.cnt;
+    }
+    __syncwarp();
+}
+// an accumulator that is already warp-reduced (every lane holds the total)
+__device__ __forceinline__ void store_acc(WarpSmem *sm, const AggAcc &acc, int lane) {
+    __syncwarp();
     if (lane == 0) {
         sm->res_lo = acc.lo;
         sm->res_hi = acc.hi;
@@ -506,39 +522,8 @@ struct FastChunk {
     uint32_t valid, term, n;
     bool wide;
 };
-#ifdef BYDB_EXP_INTERIOR
-// EXPERIMENT (off by default, `make variant EXTRA=-DBYDB_EXP_INTERIOR`): chunks that lie completely inside the page skip
-// the validity arithmetic of the front end (warp-uniform branch).
-__device__ __forceinline__ void fast_chunk_load_interior(FastChunk &fc, const uint8_t *buf, uint32_t c, uint32_t carry_sh, int lane) {
-    const uint32_t o = c * kFastChunkBytes + lane * kFastLaneBytes;
-    fc.wa = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes));
-    fc.wb = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes) + 16);
-    fc.valid = 0xffffffffu;
-    uint32_t msb = msb4(fc.wa.x);
-    msb = imad_u32(msb4(fc.wa.y), 1u << 4, msb);
-    msb = imad_u32(msb4(fc.wa.z), 1u << 8, msb);
-    msb = imad_u32(msb4(fc.wa.w), 1u << 12, msb);
-    msb = imad_u32(msb4(fc.wb.x), 1u << 16, msb);
-    msb = imad_u32(msb4(fc.wb.y), 1u << 20, msb);
-    msb = imad_u32(msb4(fc.wb.z), 1u << 24, msb);
-    msb = imad_u32(msb4(fc.wb.w), 1u << 28, msb);
-    fc.term = ~msb;
-    fc.n = __popc(fc.term);
-    const uint32_t lead = fc.term ? static_cast<uint32_t>(__ffs(fc.term) - 1) : 32u;
-    const uint32_t trail = fc.term ? static_cast<uint32_t>(__clz(fc.term)) : 32u;
-    uint32_t trail_prev = __shfl_up_sync(0xffffffffu, trail, 1);
-    if (lane == 0) trail_prev = carry_sh / 7;
-    fc.wide = __any_sync(0xffffffffu, (msb & (msb >> 1) & (msb >> 2)) != 0 || (trail_prev + lead) > 2);
-}
-#endif
 
 __device__ __forceinline__ void fast_chunk_load(FastChunk &fc, const PageStream &st, const uint8_t *buf, uint32_t c, uint32_t carry_sh, int lane) {
-#ifdef BYDB_EXP_INTERIOR
-    if (c * kFastChunkBytes >= st.pstart && (c + 1) * kFastChunkBytes <= st.pend) {
-        fast_chunk_load_interior(fc, buf, c, carry_sh, lane);
-        return;
-    }
-#endif
     const uint32_t o = c * kFastChunkBytes + lane * kFastLaneBytes;
     fc.wa = make_uint4(0, 0, 0, 0);
     fc.wb = make_uint4(0, 0, 0, 0);
@@ -644,12 +629,6 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, int lane) {
         uint32_t accv = 0, sh = 0;
         int32_t P = 0, sumP = 0, minP = INT32_MAX, maxP = INT32_MIN;
         const bool full_chunk = __all_sync(0xffffffffu, fc.valid == 0xffffffffu);
-#ifdef BYDB_EXP_ALLROWS
-        // EXPERIMENT (off by default): a query without row predicate over a block fully inside the time range needs no
-        // active-row window in the byte loop (BASELINE config 3: group-by sum over every row)
-        if (kMode == kRowsAll && full_chunk) fast_lane_decode_imad<kNeed, false, true>(fc.wa, fc.wb, fc.term, fc.term, aw, accv, sh, P, sumP, minP, maxP);
-        else
-#endif
         if (full_chunk) fast_lane_decode<true, kNeed>(fc.wa, fc.wb, fc.valid, fc.term, aw, accv, sh, P, sumP, minP, maxP);
         else fast_lane_decode<false, kNeed>(fc.wa, fc.wb, fc.valid, fc.term, aw, accv, sh, P, sumP, minP, maxP);
         // ---- head correction by the previous lane's unfinished tail
@@ -695,23 +674,116 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, int lane) {
         }
         V0 += static_cast<int64_t>(__shfl_sync(0xffffffffu, s_in, 31));
         row_base += n_tot;
-#ifdef BYDB_EXP_EARLYSTOP
-        // EXPERIMENT (off by default): rows after r1 are never active (the time range is folded into the mask too), and
-        // nothing later in the page feeds an active row, so the rest of the page is neither fetched nor decoded.  The
-        // stages already in flight are drained exactly like on the wide-varint bail-out.  (The tail is then not
-        // validated against the block's row count.)
-        if (kMode != kRowsAll && row_base > r1 && c + 1 < nchunks) {
-            stream_drain(st, sm, k);
-            if (lane == 0) sm->seq = st.seq0 + min(st.nstages, k + static_cast<uint32_t>(kStages));
-            __syncwarp();
-            publish_acc(sm, acc, lane);
-            return 0;
-        }
-#endif
         if ((c % kChunksPerStage) == kChunksPerStage - 1 || c == nchunks - 1) stream_release(st, sm, k, lane);
     }
     publish_acc(sm, acc, lane);
     return (row_base == count && carry_sh == 0) ? 0 : 2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SWAR sum decoder: EncodeTypeDelta page, every row active, only SUM / MEAN / COUNT wanted (the group-by-sum shape of
+// BASELINE configs 3/4).  See lane_decode.cuh (swar_word): the page sum is a weighted sum over BYTES, so nothing is
+// carried from byte to byte or from lane to lane except the count of terminators; per 1 KB chunk the warp does one
+// shuffle of the neighbour's last word, 8 x swar_word per lane, one scan of the lanes' terminator counts and one
+// 64-bit multiply-add.  Returns like delta_page_fast (0 done / 1 a varint of 4+ bytes was met / 2 corrupt).
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ int delta_page_sum_all(WarpSmem *sm, int lane) {
+    const uint8_t *body = sm->a_body;
+    const uint32_t len = sm->a_len, count = sm->a_count;
+    const int64_t first = sm->a_first;
+    AggAcc acc;
+    acc.init();
+    if (lane == 0) {
+        acc.add_scaled(first, count);  // n * first, exact in 128 bits
+        acc.cnt = count;
+    }
+    if (len == 0) {
+        publish_acc(sm, acc, lane);
+        return count == 1 ? 0 : 2;
+    }
+    PageStream st;
+    stream_open(st, sm, body, len, lane);
+    const uint32_t nchunks = (st.total + kFastChunkBytes - 1) / kFastChunkBytes;
+    constexpr uint32_t kChunksPerStage = kStageBytes / kFastChunkBytes;
+    int64_t S = 0;                 // this lane's share of  sum_j d_j * (n - j)
+    uint32_t tb = 0, carry_w = 0;  // terminators before this chunk; last (masked) word of the previous chunk
+    uint32_t last_byte = 0;
+    const uint8_t *buf = nullptr;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const uint32_t k = c / kChunksPerStage;
+        if ((c % kChunksPerStage) == 0) buf = stream_wait(st, sm, k);
+        const uint32_t o = c * kFastChunkBytes + lane * kFastLaneBytes;
+        const bool interior = c * kFastChunkBytes >= st.pstart && (c + 1) * kFastChunkBytes <= st.pend;  // warp-uniform
+        SwarLane sl;
+        if (interior) {
+            const uint4 wa = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes));
+            const uint4 wb = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes) + 16);
+            uint32_t pw = __shfl_up_sync(0xffffffffu, wb.w, 1);
+            if (lane == 0) pw = carry_w;
+            carry_w = __shfl_sync(0xffffffffu, wb.w, 31);
+            swar_begin(sl, pw);
+            swar_word<false>(sl, wa.x, 0u);
+            swar_word<false>(sl, wa.y, 0u);
+            swar_word<false>(sl, wa.z, 0u);
+            swar_word<false>(sl, wa.w, 0u);
+            swar_word<false>(sl, wb.x, 0u);
+            swar_word<false>(sl, wb.y, 0u);
+            swar_word<false>(sl, wb.z, 0u);
+            swar_word<false>(sl, wb.w, 0u);
+        } else {
+            uint4 wa = make_uint4(0, 0, 0, 0), wb = make_uint4(0, 0, 0, 0);
+            if (o < st.total) wa = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes));
+            if (o + 16 < st.total) wb = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes) + 16);
+            int lo_i = static_cast<int>(st.pstart) - static_cast<int>(o);
+            int hi_i = static_cast<int>(st.pend) - static_cast<int>(o);
+            lo_i = lo_i < 0 ? 0 : (lo_i > 32 ? 32 : lo_i);
+            hi_i = hi_i < 0 ? 0 : (hi_i > 32 ? 32 : hi_i);
+            const uint32_t valid = low_bits(hi_i) & ~low_bits(lo_i);
+            const uint32_t mine = wb.w & expand4(valid >> 28);
+            uint32_t pw = __shfl_up_sync(0xffffffffu, mine, 1);
+            if (lane == 0) pw = carry_w;
+            carry_w = __shfl_sync(0xffffffffu, mine, 31);
+            swar_begin(sl, pw);
+            swar_word<true>(sl, wa.x, expand4(valid));
+            swar_word<true>(sl, wa.y, expand4(valid >> 4));
+            swar_word<true>(sl, wa.z, expand4(valid >> 8));
+            swar_word<true>(sl, wa.w, expand4(valid >> 12));
+            swar_word<true>(sl, wb.x, expand4(valid >> 16));
+            swar_word<true>(sl, wb.y, expand4(valid >> 20));
+            swar_word<true>(sl, wb.z, expand4(valid >> 24));
+            swar_word<true>(sl, wb.w, expand4(valid >> 28));
+        }
+        if (__any_sync(0xffffffffu, (sl.wide & 0x80808080u) != 0)) {
+            // a varint of four or more bytes: the general decoder takes the page (same bail-out as delta_page_fast)
+            stream_drain(st, sm, k);
+            if (lane == 0) sm->seq = st.seq0 + min(st.nstages, k + static_cast<uint32_t>(kStages));
+            __syncwarp();
+            return 1;
+        }
+        int32_t T, Rp;
+        const uint32_t n = swar_end(sl, T, Rp);
+        uint32_t n_in = n;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const uint32_t on = __shfl_up_sync(0xffffffffu, n_in, sft);
+            if (lane >= sft) n_in += on;
+        }
+        // weight of a byte = (n - 1) - terminators before it = (count - tb - lb) - (rank + 1)
+        const int64_t A1 = static_cast<int64_t>(count) - static_cast<int64_t>(tb) - static_cast<int64_t>(n_in - n);
+        S += A1 * static_cast<int64_t>(T) - static_cast<int64_t>(Rp);
+        tb += __shfl_sync(0xffffffffu, n_in, 31);
+        if (c == nchunks - 1 && lane == 0) last_byte = buf[(st.pend - 1) % kStageBytes];
+        if ((c % kChunksPerStage) == kChunksPerStage - 1 || c == nchunks - 1) stream_release(st, sm, k, lane);
+    }
+    {
+        const uint64_t us = static_cast<uint64_t>(S);
+        acc.lo += us;
+        acc.hi += (S >> 63) + (acc.lo < us ? 1 : 0);
+    }
+    publish_acc(sm, acc, lane);
+    last_byte = __shfl_sync(0xffffffffu, last_byte, 0);
+    // the body must hold exactly count-1 varints and end on a terminator
+    return (tb + 1 == count && last_byte < 0x80u) ? 0 : 2;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1272,20 +1344,31 @@ __device__ __noinline__ int dod_page_fast(WarpSmem *sm, int lane) {
 constexpr uint32_t kDeferSlow = 0xffffffffu;
 
 template <int kMode, bool kFastLane>
-__device__ __forceinline__ uint32_t agg_field_page(WarpSmem *sm, const uint8_t *page, uint32_t size, bool is_float, uint32_t need,
-                                                   uint32_t count, uint32_t r0, uint32_t r1, AggAcc &out, int &exp_out, int lane) {
+// Out of line (one copy per row mode), arguments and result through the warp's shared-memory slots: the block loop of the
+// scan kernel then keeps only its own few values live across the call instead of spilling around an inlined decoder.
+// In: a_page, a_size, a_flags, a_count, a_r0, a_r1.  Out: res_* (warp-reduced accumulator), res_exp.
+__device__ __noinline__ uint32_t agg_field_page(WarpSmem *sm, int lane) {
+    const uint8_t *page = sm->a_page;
+    const uint32_t size = sm->a_size, count = sm->a_count, r0 = sm->a_r0, r1 = sm->a_r1;
+    const bool is_float = (sm->a_flags & 1u) != 0;
+    const uint32_t need = sm->a_flags >> 1;
+    int exp_out = 0;
+    AggAcc out;
     if (size < 1) return kErrCorrupt;
     const uint32_t enc = __ldg(page);
     if (enc == kEncRawCells) {
         if (kFastLane) return kDeferSlow;  // keeps the fast lane's register budget for the varint decoders
-        exp_out = is_float ? kExpRawFloat : 0;
-        return agg_raw_page(page, size, is_float, kMode, count, r0, r1, sm->mask, out, lane);
+        const uint32_t e = agg_raw_page(page, size, is_float, kMode, count, r0, r1, sm->mask, out, lane);
+        store_acc(sm, out, lane);
+        if (lane == 0) sm->res_exp = is_float ? kExpRawFloat : 0;
+        __syncwarp();
+        return e;
     }
     if (enc == 9) return kErrPlainPage;  // EncodeTypePlain fallback page that was not unpacked at admission
     const uint32_t hdr = is_float ? 11u : 9u;
     if (size < hdr) return kErrCorrupt;
-    exp_out = 0;
     if (is_float) exp_out = static_cast<int16_t>((static_cast<uint32_t>(__ldg(page + 1)) << 8) | __ldg(page + 2));
+    if (lane == 0) sm->res_exp = exp_out;
     const int64_t first = conv_bytes_to_int64(page + hdr - 8);
     const uint8_t *body = page + hdr;
     const uint32_t blen = size - hdr;
@@ -1298,7 +1381,7 @@ __device__ __forceinline__ uint32_t agg_field_page(WarpSmem *sm, const uint8_t *
             if (!read_varint_seq(body, blen, d, used) || used != blen) return kErrCorrupt;
         }
         agg_arith_page<kMode>(out, first, d, count, r0, r1, sm->mask, lane);
-        out.warp_reduce();
+        publish_acc(sm, out, lane);
         return kErrNone;
     }
     if (enc != 3 && enc != 4) return kErrBadEnc;
@@ -1315,16 +1398,14 @@ __device__ __forceinline__ uint32_t agg_field_page(WarpSmem *sm, const uint8_t *
         }
         __syncwarp();
         if (enc == 3) {
-            if (need == kNeedSum) rc = delta_page_fast<kMode, kNeedSum>(sm, lane);
+            if (need == kNeedSum && kMode == kRowsAll) rc = delta_page_sum_all(sm, lane);
+            else if (need == kNeedSum) rc = delta_page_fast<kMode, kNeedSum>(sm, lane);
             else if (need == kNeedMinMax) rc = delta_page_fast<kMode, kNeedMinMax>(sm, lane);
             else rc = delta_page_fast<kMode, kNeedSum | kNeedMinMax>(sm, lane);
         } else {
             rc = dod_page_fast<kMode, kNeedSum | kNeedMinMax>(sm, lane);
         }
-        if (rc == 0) {
-            fetch_acc(sm, out);
-            return kErrNone;
-        }
+        if (rc == 0) return kErrNone;  // the decoder left the result in the slot
         if (rc == 2) return kErrCorrupt;
         // rc == 1: a varint longer than 3 bytes -> general two-pass decoder
     }
@@ -1342,8 +1423,7 @@ __device__ __forceinline__ uint32_t agg_field_page(WarpSmem *sm, const uint8_t *
         else ok = decode_varint_page<true>(sm, body, blen, count, first, cons, lane);
         ok = __all_sync(0xffffffffu, ok);
         if (!ok) return kErrCorrupt;
-        cons.acc.warp_reduce();
-        out = cons.acc;
+        publish_acc(sm, cons.acc, lane);
         return kErrNone;
     }
 }
@@ -1595,10 +1675,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
                         }
                     } else {
                         page_bytes += col.size;
-                        if (use_mask) e2 = agg_field_page<kRowsMask, kFastLane>(sm, page, col.size, is_float, need, count, r0, r1, acc, exp, lane);
-                        else if (r0 == 0 && r1 == count - 1)
-                            e2 = agg_field_page<kRowsAll, kFastLane>(sm, page, col.size, is_float, need, count, r0, r1, acc, exp, lane);
-                        else e2 = agg_field_page<kRowsRange, kFastLane>(sm, page, col.size, is_float, need, count, r0, r1, acc, exp, lane);
+                        __syncwarp();
+                        if (lane == 0) {
+                            sm->a_page = page;
+                            sm->a_size = col.size;
+                            sm->a_flags = (is_float ? 1u : 0u) | (need << 1);
+                            sm->a_count = count;
+                            sm->a_r0 = r0;
+                            sm->a_r1 = r1;
+                        }
+                        __syncwarp();
+                        if (use_mask) e2 = agg_field_page<kRowsMask, kFastLane>(sm, lane);
+                        else if (r0 == 0 && r1 == count - 1) e2 = agg_field_page<kRowsAll, kFastLane>(sm, lane);
+                        else e2 = agg_field_page<kRowsRange, kFastLane>(sm, lane);
+                        if (e2 == kErrNone) {
+                            fetch_acc(sm, acc);
+                            exp = sm->res_exp;
+                        }
                     }
                     if (e2 == kDeferSlow) {
                         defer = true;
@@ -2006,19 +2099,17 @@ __global__ void __launch_bounds__(256) group_reduce_kernel(const __grid_constant
 }
 
 // finalisation: pkg/query/aggregation/function.go Val() + output typing aggregation.go:425-430
-__global__ void finalize_kernel(const __grid_constant__ FinalizeParams p) {
-    const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g == 0) {
-        for (uint32_t a = 0; a < p.n_aggs; ++a)
-            p.out_is_float[a] = (p.agg_func[a] != BYDB_AGG_COUNT && (p.coltype[p.agg_fcol[a]] & 0xff) == BYDB_VT_FLOAT64) ? 1 : 0;
-        uint32_t e = 0;
-        for (uint32_t c = 0; c < p.n_fcols; ++c) {
-            const uint32_t ec = static_cast<uint32_t>(p.coltype[c] >> 8);
-            e = ec > e ? ec : e;
-        }
-        if (p.err_out) *p.err_out = e;
+__device__ __forceinline__ void finalize_header(const FinalizeParams &p) {
+    for (uint32_t a = 0; a < p.n_aggs; ++a)
+        p.out_is_float[a] = (p.agg_func[a] != BYDB_AGG_COUNT && (p.coltype[p.agg_fcol[a]] & 0xff) == BYDB_VT_FLOAT64) ? 1 : 0;
+    uint32_t e = 0;
+    for (uint32_t c = 0; c < p.n_fcols; ++c) {
+        const uint32_t ec = static_cast<uint32_t>(p.coltype[c] >> 8);
+        e = ec > e ? ec : e;
     }
-    if (g >= p.n_groups) return;
+    if (p.err_out) *p.err_out = e;
+}
+__device__ __forceinline__ void finalize_group(const FinalizeParams &p, int32_t g) {
     for (uint32_t a = 0; a < p.n_aggs; ++a) {
         const uint32_t c = p.agg_fcol[a];
         const size_t o = static_cast<size_t>(g) * p.n_fcols + c;
@@ -2063,6 +2154,11 @@ __global__ void finalize_kernel(const __grid_constant__ FinalizeParams p) {
         p.out_f64[oo] = vf;
     }
 }
+__global__ void finalize_kernel(const __grid_constant__ FinalizeParams p) {
+    const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0) finalize_header(p);
+    if (g < p.n_groups) finalize_group(p, g);
+}
 
 
 // ------------------------------------------------------------------------------------------------
@@ -2101,7 +2197,14 @@ __device__ __forceinline__ uint64_t order_key_f64(double d) {
     return (b >> 63) ? ~b : (b | (1ull << 63));
 }
 
-__global__ void __launch_bounds__(1024) select_rows_kernel(const __grid_constant__ SelectParams p) {
+// kFused: the finalisation runs in this (single) CTA first -- one launch less on the tail of every query with few groups
+template <bool kFused>
+__global__ void __launch_bounds__(1024) select_rows_kernel(const __grid_constant__ SelectParams p, const __grid_constant__ FinalizeParams fp) {
+    if (kFused) {
+        if (threadIdx.x == 0) finalize_header(fp);
+        for (int32_t g = threadIdx.x; g < fp.n_groups; g += blockDim.x) finalize_group(fp, g);
+        __syncthreads();  // global writes of this CTA are visible to its own threads after the barrier
+    }
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_hist[256];
     __shared__ uint64_t s_key[kMaxDeviceTopN];
@@ -2166,6 +2269,38 @@ __global__ void __launch_bounds__(1024) select_rows_kernel(const __grid_constant
     const uint32_t n_nulls_first = p.top_desc ? 0u : min(N, s_nulls);                  // asc: nulls lead
     const uint32_t M = min(N - n_nulls_first, s_nn);                                     // competing rows to take
     const uint32_t n_nulls_last = p.top_desc ? min(N - M, s_nulls) : 0u;               // desc: nulls trail
+    if (G <= kMaxDeviceTopN) {
+        // ---- few groups: every competing row counts the rows that precede it (key desc, group asc) -- its rank IS its output
+        //      position; G^2 / 1024 compares per thread from shared memory beat eight histogram passes plus a bitonic sort
+        uint8_t *s_st = reinterpret_cast<uint8_t *>(s_gid);
+        for (int32_t g = tid; g < G; g += blockDim.x) {
+            s_key[g] = p.keys[g];
+            s_st[g] = p.kstate[g];
+        }
+        __syncthreads();
+        for (int32_t g = tid; g < G; g += blockDim.x) {
+            if (s_st[g] != 2) continue;
+            const uint64_t k = s_key[g];
+            uint32_t rank = 0;
+            for (int32_t o = 0; o < G; ++o) {
+                const uint64_t ko = s_key[o];
+                rank += (s_st[o] == 2 && (ko > k || (ko == k && o < g))) ? 1u : 0u;
+            }
+            if (rank < M) emit(n_nulls_first + rank, g);
+        }
+        const uint32_t n_nulls = n_nulls_first + n_nulls_last;
+        if (n_nulls > 0) {
+            const uint32_t at = p.top_desc ? M : 0u;
+            for (int32_t g = tid; g < G; g += blockDim.x) {
+                if (s_st[g] != 1) continue;
+                uint32_t pos = 0;
+                for (int32_t o = 0; o < g; ++o) pos += s_st[o] == 1 ? 1u : 0u;
+                if (pos < n_nulls) emit(at + pos, g);
+            }
+        }
+        if (tid == 0) *p.sel_count = M + n_nulls;
+        return;
+    }
     // ---- radix select of the M-th largest competing key
     if (tid == 0) {
         s_prefix = 0;
@@ -2272,13 +2407,13 @@ __global__ void __launch_bounds__(1024) select_rows_kernel(const __grid_constant
 // Multi-GPU reduce after ONE all-gather of the per-rank partial tables: every word of the table is
 // combined across ranks in rank order (deterministic float sums, unlike a ring all-reduce), which is
 // the liaison's reduceAccumulator.Combine (measure_plan_aggregation.go:96-124) done on the device.
-__global__ void combine_tables_kernel(uint64_t *t, uint32_t n, uint64_t words, uint64_t sf_lo, uint64_t sf_hi, uint64_t mf_lo, uint64_t mf_hi,
+__global__ void combine_tables_kernel(uint64_t *t, uint32_t n, uint64_t words, uint64_t stride, uint64_t sf_lo, uint64_t sf_hi, uint64_t mf_lo, uint64_t mf_hi,
                                       uint64_t si_lo, uint64_t si_hi, uint64_t mi_lo, uint64_t mi_hi) {
     const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= words) return;
     uint64_t a = t[i];
     for (uint32_t r = 1; r < n; ++r) {
-        const uint64_t b = t[static_cast<uint64_t>(r) * words + i];
+        const uint64_t b = t[static_cast<uint64_t>(r) * stride + i];
         if (i >= sf_lo && i < sf_hi) {
             a = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(a)) + __longlong_as_double(static_cast<long long>(b))));
         } else if (i >= mf_lo && i < mf_hi) {
@@ -2354,12 +2489,70 @@ void launch_group_reduce(const ReduceParams &p, cudaStream_t s) {
     group_reduce_kernel<<<p.n_groups, 256, 0, s>>>(p);
 }
 void launch_combine_tables(uint64_t *tables, uint32_t n_tables, uint64_t words, uint64_t sum_f64_lo, uint64_t sum_f64_hi, uint64_t max_f64_lo,
-                           uint64_t max_f64_hi, uint64_t sum_i64_lo, uint64_t sum_i64_hi, uint64_t max_i64_lo, uint64_t max_i64_hi, cudaStream_t s) {
+                           uint64_t max_f64_hi, uint64_t sum_i64_lo, uint64_t sum_i64_hi, uint64_t max_i64_lo, uint64_t max_i64_hi, cudaStream_t s,
+                           uint64_t stride_words) {
     if (words == 0 || n_tables < 2) return;
-    combine_tables_kernel<<<static_cast<unsigned>((words + 255) / 256), 256, 0, s>>>(tables, n_tables, words, sum_f64_lo, sum_f64_hi, max_f64_lo, max_f64_hi,
-                                                                                  sum_i64_lo, sum_i64_hi, max_i64_lo, max_i64_hi);
+    combine_tables_kernel<<<static_cast<unsigned>((words + 255) / 256), 256, 0, s>>>(tables, n_tables, words, stride_words ? stride_words : words, sum_f64_lo,
+                                                                                  sum_f64_hi, max_f64_lo, max_f64_hi, sum_i64_lo, sum_i64_hi, max_i64_lo,
+                                                                                  max_i64_hi);
 }
-void launch_select_rows(const SelectParams &p, cudaStream_t s) { select_rows_kernel<<<1, 1024, 0, s>>>(p); }
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU reduce without a library collective (the liaison reduce of
+// pkg/query/logical/measure/measure_plan_aggregation.go:96-124 done by the GPUs themselves): every rank's group_reduce
+// writes its partial table straight into ITS slot of the root's mailbox -- peer memory, the stores travel over
+// NVLink / NVSwitch -- and then raises its arrival flag there; the root spins on the flags, combines the slots in rank
+// order and finalises.  Flags carry the call's epoch (all ranks issue the collective calls in the same order), slots
+// alternate between two parities, and a writer first waits until the root has consumed the slot's previous use.
+// All waits are bounded: a peer that never arrives becomes an error code, never a hung GPU.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// one warp: lane r waits for word r of `flags` (stride in words) to reach `epoch`
+__global__ void comm_wait_kernel(const unsigned long long *flags, uint32_t n, unsigned long long epoch, uint32_t *err, uint32_t err_code) {
+    const uint32_t r = threadIdx.x;
+    bool ok = true;
+    if (r < n) {
+        ok = false;
+        for (uint32_t spins = 0; spins < (1u << 22); ++spins) {  // ~ seconds with the back-off below
+            if (ld_acquire_sys(flags + r) >= epoch) {
+                ok = true;
+                break;
+            }
+            __nanosleep(spins < 1024 ? 32 : 1000);
+        }
+    }
+    if (!ok && err) atomicCAS(err, 0u, err_code);
+}
+__global__ void comm_signal_kernel(unsigned long long *flag, unsigned long long epoch) {
+    __threadfence_system();  // the table stores of the kernels before this one are visible system-wide first
+    st_release_sys(flag, epoch);
+}
+void launch_comm_wait(const unsigned long long *flags, uint32_t n, unsigned long long epoch, uint32_t *err, uint32_t err_code, cudaStream_t s) {
+    comm_wait_kernel<<<1, 32, 0, s>>>(flags, n, epoch, err, err_code);
+}
+void launch_comm_signal(unsigned long long *flag, unsigned long long epoch, cudaStream_t s) { comm_signal_kernel<<<1, 1, 0, s>>>(flag, epoch); }
+void launch_select_rows(const SelectParams &p, cudaStream_t s) {
+    FinalizeParams none;
+    memset(&none, 0, sizeof none);
+    select_rows_kernel<false><<<1, 1024, 0, s>>>(p, none);
+}
+// finalisation + row selection: one launch for up to kFusedFinalizeGroups groups, two beyond
+uint32_t launch_finalize_select(const FinalizeParams &fp, const SelectParams &p, cudaStream_t s) {
+    if (fp.n_groups <= kFusedFinalizeGroups) {
+        select_rows_kernel<true><<<1, 1024, 0, s>>>(p, fp);
+        return 1;
+    }
+    launch_finalize(fp, s);
+    launch_select_rows(p, s);
+    return 2;
+}
 void launch_finalize(const FinalizeParams &p, cudaStream_t s) {
     const int threads = 128;
     const int n = p.n_groups > 0 ? p.n_groups : 1;

@@ -39,6 +39,7 @@ enum DevErr : uint32_t {
     kErrOverlap = 8,        // same series in several parts with overlapping time spans: needs version dedup
     kErrPredType = 9,       // predicate literal type does not match the stored tag column type
     kErrTmaTimeout = 10,    // a bulk copy never completed (internal error)
+    kErrPeerTimeout = 11,   // multi-GPU reduce: a peer rank never delivered its partial table / never freed the slot
 };
 
 struct DevPartRef {
@@ -160,9 +161,16 @@ struct SelectParams {
     uint32_t *sel_count;
 };
 void launch_select_rows(const SelectParams &p, cudaStream_t s);
+constexpr int kFusedFinalizeGroups = 8192;  // up to here one CTA finalises and selects in a single launch
+struct FinalizeParams;
+uint32_t launch_finalize_select(const FinalizeParams &fp, const SelectParams &p, cudaStream_t s);  // -> kernels launched
 // combines n partial tables (each `words` 8-byte words, laid out back to back) into the first one, rank order
 void launch_combine_tables(uint64_t *tables, uint32_t n_tables, uint64_t words, uint64_t sum_f64_lo, uint64_t sum_f64_hi, uint64_t max_f64_lo,
-                           uint64_t max_f64_hi, uint64_t sum_i64_lo, uint64_t sum_i64_hi, uint64_t max_i64_lo, uint64_t max_i64_hi, cudaStream_t s);
+                           uint64_t max_f64_hi, uint64_t sum_i64_lo, uint64_t sum_i64_hi, uint64_t max_i64_lo, uint64_t max_i64_hi, cudaStream_t s,
+                           uint64_t stride_words = 0);
+// peer-mailbox reduce (bydb_comm_*): bounded wait for n epoch flags, release-store of one
+void launch_comm_wait(const unsigned long long *flags, uint32_t n, unsigned long long epoch, uint32_t *err, uint32_t err_code, cudaStream_t s);
+void launch_comm_signal(unsigned long long *flag, unsigned long long epoch, cudaStream_t s);
 
 // ---- fallback-page normalisation at part admission (unpack_kernels.cu)
 constexpr uint8_t kEncRawCells = 0x40;   // numeric page rewritten as [0x40][has_nulls][6 pad][n x u64 LE][n x u8 valid]

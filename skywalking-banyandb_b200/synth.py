@@ -138,14 +138,14 @@ def write_part(series_ids, timestamps, versions, fields: Sequence[tuple], tag_fa
 
 def synth_part(n_series: int, n_points: int, fields: Sequence[Tuple[str, int]], sid0: int = 1, sid_step: int = 1,
                t0: int = 1_700_000_000_000_000_000, t_step: int = 60_000_000_000, region_values: int = 0, region_run: int = 0,
-               code_tag: bool = False, seed: int = 0xB200, threads: int = 0) -> PartImage:
+               code_tag: bool = False, seed: int = 0xB200, threads: int = 0, zone_tag: bool = False) -> PartImage:
     keep = []
     fa = (_SynthField * max(len(fields), 1))()
     for i, (name, kind) in enumerate(fields):
         nb = name.encode()
         keep.append(nb)
         fa[i].name, fa[i].kind = nb, kind
-    sp = _SynthSpec(n_series, n_points, sid0, sid_step, t0, t_step, len(fields), fa, region_values, region_run, int(code_tag), threads, seed)
+    sp = _SynthSpec(n_series, n_points, sid0, sid_step, t0, t_step, len(fields), fa, region_values, region_run, int(bool(code_tag)) | (2 if zone_tag else 0), threads, seed)
     out = C.c_void_p()
     rc = _lib().bydb_synth_part(C.byref(sp), C.byref(out))
     if rc != 0:

@@ -118,6 +118,9 @@ int main() {
         double total_n = 0;
         for (size_t r = 0; r < rows.size(); ++r) {
             CHECK(rows[r].first == first_seen[r], "group order = first appearance in scan order");
+            if (rows[r].second[1] != 3 * 400.0 || rows[r].second.size() != 3)
+                std::printf("row %zu (%s): %zu values: sum %.17g count %.17g mean %.17g\n", r, rows[r].first.c_str(), rows[r].second.size(), rows[r].second[0],
+                            rows[r].second.size() > 1 ? rows[r].second[1] : -1.0, rows[r].second.size() > 2 ? rows[r].second[2] : -1.0);
             CHECK(rows[r].second[1] == 3 * 400.0, "count per service");
             const double mean = rows[r].second[0] / rows[r].second[1];
             CHECK(rows[r].second[2] == (mean < 1 ? 1.0 : mean), "MEAN = sum/count with the <1 -> 1 rule");

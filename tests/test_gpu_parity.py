@@ -845,3 +845,205 @@ def test_prepared_query_graph_replay_equals_scan_agg(bydb, gpu_ctx):
             g.close()
     finally:
         gpu_ctx.release_part(h)
+
+
+def _c5_part(bydb, n_series, n_points, sid0=1):
+    """BASELINE configs[4] shape: 4 int64 fields (monotone delta / small fluctuations / random < 100 / counter with
+    resets) + 4 float64 fields, two dictionary string tags and one int64 tag, from the product's synthetic generator."""
+    from importlib import import_module
+    S = import_module("bydb_b200.synth")
+    fields = [("i_delta", S.I_DELTA), ("i_fluct", S.I_FLUCT), ("i_rand", S.I_RANDOM100), ("i_counter", S.I_COUNTER),
+              ("latency", S.F_LATENCY), ("walk", S.F_WALK3), ("ints", S.F_INT1000), ("f_lat2", S.F_LATENCY)]
+    return S.synth_part(n_series, n_points, fields, sid0=sid0, t0=T0, t_step=STEP, region_values=8, region_run=16, code_tag=True, zone_tag=True, seed=0xC5)
+
+
+def test_c5_shape_three_conjunctive_predicates_eight_fields(bydb, gpu_ctx):
+    # 1e6 datapoints, 8-field mixed int64 + float64 measure, region == "r3" AND zone != "z1" AND code >= 200 AND time range;
+    # every aggregation function the reference has (pkg/query/aggregation/aggregation.go:63-82: there is no percentile) over the 8 fields
+    n_series, n_points = 100, 10_000
+    img = _c5_part(bydb, n_series, n_points)
+    files = {k: v.tobytes() for k, v in img.files().items()}
+    part = O.Part.open(files)
+    usid = np.arange(1, n_series + 1, dtype=np.uint64)
+    groups = ((usid - 1) % 10).astype(np.int32)
+    names = ["i_delta", "i_fluct", "i_rand", "i_counter", "latency", "walk", "ints", "f_lat2"]
+    preds = [O.Pred("default", "region", O.OP_EQ, b"r3"), O.Pred("default", "zone", O.OP_NE, b"z1"), O.Pred("default", "code", O.OP_GE, 200)]
+    tmin, tmax = T0 + (n_points // 4) * STEP, T0 + (3 * n_points // 4) * STEP
+    for funcs in ([O.AGG_SUM, O.AGG_COUNT], [O.AGG_MIN, O.AGG_MAX], [O.AGG_MEAN]):
+        aggs = [(n, f) for n in names for f in funcs]
+        oq = O.Query([part], usid, aggs, groups=groups, n_groups=10, tmin=tmin, tmax=tmax, preds=preds)
+        h = gpu_ctx.register_part(_next_pid(), files)
+        try:
+            got = gpu_ctx.scan_agg(bydb.Query([h], usid, aggs, series_group=groups, n_groups=10, tmin=tmin, tmax=tmax,
+                                              preds=[bydb.Pred(p.family, p.tag, p.op, p.value) for p in preds]))
+        finally:
+            gpu_ctx.release_part(h)
+        want = O.run_query(oq)
+        assert_parity(got, want, aggs, f"C5/{funcs}")
+        assert got.stats.rows_matched == want.rows_matched and 0 < want.rows_matched < want.rows_scanned
+    # the same shape without predicates and over the full range: the all-rows sum path over delta and delta-of-delta pages
+    aggs = [(n, O.AGG_SUM) for n in names] + [("latency", O.AGG_COUNT)]
+    oq = O.Query([part], usid, aggs, groups=groups, n_groups=10)
+    h = gpu_ctx.register_part(_next_pid(), files)
+    try:
+        got = gpu_ctx.scan_agg(bydb.Query([h], usid, aggs, series_group=groups, n_groups=10))
+    finally:
+        gpu_ctx.release_part(h)
+    assert_parity(got, O.run_query(oq), aggs, "C5/all-rows sums")
+
+
+def test_hbm_budget_is_the_acquire_resource_mirror(bydb):
+    # banyand/measure/query.go:608-633: the reference refuses a query whose blocks exceed the protector's quota; the library's mirror is
+    # bydb_cfg.hbm_budget_bytes -> BYDB_ENOMEM at part admission (resident parts) and inside bydb_scan_agg_host (transient parts)
+    rng = np.random.default_rng(5)
+    sids, ts, ver = grid(8, 4000)
+    lat = np.round(rng.normal(30, 6, sids.size), 2)
+    part = build_part(sids, ts, ver, [("latency", O.VT_FLOAT64, lat, None)])
+    files = part.files()
+    size = sum(len(v) for v in files.values())
+    q = lambda h: bydb.Query(h, np.unique(sids), [("latency", O.AGG_SUM)])  # noqa: E731
+    with bydb.Context(device=0, hbm_budget_bytes=size // 2) as small:
+        with pytest.raises(bydb.BydbError) as ei:
+            small.register_part(1, files)
+        assert ei.value.code == bydb.capi.ENOMEM and "budget" in ei.value.msg
+        with pytest.raises(bydb.BydbError) as ei:
+            small.scan_agg_host([files], q([]))
+        assert ei.value.code == bydb.capi.ENOMEM
+    with bydb.Context(device=0, hbm_budget_bytes=4 * size + (1 << 20)) as roomy:
+        h1 = roomy.register_part(1, files)
+        info = roomy.part_info(h1)
+        assert 0 < info["hbm_bytes"] <= 4 * size + (1 << 20)
+        want = roomy.scan_agg(q([h1]))
+        # the budget is an account, not a high-water mark: releasing gives the bytes back, and a failed admission leaves nothing behind
+        for i in range(6):
+            h2 = roomy.register_part(100 + i, files)
+            roomy.release_part(h2)
+        got = roomy.scan_agg_host([files], q([]))
+        assert got.val_f64.tolist() == want.val_f64.tolist()
+        h3 = roomy.register_part(2, files)
+        with pytest.raises(bydb.BydbError) as ei:
+            for i in range(8):
+                roomy.register_part(200 + i, files)
+        assert ei.value.code == bydb.capi.ENOMEM
+        assert roomy.scan_agg(q([h1, ])).val_f64.tolist() == want.val_f64.tolist()
+        roomy.release_part(h3)
+
+
+def _comm_pair(bydb, n_ranks, devices):
+    """n contexts (one per rank) with their mailboxes connected; same process, so the handles carry plain pointers."""
+    ctxs = [bydb.Context(device=d) for d in devices]
+    handles = [c.comm_export(1 << 20, n_ranks) for c in ctxs]
+    for r, c in enumerate(ctxs):
+        c.comm_connect(r, n_ranks, handles)
+    return ctxs
+
+
+def test_scan_reduce_peer_mailboxes_equal_the_single_context_answer(bydb, gpu_ctx):
+    # bydb_comm_export / _connect / bydb_scan_reduce: the series of one measure sharded over R ranks (R contexts; on a one-GPU box
+    # they share the device, on a multi-GPU box each takes its own), every rank scans its shard and writes its partial table into
+    # the root's mailbox, the root combines in rank order and finalises -- the liaison reduce of measure_plan_aggregation.go:96-124.
+    # Must equal one context scanning everything, for grouped Top-N, MEAN / MIN / MAX finalisation and a rank without matching rows.
+    import threading
+    import torch
+    n_dev = torch.cuda.device_count()
+    rng = np.random.default_rng(314)
+    R = 3
+    sids, ts, ver = grid(30, 2600)
+    lat = np.round(rng.normal(30, 6, sids.size), 2)
+    calls = rng.integers(-50, 500, sids.size)
+    region = [b"r%d" % v for v in rng.integers(0, 4, sids.size)]
+    usid = np.unique(sids)
+    shard_of = (np.arange(usid.size) * R) // usid.size
+    parts = []
+    for r in range(R):
+        m = np.isin(sids, usid[shard_of == r])
+        parts.append(build_part(sids[m], ts[m], ver[m], [("latency", O.VT_FLOAT64, lat[m], None), ("calls", O.VT_INT64, calls[m], None)],
+                                [("default", [("region", O.VT_STR, [x for x, k in zip(region, m) if k], None)])]))
+    groups = (np.arange(usid.size) % 7).astype(np.int32)
+    queries = [
+        dict(aggs=[("latency", O.AGG_SUM), ("latency", O.AGG_COUNT)], top_n=3, top_agg=0, top_desc=True),
+        dict(aggs=[("latency", O.AGG_MEAN), ("calls", O.AGG_MIN), ("calls", O.AGG_MAX), ("latency", O.AGG_MAX), ("calls", O.AGG_MEAN)],
+             preds=[bydb.Pred("default", "region", O.OP_EQ, b"r2")], tmin=T0 + 200 * STEP, tmax=T0 + 2300 * STEP),
+        dict(aggs=[("calls", O.AGG_SUM)], tmin=T0 + 10 * STEP, tmax=T0 + 20 * STEP),
+    ]
+    whole = [gpu_ctx.register_part(_next_pid(), p.files()) for p in parts]
+    ctxs = _comm_pair(bydb, R, [r % n_dev for r in range(R)])
+    try:
+        hs = [c.register_part(1, p.files()) for c, p in zip(ctxs, parts)]
+        for root in (0, 2):
+            for kw in queries:
+                want = gpu_ctx.scan_agg(bydb.Query(whole, usid, series_group=groups, n_groups=7, **kw))
+                got, errs = [None] * R, []
+
+                def run(r):
+                    try:
+                        mine = shard_of == r
+                        got[r] = ctxs[r].scan_reduce(bydb.Query([hs[r]], usid[mine], series_group=groups[mine], n_groups=7, **kw), root=root)
+                    except Exception as e:  # noqa: BLE001
+                        errs.append(repr(e))
+                th = [threading.Thread(target=run, args=(r,)) for r in range(R)]
+                for t in th:
+                    t.start()
+                for t in th:
+                    t.join()
+                assert not errs, errs
+                g = got[root]
+                assert g.group_id.tolist() == want.group_id.tolist() and g.rows.tolist() == want.rows.tolist()
+                assert g.val_i64.tolist() == want.val_i64.tolist()
+                assert np.allclose(g.val_f64, want.val_f64, rtol=1e-12, atol=0)
+                for r in range(R):
+                    if r != root:
+                        assert got[r].group_id.size == 0 and got[r].stats.blocks_scanned > 0
+        # the same collective with HOST file images on every rank (bydb_scan_reduce_host: the cold distributed query, end to end)
+        kw = queries[1]
+        want = gpu_ctx.scan_agg(bydb.Query(whole, usid, series_group=groups, n_groups=7, **kw))
+        got, errs = [None] * R, []
+
+        def run_host(r):
+            try:
+                mine = shard_of == r
+                got[r] = ctxs[r].scan_reduce_host([parts[r].files()], bydb.Query([], usid[mine], series_group=groups[mine], n_groups=7, **kw), root=1)
+            except Exception as e:  # noqa: BLE001
+                errs.append(repr(e))
+        th = [threading.Thread(target=run_host, args=(r,)) for r in range(R)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not errs, errs
+        assert got[1].group_id.tolist() == want.group_id.tolist() and got[1].val_i64.tolist() == want.val_i64.tolist()
+        assert np.allclose(got[1].val_f64, want.val_f64, rtol=1e-12, atol=0) and got[1].stats.h2d_bytes > 0
+        # a device-side failure on ONE rank (predicate literal of the wrong type) fails the root's call with that error
+        res = [None] * R
+
+        def run_bad(r):
+            preds = [bydb.Pred("default", "region", O.OP_EQ, 5)] if r == 1 else []
+            mine = shard_of == r
+            try:
+                ctxs[r].scan_reduce(bydb.Query([hs[r]], usid[mine], [("calls", O.AGG_SUM)], preds=preds), root=0)
+                res[r] = 0
+            except bydb.BydbError as e:
+                res[r] = e.code
+        th = [threading.Thread(target=run_bad, args=(r,)) for r in range(R)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert res[0] == -22 and res[1] == -22 and res[2] == 0, res
+        # and the mailboxes stay usable afterwards
+        got = [None] * R
+
+        def run_ok(r):
+            mine = shard_of == r
+            got[r] = ctxs[r].scan_reduce(bydb.Query([hs[r]], usid[mine], [("calls", O.AGG_SUM)]), root=0)
+        th = [threading.Thread(target=run_ok, args=(r,)) for r in range(R)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert int(got[0].val_i64[0, 0]) == int(calls.sum())
+    finally:
+        for c in ctxs:
+            c.close()
+        for h in whole:
+            gpu_ctx.release_part(h)
