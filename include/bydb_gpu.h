@@ -226,6 +226,27 @@ int bydb_partials_combine(bydb_ctx *ctx, const bydb_query *q, void *d_tables, ui
 /* Finalize a (reduced) partial table: MEAN finalisation, output typing, Top-N; copies the result to host. */
 int bydb_reduce_finalize(bydb_ctx *ctx, const bydb_query *q, const void *d_partials, uint64_t bytes, void *stream, bydb_result *out);
 
+/* Map-phase rows in the reference's wire shape (a18 / f3): what a data node answers when the liaison asks for partials
+ * (InternalQueryRequest.agg_return_partial -> mapAccumulator.Result with emitPartial, measure_plan_aggregation.go:67-84;
+ * aggregation.PartialToFieldValues, pkg/query/aggregation/aggregation.go:128-145).  One row per group that appeared; aggregate a
+ * carries Partial.Value -- SUM: the sum, COUNT: the count, MAX / MIN: the extreme (the N-typed sentinel when no value was
+ * folded, aggregation.go:169-191), MEAN: the SUM -- and, for MEAN only, Partial.Count, which the Go side ships as the extra
+ * field "__agg_count".  Everything is typed like the FIELD (the row path is N-typed: the count over a float64 field is a
+ * float64; function.go:20-236).  The liaison's reduceAccumulator.Combine consumes exactly these pairs. */
+typedef struct {
+    int32_t n_rows;
+    int32_t n_aggs;
+    const int32_t *group_id;  /* [n_rows]                                             */
+    const uint8_t *is_float;  /* [n_aggs] N of aggregate a = its field's type         */
+    const int64_t *val_i64;   /* [n_rows * n_aggs] Partial.Value when !is_float[a]    */
+    const double *val_f64;    /* [n_rows * n_aggs] Partial.Value when  is_float[a]    */
+    const int64_t *cnt_i64;   /* [n_rows * n_aggs] Partial.Count (MEAN only, else 0)  */
+    const double *cnt_f64;
+    void *owner;              /* private                                              */
+} bydb_partial_rows;
+int bydb_partials_rows(bydb_ctx *ctx, const bydb_query *q, const void *d_partials, uint64_t bytes, void *stream, bydb_partial_rows *out);
+void bydb_partial_rows_free(bydb_ctx *ctx, bydb_partial_rows *r);
+
 /* ---- multi-GPU reduce behind the C ABI: one process (or thread) per GPU, no torch, no NCCL ----
  * Replaces the liaison gather + reduceAccumulator.Combine (pkg/query/logical/measure/measure_plan_aggregation.go:96-124,
  * measure_plan_distributed.go:254-328) inside one node: every rank owns a MAILBOX in its GPU's memory; in a collective

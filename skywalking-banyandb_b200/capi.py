@@ -69,6 +69,12 @@ class _Result(C.Structure):
                 ("owner", C.c_void_p)]
 
 
+class _PartialRows(C.Structure):
+    _fields_ = [("n_rows", C.c_int32), ("n_aggs", C.c_int32), ("group_id", C.POINTER(C.c_int32)), ("is_float", C.POINTER(C.c_uint8)),
+                ("val_i64", C.POINTER(C.c_int64)), ("val_f64", C.POINTER(C.c_double)), ("cnt_i64", C.POINTER(C.c_int64)),
+                ("cnt_f64", C.POINTER(C.c_double)), ("owner", C.c_void_p)]
+
+
 class _Layout(C.Structure):
     _fields_ = [("total_bytes", C.c_uint64), ("off_sum_f64", C.c_uint64), ("off_max_f64", C.c_uint64),
                 ("off_sum_i64", C.c_uint64), ("off_max_i64", C.c_uint64), ("n_sum_f64", C.c_uint64),
@@ -79,7 +85,7 @@ class _Layout(C.Structure):
 EXPORTS = ["bydb_init", "bydb_shutdown", "bydb_part_register", "bydb_part_release", "bydb_part_info", "bydb_part_fallback_pages",
            "bydb_scan_agg", "bydb_scan_agg_host", "bydb_result_free", "bydb_query_prepare", "bydb_scan_agg_prepared",
            "bydb_query_release", "bydb_partials_layout",
-           "bydb_scan_partials", "bydb_partials_combine", "bydb_reduce_finalize", "bydb_comm_export", "bydb_comm_connect",
+           "bydb_scan_partials", "bydb_partials_combine", "bydb_reduce_finalize", "bydb_partials_rows", "bydb_partial_rows_free", "bydb_comm_export", "bydb_comm_connect",
            "bydb_scan_reduce", "bydb_scan_reduce_host", "bydb_last_error", "bydb_version"]
 
 _lib = None
@@ -119,6 +125,9 @@ def load_library():
     L.bydb_scan_partials.argtypes = [C.c_void_p, C.POINTER(_Query), C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(_Stats)]
     L.bydb_partials_combine.argtypes = [C.c_void_p, C.POINTER(_Query), C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p]
     L.bydb_reduce_finalize.argtypes = [C.c_void_p, C.POINTER(_Query), C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(_Result)]
+    L.bydb_partials_rows.argtypes = [C.c_void_p, C.POINTER(_Query), C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(_PartialRows)]
+    L.bydb_partial_rows_free.argtypes = [C.c_void_p, C.POINTER(_PartialRows)]
+    L.bydb_partial_rows_free.restype = None
     L.bydb_comm_export.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p]
     L.bydb_comm_connect.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     L.bydb_scan_reduce.argtypes = [C.c_void_p, C.POINTER(_Query), C.c_int32, C.POINTER(_Result)]
@@ -412,6 +421,21 @@ class Context:
         st = _Stats()
         _check(self._L.bydb_scan_partials(self._h, C.byref(cq), d_ptr, nbytes, stream or None, C.byref(st)))
         return Stats.of(st)
+
+    def partials_rows(self, q, d_ptr: int, nbytes: int, stream: int = 0) -> Dict[str, np.ndarray]:
+        """Map-phase rows of a partial table in the reference's wire shape (emitPartial): per group and aggregate
+        Partial.Value (+ Partial.Count for MEAN), typed like the field."""
+        cq, keep = _cq(q)
+        r = _PartialRows()
+        _check(self._L.bydb_partials_rows(self._h, C.byref(cq), d_ptr, nbytes, stream or None, C.byref(r)))
+        try:
+            n, a = r.n_rows, r.n_aggs
+            f = lambda ptr, cnt, dt: np.array(ptr[:cnt], dtype=dt)  # noqa: E731
+            return dict(group_id=f(r.group_id, n, np.int32), is_float=f(r.is_float, a, np.uint8).astype(bool),
+                        val_i64=f(r.val_i64, n * a, np.int64).reshape(n, a), val_f64=f(r.val_f64, n * a, np.float64).reshape(n, a),
+                        cnt_i64=f(r.cnt_i64, n * a, np.int64).reshape(n, a), cnt_f64=f(r.cnt_f64, n * a, np.float64).reshape(n, a))
+        finally:
+            self._L.bydb_partial_rows_free(self._h, C.byref(r))
 
     # ---- multi-GPU reduce behind the C ABI (peer mailboxes over NVLink; no torch / NCCL on the data path)
     def comm_export(self, max_table_bytes: int, max_ranks: int) -> bytes:

@@ -1593,6 +1593,82 @@ int bydb_scan_agg_prepared(bydb_ctx *ctx, bydb_prepared *p, bydb_result *out) {
 }
 
 
+struct PartialRowsOwner {
+    std::vector<int32_t> group_id;
+    std::vector<uint8_t> is_float;
+    std::vector<int64_t> val_i64, cnt_i64;
+    std::vector<double> val_f64, cnt_f64;
+};
+
+int bydb_partials_rows(bydb_ctx *ctx, const bydb_query *q, const void *d_partials, uint64_t bytes, void *stream, bydb_partial_rows *out) {
+    return guarded([&]() -> int {
+    if (!ctx || !d_partials || !out) return fail(BYDB_EINVAL, "NULL argument");
+    memset(out, 0, sizeof *out);
+    int rc = validate_query(q, false);
+    if (rc) return rc;
+    std::vector<std::string> fcols;
+    std::vector<int> agg_fcol;
+    distinct_fields(q, fcols, agg_fcol);
+    const size_t G = static_cast<size_t>(q->series_group ? q->n_groups : 1), F = fcols.size(), A = q->n_aggs;
+    TableLayout tl(G, F);
+    if (bytes < tl.total) return fail(BYDB_EINVAL, "partial table buffer too small");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    std::vector<uint8_t> h(tl.total);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), d_partials, tl.total, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    const double *sum_f = reinterpret_cast<const double *>(h.data() + tl.off_sum_f64), *max_f = reinterpret_cast<const double *>(h.data() + tl.off_max_f64),
+                 *negmin_f = reinterpret_cast<const double *>(h.data() + tl.off_negmin_f64);
+    const int64_t *sum_i = reinterpret_cast<const int64_t *>(h.data() + tl.off_sum_i64), *cnt = reinterpret_cast<const int64_t *>(h.data() + tl.off_cnt),
+                  *rows = reinterpret_cast<const int64_t *>(h.data() + tl.off_rows), *max_i = reinterpret_cast<const int64_t *>(h.data() + tl.off_max_i64),
+                  *notmin_i = reinterpret_cast<const int64_t *>(h.data() + tl.off_notmin_i64), *coltype = reinterpret_cast<const int64_t *>(h.data() + tl.off_coltype);
+    uint32_t dev_err = 0;
+    for (size_t c = 0; c < F; ++c) dev_err = std::max(dev_err, static_cast<uint32_t>(coltype[c] >> 8));
+    if (dev_err) return fail(dev_err_code(dev_err), std::string(dev_err_text(dev_err)) + " (status carried in a partial table)");
+    auto owner = std::make_unique<PartialRowsOwner>();
+    owner->is_float.resize(A);
+    for (size_t a = 0; a < A; ++a) owner->is_float[a] = (coltype[agg_fcol[a]] & 0xff) == BYDB_VT_FLOAT64 ? 1 : 0;
+    for (size_t g = 0; g < G; ++g) {
+        if (rows[g] <= 0) continue;  // the group never appeared on this node
+        owner->group_id.push_back(static_cast<int32_t>(g));
+        for (size_t a = 0; a < A; ++a) {
+            const size_t o = g * F + static_cast<size_t>(agg_fcol[a]);
+            const bool isf = owner->is_float[a] != 0;
+            const int64_t n = cnt[o];
+            int64_t vi = 0, ci = 0;
+            double vf = 0.0, cf = 0.0;
+            switch (q->aggs[a].func) {
+                case BYDB_AGG_SUM: vi = sum_i[o]; vf = sum_f[o]; break;
+                case BYDB_AGG_COUNT: vi = n; vf = static_cast<double>(n); break;
+                case BYDB_AGG_MAX: vi = n > 0 ? max_i[o] : INT64_MIN; vf = n > 0 ? max_f[o] : -1.7976931348623157e308; break;
+                case BYDB_AGG_MIN: vi = n > 0 ? ~notmin_i[o] : INT64_MAX; vf = n > 0 ? -negmin_f[o] : 1.7976931348623157e308; break;
+                case BYDB_AGG_MEAN: vi = sum_i[o]; vf = sum_f[o]; ci = n; cf = static_cast<double>(n); break;
+            }
+            owner->val_i64.push_back(isf ? 0 : vi);
+            owner->val_f64.push_back(isf ? vf : 0.0);
+            owner->cnt_i64.push_back(isf ? 0 : ci);
+            owner->cnt_f64.push_back(isf ? cf : 0.0);
+        }
+    }
+    out->n_rows = static_cast<int32_t>(owner->group_id.size());
+    out->n_aggs = static_cast<int32_t>(A);
+    out->group_id = owner->group_id.data();
+    out->is_float = owner->is_float.data();
+    out->val_i64 = owner->val_i64.data();
+    out->val_f64 = owner->val_f64.data();
+    out->cnt_i64 = owner->cnt_i64.data();
+    out->cnt_f64 = owner->cnt_f64.data();
+    out->owner = owner.release();
+    return 0;
+    });
+}
+
+void bydb_partial_rows_free(bydb_ctx *, bydb_partial_rows *r) {
+    if (!r) return;
+    delete static_cast<PartialRowsOwner *>(r->owner);
+    memset(r, 0, sizeof *r);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Multi-GPU reduce behind the C ABI: peer mailboxes over NVLink (see scan_kernels.cu, comm_*_kernel)
 // ------------------------------------------------------------------------------------------------

@@ -1047,3 +1047,79 @@ def test_scan_reduce_peer_mailboxes_equal_the_single_context_answer(bydb, gpu_ct
             c.close()
         for h in whole:
             gpu_ctx.release_part(h)
+
+
+def test_partial_rows_in_the_reference_wire_shape(bydb, gpu_ctx):
+    # a18 / f3: bydb_partials_rows turns a data node's partial table into the rows mapAccumulator.Result(emitPartial) ships
+    # (Partial.Value, + Partial.Count as "__agg_count" for MEAN; everything N-typed by the field, function.go:42-44,91-93,129-131,
+    # 169-171,211-213).  Two "data nodes" (two shards of the series); the liaison's reduceAccumulator.Combine + Val()
+    # (function.go:57-71,104-110,142-148,182-190,224-232), restated here in a few lines, must reproduce the oracle's whole-query answer.
+    import torch
+    rng = np.random.default_rng(2718)
+    sids, ts, ver = grid(24, 1500)
+    lat = np.round(rng.normal(0.4, 0.3, sids.size), 2)        # means below 1: the MEAN clamp of function.go:31-40 matters
+    calls = rng.integers(-20, 90, sids.size)
+    usid = np.unique(sids)
+    groups = (np.arange(usid.size) % 5).astype(np.int32)
+    aggs = [("latency", O.AGG_MEAN), ("latency", O.AGG_COUNT), ("latency", O.AGG_MAX), ("calls", O.AGG_MEAN), ("calls", O.AGG_MIN), ("calls", O.AGG_SUM),
+            ("calls", O.AGG_COUNT), ("latency", O.AGG_SUM), ("latency", O.AGG_MIN), ("calls", O.AGG_MAX)]
+    shards = [usid[:9], usid[9:]]     # group 4 has no series in ... both shards hold every group; a time range empties some
+    tmin, tmax = T0 + 100 * STEP, T0 + 1200 * STEP
+    whole = build_part(sids, ts, ver, [("latency", O.VT_FLOAT64, lat, None), ("calls", O.VT_INT64, calls, None)])
+    want = O.run_query(O.Query([whole], usid, aggs, groups=groups, n_groups=5, tmin=tmin, tmax=tmax))
+    node_rows = []
+    for sh in shards:
+        m = np.isin(sids, sh)
+        part = build_part(sids[m], ts[m], ver[m], [("latency", O.VT_FLOAT64, lat[m], None), ("calls", O.VT_INT64, calls[m], None)])
+        h = gpu_ctx.register_part(_next_pid(), part.files())
+        try:
+            q = bydb.Query([h], sh, aggs, series_group=groups[np.isin(usid, sh)], n_groups=5, tmin=tmin, tmax=tmax)
+            lay = gpu_ctx.partials_layout(q)
+            table = torch.zeros(lay["total_bytes"] // 8, dtype=torch.float64, device="cuda")
+            gpu_ctx.scan_partials(q, table.data_ptr(), lay["total_bytes"], torch.cuda.current_stream().cuda_stream)
+            rows = gpu_ctx.partials_rows(q, table.data_ptr(), lay["total_bytes"], torch.cuda.current_stream().cuda_stream)
+            # the map rows of one node against the oracle run on that node's part alone: Value / Count per function
+            own = O.run_query(O.Query([part], sh, [(f, fn) for f, _ in aggs for fn in (O.AGG_SUM, O.AGG_COUNT, O.AGG_MAX, O.AGG_MIN)], groups=groups[np.isin(usid, sh)],
+                                      n_groups=5, tmin=tmin, tmax=tmax))
+            assert rows["group_id"].tolist() == own.group_id.tolist()
+            assert rows["is_float"].tolist() == [f == "latency" for f, _ in aggs]     # N-typed: COUNT over a float field is a float
+            for a, (f, fn) in enumerate(aggs):
+                isf = f == "latency"
+                got_v = rows["val_f64"][:, a] if isf else rows["val_i64"][:, a]
+                got_c = rows["cnt_f64"][:, a] if isf else rows["cnt_i64"][:, a]
+                o_sum = own.val_f64[:, 4 * a] if isf else own.val_i64[:, 4 * a]
+                o_cnt, o_max, o_min = own.val_i64[:, 4 * a + 1], (own.val_f64 if isf else own.val_i64)[:, 4 * a + 2], (own.val_f64 if isf else own.val_i64)[:, 4 * a + 3]
+                exp_v = {O.AGG_SUM: o_sum, O.AGG_MEAN: o_sum, O.AGG_COUNT: o_cnt.astype(got_v.dtype), O.AGG_MAX: o_max, O.AGG_MIN: o_min}[fn]
+                if isf and fn in (O.AGG_SUM, O.AGG_MEAN):
+                    assert np.allclose(got_v, exp_v, rtol=1e-9, atol=0), (a, got_v, exp_v)
+                else:
+                    assert got_v.tolist() == exp_v.tolist(), (a, got_v, exp_v)
+                assert got_c.tolist() == (o_cnt.astype(got_c.dtype).tolist() if fn == O.AGG_MEAN else [0] * len(got_c)), a
+            node_rows.append(rows)
+        finally:
+            gpu_ctx.release_part(h)
+    # liaison: reduceAccumulator.Combine over the nodes' rows, then Val()
+    for gi, g in enumerate(want.group_id.tolist()):
+        for a, (f, fn) in enumerate(aggs):
+            isf = f == "latency"
+            parts = []
+            for rows in node_rows:
+                k = np.nonzero(rows["group_id"] == g)[0]
+                if k.size:
+                    parts.append(((rows["val_f64"] if isf else rows["val_i64"])[k[0], a].item(), (rows["cnt_f64"] if isf else rows["cnt_i64"])[k[0], a].item()))
+            assert parts
+            if fn == O.AGG_MEAN:
+                s_, c_ = sum(p[0] for p in parts), sum(p[1] for p in parts)
+                val = 0 if c_ == 0 else (s_ / c_ if isf else int(s_ / c_))
+                val = 1 if (c_ != 0 and val < 1) else val
+            elif fn in (O.AGG_SUM, O.AGG_COUNT):
+                val = sum(p[0] for p in parts)
+            elif fn == O.AGG_MAX:
+                val = max(p[0] for p in parts)
+            else:
+                val = min(p[0] for p in parts)
+            ref = want.val_f64[gi, a] if want.is_float[a] else want.val_i64[gi, a]
+            if isf and fn in (O.AGG_SUM, O.AGG_MEAN):
+                assert abs(val - ref) <= 1e-9 * max(abs(ref), 1e-300), (g, a, val, ref)
+            else:
+                assert val == ref, (g, a, fn, val, ref)     # COUNT over a float field: 1380.0 == 1380 (vec types it int64, the row path float)
