@@ -22,3 +22,20 @@ def test_c_caller_links_and_runs(tmp_path, bydb):
     import torch
     if not torch.cuda.is_available():
         assert "init refused" in out.stdout
+
+
+@pytest.mark.gpu
+def test_multi_process_reduce_without_torch(tmp_path, bydb):
+    """tests/native/comm_ranks.c: one process per rank, mailbox handles over a pipe, bydb_scan_reduce with rotating roots, checked
+    against a single context scanning all shards.  One device: the ranks share it (CUDA IPC works within a device); more: round-robin."""
+    import torch
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    lib_dir = os.path.dirname(bydb.library_path())
+    exe = tmp_path / "comm_ranks"
+    subprocess.check_call(["gcc", "-std=c99", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe),
+                           os.path.join(ROOT, "tests", "native", "comm_ranks.c"), "-L", lib_dir, "-lbydbgpu", "-lm", "-Wl,-rpath," + lib_dir])
+    ndev = max(1, torch.cuda.device_count())
+    for nranks in sorted({2, min(4, max(2, ndev))}):
+        out = subprocess.run([str(exe), str(nranks), str(ndev)], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
