@@ -544,13 +544,14 @@ def main():
         try:
             if world > 1:
                 raise RuntimeError("single-GPU leg")
-            staged, _ = e2e_leg(0, 2, files)
+            staged, _ = e2e_leg(0, 3, files)
             staged["pinned_by_caller"] = False
-            staged["note"] = ("bydb_scan_agg_host without the zero-copy flag on PAGEABLE images: every file of the part is copied to HBM "
-                              "(cudaMemcpyAsync from pageable memory), scanned, result copied back")
-            e2e["unpinned_staged_upload"] = staged
+            staged["note"] = ("bydb_scan_agg_host on PAGEABLE images (not pinned by the caller, like BanyanDB's mmap'd part files): the block index "
+                              "is parsed, the host selects the blocks and gathers only the pages the query reads into a pinned staging ring "
+                              "(64 MB chunks, worker pool), asynchronous copies, scan, result copied back")
+            e2e["unpinned_gather"] = staged
         except Exception as ex:  # noqa: BLE001
-            e2e["unpinned_staged_upload"] = {"error": str(ex)[:200]}
+            e2e["unpinned_gather"] = {"error": str(ex)[:200]}
         del pinned, keep_pinned
 
     clocks = None

@@ -1123,3 +1123,36 @@ def test_partial_rows_in_the_reference_wire_shape(bydb, gpu_ctx):
                 assert abs(val - ref) <= 1e-9 * max(abs(ref), 1e-300), (g, a, val, ref)
             else:
                 assert val == ref, (g, a, fn, val, ref)     # COUNT over a float field: 1380.0 == 1380 (vec types it int64, the row path float)
+
+
+def test_gather_path_for_pageable_host_images(bydb, gpu_ctx):
+    # bydb_scan_agg_host on PAGEABLE images (BanyanDB's mmap'd part files are not pinned): the host selects the blocks like plan_blocks
+    # and stages only the pages the query reads, in 64 MB chunks through a pinned ring.  3e7 datapoints x 2 touched fields = more
+    # than one chunk; a series subset + time range + predicate exercises the block selection and the rewritten page offsets.
+    from importlib import import_module
+    S = import_module("bydb_b200.synth")
+    n_series, n_points = 300, 100_000
+    img = S.synth_part(n_series, n_points, [("latency", S.F_LATENCY), ("walk", S.F_WALK3), ("ints", S.F_INT1000)], sid0=1, t0=T0, t_step=STEP,
+                       region_values=8, region_run=16, seed=0x6A7)
+    files = img.files()
+    usid = np.arange(1, n_series + 1, dtype=np.uint64)
+    groups = ((usid - 1) % 11).astype(np.int32)
+    h = gpu_ctx.register_part(_next_pid(), files)
+    try:
+        cases = [
+            dict(series=usid, kw=dict(aggs=[("latency", O.AGG_SUM), ("walk", O.AGG_MAX), ("latency", O.AGG_COUNT)], series_group=groups, n_groups=11)),
+            dict(series=usid[5::3], kw=dict(aggs=[("walk", O.AGG_MEAN), ("ints", O.AGG_MIN)], series_group=groups[5::3], n_groups=11,
+                                            tmin=T0 + 20_000 * STEP + 7, tmax=T0 + 71_234 * STEP, preds=[bydb.Pred("default", "region", O.OP_NE, b"r5")])),
+            dict(series=np.array([400, 500], dtype=np.uint64), kw=dict(aggs=[("latency", O.AGG_SUM)])),   # selects nothing at all
+        ]
+        for c in cases:
+            want = gpu_ctx.scan_agg(bydb.Query([h], c["series"], **c["kw"]))
+            got = gpu_ctx.scan_agg_host([files], bydb.Query([], c["series"], **c["kw"]))
+            assert got.group_id.tolist() == want.group_id.tolist() and got.rows.tolist() == want.rows.tolist()
+            assert got.is_float.tolist() == want.is_float.tolist() and got.val_i64.tolist() == want.val_i64.tolist()
+            assert np.allclose(got.val_f64, want.val_f64, rtol=1e-12, atol=0)
+            assert got.stats.rows_scanned == want.stats.rows_scanned and got.stats.page_bytes == want.stats.page_bytes
+            total = sum(v.size for v in files.values())
+            assert got.stats.h2d_bytes < 0.8 * total, "only the touched pages may travel"
+    finally:
+        gpu_ctx.release_part(h)
