@@ -105,6 +105,11 @@ typedef struct {
                                     16-byte aligned, with >= 64 readable bytes after each buffer; the kernels then read
                                     only the pages the query touches, in place over PCIe (no staging copy) */
 
+#define BYDB_Q_ROW_PATH_TYPES 2u /* result typing of the reference's ROW path (a14 / a15): every aggregate, COUNT included, is typed
+                                    like its field -- countFunc[N] is N-typed (pkg/query/aggregation/function.go:78-93,
+                                    measure_plan_aggregation.go:152-175), so the count over a float64 field comes back as a float64.
+                                    Default (flag clear) is the vectorized path's typing: COUNT is int64 (aggregation.go:425-430) */
+
 /* One query = selected series (+ their dense group ids) x parts x predicates x aggregations.
  * Mirrors model.MeasureQueryOptions (pkg/query/model/model.go:75-88) after series resolution:
  * series_ids is what searchSeriesList returned (ascending, query.go:601), series_group is the

@@ -167,6 +167,7 @@ class Query:
 
 
 Q_HOST_ZERO_COPY = 1
+Q_ROW_PATH_TYPES = 2
 
 
 @dataclass

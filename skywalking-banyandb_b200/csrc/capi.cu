@@ -804,6 +804,7 @@ int finalize_enqueue(const bydb_query *q, const Plan &plan, ExecSlot &slot, cuda
     fp.n_groups = G;
     fp.n_fcols = static_cast<uint32_t>(F);
     fp.n_aggs = static_cast<uint32_t>(A);
+    fp.row_path_types = (q->flags & BYDB_Q_ROW_PATH_TYPES) ? 1u : 0u;
     for (size_t a = 0; a < A; ++a) {
         fp.agg_fcol[a] = plan.agg_fcol[a];
         fp.agg_func[a] = q->aggs[a].func;

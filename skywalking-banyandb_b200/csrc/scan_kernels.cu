@@ -2101,7 +2101,7 @@ __global__ void __launch_bounds__(256) group_reduce_kernel(const __grid_constant
 // finalisation: pkg/query/aggregation/function.go Val() + output typing aggregation.go:425-430
 __device__ __forceinline__ void finalize_header(const FinalizeParams &p) {
     for (uint32_t a = 0; a < p.n_aggs; ++a)
-        p.out_is_float[a] = (p.agg_func[a] != BYDB_AGG_COUNT && (p.coltype[p.agg_fcol[a]] & 0xff) == BYDB_VT_FLOAT64) ? 1 : 0;
+        p.out_is_float[a] = ((p.agg_func[a] != BYDB_AGG_COUNT || p.row_path_types) && (p.coltype[p.agg_fcol[a]] & 0xff) == BYDB_VT_FLOAT64) ? 1 : 0;
     uint32_t e = 0;
     for (uint32_t c = 0; c < p.n_fcols; ++c) {
         const uint32_t ec = static_cast<uint32_t>(p.coltype[c] >> 8);
@@ -2122,6 +2122,7 @@ __device__ __forceinline__ void finalize_group(const FinalizeParams &p, int32_t 
         if (typ != 0) {
             if (fn == BYDB_AGG_COUNT) {
                 vi = cnt;
+                if (p.row_path_types && typ == BYDB_VT_FLOAT64) vf = __ll2double_rn(cnt);  // countFunc[float64], function.go:78-93
             } else if (typ == BYDB_VT_FLOAT64) {
                 switch (fn) {
                     case BYDB_AGG_SUM: vf = p.sum_f64[o]; break;

@@ -131,7 +131,7 @@ struct FinalizeParams {
     int32_t n_groups;
     uint32_t n_fcols;
     uint32_t n_aggs;
-    uint32_t pad;
+    uint32_t row_path_types;      // 1 = COUNT is typed like its field (the row path's N-typed countFunc) instead of int64
     int32_t agg_fcol[32];
     int32_t agg_func[32];
     const double *sum_f64, *max_f64, *negmin_f64;

@@ -1156,3 +1156,25 @@ def test_gather_path_for_pageable_host_images(bydb, gpu_ctx):
             assert got.stats.h2d_bytes < 0.8 * total, "only the touched pages may travel"
     finally:
         gpu_ctx.release_part(h)
+
+
+def test_row_path_result_typing_flag(bydb, gpu_ctx):
+    # a14 / a15: the reference's ROW path types every aggregate like its field -- countFunc[N] is N-typed (function.go:78-93,
+    # measure_plan_aggregation.go:152-175): COUNT over a float64 field is a float64; the vectorized path types COUNT int64
+    # (aggregation.go:425-430, the default here).  BYDB_Q_ROW_PATH_TYPES selects the former; values are the same numbers.
+    from bydb_b200.capi import Q_ROW_PATH_TYPES
+    rng = np.random.default_rng(99)
+    sids, ts, ver = grid(6, 700)
+    lat = np.round(rng.normal(30, 6, sids.size), 2)
+    calls = rng.integers(0, 50, sids.size)
+    part = build_part(sids, ts, ver, [("latency", O.VT_FLOAT64, lat, None), ("calls", O.VT_INT64, calls, None)])
+    h = gpu_ctx.register_part(_next_pid(), part.files())
+    try:
+        aggs = [("latency", O.AGG_COUNT), ("calls", O.AGG_COUNT), ("latency", O.AGG_MEAN), ("calls", O.AGG_SUM)]
+        vec = gpu_ctx.scan_agg(bydb.Query([h], np.unique(sids), aggs))
+        row = gpu_ctx.scan_agg(bydb.Query([h], np.unique(sids), aggs, flags=Q_ROW_PATH_TYPES))
+        assert vec.is_float.tolist() == [False, False, True, False] and row.is_float.tolist() == [True, False, True, False]
+        assert float(row.val_f64[0, 0]) == float(vec.val_i64[0, 0]) == sids.size
+        assert row.val_i64[0, 1] == vec.val_i64[0, 1] and row.val_f64[0, 2] == vec.val_f64[0, 2] and row.val_i64[0, 3] == vec.val_i64[0, 3]
+    finally:
+        gpu_ctx.release_part(h)
