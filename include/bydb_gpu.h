@@ -67,9 +67,12 @@ typedef struct {
     int32_t device;            /* CUDA device ordinal                                    */
     int32_t warps_per_sm;      /* scan workers per SM; 0 = default (16)                  */
     uint64_t hbm_budget_bytes; /* cap on resident part bytes; 0 = no cap                 */
-    uint32_t flags;            /* reserved, 0                                            */
+    uint32_t flags;            /* BYDB_CFG_*                                             */
     uint32_t reserved;
 } bydb_cfg;
+#define BYDB_CFG_HOST_INDEX 1u /* bydb_part_register: parse the block index (meta.bin / primary.bin / *.tfm) on the host instead of
+                                  with the device kernels (the default; both build the same directory -- the host parser is what
+                                  the cold host-buffer paths use, where one frame's latency matters more than throughput) */
 
 /* One file image of a part (banyand/measure/part.go:40-55).  name is one of "meta.bin",
  * "primary.bin", "timestamps.bin", "fv.bin", "<family>.tf", "<family>.tfm". */
@@ -178,6 +181,11 @@ int bydb_part_info(bydb_ctx *ctx, bydb_part_h part, uint64_t *hbm_bytes, uint64_
  * 291-304): `unpacked` were rewritten into scan-friendly pages in HBM when the part was registered, `left` could
  * not be (a query that touches one of those returns BYDB_ENOTSUP). */
 int bydb_part_fallback_pages(bydb_ctx *ctx, bydb_part_h part, uint64_t *unpacked, uint64_t *left);
+/* Diagnostics: copies the part's DEVICE block directory (the DevBlock[64 B] / DevCol[16 B] records the scan kernels read,
+ * csrc/part_dir.hpp) into caller buffers; either pointer may be NULL to only query the counts.  Tests compare the directory the
+ * device index kernels build with the host parser's. */
+int bydb_part_directory(bydb_ctx *ctx, bydb_part_h part, void *blocks_out, uint64_t blocks_cap_bytes, void *cols_out, uint64_t cols_cap_bytes,
+                        uint64_t *n_blocks, uint64_t *n_cols);
 
 /* Scan -> filter -> aggregate over parts already resident in HBM. */
 int bydb_scan_agg(bydb_ctx *ctx, const bydb_query *q, bydb_result *out);

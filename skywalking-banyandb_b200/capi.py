@@ -82,7 +82,7 @@ class _Layout(C.Structure):
 
 
 # every symbol include/bydb_gpu.h declares (tests/test_capi_symbols.py checks the list against the header)
-EXPORTS = ["bydb_init", "bydb_shutdown", "bydb_part_register", "bydb_part_release", "bydb_part_info", "bydb_part_fallback_pages",
+EXPORTS = ["bydb_init", "bydb_shutdown", "bydb_part_register", "bydb_part_release", "bydb_part_info", "bydb_part_fallback_pages", "bydb_part_directory",
            "bydb_scan_agg", "bydb_scan_agg_host", "bydb_result_free", "bydb_query_prepare", "bydb_scan_agg_prepared",
            "bydb_query_release", "bydb_partials_layout",
            "bydb_scan_partials", "bydb_partials_combine", "bydb_reduce_finalize", "bydb_partials_rows", "bydb_partial_rows_free", "bydb_comm_export", "bydb_comm_connect",
@@ -114,6 +114,7 @@ def load_library():
     L.bydb_part_release.argtypes = [C.c_void_p, C.c_uint64]
     L.bydb_part_info.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.bydb_part_fallback_pages.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.bydb_part_directory.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.bydb_scan_agg.argtypes = [C.c_void_p, C.POINTER(_Query), C.POINTER(_Result)]
     L.bydb_scan_agg_host.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_PartFiles), C.POINTER(_Query), C.POINTER(_Result)]
     L.bydb_result_free.argtypes = [C.c_void_p, C.POINTER(_Result)]
@@ -331,9 +332,9 @@ class GraphQuery:
 class Context:
     """bydb_ctx: one device, its streams and the HBM part cache."""
 
-    def __init__(self, device: int = 0, warps_per_sm: int = 0, hbm_budget_bytes: int = 0):
+    def __init__(self, device: int = 0, warps_per_sm: int = 0, hbm_budget_bytes: int = 0, host_index: bool = False):
         self._L = load_library()
-        cfg = _Cfg(device, warps_per_sm, hbm_budget_bytes, 0, 0)
+        cfg = _Cfg(device, warps_per_sm, hbm_budget_bytes, 1 if host_index else 0, 0)
         h = C.c_void_p()
         _check(self._L.bydb_init(C.byref(cfg), C.byref(h)))
         self._h = h
@@ -369,6 +370,15 @@ class Context:
         u, l = C.c_uint64(), C.c_uint64()
         _check(self._L.bydb_part_fallback_pages(self._h, handle, C.byref(u), C.byref(l)))
         return dict(hbm_bytes=a.value, n_blocks=b.value, n_rows=c.value, fallback_unpacked=u.value, fallback_left=l.value)
+
+    def part_directory(self, handle: int):
+        """-> (blocks [n, 64] uint8, cols [n, 16] uint8): the part's device block directory, byte for byte (diagnostics)."""
+        nb, nc = C.c_uint64(), C.c_uint64()
+        _check(self._L.bydb_part_directory(self._h, handle, None, 0, None, 0, C.byref(nb), C.byref(nc)))
+        blocks = np.zeros((nb.value, 64), dtype=np.uint8)
+        cols = np.zeros((nc.value, 16), dtype=np.uint8)
+        _check(self._L.bydb_part_directory(self._h, handle, blocks.ctypes.data, blocks.nbytes, cols.ctypes.data, cols.nbytes, C.byref(nb), C.byref(nc)))
+        return blocks, cols
 
     # ---- queries
     def prepare(self, q: Query) -> PreparedQuery:

@@ -23,6 +23,7 @@
 #include "../../include/bydb_gpu.h"
 #include "part_dir.hpp"
 #include "scan_kernels.cuh"
+#include "index_kernels.cuh"
 
 using namespace bydb;
 
@@ -193,6 +194,7 @@ struct bydb_ctx {
     int ctas_per_sm_fast = 2;  // fast lane
     uint64_t hbm_budget = 0;
     uint64_t hbm_used = 0;
+    bool host_index = false;   // BYDB_CFG_HOST_INDEX: parse the block index of resident parts on the host (part_dir.cc)
     std::mutex mu;
     NameTable names;
     std::unordered_map<bydb_part_h, std::shared_ptr<Part>> parts;
@@ -343,10 +345,12 @@ struct TableLayout {
 // zero_copy: the data files stay in (pinned, device-mapped) host memory and the kernels read the
 // pages they need straight over PCIe; only the block directory is uploaded.
 int unpack_fallback_pages(bydb_ctx *ctx, Part &part, size_t n_files, cudaStream_t s);
+int build_part_dir_device(bydb_ctx *ctx, const std::vector<FileImage> &imgs, Part &part, const std::vector<std::string> &families, cudaStream_t s, size_t n_files,
+                          size_t *dir_bytes_out);
 
 int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_files *files, std::shared_ptr<Part> &out, uint64_t *h2d,
                               bool zero_copy = false, bool transient = false, size_t batch = 0, size_t n_batches = 1, bool unpack = false,
-                              PartDir *parsed = nullptr) {
+                              PartDir *parsed = nullptr, bool device_index = false) {
     if (!files || files->n_files == 0 || !files->files) return fail(BYDB_EINVAL, "no files");
     std::vector<FileImage> imgs;
     for (uint32_t i = 0; i < files->n_files; ++i) {
@@ -358,7 +362,17 @@ int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_f
     part->id = part_id;
     part->device = ctx->device;
     std::string err;
-    if (parsed) {
+    // resident parts: the block index is inflated and parsed by kernels (index_kernels.cu); the host only decides the file table
+    const bool dev_index = device_index && !parsed && n_batches == 1 && !zero_copy;
+    std::vector<std::string> families;
+    if (dev_index) {
+        for (const auto &f : imgs)
+            if (f.name.size() > 4 && f.name.compare(f.name.size() - 4, 4, ".tfm") == 0) families.push_back(f.name.substr(0, f.name.size() - 4));
+        std::sort(families.begin(), families.end());
+        if (families.size() > 250) return fail(BYDB_EINVAL, "too many tag family files");
+        part->dir.files = {"timestamps.bin", "fv.bin"};
+        for (const auto &fam : families) part->dir.files.push_back(fam + ".tf");
+    } else if (parsed) {
         part->dir = std::move(*parsed);  // the caller parsed this slice of the block index already (cold path, in the background)
     } else {
         int rc = build_part_dir(imgs, ctx->names, part->dir, err, batch, n_batches);
@@ -392,7 +406,7 @@ int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_f
         arena = 0;
     }
     const size_t nb = part->dir.blocks.size(), nc = part->dir.cols.size(), nf = order.size();
-    const size_t dir_bytes = align_up(nb * sizeof(DevBlock), 256) + align_up(nc * sizeof(DevCol), 256) + align_up((nf + 1) * sizeof(void *), 256);
+    const size_t dir_bytes = dev_index ? 0 : align_up(nb * sizeof(DevBlock), 256) + align_up(nc * sizeof(DevCol), 256) + align_up((nf + 1) * sizeof(void *), 256);
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         if (ctx->hbm_budget && ctx->hbm_used + arena + dir_bytes > ctx->hbm_budget) return fail(BYDB_ENOMEM, "HBM budget exceeded");
@@ -413,10 +427,10 @@ int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_f
     if (transient) {
         part->pool_stream = s;
         alloc_ok = cudaMallocAsync(reinterpret_cast<void **>(&part->d_arena), arena ? arena : 256, s) == cudaSuccess &&
-                   cudaMallocAsync(reinterpret_cast<void **>(&part->d_dir), dir_bytes ? dir_bytes : 256, s) == cudaSuccess;
+                   (dev_index || cudaMallocAsync(reinterpret_cast<void **>(&part->d_dir), dir_bytes ? dir_bytes : 256, s) == cudaSuccess);
     } else {
         alloc_ok = cudaMalloc(reinterpret_cast<void **>(&part->d_arena), arena ? arena : 256) == cudaSuccess &&
-                   cudaMalloc(reinterpret_cast<void **>(&part->d_dir), dir_bytes ? dir_bytes : 256) == cudaSuccess;
+                   (dev_index || cudaMalloc(reinterpret_cast<void **>(&part->d_dir), dir_bytes ? dir_bytes : 256) == cudaSuccess);
     }
     if (!alloc_ok) {
         undo_budget();
@@ -427,6 +441,38 @@ int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_f
         e = cudaMemsetAsync(part->d_arena, 0, arena ? arena : 256, s);
         for (size_t i = 0; i < nf && e == cudaSuccess; ++i)
             if (order[i]->len) e = cudaMemcpyAsync(part->d_arena + offs[i], order[i]->data, order[i]->len, cudaMemcpyHostToDevice, s);
+    }
+    if (dev_index) {
+        if (e != cudaSuccess) {
+            undo_budget();
+            return fail(BYDB_EIO, std::string("part upload: ") + cudaGetErrorString(e));
+        }
+        size_t dbytes = 0;
+        int rc = build_part_dir_device(ctx, imgs, *part, families, s, nf, &dbytes);
+        std::vector<const uint8_t *> table(nf + 1, nullptr);
+        for (size_t i = 0; i < nf; ++i) table[i] = part->d_arena + offs[i];
+        if (!rc && cudaMemcpyAsync(const_cast<uint8_t **>(reinterpret_cast<const uint8_t *const *>(part->d_files)), table.data(), nf * sizeof(void *),
+                                   cudaMemcpyHostToDevice, s) != cudaSuccess)
+            rc = fail(BYDB_EIO, "part upload: file table");
+        if (!rc && cudaStreamSynchronize(s) != cudaSuccess) rc = fail(BYDB_EIO, "part upload: synchronize");
+        if (rc) {
+            cudaStreamSynchronize(s);
+            undo_budget();
+            return rc;
+        }
+        if (h2d) {
+            for (size_t i = 0; i < nf; ++i) *h2d += order[i]->len;
+            *h2d += dbytes;
+        }
+        if (unpack) {
+            rc = unpack_fallback_pages(ctx, *part, nf, s);
+            if (rc) {
+                undo_budget();
+                return rc;
+            }
+        }
+        out = part;
+        return 0;
     }
     // directory
     if (lease.slot->ensure_pinned(dir_bytes ? dir_bytes : 256)) {
@@ -464,6 +510,205 @@ int register_part_locked_free(bydb_ctx *ctx, uint64_t part_id, const bydb_part_f
         }
     }
     out = part;
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Block index on the device (index_kernels.cu): meta.bin / primary.bin / *.tfm go up as they are, the zstd frames are
+// inflated and the blockMetadata records walked by kernels; the host only sizes the buffers between the phases and maps
+// the handful of interned column names to the context's ids.  Fills part.dir (host copy of the directory) and writes
+// DevBlock[] / DevCol[] straight into the part's device directory.
+// ------------------------------------------------------------------------------------------------
+struct DevTmp {
+    uint8_t *p = nullptr;
+    cudaStream_t s = nullptr;
+    ~DevTmp() {
+        if (p) cudaFreeAsync(p, s);
+    }
+    int alloc(size_t n, cudaStream_t st) {
+        s = st;
+        return cudaMallocAsync(reinterpret_cast<void **>(&p), n ? n : 256, st) == cudaSuccess ? 0 : -1;
+    }
+};
+
+const char *index_err_text(uint32_t e) {
+    switch (e) {
+        case kIdxBadMeta: return "meta.bin: not a zstd frame of 40-byte primaryBlockMetadata records in order inside primary.bin";
+        case kIdxBadFrame: return "primary block does not inflate to its declared size";
+        case kIdxBadBlock: return "corrupt blockMetadata";
+        case kIdxBadEnc: return "unexpected timestamps encode type";
+        case kIdxBadColumn: return "corrupt columnMetadata";
+        case kIdxFamily: return "tag family: missing or truncated .tf/.tfm";
+        case kIdxOrder: return "blockMetadata out of order";
+        case kIdxNames: return "too many / too long column names for the device index";
+        case kIdxTooManyFamilies: return "more than 16 tag families in a block";
+    }
+    return "block index error";
+}
+
+// files: the part's file table (timestamps.bin, fv.bin, <family>.tf ...) is already decided by the caller; d_dir_* are
+// allocated here once the counts are known.
+int build_part_dir_device(bydb_ctx *ctx, const std::vector<FileImage> &imgs, Part &part, const std::vector<std::string> &families, cudaStream_t s,
+                          size_t n_files, size_t *dir_bytes_out) {
+    auto find = [&](const std::string &name) -> const FileImage * {
+        for (const auto &f : imgs)
+            if (f.name == name) return &f;
+        return nullptr;
+    };
+    const FileImage *meta = find("meta.bin"), *primary = find("primary.bin"), *tsf = find("timestamps.bin"), *fvf = find("fv.bin");
+    if (!meta || !primary || !tsf || !fvf) return fail(BYDB_ENOENT, "part needs meta.bin, primary.bin, timestamps.bin and fv.bin");
+    // ---- the index files go up verbatim: [meta | primary | tfm ... | family names]
+    std::vector<const FileImage *> tfm(families.size()), tf(families.size());
+    size_t up = align_up(meta->len, 256) + align_up(primary->len, 256);
+    const size_t off_primary = align_up(meta->len, 256);
+    std::vector<size_t> off_tfm(families.size()), off_name(families.size());
+    for (size_t i = 0; i < families.size(); ++i) {
+        tfm[i] = find(families[i] + ".tfm");
+        tf[i] = find(families[i] + ".tf");
+        if (!tfm[i] || !tf[i]) return fail(BYDB_EINVAL, "tag family '" + families[i] + "': missing .tf/.tfm");
+        off_tfm[i] = up;
+        up += align_up(tfm[i]->len, 256);
+    }
+    for (size_t i = 0; i < families.size(); ++i) {
+        off_name[i] = up;
+        up += align_up(families[i].size(), 16);
+    }
+    const size_t off_fams = align_up(up, 256);
+    up = off_fams + align_up(families.size() * sizeof(IndexFamily), 256);
+    const size_t off_ctl = up;
+    up += 256;
+    const size_t off_names = up;
+    up += kIndexMaxNames * sizeof(IndexName);
+    const size_t off_map = up;
+    up += align_up(kIndexMaxNames * sizeof(uint16_t), 256);
+    DevTmp in;
+    if (in.alloc(up, s)) return fail(BYDB_ENOMEM, "device allocation failed (index files)");
+    CUDA_TRY(cudaMemsetAsync(in.p + off_ctl, 0, 256 + kIndexMaxNames * sizeof(IndexName), s));
+    if (meta->len) CUDA_TRY(cudaMemcpyAsync(in.p, meta->data, meta->len, cudaMemcpyHostToDevice, s));
+    if (primary->len) CUDA_TRY(cudaMemcpyAsync(in.p + off_primary, primary->data, primary->len, cudaMemcpyHostToDevice, s));
+    std::vector<IndexFamily> fams(families.size());
+    for (size_t i = 0; i < families.size(); ++i) {
+        if (tfm[i]->len) CUDA_TRY(cudaMemcpyAsync(in.p + off_tfm[i], tfm[i]->data, tfm[i]->len, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(in.p + off_name[i], families[i].data(), families[i].size(), cudaMemcpyHostToDevice, s));
+        memset(&fams[i], 0, sizeof fams[i]);
+        fams[i].name = in.p + off_name[i];
+        fams[i].name_len = static_cast<uint32_t>(families[i].size());
+        fams[i].tfm = in.p + off_tfm[i];
+        fams[i].tfm_len = tfm[i]->len;
+        fams[i].tf_len = tf[i]->len;
+        fams[i].file_id = static_cast<uint8_t>(2 + i);
+    }
+    if (!fams.empty()) CUDA_TRY(cudaMemcpyAsync(in.p + off_fams, fams.data(), fams.size() * sizeof(IndexFamily), cudaMemcpyHostToDevice, s));
+    IndexCtl ctl0;
+    memset(&ctl0, 0, sizeof ctl0);
+    ctl0.min_ts = INT64_MAX;
+    ctl0.max_ts = INT64_MIN;
+    CUDA_TRY(cudaMemcpyAsync(in.p + off_ctl, &ctl0, sizeof ctl0, cudaMemcpyHostToDevice, s));
+    IndexParams ip;
+    memset(&ip, 0, sizeof ip);
+    ip.meta = in.p;
+    ip.primary = in.p + off_primary;
+    ip.meta_len = meta->len;
+    ip.primary_len = primary->len;
+    ip.ts_len = tsf->len;
+    ip.fv_len = fvf->len;
+    ip.n_families = static_cast<uint32_t>(families.size());
+    ip.families = reinterpret_cast<const IndexFamily *>(in.p + off_fams);
+    ip.ctl = reinterpret_cast<IndexCtl *>(in.p + off_ctl);
+    ip.names = reinterpret_cast<IndexName *>(in.p + off_names);
+    ip.name_map = reinterpret_cast<const uint16_t *>(in.p + off_map);
+    IndexCtl ctl;
+    auto read_ctl = [&]() -> int {
+        CUDA_TRY(cudaMemcpyAsync(&ctl, in.p + off_ctl, sizeof ctl, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (ctl.err) return fail(BYDB_EINVAL, "part " + std::to_string(part.id) + ": " + index_err_text(ctl.err) + " (#" + std::to_string(ctl.err_where) + ")");
+        return 0;
+    };
+    // ---- meta.bin: size, then inflate + the primary frames' sizes
+    DevTmp scratch0;
+    if (scratch0.alloc(index_scratch_stride(), s)) return fail(BYDB_ENOMEM, "device allocation failed (index scratch)");
+    ip.scratch = scratch0.p;
+    launch_index_meta(ip, 0, s);
+    int rc = read_ctl();
+    if (rc) return rc;
+    const size_t n_primary = static_cast<size_t>(ctl.meta_raw / 40);
+    DevTmp meta_raw, pbs;
+    if (meta_raw.alloc(ctl.meta_raw, s) || pbs.alloc(n_primary * sizeof(IndexPrimary), s)) return fail(BYDB_ENOMEM, "device allocation failed (index)");
+    CUDA_TRY(cudaMemsetAsync(pbs.p, 0, n_primary ? n_primary * sizeof(IndexPrimary) : 256, s));
+    ip.meta_raw = meta_raw.p;
+    ip.meta_raw_cap = ctl.meta_raw;
+    ip.pb = reinterpret_cast<IndexPrimary *>(pbs.p);
+    launch_index_meta(ip, 1, s);
+    rc = read_ctl();
+    if (rc) return rc;
+    // ---- primary blocks: inflate, count
+    ip.n_primary = static_cast<uint32_t>(n_primary);
+    DevTmp raw, scratch;
+    if (raw.alloc(ctl.raw_total + 256, s) || scratch.alloc(std::max<size_t>(1, n_primary) * index_scratch_stride(), s))
+        return fail(BYDB_ENOMEM, "device allocation failed (inflated index)");
+    ip.raw = raw.p;
+    ip.scratch = scratch.p;
+    launch_index_inflate(ip, s);
+    launch_index_walk(ip, false, s);
+    std::vector<IndexPrimary> hpb(n_primary);
+    std::vector<IndexName> hnames(kIndexMaxNames);
+    if (n_primary) CUDA_TRY(cudaMemcpyAsync(hpb.data(), pbs.p, n_primary * sizeof(IndexPrimary), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(hnames.data(), in.p + off_names, kIndexMaxNames * sizeof(IndexName), cudaMemcpyDeviceToHost, s));
+    rc = read_ctl();
+    if (rc) return rc;
+    uint64_t nb = 0, nc = 0;
+    for (auto &e : hpb) {
+        e.block_base = nb;
+        e.col_base = nc;
+        nb += e.n_blocks;
+        nc += e.n_cols;
+    }
+    if (nb > 0x7fffffffull || nc > 0xffffffffull) return fail(BYDB_EINVAL, "too many blocks / columns");
+    // ---- the interned names -> the context's ids (a few dozen short strings: the only index bytes the host looks at)
+    std::vector<uint16_t> map(kIndexMaxNames, 0);
+    for (uint32_t i = 0; i < ctl.n_names && i < kIndexMaxNames; ++i) {
+        const IndexName &e = hnames[i];
+        std::string key = e.kind == 'f' ? "f:" : "t:" + families[e.fam] + "/";
+        key.append(reinterpret_cast<const char *>(e.bytes), e.len);
+        map[i] = ctx->names.intern(key);
+    }
+    if (n_primary) CUDA_TRY(cudaMemcpyAsync(pbs.p, hpb.data(), n_primary * sizeof(IndexPrimary), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(in.p + off_map, map.data(), kIndexMaxNames * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+    // ---- the part's device directory, filled by the second walk
+    const size_t off_cols = align_up(nb * sizeof(DevBlock), 256);
+    const size_t off_files = off_cols + align_up(nc * sizeof(DevCol), 256);
+    const size_t dir_bytes = off_files + align_up((n_files + 1) * sizeof(void *), 256);
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ctx->hbm_budget && ctx->hbm_used + dir_bytes > ctx->hbm_budget) return fail(BYDB_ENOMEM, "HBM budget exceeded");
+        ctx->hbm_used += dir_bytes;
+    }
+    part.hbm_bytes += dir_bytes;
+    *dir_bytes_out = dir_bytes;
+    const cudaError_t ae = part.pool_stream ? cudaMallocAsync(reinterpret_cast<void **>(&part.d_dir), dir_bytes, s) : cudaMalloc(reinterpret_cast<void **>(&part.d_dir), dir_bytes);
+    if (ae != cudaSuccess) {
+        part.d_dir = nullptr;
+        return fail(BYDB_ENOMEM, "device allocation failed for the directory of part " + std::to_string(part.id));
+    }
+    ip.blocks = reinterpret_cast<DevBlock *>(part.d_dir);
+    ip.cols = reinterpret_cast<DevCol *>(part.d_dir + off_cols);
+    ip.n_blocks = nb;
+    launch_index_walk(ip, true, s);
+    launch_index_order(ip, s);
+    part.dir.blocks.resize(nb);
+    part.dir.cols.resize(nc);
+    if (nb) CUDA_TRY(cudaMemcpyAsync(part.dir.blocks.data(), ip.blocks, nb * sizeof(DevBlock), cudaMemcpyDeviceToHost, s));
+    if (nc) CUDA_TRY(cudaMemcpyAsync(part.dir.cols.data(), ip.cols, nc * sizeof(DevCol), cudaMemcpyDeviceToHost, s));
+    rc = read_ctl();
+    if (rc) return rc;
+    part.dir.total_rows = ctl.total_rows;
+    part.dir.max_block_rows = ctl.max_block_rows;
+    part.dir.min_ts = nb ? ctl.min_ts : 0;
+    part.dir.max_ts = nb ? ctl.max_ts : 0;
+    part.d_blocks = ip.blocks;
+    part.d_cols = ip.cols;
+    part.d_files = reinterpret_cast<const uint8_t *const *>(part.d_dir + off_files);
     return 0;
 }
 
@@ -1083,6 +1328,7 @@ int bydb_init(const bydb_cfg *cfg, bydb_ctx **out) {
     ctx->device = dev;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->hbm_budget = cfg ? cfg->hbm_budget_bytes : 0;
+    ctx->host_index = cfg && (cfg->flags & BYDB_CFG_HOST_INDEX) != 0;
     if (upload_pow10_table()) {
         delete ctx;
         return fail(BYDB_EIO, "cannot upload constant tables (is the library built for this GPU?)");
@@ -1143,7 +1389,7 @@ int bydb_part_register(bydb_ctx *ctx, uint64_t part_id, const bydb_part_files *f
     }
     CUDA_TRY(cudaSetDevice(ctx->device));
     std::shared_ptr<Part> part;
-    int rc = register_part_locked_free(ctx, part_id, files, part, nullptr, false, false, 0, 1, true);
+    int rc = register_part_locked_free(ctx, part_id, files, part, nullptr, false, false, 0, 1, true, nullptr, !ctx->host_index);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
     auto again = ctx->by_id.find(part_id);
@@ -1201,6 +1447,33 @@ int bydb_part_fallback_pages(bydb_ctx *ctx, bydb_part_h h, uint64_t *unpacked, u
     if (it == ctx->parts.end()) return fail(BYDB_ENOENT, "unknown part handle");
     if (unpacked) *unpacked = it->second->unpacked_pages;
     if (left) *left = it->second->unpack_skipped;
+    return 0;
+    });
+}
+
+int bydb_part_directory(bydb_ctx *ctx, bydb_part_h h, void *blocks_out, uint64_t blocks_cap_bytes, void *cols_out, uint64_t cols_cap_bytes, uint64_t *n_blocks,
+                        uint64_t *n_cols) {
+    return guarded([&]() -> int {
+    if (!ctx) return fail(BYDB_EINVAL, "ctx is NULL");
+    std::shared_ptr<Part> part;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        auto it = ctx->parts.find(h);
+        if (it == ctx->parts.end()) return fail(BYDB_ENOENT, "unknown part handle");
+        part = it->second;
+    }
+    const uint64_t nb = part->dir.blocks.size(), nc = part->dir.cols.size();
+    if (n_blocks) *n_blocks = nb;
+    if (n_cols) *n_cols = nc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (blocks_out) {
+        if (blocks_cap_bytes < nb * sizeof(DevBlock)) return fail(BYDB_EINVAL, "blocks buffer too small");
+        if (nb) CUDA_TRY(cudaMemcpy(blocks_out, part->d_blocks, nb * sizeof(DevBlock), cudaMemcpyDeviceToHost));
+    }
+    if (cols_out) {
+        if (cols_cap_bytes < nc * sizeof(DevCol)) return fail(BYDB_EINVAL, "cols buffer too small");
+        if (nc) CUDA_TRY(cudaMemcpy(cols_out, part->d_cols, nc * sizeof(DevCol), cudaMemcpyDeviceToHost));
+    }
     return 0;
     });
 }

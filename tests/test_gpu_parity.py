@@ -1178,3 +1178,64 @@ def test_row_path_result_typing_flag(bydb, gpu_ctx):
         assert row.val_i64[0, 1] == vec.val_i64[0, 1] and row.val_f64[0, 2] == vec.val_f64[0, 2] and row.val_i64[0, 3] == vec.val_i64[0, 3]
     finally:
         gpu_ctx.release_part(h)
+
+
+def test_block_index_decoded_on_the_device_equals_the_host_parser(bydb):
+    # f1: bydb_part_register inflates meta.bin / primary.bin with the device zstd decoder and walks the blockMetadata records in
+    # kernels (index_kernels.cu; part_iter.go:184-208, block_metadata.go:133-168, column_metadata.go:108-122, primary_metadata.go:47-83).
+    # The directory it builds must be the host parser's (csrc/part_dir.cc, BYDB_CFG_HOST_INDEX) byte for byte, up to the numbering
+    # of the interned column names (an arbitrary per-context id): many primary blocks, several tag columns, fallback pages, nulls.
+    from importlib import import_module
+    S = import_module("bydb_b200.synth")
+    rng = np.random.default_rng(1234)
+    parts = {}
+    parts["many primary blocks"] = S.synth_part(6000, 40, [("latency", S.F_LATENCY), ("calls", S.I_FLUCT)], sid0=7, sid_step=2, t0=T0, t_step=STEP,
+                                                region_values=8, region_run=4, code_tag=True, zone_tag=True, seed=5).files()
+    parts["eight fields, long blocks"] = _c5_part(bydb, 40, 20_000).files()
+    fb, _, _ = _fallback_part(rng, n_series=3)
+    parts["fallback pages"] = fb.files()
+    sids, ts, ver = grid(5, 300)
+    parts["no tags"] = build_part(sids, ts, ver, [("v", O.VT_INT64, rng.integers(0, 9, sids.size), None)]).files()
+    col_dt = np.dtype([("off", "<u8"), ("size", "<u4"), ("name_id", "<u2"), ("value_type", "u1"), ("file_id", "u1")])
+    with bydb.Context(device=0, host_index=True) as host, bydb.Context(device=0) as dev:
+        for name, files in parts.items():
+            hh, hd = host.register_part(1, files), dev.register_part(1, files)
+            try:
+                hb, hc = host.part_directory(hh)
+                db, dc = dev.part_directory(hd)
+                assert hb.shape == db.shape and hb.shape[0] > 0, name
+                assert (hb == db).all(), f"{name}: DevBlock records differ"
+                hcv, dcv = hc.view(col_dt).reshape(-1), dc.view(col_dt).reshape(-1)
+                for f in ("size", "value_type", "file_id"):
+                    assert (hcv[f] == dcv[f]).all(), f"{name}: DevCol.{f} differs"
+                # pages unpacked at admission live in a side arena whose slots are handed out by an atomic counter: their offsets are
+                # not reproducible from one registration to the next, everything else is
+                in_arena = (hcv["file_id"] == hcv["file_id"].max()) if host.part_info(hh)["fallback_unpacked"] else np.zeros(hcv.size, bool)
+                assert ((hcv["off"] == dcv["off"]) | in_arena).all(), f"{name}: DevCol.off differs"
+                pairs = set(zip(hcv["name_id"].tolist(), dcv["name_id"].tolist()))
+                assert len(pairs) == len({a for a, _ in pairs}) == len({b for _, b in pairs}), f"{name}: name ids are not a relabelling"
+                assert host.part_info(hh) == dev.part_info(hd), name
+                # and the scans agree
+                usid = np.unique(hb[:, :8].copy().view("<u8").reshape(-1))
+                fld = "latency" if name != "no tags" and name != "fallback pages" else ("v" if name == "no tags" else "calls")
+                q = lambda h: bydb.Query([h], usid, [(fld, O.AGG_SUM), (fld, O.AGG_MAX), (fld, O.AGG_COUNT)])  # noqa: E731
+                a, b = host.scan_agg(q(hh)), dev.scan_agg(q(hd))
+                assert a.val_i64.tolist() == b.val_i64.tolist() and a.val_f64.view(np.uint64).tolist() == b.val_f64.view(np.uint64).tolist(), name
+            finally:
+                host.release_part(hh)
+                dev.release_part(hd)
+        # a corrupt index fails on the device like on the host: truncated primary.bin, garbage meta.bin
+        files = dict(parts["no tags"])
+        bad = dict(files)
+        bad["primary.bin"] = bytes(files["primary.bin"])[:-7]
+        for ctx in (host, dev):
+            with pytest.raises(bydb.BydbError) as ei:
+                ctx.register_part(9, bad)
+            assert ei.value.code == -22
+        bad = dict(files)
+        bad["meta.bin"] = b"\x28\xb5\x2f\xfd" + bytes(20)
+        for ctx in (host, dev):
+            with pytest.raises(bydb.BydbError):
+                ctx.register_part(9, bad)
+            h = ctx.register_part(10, files)   # and the context is still usable
+            ctx.release_part(h)
