@@ -172,6 +172,7 @@ struct Comm {
     std::vector<bool> ipc_opened;
     std::vector<size_t> peer_slot_bytes;
     uint64_t epoch = 0;
+    std::vector<uint64_t> last_use;     // [root * 2 + parity] epoch of the previous collective that used that root's slots of that parity
     std::mutex mu;                      // collective calls are issued one at a time per context
 };
 
@@ -2238,6 +2239,7 @@ int bydb_comm_connect(bydb_ctx *ctx, int32_t rank, int32_t nranks, const bydb_co
     cm.rank = rank;
     cm.nranks = nranks;
     cm.epoch = 0;
+    cm.last_use.assign(2 * static_cast<size_t>(nranks), 0);
     return 0;
     });
 }
@@ -2280,8 +2282,11 @@ static int scan_reduce_impl(bydb_ctx *ctx, const bydb_query *q, const std::vecto
     }
     memset(&out->stats, 0, sizeof out->stats);
     out->stats.h2d_bytes = h2d_pre;
-    // the slot's previous use (epoch - 2) must have been consumed by the root before it is overwritten
-    if (epoch > 2) launch_comm_wait(done, 1, epoch - 2, my_err, kErrPeerTimeout, s);
+    // the slots' previous use -- the last collective with THIS root and parity, the same epoch on every rank -- must have been
+    // consumed by the root (its `done` word only ever grows) before they are overwritten
+    const uint64_t prev_use = cm.last_use[2 * static_cast<size_t>(root) + parity];
+    cm.last_use[2 * static_cast<size_t>(root) + parity] = epoch;
+    if (prev_use) launch_comm_wait(done, 1, prev_use, my_err, kErrPeerTimeout, s);
     // map: this rank's group_reduce writes the table straight into the root's memory (P2P stores over NVLink)
     if (!rc) rc = run_scan(ctx, q, plan, es, s, my_slot, tl, &out->stats);
     const std::string my_msg = rc ? g_last_error : std::string();

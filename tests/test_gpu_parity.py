@@ -909,10 +909,12 @@ def test_hbm_budget_is_the_acquire_resource_mirror(bydb):
         with pytest.raises(bydb.BydbError) as ei:
             small.scan_agg_host([files], q([]))
         assert ei.value.code == bydb.capi.ENOMEM
-    with bydb.Context(device=0, hbm_budget_bytes=4 * size + (1 << 20)) as roomy:
+    with bydb.Context(device=0) as probe:
+        per = probe.part_info(probe.register_part(1, files))["hbm_bytes"]     # what one resident copy of this part accounts for
+    with bydb.Context(device=0, hbm_budget_bytes=int(3.5 * per)) as roomy:
         h1 = roomy.register_part(1, files)
         info = roomy.part_info(h1)
-        assert 0 < info["hbm_bytes"] <= 4 * size + (1 << 20)
+        assert info["hbm_bytes"] == per
         want = roomy.scan_agg(q([h1]))
         # the budget is an account, not a high-water mark: releasing gives the bytes back, and a failed admission leaves nothing behind
         for i in range(6):
@@ -1079,8 +1081,13 @@ def test_partial_rows_in_the_reference_wire_shape(bydb, gpu_ctx):
             gpu_ctx.scan_partials(q, table.data_ptr(), lay["total_bytes"], torch.cuda.current_stream().cuda_stream)
             rows = gpu_ctx.partials_rows(q, table.data_ptr(), lay["total_bytes"], torch.cuda.current_stream().cuda_stream)
             # the map rows of one node against the oracle run on that node's part alone: Value / Count per function
-            own = O.run_query(O.Query([part], sh, [(f, fn) for f, _ in aggs for fn in (O.AGG_SUM, O.AGG_COUNT, O.AGG_MAX, O.AGG_MIN)], groups=groups[np.isin(usid, sh)],
-                                      n_groups=5, tmin=tmin, tmax=tmax))
+            own_parts = [O.run_query(O.Query([part], sh, [(f, fn) for fn in (O.AGG_SUM, O.AGG_COUNT, O.AGG_MAX, O.AGG_MIN)], groups=groups[np.isin(usid, sh)],
+                                             n_groups=5, tmin=tmin, tmax=tmax)) for f, _ in aggs]
+
+            class own:   # the per-aggregate oracle runs side by side: columns 4a .. 4a+3 belong to aggregate a
+                group_id = own_parts[0].group_id
+                val_i64 = np.concatenate([o.val_i64 for o in own_parts], axis=1)
+                val_f64 = np.concatenate([o.val_f64 for o in own_parts], axis=1)
             assert rows["group_id"].tolist() == own.group_id.tolist()
             assert rows["is_float"].tolist() == [f == "latency" for f, _ in aggs]     # N-typed: COUNT over a float field is a float
             for a, (f, fn) in enumerate(aggs):
