@@ -817,6 +817,7 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
     const size_t off_gstart = carve((static_cast<size_t>(G) + 1) * 4);
     const size_t off_worklist = carve(NB * 4);
     const size_t off_slowlist = carve(NB * 4);
+    const size_t off_restlist = carve(NB * 4);
     const size_t off_qsid = carve(NB * 4);
     const size_t off_P = carve(NB * F * sizeof(BlockPartial));
     const size_t off_Prows = carve(NB * 4);
@@ -967,6 +968,19 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
             extra_launches += 2;
         }
         rp.dedup_done = 1;
+    }
+    {
+        // express lane (scan_sum_express_kernel): all-rows SUM / MEAN / COUNT without row predicates or version dedup -- the
+        // group-by-sum shape; every block it cannot take (time-range cut, non-delta page, ...) goes on to the regular lane
+        bool sums_only = q->n_preds == 0 && !parts_overlap && NB > 0;
+        for (size_t c = 0; c < F; ++c) sums_only = sums_only && (sp.fcol_need[c] & 2) == 0;
+        static const bool no_express = getenv("BYDB_NO_EXPRESS") != nullptr;  // A/B timing of the two lanes
+        if (sums_only && !no_express) {
+            sp.rest_list = reinterpret_cast<uint32_t *>(d + off_restlist);
+            sp.rest_count = z32 + 30;  // bytes 120..127 of the zero page
+            sp.rest_next = z32 + 31;
+            if (stats) stats->kernel_launches += 1;
+        }
     }
     CUDA_TRY(cudaEventRecord(ev[1], stream));
     launch_scan_blocks(sp, ctx->sm_count * ctx->ctas_per_sm_fast, ctx->sm_count * ctx->ctas_per_sm, stream);

@@ -83,6 +83,9 @@ struct __align__(128) WarpSmem {
     int res_exp;                 // decimal exponent of the page just aggregated (kExpRawFloat for raw float cells)
     const uint8_t *a_page;       // arguments of agg_field_page
     uint32_t a_size, a_flags;    // a_flags: bit 0 = float64 field, bits 1.. = kNeed*
+    // the warp's statistics (lane 0 only), flushed to the query's counters once when the warp runs out of work
+    unsigned long long st_rows, st_matched, st_bytes;
+    uint32_t st_blocks, st_deferred, st_why, pad2;
 };
 
 size_t scan_smem_bytes() { return sizeof(WarpSmem) * kWarpsPerCta; }
@@ -680,6 +683,62 @@ __device__ __noinline__ int delta_page_fast(WarpSmem *sm, int lane) {
     return (row_base == count && carry_sh == 0) ? 0 : 2;
 }
 
+// One 1 KB chunk of a delta page through the SWAR lane decoder: loads the lane's 32 bytes from the staged tile, hands the
+// neighbour's last word on, and returns the lane's terminator count n, its byte-linear sums T / R' and the wide flag.
+// c: chunk index inside the page window; carry_w: the (masked) last word of the previous chunk, updated.
+struct SwarChunk {
+    int32_t T, Rp;
+    uint32_t n;
+    bool wide;
+};
+__device__ __forceinline__ SwarChunk swar_chunk(const uint8_t *buf, uint32_t c, uint32_t pstart, uint32_t pend, uint32_t total, uint32_t &carry_w, int lane) {
+    const uint32_t o = c * kFastChunkBytes + lane * kFastLaneBytes;
+    const bool interior = c * kFastChunkBytes >= pstart && (c + 1) * kFastChunkBytes <= pend;  // warp-uniform
+    SwarLane sl;
+    if (interior) {
+        const uint4 wa = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes));
+        const uint4 wb = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes) + 16);
+        uint32_t pw = __shfl_up_sync(0xffffffffu, wb.w, 1);
+        if (lane == 0) pw = carry_w;
+        carry_w = __shfl_sync(0xffffffffu, wb.w, 31);
+        swar_begin(sl, pw);
+        swar_word<false>(sl, wa.x, 0u);
+        swar_word<false>(sl, wa.y, 0u);
+        swar_word<false>(sl, wa.z, 0u);
+        swar_word<false>(sl, wa.w, 0u);
+        swar_word<false>(sl, wb.x, 0u);
+        swar_word<false>(sl, wb.y, 0u);
+        swar_word<false>(sl, wb.z, 0u);
+        swar_word<false>(sl, wb.w, 0u);
+    } else {
+        uint4 wa = make_uint4(0, 0, 0, 0), wb = make_uint4(0, 0, 0, 0);
+        if (o < total) wa = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes));
+        if (o + 16 < total) wb = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes) + 16);
+        int lo_i = static_cast<int>(pstart) - static_cast<int>(o);
+        int hi_i = static_cast<int>(pend) - static_cast<int>(o);
+        lo_i = lo_i < 0 ? 0 : (lo_i > 32 ? 32 : lo_i);
+        hi_i = hi_i < 0 ? 0 : (hi_i > 32 ? 32 : hi_i);
+        const uint32_t valid = low_bits(hi_i) & ~low_bits(lo_i);
+        const uint32_t mine = wb.w & expand4(valid >> 28);
+        uint32_t pw = __shfl_up_sync(0xffffffffu, mine, 1);
+        if (lane == 0) pw = carry_w;
+        carry_w = __shfl_sync(0xffffffffu, mine, 31);
+        swar_begin(sl, pw);
+        swar_word<true>(sl, wa.x, expand4(valid));
+        swar_word<true>(sl, wa.y, expand4(valid >> 4));
+        swar_word<true>(sl, wa.z, expand4(valid >> 8));
+        swar_word<true>(sl, wa.w, expand4(valid >> 12));
+        swar_word<true>(sl, wb.x, expand4(valid >> 16));
+        swar_word<true>(sl, wb.y, expand4(valid >> 20));
+        swar_word<true>(sl, wb.z, expand4(valid >> 24));
+        swar_word<true>(sl, wb.w, expand4(valid >> 28));
+    }
+    SwarChunk r;
+    r.wide = __any_sync(0xffffffffu, (sl.wide & 0x80808080u) != 0);
+    r.n = swar_end(sl, r.T, r.Rp);
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------
 // SWAR sum decoder: EncodeTypeDelta page, every row active, only SUM / MEAN / COUNT wanted (the group-by-sum shape of
 // BASELINE configs 3/4).  See lane_decode.cuh (swar_word): the page sum is a weighted sum over BYTES, so nothing is
@@ -712,56 +771,16 @@ __device__ __noinline__ int delta_page_sum_all(WarpSmem *sm, int lane) {
     for (uint32_t c = 0; c < nchunks; ++c) {
         const uint32_t k = c / kChunksPerStage;
         if ((c % kChunksPerStage) == 0) buf = stream_wait(st, sm, k);
-        const uint32_t o = c * kFastChunkBytes + lane * kFastLaneBytes;
-        const bool interior = c * kFastChunkBytes >= st.pstart && (c + 1) * kFastChunkBytes <= st.pend;  // warp-uniform
-        SwarLane sl;
-        if (interior) {
-            const uint4 wa = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes));
-            const uint4 wb = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes) + 16);
-            uint32_t pw = __shfl_up_sync(0xffffffffu, wb.w, 1);
-            if (lane == 0) pw = carry_w;
-            carry_w = __shfl_sync(0xffffffffu, wb.w, 31);
-            swar_begin(sl, pw);
-            swar_word<false>(sl, wa.x, 0u);
-            swar_word<false>(sl, wa.y, 0u);
-            swar_word<false>(sl, wa.z, 0u);
-            swar_word<false>(sl, wa.w, 0u);
-            swar_word<false>(sl, wb.x, 0u);
-            swar_word<false>(sl, wb.y, 0u);
-            swar_word<false>(sl, wb.z, 0u);
-            swar_word<false>(sl, wb.w, 0u);
-        } else {
-            uint4 wa = make_uint4(0, 0, 0, 0), wb = make_uint4(0, 0, 0, 0);
-            if (o < st.total) wa = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes));
-            if (o + 16 < st.total) wb = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes) + 16);
-            int lo_i = static_cast<int>(st.pstart) - static_cast<int>(o);
-            int hi_i = static_cast<int>(st.pend) - static_cast<int>(o);
-            lo_i = lo_i < 0 ? 0 : (lo_i > 32 ? 32 : lo_i);
-            hi_i = hi_i < 0 ? 0 : (hi_i > 32 ? 32 : hi_i);
-            const uint32_t valid = low_bits(hi_i) & ~low_bits(lo_i);
-            const uint32_t mine = wb.w & expand4(valid >> 28);
-            uint32_t pw = __shfl_up_sync(0xffffffffu, mine, 1);
-            if (lane == 0) pw = carry_w;
-            carry_w = __shfl_sync(0xffffffffu, mine, 31);
-            swar_begin(sl, pw);
-            swar_word<true>(sl, wa.x, expand4(valid));
-            swar_word<true>(sl, wa.y, expand4(valid >> 4));
-            swar_word<true>(sl, wa.z, expand4(valid >> 8));
-            swar_word<true>(sl, wa.w, expand4(valid >> 12));
-            swar_word<true>(sl, wb.x, expand4(valid >> 16));
-            swar_word<true>(sl, wb.y, expand4(valid >> 20));
-            swar_word<true>(sl, wb.z, expand4(valid >> 24));
-            swar_word<true>(sl, wb.w, expand4(valid >> 28));
-        }
-        if (__any_sync(0xffffffffu, (sl.wide & 0x80808080u) != 0)) {
+        const SwarChunk ch = swar_chunk(buf, c, st.pstart, st.pend, st.total, carry_w, lane);
+        if (ch.wide) {
             // a varint of four or more bytes: the general decoder takes the page (same bail-out as delta_page_fast)
             stream_drain(st, sm, k);
             if (lane == 0) sm->seq = st.seq0 + min(st.nstages, k + static_cast<uint32_t>(kStages));
             __syncwarp();
             return 1;
         }
-        int32_t T, Rp;
-        const uint32_t n = swar_end(sl, T, Rp);
+        const int32_t T = ch.T, Rp = ch.Rp;
+        const uint32_t n = ch.n;
         uint32_t n_in = n;
 #pragma unroll
         for (int sft = 1; sft < 32; sft <<= 1) {
@@ -1428,8 +1447,23 @@ __device__ __noinline__ uint32_t agg_field_page(WarpSmem *sm, int lane) {
     }
 }
 
+// The value type of aggregated field c must be the same in every block of the query (kErrTypeMix otherwise).  One global word
+// per field records it; `known` caches what this thread has already seen (4 bits per field), so the common case costs no
+// memory access at all -- a compare-and-swap per block on one hot address used to be a fifth of the kernel's stall samples
+// once the page decode got cheap (ncu r02b).  Returns false on a mismatch.
+__device__ __forceinline__ bool check_col_type(const ScanParams &p, uint32_t c, uint8_t vt, uint32_t &known) {
+    const uint32_t have = (known >> (4 * c)) & 0xfu;
+    if (have == vt) return true;
+    if (have != 0) return false;
+    int32_t old = __ldcg(&p.col_type[c]);
+    if (old == 0) old = atomicCAS(&p.col_type[c], 0, static_cast<int32_t>(vt));
+    if (old != 0 && old != static_cast<int32_t>(vt)) return false;
+    known |= static_cast<uint32_t>(vt) << (4 * c);
+    return true;
+}
+
 template <bool kFastLane>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blocks_kernel(const __grid_constant__ ScanParams p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? BYDB_FAST_CTAS : 2) scan_blocks_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -1437,19 +1471,30 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
     if (lane == 0) {
         sm->fault = 0;
         sm->seq = 0;
+        sm->st_rows = sm->st_matched = sm->st_bytes = 0;
+        sm->st_blocks = sm->st_deferred = sm->st_why = 0;
         for (int s = 0; s < kStages; ++s) mbar_init(&sm->bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // fast lane: the planned work list; slow lane: the blocks the fast lane deferred
-    const uint32_t nwork = kFastLane ? *p.work_count : *p.slow_count;
-    const uint32_t *list = kFastLane ? p.worklist : p.slow_list;
-    uint32_t *cursor = kFastLane ? p.work_next : p.slow_next;
+    // fast lane: the planned work list, or what the express lane left over; slow lane: the blocks the fast lane deferred
+    const bool after_express = kFastLane && p.rest_list != nullptr;
+    const uint32_t nwork = kFastLane ? (after_express ? *p.rest_count : *p.work_count) : *p.slow_count;
+    const uint32_t *list = kFastLane ? (after_express ? p.rest_list : p.worklist) : p.slow_list;
+    uint32_t *cursor = kFastLane ? (after_express ? p.rest_next : p.work_next) : p.slow_next;
+    // per-warp statistics, flushed once at the end: four atomics per block on four hot words serialise in the L2
+    uint32_t known_types = 0;
+    constexpr uint32_t kGrab = 4;  // blocks per cursor increment: the atomic's round trip is paid once per kGrab blocks
+    uint32_t wi_next = 0, wi_end = 0;
     for (;;) {
-        uint32_t wi = 0;
-        if (lane == 0) wi = atomicAdd(cursor, 1u);
-        wi = __shfl_sync(0xffffffffu, wi, 0);
-        if (wi >= nwork) break;
+        if (wi_next == wi_end) {
+            uint32_t wb = 0;
+            if (lane == 0) wb = atomicAdd(cursor, kGrab);
+            wi_next = __shfl_sync(0xffffffffu, wb, 0);
+            if (wi_next >= nwork) break;
+            wi_end = min(nwork, wi_next + kGrab);
+        }
+        const uint32_t wi = wi_next++;
         const uint32_t g = list[wi];
         bool defer = false;
         uint32_t defer_why = 0;
@@ -1641,11 +1686,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
                 if (!is_float && col.value_type != BYDB_VT_INT64) {
                     err = kErrTypeMix;
                 } else {
-                    if (lane == 0) {
-                        const int32_t old = atomicCAS(&p.col_type[c], 0, static_cast<int32_t>(col.value_type));
-                        if (old != 0 && old != static_cast<int32_t>(col.value_type)) err = kErrTypeMix;
-                    }
-                    err = __shfl_sync(0xffffffffu, err, 0);
+                    if (!check_col_type(p, c, col.value_type, known_types)) err = kErrTypeMix;  // warp-uniform: every lane keeps the cache
                     const uint8_t *page = part.files[col.file_id] + col.off;
                     AggAcc acc;
                     acc.init();
@@ -1730,8 +1771,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
             // hand the whole block to the slow lane (launched right after this kernel)
             if (lane == 0) {
                 p.slow_list[atomicAdd(p.slow_count, 1u)] = g;
-                atomicAdd(&p.stats[4], 1ull);
-                atomicOr(&p.stats[5], static_cast<unsigned long long>(defer_why));
+                sm->st_deferred += 1;
+                sm->st_why |= defer_why;
             }
             continue;
         }
@@ -1741,12 +1782,271 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? 3 : 2) scan_blo
         }
         if (lane == 0) {
             p.Prows[g] = rows;
-            atomicAdd(&p.stats[0], static_cast<unsigned long long>(count));
-            atomicAdd(&p.stats[1], static_cast<unsigned long long>(rows));
-            atomicAdd(&p.stats[2], static_cast<unsigned long long>(page_bytes));
-            atomicAdd(&p.stats[3], 1ull);
+            sm->st_rows += count;
+            sm->st_matched += rows;
+            sm->st_bytes += page_bytes;
+            sm->st_blocks += 1;
         }
     }
+    if (lane == 0) {
+        if (sm->st_blocks) {
+            atomicAdd(&p.stats[0], sm->st_rows);
+            atomicAdd(&p.stats[1], sm->st_matched);
+            atomicAdd(&p.stats[2], sm->st_bytes);
+            atomicAdd(&p.stats[3], static_cast<unsigned long long>(sm->st_blocks));
+        }
+        if (sm->st_deferred) {
+            atomicAdd(&p.stats[4], static_cast<unsigned long long>(sm->st_deferred));
+            atomicOr(&p.stats[5], static_cast<unsigned long long>(sm->st_why));
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Express lane: the all-rows SUM / MEAN / COUNT scan (BASELINE configs 3/4: group-by sum, no row predicate) without the
+// per-block latency chain.  With the SWAR decoder a 16 KB page costs ~5 k warp instructions, so the dependent loads in front
+// of every page (work cursor -> work list -> DevBlock -> DevCol -> page header -> first TMA stage) weighed as much as the
+// decode (ncu r02b: issue slots 46 % busy, long-scoreboard stalls 8 per issue).  Here a warp takes kExpressBatch blocks per
+// cursor increment; lane l resolves block l (directory entry, column lookup, page header) -- eight dependent chains overlap in
+// the lanes of one warp -- and then the warp streams the batch's pages through ONE continuous TMA ring: the first stages of
+// page k+1 are in flight while page k is being decoded.  Blocks that are not plain (cut by the time range, a page that is not
+// a narrow EncodeTypeDelta page, nulls, type mix ...) are handed to the regular fast lane through `rest_list`; the express
+// lane never reports an error itself.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kExpressBatch = 8;
+
+__device__ __forceinline__ const uint8_t *ring_wait(WarpSmem *sm, uint32_t n) {
+    const uint32_t slot = n % kStages;
+    const uint32_t parity = (n / kStages) & 1u;
+    for (uint32_t spins = 0; !mbar_try_wait(&sm->bar[slot], parity); ++spins) {
+        if (spins > (1u << 24)) {
+            sm->fault = 1;
+            break;
+        }
+    }
+    return sm->stage[slot];
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, BYDB_FAST_CTAS) scan_sum_express_kernel(const __grid_constant__ ScanParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    WarpSmem *sm = reinterpret_cast<WarpSmem *>(smem_raw) + warp;
+    if (lane == 0) {
+        sm->fault = 0;
+        sm->seq = 0;
+        sm->st_rows = sm->st_matched = sm->st_bytes = 0;
+        sm->st_blocks = sm->st_deferred = sm->st_why = 0;
+        for (int s = 0; s < kStages; ++s) mbar_init(&sm->bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t nwork = *p.work_count;
+    constexpr uint32_t kChunksPerStage = kStageBytes / kFastChunkBytes;
+    uint32_t seq = 0;  // stages issued so far by this warp (mbarrier phase bookkeeping; the kernel owns the ring from start to end)
+    unsigned long long st_rows = 0, st_bytes = 0;  // per-warp statistics, flushed once at the end
+    uint32_t st_blocks = 0, known_types = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(p.work_next, kExpressBatch);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= nwork) break;
+        const uint32_t nb = min(kExpressBatch, nwork - base);
+        // ---- resolve: lane l < nb owns block l of the batch
+        const bool mine = static_cast<uint32_t>(lane) < nb;
+        uint32_t g = 0, count = 0, col_begin = 0, n_cols = 0, pi = 0;
+        bool ok = mine;
+        if (mine) {
+            g = p.worklist[base + lane];
+            while (pi + 1 < p.n_parts && g >= p.parts[pi + 1].block_base) ++pi;
+            const DevBlock *b = p.parts[pi].blocks + (g - p.parts[pi].block_base);
+            count = b->count;
+            col_begin = b->col_begin;
+            n_cols = b->n_cols;
+            ok = p.tmin <= b->ts_min && p.tmax >= b->ts_max && count >= 1;  // every row of the block is active
+        }
+        uint32_t page_bytes = 0;
+        for (uint32_t c = 0; c < p.n_fcols; ++c) {
+            // ---- this lane's page of field c
+            const uint8_t *abase = nullptr;
+            uint32_t pstart = 0, pend = 0, total = 0, nst = 0;
+            int64_t first = 0;
+            int exp = 0;
+            bool has_page = false, is_float = false, count_only = false;
+            if (ok) {
+                const DevCol *cols = p.parts[pi].cols + col_begin;
+                DevCol col{};
+                bool found = false;
+                for (uint32_t i = 0; i < n_cols && !found; ++i) {
+                    const DevCol cc = cols[i];
+                    if (cc.name_id == p.fcol_name[c]) {
+                        col = cc;
+                        found = true;
+                    }
+                }
+                if (found) {
+                    is_float = col.value_type == BYDB_VT_FLOAT64;
+                    if (!is_float && col.value_type != BYDB_VT_INT64) {
+                        ok = false;
+                    } else if (!check_col_type(p, c, col.value_type, known_types)) {
+                        ok = false;  // the regular lane reports the type mix
+                    }
+                    const uint8_t *page = p.parts[pi].files[col.file_id] + col.off;
+                    const uint32_t hdr = is_float ? 11u : 9u;
+                    if (ok && p.fcol_need[c] == 0) {
+                        // COUNT only: numeric pages hold no nulls unless they are fallback pages
+                        if (col.size < 2 || __ldg(page) == 9 || (__ldg(page) == kEncRawCells && __ldg(page + 1))) ok = false;
+                        count_only = ok;
+                        page_bytes += 1;
+                    } else if (ok) {
+                        if (col.size < hdr || __ldg(page) != 3) {
+                            ok = false;  // not a plain EncodeTypeDelta page
+                        } else {
+                            if (is_float) exp = static_cast<int16_t>((static_cast<uint32_t>(__ldg(page + 1)) << 8) | __ldg(page + 2));
+                            first = conv_bytes_to_int64(page + hdr - 8);
+                            const uintptr_t a = reinterpret_cast<uintptr_t>(page + hdr);
+                            abase = reinterpret_cast<const uint8_t *>(a & ~static_cast<uintptr_t>(15));
+                            pstart = static_cast<uint32_t>(a & 15);
+                            pend = pstart + (col.size - hdr);
+                            total = (pend + 15u) & ~15u;
+                            nst = pend > pstart ? (total + kStageBytes - 1) / kStageBytes : 0;
+                            has_page = true;
+                            page_bytes += col.size;
+                        }
+                    }
+                }
+            }
+            const bool streams = ok && has_page && nst > 0;
+            // ---- one continuous ring over the batch's pages: stage s of the batch belongs to the lane with sb <= s < sb + nst
+            uint32_t sb = streams ? nst : 0;
+#pragma unroll
+            for (int sft = 1; sft < static_cast<int>(kExpressBatch); sft <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, sb, sft);
+                if (lane >= sft) sb += o;
+            }
+            const uint32_t ts = __shfl_sync(0xffffffffu, sb, kExpressBatch - 1);  // stages of the whole batch
+            sb -= streams ? nst : 0;                                               // exclusive
+            const uint32_t seq0 = seq;
+            auto issue = [&](uint32_t s) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, streams && s >= sb && s < sb + nst);
+                const int src = __ffs(bal) - 1;
+                const uint64_t ab = shfl_u64(reinterpret_cast<uint64_t>(abase), src);
+                const uint32_t tot = __shfl_sync(0xffffffffu, total, src);
+                const uint32_t off = (s - __shfl_sync(0xffffffffu, sb, src)) * kStageBytes;
+                if (lane == 0) {
+                    const uint32_t bytes = min(static_cast<uint32_t>(kStageBytes), tot - off);
+                    const uint32_t slot = (seq0 + s) % kStages;
+                    mbar_expect_tx(&sm->bar[slot], bytes);
+                    tma_load_1d(sm->stage[slot], reinterpret_cast<const uint8_t *>(ab) + off, bytes, &sm->bar[slot]);
+                }
+            };
+            __syncwarp();
+            for (uint32_t s = 0; s < ts && s < static_cast<uint32_t>(kStages); ++s) issue(s);
+            seq += ts;
+            for (uint32_t k = 0; k < nb; ++k) {
+                const bool okk = __shfl_sync(0xffffffffu, ok, k);
+                if (!okk) continue;
+                const bool pagek = __shfl_sync(0xffffffffu, has_page, k);
+                const bool cok = __shfl_sync(0xffffffffu, count_only, k);
+                const uint32_t count_k = __shfl_sync(0xffffffffu, count, k);
+                AggAcc acc;
+                acc.init();
+                bool good = true;
+                if (pagek) {
+                    const uint32_t nst_k = __shfl_sync(0xffffffffu, nst, k), sb_k = __shfl_sync(0xffffffffu, sb, k);
+                    const uint32_t ps_k = __shfl_sync(0xffffffffu, pstart, k), pe_k = __shfl_sync(0xffffffffu, pend, k);
+                    const uint32_t tot_k = __shfl_sync(0xffffffffu, total, k);
+                    const int64_t first_k = static_cast<int64_t>(shfl_u64(static_cast<uint64_t>(first), k));
+                    const uint32_t nchunks = (tot_k + kFastChunkBytes - 1) / kFastChunkBytes;
+                    int64_t S = 0;
+                    uint32_t tb = 0, carry_w = 0, last_byte = 0;
+                    for (uint32_t j = 0; j < nst_k; ++j) {
+                        const uint32_t s = sb_k + j;
+                        const uint8_t *buf = ring_wait(sm, seq0 + s);
+                        const uint32_t c1 = min(nchunks, (j + 1) * kChunksPerStage);
+                        for (uint32_t cc = j * kChunksPerStage; cc < c1; ++cc) {
+                            if (good) {
+                                const SwarChunk ch = swar_chunk(buf, cc, ps_k, pe_k, tot_k, carry_w, lane);
+                                if (ch.wide) {
+                                    good = false;  // keep consuming the page's stages (the ring stays in step), stop decoding
+                                } else {
+                                    uint32_t n_in = ch.n;
+#pragma unroll
+                                    for (int sft = 1; sft < 32; sft <<= 1) {
+                                        const uint32_t on = __shfl_up_sync(0xffffffffu, n_in, sft);
+                                        if (lane >= sft) n_in += on;
+                                    }
+                                    const int64_t A1 = static_cast<int64_t>(count_k) - static_cast<int64_t>(tb) - static_cast<int64_t>(n_in - ch.n);
+                                    S += A1 * static_cast<int64_t>(ch.T) - static_cast<int64_t>(ch.Rp);
+                                    tb += __shfl_sync(0xffffffffu, n_in, 31);
+                                }
+                            }
+                            if (cc == nchunks - 1 && lane == 0) last_byte = buf[(pe_k - 1) % kStageBytes];
+                        }
+                        __syncwarp();
+                        if (s + kStages < ts) issue(s + kStages);
+                    }
+                    last_byte = __shfl_sync(0xffffffffu, last_byte, 0);
+                    if (nst_k == 0) good = count_k == 1;  // an empty body: the page holds `first` alone
+                    else good = good && tb + 1 == count_k && last_byte < 0x80u;
+#pragma unroll
+                    for (int m = 16; m >= 1; m >>= 1) S += static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(S), m));
+                    acc.add_scaled(first_k, count_k);
+                    const uint64_t us = static_cast<uint64_t>(S);
+                    acc.lo += us;
+                    acc.hi += (S >> 63) + (acc.lo < us ? 1 : 0);
+                    acc.cnt = count_k;
+                } else if (cok) {
+                    acc.cnt = count_k;
+                }
+                if (static_cast<uint32_t>(lane) == k) {
+                    if (!good) {
+                        ok = false;
+                    } else {
+                        BlockPartial bp;
+                        bp.sum.i = 0;
+                        bp.mn.i = 0;
+                        bp.mx.i = 0;
+                        bp.cnt = acc.cnt;
+                        if (acc.cnt > 0 && is_float) {
+                            double sd;
+                            if (acc.hi == (static_cast<int64_t>(acc.lo) >> 63)) sd = __ll2double_rn(static_cast<int64_t>(acc.lo));
+                            else sd = __ll2double_rn(acc.hi) * 18446744073709551616.0 + __ull2double_rn(acc.lo);
+                            bp.sum.f = scale_decimal(sd, exp);
+                            bp.mn.f = scale_decimal(__ll2double_rn(acc.mn), exp);
+                            bp.mx.f = scale_decimal(__ll2double_rn(acc.mx), exp);
+                        } else if (acc.cnt > 0) {
+                            bp.sum.i = static_cast<int64_t>(acc.lo);
+                            bp.mn.i = acc.mn;
+                            bp.mx.i = acc.mx;
+                        }
+                        p.P[static_cast<size_t>(g) * p.n_fcols + c] = bp;
+                    }
+                }
+            }
+        }
+        // ---- finish: completed blocks are accounted, the others go to the regular fast lane
+        const bool done = mine && ok;
+        if (done) p.Prows[g] = count;
+        const uint32_t rows_sum = __reduce_add_sync(0xffffffffu, done ? count : 0u);
+        const uint32_t bytes_sum = __reduce_add_sync(0xffffffffu, done ? page_bytes : 0u);
+        const uint32_t done_bal = __ballot_sync(0xffffffffu, done), rest_bal = __ballot_sync(0xffffffffu, mine && !ok);
+        uint32_t rbase = 0;
+        st_rows += rows_sum;
+        st_bytes += bytes_sum;
+        st_blocks += __popc(done_bal);
+        if (lane == 0 && rest_bal) rbase = atomicAdd(p.rest_count, static_cast<uint32_t>(__popc(rest_bal)));
+        rbase = __shfl_sync(0xffffffffu, rbase, 0);
+        if (mine && !ok) p.rest_list[rbase + __popc(rest_bal & ((1u << lane) - 1u))] = g;
+    }
+    if (lane == 0 && st_blocks) {
+        atomicAdd(&p.stats[0], st_rows);
+        atomicAdd(&p.stats[1], st_rows);
+        atomicAdd(&p.stats[2], st_bytes);
+        atomicAdd(&p.stats[3], static_cast<unsigned long long>(st_blocks));
+    }
+    if (sm->fault && lane == 0) atomicCAS(&p.err[0], 0u, static_cast<uint32_t>(kErrTmaTimeout));
 }
 
 
@@ -1854,6 +2154,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) dedup_kernel(const __gri
     if (lane == 0) {
         sm->fault = 0;
         sm->seq = 0;
+        sm->st_rows = sm->st_matched = sm->st_bytes = 0;
+        sm->st_blocks = sm->st_deferred = sm->st_why = 0;
         for (int s = 0; s < kStages; ++s) mbar_init(&sm->bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -2270,45 +2572,14 @@ __global__ void __launch_bounds__(1024) select_rows_kernel(const __grid_constant
     const uint32_t n_nulls_first = p.top_desc ? 0u : min(N, s_nulls);                  // asc: nulls lead
     const uint32_t M = min(N - n_nulls_first, s_nn);                                     // competing rows to take
     const uint32_t n_nulls_last = p.top_desc ? min(N - M, s_nulls) : 0u;               // desc: nulls trail
-    if (G <= kMaxDeviceTopN) {
-        // ---- few groups: every competing row counts the rows that precede it (key desc, group asc) -- its rank IS its output
-        //      position; G^2 / 1024 compares per thread from shared memory beat eight histogram passes plus a bitonic sort
-        uint8_t *s_st = reinterpret_cast<uint8_t *>(s_gid);
-        for (int32_t g = tid; g < G; g += blockDim.x) {
-            s_key[g] = p.keys[g];
-            s_st[g] = p.kstate[g];
-        }
-        __syncthreads();
-        for (int32_t g = tid; g < G; g += blockDim.x) {
-            if (s_st[g] != 2) continue;
-            const uint64_t k = s_key[g];
-            uint32_t rank = 0;
-            for (int32_t o = 0; o < G; ++o) {
-                const uint64_t ko = s_key[o];
-                rank += (s_st[o] == 2 && (ko > k || (ko == k && o < g))) ? 1u : 0u;
-            }
-            if (rank < M) emit(n_nulls_first + rank, g);
-        }
-        const uint32_t n_nulls = n_nulls_first + n_nulls_last;
-        if (n_nulls > 0) {
-            const uint32_t at = p.top_desc ? M : 0u;
-            for (int32_t g = tid; g < G; g += blockDim.x) {
-                if (s_st[g] != 1) continue;
-                uint32_t pos = 0;
-                for (int32_t o = 0; o < g; ++o) pos += s_st[o] == 1 ? 1u : 0u;
-                if (pos < n_nulls) emit(at + pos, g);
-            }
-        }
-        if (tid == 0) *p.sel_count = M + n_nulls;
-        return;
-    }
+    const bool few = G <= kMaxDeviceTopN;  // few groups: no selection pass -- all of them go through the bitonic sort below
     // ---- radix select of the M-th largest competing key
     if (tid == 0) {
         s_prefix = 0;
         s_remaining = M;
     }
     __syncthreads();
-    if (M > 0) {
+    if (M > 0 && !few) {
         for (int pass = 7; pass >= 0; --pass) {
             for (int i = tid; i < 256; i += blockDim.x) s_hist[i] = 0;
             __syncthreads();
@@ -2339,7 +2610,7 @@ __global__ void __launch_bounds__(1024) select_rows_kernel(const __grid_constant
     if (tid == 0) s_count = 0;
     __syncthreads();
     uint32_t eq_base = 0;
-    for (int32_t g0 = 0; g0 < G && M > 0; g0 += blockDim.x) {
+    for (int32_t g0 = 0; g0 < G && M > 0 && !few; g0 += blockDim.x) {
         const int32_t g = g0 + tid;
         const uint64_t k = g < G ? p.keys[g] : 0;
         const bool comp = g < G && p.kstate[g] == 2;
@@ -2357,10 +2628,19 @@ __global__ void __launch_bounds__(1024) select_rows_kernel(const __grid_constant
         __syncthreads();
     }
     __syncthreads();
-    // ---- bitonic sort (key desc, group asc)
+    // ---- bitonic sort (key desc, group asc) of the selected rows -- or, with few groups, of every group: rows that do not
+    //      compete carry (key 0, group INT32_MAX) and sort behind every competing row, the first M entries are the answer
+    const uint32_t n_sort = few ? static_cast<uint32_t>(G) : M;
+    if (few) {
+        for (int32_t g = tid; g < G; g += blockDim.x) {
+            const bool comp = p.kstate[g] == 2;
+            s_key[g] = comp ? p.keys[g] : 0ull;
+            s_gid[g] = comp ? g : INT32_MAX;
+        }
+    }
     uint32_t P2 = 1;
-    while (P2 < M) P2 <<= 1;
-    for (uint32_t i = M + tid; i < P2; i += blockDim.x) {
+    while (P2 < n_sort) P2 <<= 1;
+    for (uint32_t i = n_sort + tid; i < P2; i += blockDim.x) {
         s_key[i] = 0;
         s_gid[i] = INT32_MAX;
     }
@@ -2448,6 +2728,7 @@ static void scan_set_attrs() {
     const int smem = static_cast<int>(scan_smem_bytes());
     cudaFuncSetAttribute(scan_blocks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(scan_blocks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(scan_sum_express_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (dev >= 0 && dev < 64) g_attr_set[dev].store(true, std::memory_order_release);
 }
@@ -2455,6 +2736,7 @@ static void scan_set_attrs() {
 void launch_scan_blocks(const ScanParams &p, int grid_fast, int grid_slow, cudaStream_t s) {
     scan_set_attrs();
     const size_t smem = scan_smem_bytes();
+    if (p.rest_list) scan_sum_express_kernel<<<grid_fast, kWarpsPerCta * 32, smem, s>>>(p);
     scan_blocks_kernel<true><<<grid_fast, kWarpsPerCta * 32, smem, s>>>(p);
     scan_blocks_kernel<false><<<grid_slow, kWarpsPerCta * 32, smem, s>>>(p);
 }

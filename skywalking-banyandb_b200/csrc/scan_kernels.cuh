@@ -17,6 +17,9 @@ constexpr int kWarpsPerCta = 8;          // 256 threads; every warp is an indepe
 #ifndef BYDB_STAGES
 #define BYDB_STAGES 2
 #endif
+#ifndef BYDB_FAST_CTAS
+#define BYDB_FAST_CTAS 3                 // resident CTAs per SM the fast lane is compiled for (register cap 65536 / (256 x n))
+#endif
 constexpr int kStageBytes = BYDB_STAGE_BYTES;  // one TMA bulk copy (cp.async.bulk) per stage
 constexpr int kStages = BYDB_STAGES;           // per-warp ring: decode stage k while stage k+1 lands
 constexpr int kChunkBytes = 512;         // 32 lanes x 16 B per decode iteration
@@ -82,6 +85,9 @@ struct ScanParams {
     uint32_t *worklist;           // [total_blocks] global block indices selected by plan_blocks
     uint32_t *work_count;
     uint32_t *work_next;
+    uint32_t *rest_list;          // [total_blocks] express lane only (else NULL): blocks it left to the regular fast lane
+    uint32_t *rest_count;
+    uint32_t *rest_next;
     uint32_t *slow_list;          // [total_blocks] blocks the fast lane deferred to the general decoder
     uint32_t *slow_count;
     uint32_t *slow_next;

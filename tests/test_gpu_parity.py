@@ -1196,9 +1196,10 @@ def test_block_index_decoded_on_the_device_equals_the_host_parser(bydb):
     S = import_module("bydb_b200.synth")
     rng = np.random.default_rng(1234)
     parts = {}
-    parts["many primary blocks"] = S.synth_part(6000, 40, [("latency", S.F_LATENCY), ("calls", S.I_FLUCT)], sid0=7, sid_step=2, t0=T0, t_step=STEP,
-                                                region_values=8, region_run=4, code_tag=True, zone_tag=True, seed=5).files()
-    parts["eight fields, long blocks"] = _c5_part(bydb, 40, 20_000).files()
+    keep = [S.synth_part(6000, 40, [("latency", S.F_LATENCY), ("calls", S.I_FLUCT)], sid0=7, sid_step=2, t0=T0, t_step=STEP, region_values=8,
+                         region_run=4, code_tag=True, zone_tag=True, seed=5), _c5_part(bydb, 40, 20_000)]   # files() are views into the images
+    parts["many primary blocks"] = keep[0].files()
+    parts["eight fields, long blocks"] = keep[1].files()
     fb, _, _ = _fallback_part(rng, n_series=3)
     parts["fallback pages"] = fb.files()
     sids, ts, ver = grid(5, 300)
