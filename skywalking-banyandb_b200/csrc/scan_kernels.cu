@@ -1359,6 +1359,116 @@ __device__ __noinline__ int dod_page_fast(WarpSmem *sm, int lane) {
     return (row_base == count && carry_sh == 0) ? 0 : 2;
 }
 
+// ------------------------------------------------------------------------------------------------
+// int64 TAG predicate on a narrow EncodeTypeDelta page, in the fast lane (BASELINE config 5: `code >= 200`).  Two passes per
+// 1 KB chunk like dod_page_fast: (1) the lane's delta total with the multiply-add decoder, one warp scan -> the value in
+// front of every lane; (2) the lane decodes again, compares each value with the literal and clears the mask bits of the rows
+// that fail.  Arguments through the shared slots (a_body, a_len, a_count, a_first; a_r0 = operator, res_lo = literal).
+// Returns like delta_page_fast (1 = a varint of 4+ bytes: the block goes to the general lane).
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ int delta_pred_fast(WarpSmem *sm, int lane) {
+    const uint8_t *body = sm->a_body;
+    const uint32_t len = sm->a_len, count = sm->a_count;
+    const int op = static_cast<int>(sm->a_r0);
+    const int64_t first = sm->a_first, lit = static_cast<int64_t>(sm->res_lo);
+    auto pass = [&](int64_t v) { return cmp_op(op, true, v < lit ? -1 : (v > lit ? 1 : 0)); };
+    if (lane == 0 && !pass(first)) atomicAnd(&sm->mask[0], ~1u);
+    if (len == 0) return count == 1 ? 0 : 2;
+    PageStream st;
+    stream_open(st, sm, body, len, lane);
+    const uint32_t nchunks = (st.total + kFastChunkBytes - 1) / kFastChunkBytes;
+    constexpr uint32_t kChunksPerStage = kStageBytes / kFastChunkBytes;
+    int64_t V0 = first;
+    uint32_t carry_acc = 0, carry_sh = 0;
+    uint32_t row_base = 1;
+    const uint8_t *buf = nullptr;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const uint32_t k = c / kChunksPerStage;
+        if ((c % kChunksPerStage) == 0) buf = stream_wait(st, sm, k);
+        FastChunk fc;
+        fast_chunk_load(fc, st, buf, c, carry_sh, lane);
+        if (fc.wide) {
+            stream_drain(st, sm, k);
+            if (lane == 0) sm->seq = st.seq0 + min(st.nstages, k + static_cast<uint32_t>(kStages));
+            __syncwarp();
+            return 1;
+        }
+        const uint32_t n = fc.n;
+        // ---- pass 1: the lane's delta total
+        uint32_t accv = 0, sh = 0;
+        int32_t P = 0, sumP = 0, mnu = 0, mxu = 0;
+        const bool full = __all_sync(0xffffffffu, fc.valid == 0xffffffffu);
+        if (full) fast_lane_decode<true, kNeedSum>(fc.wa, fc.wb, fc.valid, fc.term, 0u, accv, sh, P, sumP, mnu, mxu);
+        else fast_lane_decode<false, kNeedSum>(fc.wa, fc.wb, fc.valid, fc.term, 0u, accv, sh, P, sumP, mnu, mxu);
+        uint32_t prev_acc = __shfl_up_sync(0xffffffffu, accv, 1);
+        uint32_t prev_sh = __shfl_up_sync(0xffffffffu, sh, 1);
+        if (lane == 0) {
+            prev_acc = carry_acc;
+            prev_sh = carry_sh;
+        }
+        carry_acc = __shfl_sync(0xffffffffu, accv, 31);
+        carry_sh = __shfl_sync(0xffffffffu, sh, 31);
+        if (n > 0 && prev_sh != 0) P += head_delta(fc.wa.x, fc.term, prev_acc, prev_sh);
+        uint32_t n_in = n;
+        int32_t s_in = P;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const uint32_t on = __shfl_up_sync(0xffffffffu, n_in, sft);
+            const int32_t os = __shfl_up_sync(0xffffffffu, s_in, sft);
+            if (lane >= sft) {
+                n_in += on;
+                s_in += os;
+            }
+        }
+        // ---- pass 2: true values of the lane's rows against the literal
+        int64_t v = V0 + static_cast<int64_t>(s_in - P);
+        uint32_t fail = 0, bit = 1;
+        accv = prev_acc;
+        sh = prev_sh;
+        uint32_t w0 = fc.wa.x, w1 = fc.wa.y, w2 = fc.wa.z, w3 = fc.wa.w, w4 = fc.wb.x, w5 = fc.wb.y, w6 = fc.wb.z, w7 = fc.wb.w;
+        uint32_t vm = fc.valid, tm = fc.term;
+#pragma unroll 1
+        for (int q8 = 0; q8 < 8; ++q8) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t b = (w0 >> (8 * j)) & 0xffu;
+                if ((vm >> j) & 1u) {
+                    accv |= (b & 0x7fu) << sh;
+                    sh += 7;
+                }
+                if ((tm >> j) & 1u) {
+                    v += static_cast<int64_t>(static_cast<int32_t>(accv >> 1) ^ -static_cast<int32_t>(accv & 1u));
+                    if (!pass(v)) fail |= bit;
+                    bit <<= 1;
+                    accv = 0;
+                    sh = 0;
+                }
+            }
+            w0 = w1;
+            w1 = w2;
+            w2 = w3;
+            w3 = w4;
+            w4 = w5;
+            w5 = w6;
+            w6 = w7;
+            vm >>= 4;
+            tm >>= 4;
+        }
+        // rows row0 .. row0+n-1 of this lane: clear the failing ones (a corrupt page may hold more varints than rows)
+        const uint32_t row0 = row_base + n_in - n;
+        if (fail && row0 < kMaskWords * 32) {
+            const uint32_t w = row0 >> 5, shb = row0 & 31;
+            atomicAnd(&sm->mask[w], ~(fail << shb));
+            if (shb && w + 1 < kMaskWords) atomicAnd(&sm->mask[w + 1], ~(fail >> (32 - shb)));
+        }
+        V0 += static_cast<int64_t>(__shfl_sync(0xffffffffu, s_in, 31));
+        row_base += __shfl_sync(0xffffffffu, n_in, 31);
+        if ((c % kChunksPerStage) == kChunksPerStage - 1 || c == nchunks - 1) stream_release(st, sm, k, lane);
+    }
+    __syncwarp();
+    return (row_base == count && carry_sh == 0) ? 0 : 2;
+}
+
 // kDeferSlow is returned by the fast lane when a page needs the general decoder
 constexpr uint32_t kDeferSlow = 0xffffffffu;
 
@@ -1632,7 +1742,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? BYDB_FAST_CTAS 
                                         if (!cmp_op(pr.op, true, c)) atomicAnd(&sm->mask[row >> 5], ~(1u << (row & 31)));
                                     }
                                 }
-                            } else if ((enc == 3 || enc == 4) && kFastLane) {
+                            } else if (enc == 3 && kFastLane) {
+                                // narrow delta page: compared in the fast lane; anything wider goes to the general lane
+                                __syncwarp();
+                                if (lane == 0) {
+                                    sm->a_body = body;
+                                    sm->a_len = blen;
+                                    sm->a_count = count;
+                                    sm->a_first = first;
+                                    sm->a_r0 = pr.op;
+                                    sm->res_lo = static_cast<unsigned long long>(pr.lit_i64);
+                                }
+                                __syncwarp();
+                                const int rc = delta_pred_fast(sm, lane);
+                                if (rc == 2) err = kErrCorrupt;
+                                if (rc == 1) {
+                                    defer = true;
+                                    defer_why |= 2u;
+                                }
+                            } else if (enc == 4 && kFastLane) {
                                 defer = true;
                                 defer_why |= 2u;
                             } else if (enc == 3 || enc == 4) {
