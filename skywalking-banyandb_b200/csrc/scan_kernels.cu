@@ -1557,6 +1557,25 @@ __device__ __noinline__ uint32_t agg_field_page(WarpSmem *sm, int lane) {
     }
 }
 
+// Guided self-scheduling of the persistent warps: a warp takes up to `most` work items per cursor increment (one atomic
+// round trip for several blocks) while plenty of work is left, and single items towards the end, so short work lists -- a
+// slice of the cold path, one rank's shard of a strong-scaled query -- still spread over every warp.
+__device__ __forceinline__ uint32_t grab_work(uint32_t *cursor, uint32_t nwork, uint32_t most, uint32_t &count, int lane) {
+    uint32_t base = 0, want = 1;
+    if (lane == 0) {
+        const uint32_t seen = *reinterpret_cast<volatile uint32_t *>(cursor);
+        const uint32_t left = seen < nwork ? nwork - seen : 0u;
+        const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+        want = left / (2u * warps);
+        want = want < 1u ? 1u : (want > most ? most : want);
+        base = atomicAdd(cursor, want);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    want = __shfl_sync(0xffffffffu, want, 0);
+    count = base < nwork ? min(want, nwork - base) : 0u;
+    return base;
+}
+
 // The value type of aggregated field c must be the same in every block of the query (kErrTypeMix otherwise).  One global word
 // per field records it; `known` caches what this thread has already seen (4 bits per field), so the common case costs no
 // memory access at all -- a compare-and-swap per block on one hot address used to be a fifth of the kernel's stall samples
@@ -1598,11 +1617,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? BYDB_FAST_CTAS 
     uint32_t wi_next = 0, wi_end = 0;
     for (;;) {
         if (wi_next == wi_end) {
-            uint32_t wb = 0;
-            if (lane == 0) wb = atomicAdd(cursor, kGrab);
-            wi_next = __shfl_sync(0xffffffffu, wb, 0);
-            if (wi_next >= nwork) break;
-            wi_end = min(nwork, wi_next + kGrab);
+            uint32_t got = 0;
+            wi_next = grab_work(cursor, nwork, kGrab, got, lane);
+            if (got == 0) break;
+            wi_end = wi_next + got;
         }
         const uint32_t wi = wi_next++;
         const uint32_t g = list[wi];
@@ -1976,11 +1994,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, BYDB_FAST_CTAS) scan_sum_ex
     unsigned long long st_rows = 0, st_bytes = 0;  // per-warp statistics, flushed once at the end
     uint32_t st_blocks = 0, known_types = 0;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(p.work_next, kExpressBatch);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= nwork) break;
-        const uint32_t nb = min(kExpressBatch, nwork - base);
+        uint32_t nb = 0;
+        const uint32_t base = grab_work(p.work_next, nwork, kExpressBatch, nb, lane);
+        if (nb == 0) break;
         // ---- resolve: lane l < nb owns block l of the batch
         const bool mine = static_cast<uint32_t>(lane) < nb;
         uint32_t g = 0, count = 0, col_begin = 0, n_cols = 0, pi = 0;
@@ -2931,12 +2947,19 @@ __global__ void comm_wait_kernel(const unsigned long long *flags, uint32_t n, un
     bool ok = true;
     if (r < n) {
         ok = false;
-        for (uint32_t spins = 0; spins < (1u << 22); ++spins) {  // ~ seconds with the back-off below
+        // bounded by wall time: a peer's first call may spend seconds loading its kernels onto a fresh device
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (uint32_t spins = 0;; ++spins) {
             if (ld_acquire_sys(flags + r) >= epoch) {
                 ok = true;
                 break;
             }
             __nanosleep(spins < 1024 ? 32 : 1000);
+            if ((spins & 1023u) == 1023u) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 60ull * 1000000000ull) break;  // 60 s
+            }
         }
     }
     if (!ok && err) atomicCAS(err, 0u, err_code);
