@@ -280,6 +280,10 @@ typedef struct { uint8_t bytes[128]; } bydb_comm_handle;
 int bydb_comm_export(bydb_ctx *ctx, uint64_t max_table_bytes, int32_t max_ranks, bydb_comm_handle *out);
 int bydb_comm_connect(bydb_ctx *ctx, int32_t rank, int32_t nranks, const bydb_comm_handle *all);
 int bydb_scan_reduce(bydb_ctx *ctx, const bydb_query *q, int32_t root, bydb_result *out);
+/* The same collective for a prepared query (bydb_query_prepare): from its second execution on, per root, the rank's whole step is
+ * replayed as ONE captured CUDA graph -- the epoch of the call travels in a small device block that a memcpy node of the graph
+ * refreshes.  Ranks may mix bydb_scan_reduce and bydb_scan_reduce_prepared within one collective. */
+int bydb_scan_reduce_prepared(bydb_ctx *ctx, bydb_prepared *pq, int32_t root, bydb_result *out);
 /* The same collective with every rank's parts given as HOST file images (cold distributed query, end to end): admitted for
  * the duration of the call (with BYDB_Q_HOST_ZERO_COPY only the block directory is uploaded and the scan pulls the pages it
  * touches over PCIe), scanned into the root's mailbox, dropped.  q->parts / q->n_parts are ignored. */

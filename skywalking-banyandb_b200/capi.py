@@ -86,7 +86,7 @@ EXPORTS = ["bydb_init", "bydb_shutdown", "bydb_part_register", "bydb_part_releas
            "bydb_scan_agg", "bydb_scan_agg_host", "bydb_result_free", "bydb_query_prepare", "bydb_scan_agg_prepared",
            "bydb_query_release", "bydb_partials_layout",
            "bydb_scan_partials", "bydb_partials_combine", "bydb_reduce_finalize", "bydb_partials_rows", "bydb_partial_rows_free", "bydb_comm_export", "bydb_comm_connect",
-           "bydb_scan_reduce", "bydb_scan_reduce_host", "bydb_last_error", "bydb_version"]
+           "bydb_scan_reduce", "bydb_scan_reduce_prepared", "bydb_scan_reduce_host", "bydb_last_error", "bydb_version"]
 
 _lib = None
 
@@ -132,6 +132,7 @@ def load_library():
     L.bydb_comm_export.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p]
     L.bydb_comm_connect.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     L.bydb_scan_reduce.argtypes = [C.c_void_p, C.POINTER(_Query), C.c_int32, C.POINTER(_Result)]
+    L.bydb_scan_reduce_prepared.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(_Result)]
     L.bydb_scan_reduce_host.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_PartFiles), C.POINTER(_Query), C.c_int32, C.POINTER(_Result)]
     _lib = L
     return L
@@ -318,6 +319,15 @@ class GraphQuery:
     def run(self) -> Result:
         r = _Result()
         _check(self._ctx._L.bydb_scan_agg_prepared(self._ctx._h, self._h, C.byref(r)))
+        try:
+            return _read_result(r)
+        finally:
+            self._ctx._L.bydb_result_free(self._ctx._h, C.byref(r))
+
+    def run_reduce(self, root: int = 0) -> Result:
+        """The collective form (bydb_scan_reduce_prepared): graph replay from the second execution on."""
+        r = _Result()
+        _check(self._ctx._L.bydb_scan_reduce_prepared(self._ctx._h, self._h, root, C.byref(r)))
         try:
             return _read_result(r)
         finally:

@@ -163,7 +163,7 @@ class WorkPool {
 //                    that rank's call) at 1024, `done` epoch at 2048, error word of this rank's wait kernels at 2056
 //   [4096, ...)      2 parities x nranks slots of slot_bytes each (partial tables written by the peers)
 constexpr int kCommMaxRanks = 64;
-constexpr size_t kCommCtl = 4096, kCommStatusOff = 1024, kCommDoneOff = 2048, kCommErrOff = 2056;
+constexpr size_t kCommCtl = 4096, kCommStatusOff = 1024, kCommDoneOff = 2048, kCommErrOff = 2056, kCommArgsOff = 2112;
 struct Comm {
     int rank = -1, nranks = 0;
     uint8_t *mine = nullptr;            // this rank's mailbox (cudaMalloc)
@@ -1246,6 +1246,16 @@ struct bydb_prepared {
     bydb_stats captured{};             // host-side counters of one step (launch counts, byte counts)
     uint64_t runs = 0;
     bool capturable = true;
+    // the collective form (bydb_scan_reduce_prepared): one captured graph per (root, slot parity)
+    struct ReduceGraph {
+        cudaGraphExec_t exec = nullptr;
+        FinalLayout fl;
+        bydb_stats captured{};
+        std::vector<std::shared_ptr<Part>> held;
+    };
+    std::unordered_map<int, ReduceGraph> reduce_graphs;  // key = root * 2 + parity
+    uint64_t reduce_runs = 0;
+    bool reduce_capturable = true;
 };
 
 namespace {
@@ -1253,6 +1263,8 @@ namespace {
 void prepared_destroy(bydb_prepared *p) {
     if (!p) return;
     if (p->exec) cudaGraphExecDestroy(p->exec);
+    for (auto &kv : p->reduce_graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (p->t0) cudaEventDestroy(p->t0);
     if (p->t1) cudaEventDestroy(p->t1);
     if (p->slot) {
@@ -2354,6 +2366,171 @@ int bydb_scan_reduce(bydb_ctx *ctx, const bydb_query *q, int32_t root, bydb_resu
     if (!ctx || !out) return fail(BYDB_EINVAL, "ctx/out is NULL");
     memset(out, 0, sizeof *out);
     return scan_reduce_impl(ctx, q, nullptr, 0, 0, root, out);
+    });
+}
+
+// The collective as a prepared query: from its second execution on (per root and slot parity) the rank's whole step -- argument
+// refresh, wait for the slots, staging copy, block selection, scan, reduce into the root's mailbox, status + arrival flag, and on
+// the root the wait for all ranks, combine, finalisation, row selection, `done` word and read-back -- is ONE captured CUDA graph:
+// one launch and one synchronisation per call.  Semantics are bydb_scan_reduce's; ranks may mix the two freely.
+int bydb_scan_reduce_prepared(bydb_ctx *ctx, bydb_prepared *p, int32_t root, bydb_result *out) {
+    return guarded([&]() -> int {
+    if (!ctx || !p || !out) return fail(BYDB_EINVAL, "NULL argument");
+    memset(out, 0, sizeof *out);
+    std::lock_guard<std::mutex> lkp(p->mu);
+    Comm &cm = ctx->comm;
+    if (cm.nranks == 0) return fail(BYDB_EINVAL, "bydb_comm_connect was not called on this context");
+    if (root < 0 || root >= cm.nranks) return fail(BYDB_EINVAL, "bad root");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    g_last_dev_err = 0;
+    const uint64_t run = p->reduce_runs++;
+    if (run == 0 || !p->reduce_capturable) return scan_reduce_impl(ctx, &p->q, nullptr, 0, 0, root, out);
+    std::unique_lock<std::mutex> lk(cm.mu);
+    const uint64_t epoch = cm.epoch + 1;
+    const size_t parity = static_cast<size_t>(epoch & 1u);
+    const size_t slot_bytes = cm.peer_slot_bytes[static_cast<size_t>(root)];
+    uint8_t *root_mb = cm.peer[static_cast<size_t>(root)];
+    uint8_t *slots0 = root_mb + kCommCtl + parity * static_cast<size_t>(cm.nranks) * slot_bytes;
+    uint8_t *my_slot = slots0 + static_cast<size_t>(cm.rank) * slot_bytes;
+    unsigned long long *flags = reinterpret_cast<unsigned long long *>(root_mb);
+    unsigned long long *status = reinterpret_cast<unsigned long long *>(root_mb + kCommStatusOff);
+    unsigned long long *done = reinterpret_cast<unsigned long long *>(root_mb + kCommDoneOff);
+    uint32_t *my_err = reinterpret_cast<uint32_t *>(cm.mine + kCommErrOff);
+    CommArgs *d_args = reinterpret_cast<CommArgs *>(cm.mine + kCommArgsOff);
+    ExecSlot &es = *p->slot;
+    // pinned words of this prepared query that the graph's memcpy nodes read / write: the last two zero pages of its slot
+    CommArgs *h_args = reinterpret_cast<CommArgs *>(es.zpage + 256 * 7);
+    uint8_t *h_back = es.zpage + 256 * 6;  // [0,4) this rank's wait-kernel error word, [8, 8 + 8 * nranks) the status words (root)
+    if (static_cast<size_t>(cm.nranks) * 8 + 8 > 256) {  // more ranks than the pinned read-back page holds status words for
+        lk.unlock();
+        return scan_reduce_impl(ctx, &p->q, nullptr, 0, 0, root, out);
+    }
+    auto &rg = p->reduce_graphs[root * 2 + static_cast<int>(parity)];
+    // a graph reads its parts through the pointers captured with it (same rule as bydb_scan_agg_prepared)
+    if (rg.exec) {
+        std::lock_guard<std::mutex> lk2(ctx->mu);
+        bool same = rg.held.size() == p->parts.size(), missing = false;
+        for (size_t i = 0; i < p->parts.size(); ++i) {
+            auto it = ctx->parts.find(p->parts[i]);
+            if (it == ctx->parts.end()) missing = true;
+            else if (same && it->second != rg.held[i]) same = false;
+        }
+        if (missing || !same) {
+            cudaGraphExecDestroy(rg.exec);
+            rg.exec = nullptr;
+            rg.held.clear();
+        }
+    }
+    if (!rg.exec) {
+        Plan plan;
+        int rc = make_plan(ctx, &p->q, nullptr, plan);
+        if (rc) {
+            lk.unlock();
+            return scan_reduce_impl(ctx, &p->q, nullptr, 0, 0, root, out);  // takes part in the collective and reports the failure
+        }
+        bool overlap = false;  // the version-dedup precheck synchronises: such queries keep the plain path
+        for (size_t a = 0; a < plan.parts.size(); ++a)
+            for (size_t b = a + 1; b < plan.parts.size(); ++b) {
+                const PartDir &x = plan.parts[a]->dir, &y = plan.parts[b]->dir;
+                if (x.blocks.empty() || y.blocks.empty()) continue;
+                if (std::max(std::max(x.min_ts, y.min_ts), p->q.tmin) <= std::min(std::min(x.max_ts, y.max_ts), p->q.tmax)) overlap = true;
+            }
+        TableLayout tl(static_cast<size_t>(plan.n_groups), plan.fcols.size());
+        const size_t G = static_cast<size_t>(plan.n_groups), A = p->q.n_aggs, NS = p->q.n_series;
+        const size_t stage = align_up(NS * 12 + (G + 1) * 4 + 512, 256);
+        p->host_off = stage;
+        if (overlap || tl.total > slot_bytes || es.ensure_pinned(stage + G * (12 + 16 * A) + 16 * A + 16384)) {
+            p->reduce_capturable = false;
+            lk.unlock();
+            return scan_reduce_impl(ctx, &p->q, nullptr, 0, 0, root, out);
+        }
+        memset(&rg.captured, 0, sizeof rg.captured);
+        cudaStream_t s = es.stream;
+        cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            Scratch fin;
+            bool ok = cudaMemcpyAsync(d_args, h_args, sizeof(CommArgs), cudaMemcpyHostToDevice, s) == cudaSuccess;
+            launch_comm_wait_args(done, 1, d_args, 1, my_err, kErrPeerTimeout, s);
+            ok = ok && run_scan(ctx, &p->q, plan, es, s, my_slot, tl, &rg.captured, 0, true) == 0;
+            launch_comm_signal_args(flags + cm.rank, status + cm.rank, d_args, s);
+            if (cm.rank == root) {
+                launch_comm_wait_args(flags, static_cast<uint32_t>(cm.nranks), d_args, 0, my_err, kErrPeerTimeout, s);
+                launch_combine_tables(reinterpret_cast<uint64_t *>(slots0), static_cast<uint32_t>(cm.nranks), tl.total / 8, tl.off_sum_f64 / 8,
+                                      tl.off_max_f64 / 8, tl.off_max_f64 / 8, tl.off_sum_i64 / 8, tl.off_sum_i64 / 8, tl.off_max_i64 / 8, tl.off_max_i64 / 8,
+                                      tl.total / 8, s, slot_bytes / 8);
+                ok = ok && finalize_enqueue(&p->q, plan, es, s, slots0, tl, p->host_off, rg.fl, fin) == 0;
+                launch_comm_done_args(done, d_args, s);
+                ok = ok && cudaMemcpyAsync(h_back + 8, status, sizeof(unsigned long long) * static_cast<size_t>(cm.nranks), cudaMemcpyDeviceToHost, s) == cudaSuccess;
+                rg.captured.kernel_launches += 3 + rg.fl.launches;
+            }
+            ok = ok && cudaMemcpyAsync(h_back, my_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, s) == cudaSuccess;
+            rg.captured.kernel_launches += 2;
+            cudaGraph_t graph = nullptr;
+            e = cudaStreamEndCapture(s, &graph);
+            if (ok && e == cudaSuccess && graph) e = cudaGraphInstantiate(&rg.exec, graph, 0);
+            else e = cudaErrorUnknown;
+            if (graph) cudaGraphDestroy(graph);
+        }
+        if (e != cudaSuccess || !rg.exec) {
+            cudaGetLastError();
+            rg.exec = nullptr;
+            p->reduce_capturable = false;  // the plain path from here on
+            lk.unlock();
+            return scan_reduce_impl(ctx, &p->q, nullptr, 0, 0, root, out);
+        }
+        rg.held = plan.parts;
+    }
+    // ---- replay
+    cm.epoch = epoch;
+    const uint64_t prev_use = cm.last_use[2 * static_cast<size_t>(root) + parity];
+    cm.last_use[2 * static_cast<size_t>(root) + parity] = epoch;
+    h_args->epoch = epoch;
+    h_args->prev_use = prev_use;
+    memset(h_back, 0, 256);
+    memset(es.zpage, 0, 256);
+    cudaStream_t s = es.stream;
+    CUDA_TRY(cudaEventRecord(p->t0, s));
+    CUDA_TRY(cudaGraphLaunch(rg.exec, s));
+    CUDA_TRY(cudaEventRecord(p->t1, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaGetLastError());
+    out->stats = rg.captured;
+    const uint32_t *hz = reinterpret_cast<const uint32_t *>(es.zpage);
+    const unsigned long long *hs = reinterpret_cast<const unsigned long long *>(es.zpage + 16);
+    out->stats.rows_scanned = hs[0];
+    out->stats.rows_matched = hs[1];
+    out->stats.page_bytes = hs[2];
+    out->stats.blocks_scanned = hs[3];
+    out->stats.blocks_slow_lane = static_cast<uint32_t>(hs[4]);
+    out->stats.slow_lane_reasons = static_cast<uint32_t>(hs[5]);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p->t0, p->t1);
+    out->stats.device_ms = ms;
+    out->stats.scan_kernel_ms = 0;  // per-kernel events are not available inside a graph replay
+    const uint32_t perr = *reinterpret_cast<const uint32_t *>(h_back);
+    if (perr != 0) cudaMemset(my_err, 0, sizeof perr);
+    if (hz[2] != 0) {
+        g_last_dev_err = hz[2];
+        char buf[96];
+        snprintf(buf, sizeof buf, " (block/series #%u)", hz[3]);
+        return fail(dev_err_code(hz[2]), std::string(dev_err_text(hz[2])) + buf);
+    }
+    if (perr != 0) return fail(dev_err_code(perr), dev_err_text(perr));
+    if (cm.rank != root) return 0;
+    const unsigned long long *peer_status = reinterpret_cast<const unsigned long long *>(h_back + 8);
+    for (int r = 0; r < cm.nranks; ++r) {
+        const unsigned long long w = peer_status[r];
+        if ((w >> 32) == (epoch & 0xffffffffull) && static_cast<uint32_t>(w) != 0)
+            return fail(-static_cast<int>(static_cast<uint32_t>(w)), "multi-GPU reduce: rank " + std::to_string(r) + " failed before its scan");
+    }
+    const uint8_t *h = es.pinned + p->host_off;
+    const uint32_t e_in = *reinterpret_cast<const uint32_t *>(h + (rg.fl.o_cnt - rg.fl.o_out) + 8);
+    if (e_in != 0) {
+        g_last_dev_err = e_in;
+        return fail(dev_err_code(e_in), std::string(dev_err_text(e_in)) + " (status carried in a partial table)");
+    }
+    finalize_parse(h, rg.fl, out);
+    return 0;
     });
 }
 

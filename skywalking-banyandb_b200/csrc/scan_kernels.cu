@@ -2968,6 +2968,46 @@ __global__ void comm_signal_kernel(unsigned long long *flag, unsigned long long 
     __threadfence_system();  // the table stores of the kernels before this one are visible system-wide first
     st_release_sys(flag, epoch);
 }
+// The same three steps with the epoch read from DEVICE memory: a captured CUDA graph bakes its kernel arguments in, so a
+// replayed collective gets its epoch (and the epoch its slots were last used) from a CommArgs block that a memcpy node at the
+// head of the graph refreshes from pinned host memory before every launch.
+__global__ void comm_wait_args_kernel(const unsigned long long *flags, uint32_t n, const CommArgs *a, int which, uint32_t *err, uint32_t err_code) {
+    const unsigned long long thr = which ? a->prev_use : a->epoch;
+    if (thr == 0) return;  // nothing to wait for (the slots were never used before)
+    const uint32_t r = threadIdx.x;
+    bool ok = true;
+    if (r < n) {
+        ok = false;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (uint32_t spins = 0;; ++spins) {
+            if (ld_acquire_sys(flags + r) >= thr) {
+                ok = true;
+                break;
+            }
+            __nanosleep(spins < 1024 ? 32 : 1000);
+            if ((spins & 1023u) == 1023u) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 60ull * 1000000000ull) break;
+            }
+        }
+    }
+    if (!ok && err) atomicCAS(err, 0u, err_code);
+}
+__global__ void comm_signal_args_kernel(unsigned long long *flag, unsigned long long *status, const CommArgs *a) {
+    *status = a->epoch << 32;  // no host-side failure can happen inside a replayed graph
+    __threadfence_system();
+    st_release_sys(flag, a->epoch);
+}
+__global__ void comm_done_args_kernel(unsigned long long *done, const CommArgs *a) { st_release_sys(done, a->epoch); }
+void launch_comm_wait_args(const unsigned long long *flags, uint32_t n, const CommArgs *a, int which, uint32_t *err, uint32_t err_code, cudaStream_t s) {
+    comm_wait_args_kernel<<<1, 32, 0, s>>>(flags, n, a, which, err, err_code);
+}
+void launch_comm_signal_args(unsigned long long *flag, unsigned long long *status, const CommArgs *a, cudaStream_t s) {
+    comm_signal_args_kernel<<<1, 1, 0, s>>>(flag, status, a);
+}
+void launch_comm_done_args(unsigned long long *done, const CommArgs *a, cudaStream_t s) { comm_done_args_kernel<<<1, 1, 0, s>>>(done, a); }
+
 void launch_comm_wait(const unsigned long long *flags, uint32_t n, unsigned long long epoch, uint32_t *err, uint32_t err_code, cudaStream_t s) {
     comm_wait_kernel<<<1, 32, 0, s>>>(flags, n, epoch, err, err_code);
 }

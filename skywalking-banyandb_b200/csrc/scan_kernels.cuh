@@ -177,6 +177,13 @@ void launch_combine_tables(uint64_t *tables, uint32_t n_tables, uint64_t words, 
 // peer-mailbox reduce (bydb_comm_*): bounded wait for n epoch flags, release-store of one
 void launch_comm_wait(const unsigned long long *flags, uint32_t n, unsigned long long epoch, uint32_t *err, uint32_t err_code, cudaStream_t s);
 void launch_comm_signal(unsigned long long *flag, unsigned long long epoch, cudaStream_t s);
+// graph-replayable forms: the epoch comes from a device block refreshed by a memcpy node of the graph
+struct CommArgs {
+    unsigned long long epoch, prev_use;
+};
+void launch_comm_wait_args(const unsigned long long *flags, uint32_t n, const CommArgs *a, int which, uint32_t *err, uint32_t err_code, cudaStream_t s);
+void launch_comm_signal_args(unsigned long long *flag, unsigned long long *status, const CommArgs *a, cudaStream_t s);
+void launch_comm_done_args(unsigned long long *done, const CommArgs *a, cudaStream_t s);
 
 // ---- fallback-page normalisation at part admission (unpack_kernels.cu)
 constexpr uint8_t kEncRawCells = 0x40;   // numeric page rewritten as [0x40][has_nulls][6 pad][n x u64 LE][n x u8 valid]

@@ -996,6 +996,35 @@ def test_scan_reduce_peer_mailboxes_equal_the_single_context_answer(bydb, gpu_ct
                 for r in range(R):
                     if r != root:
                         assert got[r].group_id.size == 0 and got[r].stats.blocks_scanned > 0
+        # the collective as a prepared query (bydb_scan_reduce_prepared): run 1 plain, then one captured graph per (root, slot parity);
+        # ranks 0 and 1 use the prepared form, rank 2 keeps calling bydb_scan_reduce -- the two mix within one collective
+        for kw in (queries[0], queries[1]):
+            want = gpu_ctx.scan_agg(bydb.Query(whole, usid, series_group=groups, n_groups=7, **kw))
+            qs = [bydb.Query([hs[r]], usid[shard_of == r], series_group=groups[shard_of == r], n_groups=7, **kw) for r in range(R)]
+            gqs = [ctxs[r].prepare_graph(qs[r]) for r in range(2)]
+            try:
+                for it in range(7):
+                    root = it % 2
+                    got, errs = [None] * R, []
+
+                    def run_p(r):
+                        try:
+                            got[r] = gqs[r].run_reduce(root=root) if r < 2 else ctxs[r].scan_reduce(qs[r], root=root)
+                        except Exception as e:  # noqa: BLE001
+                            errs.append(repr(e))
+                    th = [threading.Thread(target=run_p, args=(r,)) for r in range(R)]
+                    for t in th:
+                        t.start()
+                    for t in th:
+                        t.join()
+                    assert not errs, (it, errs)
+                    g = got[root]
+                    assert g.group_id.tolist() == want.group_id.tolist() and g.rows.tolist() == want.rows.tolist(), it
+                    assert g.val_i64.tolist() == want.val_i64.tolist() and np.allclose(g.val_f64, want.val_f64, rtol=1e-12, atol=0), it
+                    assert got[1 - root].group_id.size == 0 and got[1 - root].stats.blocks_scanned > 0
+            finally:
+                for gq in gqs:
+                    gq.close()
         # the same collective with HOST file images on every rank (bydb_scan_reduce_host: the cold distributed query, end to end)
         kw = queries[1]
         want = gpu_ctx.scan_agg(bydb.Query(whole, usid, series_group=groups, n_groups=7, **kw))
