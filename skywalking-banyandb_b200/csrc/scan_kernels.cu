@@ -1593,6 +1593,10 @@ __device__ __forceinline__ bool check_col_type(const ScanParams &p, uint32_t c, 
 
 template <bool kFastLane>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? BYDB_FAST_CTAS : 2) scan_blocks_kernel(const __grid_constant__ ScanParams p) {
+    // fast lane: the planned work list, or what the express lane left over; slow lane: the blocks the fast lane deferred
+    const bool after_express = kFastLane && p.rest_list != nullptr;
+    const uint32_t nwork = kFastLane ? (after_express ? *p.rest_count : *p.work_count) : *p.slow_count;
+    if (nwork == 0) return;  // the usual case of the lanes behind the express / fast lane: nothing left over (whole grid, uniform)
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -1606,9 +1610,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? BYDB_FAST_CTAS 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // fast lane: the planned work list, or what the express lane left over; slow lane: the blocks the fast lane deferred
-    const bool after_express = kFastLane && p.rest_list != nullptr;
-    const uint32_t nwork = kFastLane ? (after_express ? *p.rest_count : *p.work_count) : *p.slow_count;
     const uint32_t *list = kFastLane ? (after_express ? p.rest_list : p.worklist) : p.slow_list;
     uint32_t *cursor = kFastLane ? (after_express ? p.rest_next : p.work_next) : p.slow_next;
     // per-warp statistics, flushed once at the end: four atomics per block on four hot words serialise in the L2
