@@ -129,7 +129,7 @@ class WorkPool {
             std::lock_guard<std::mutex> lk(mu_);
             if (th_.empty()) {
                 unsigned hw = std::thread::hardware_concurrency();
-                const unsigned n = std::max(2u, std::min(16u, hw ? hw : 4u));
+                const unsigned n = std::max(2u, std::min(32u, hw ? hw / 2 : 4u));  // index parsing + page gathering: memory-bound helpers
                 for (unsigned i = 0; i < n; ++i) th_.emplace_back([this] { run(); });
             }
             q_.push_back(std::move(fn));
@@ -1623,7 +1623,7 @@ static int upload_gather(bydb_ctx *ctx, GatherImage &g, uint8_t *d_arena, cudaSt
         size_t sj = si;
         while (sj < g.segs.size() && g.segs[sj].dst < c1) ++sj;
         const size_t n = sj - si;
-        const size_t tasks = std::max<size_t>(1, std::min<size_t>(16, n / 64));
+        const size_t tasks = std::max<size_t>(1, std::min<size_t>(32, n / 64));
         std::vector<std::future<void>> futs;
         for (size_t t = 0; t < tasks; ++t) {
             const size_t a = si + n * t / tasks, b = si + n * (t + 1) / tasks;
