@@ -402,6 +402,20 @@ def main():
             phase["combine_finalize_sync"] += td - tc
             return res
 
+    if world > 1:
+        from importlib import import_module
+        multi = import_module("bydb_b200.multi")
+
+        def allreduce_step():
+            # north_star's literal form: the partial table all-reduced in place over NVLink (SUM / MAX over its four typed ranges,
+            # skywalking-banyandb_b200/multi.py), finalised on rank 0.  Float sums then depend on NCCL's reduction order.
+            ctx.scan_partials(pq, table.data_ptr(), lay["total_bytes"], stream, want_stats=False)
+            multi.allreduce_partial_table(table, lay, dist)
+            if rank == 0:
+                return ctx.reduce_finalize(pq, table.data_ptr(), lay["total_bytes"], stream)
+            torch.cuda.current_stream().synchronize()
+            return None
+
     def timed(fn, steps):
         barrier()
         t = time.perf_counter()
@@ -482,6 +496,13 @@ def main():
                                                "host_phase_ms_per_step_rank0": {k: v / args.steps * 1e3 for k, v in phase.items()},
                                                "note": "bydb_scan_partials (asynchronous) -> one NCCL all-gather of the partial tables -> bydb_partials_combine + "
                                                        "bydb_reduce_finalize on rank 0"}
+        if world > 1:
+            for _ in range(warm):
+                allreduce_step()
+            da, ra = timed(allreduce_step, args.steps)
+            extra["nccl_allreduce_variant"] = {"steps": args.steps, "ms_per_step": da / args.steps * 1e3, "value": total_rows_step * args.steps / da, "unit": "datapoints/s",
+                                               "same_top100_groups": bool(ra.group_id.tolist() == last.group_id.tolist()) if rank == 0 and ra is not None and last is not None else None,
+                                               "note": "bydb_scan_partials -> NCCL all-reduce of the table in place (4 typed ranges) -> bydb_reduce_finalize on rank 0"}
         if world == 1:
             # second leg: BASELINE configs[1]'s query over the same part
             q2 = ctx.prepare(c2_query(pkg, [h], sids, n_points))
