@@ -691,47 +691,62 @@ struct SwarChunk {
     uint32_t n;
     bool wide;
 };
+// 2 KB per warp iteration, 64 contiguous bytes per lane: the per-chunk work (neighbour shuffle, vote, scan of the terminator
+// counts, 64-bit multiply-add, stage bookkeeping: ~160 instructions) is paid once per 16 words instead of once per 8.
+constexpr uint32_t kSwarLaneBytes = 64;
+constexpr uint32_t kSwarChunkBytes = 32 * kSwarLaneBytes;
+static_assert(kStageBytes % kSwarChunkBytes == 0, "a TMA stage holds whole SWAR chunks");
 __device__ __forceinline__ SwarChunk swar_chunk(const uint8_t *buf, uint32_t c, uint32_t pstart, uint32_t pend, uint32_t total, uint32_t &carry_w, int lane) {
-    const uint32_t o = c * kFastChunkBytes + lane * kFastLaneBytes;
-    const bool interior = c * kFastChunkBytes >= pstart && (c + 1) * kFastChunkBytes <= pend;  // warp-uniform
+    const uint32_t o = c * kSwarChunkBytes + lane * kSwarLaneBytes;
+    const bool interior = c * kSwarChunkBytes >= pstart && (c + 1) * kSwarChunkBytes <= pend;  // warp-uniform
+    const uint8_t *src = buf + (o % kStageBytes);
     SwarLane sl;
     if (interior) {
-        const uint4 wa = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes));
-        const uint4 wb = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes) + 16);
-        uint32_t pw = __shfl_up_sync(0xffffffffu, wb.w, 1);
+        // the neighbour only needs this lane's last word: fetch it first, then the two halves one after the other so that
+        // only 8 data words are live at a time
+        const uint32_t lastw = *reinterpret_cast<const uint32_t *>(src + kSwarLaneBytes - 4);
+        uint32_t pw = __shfl_up_sync(0xffffffffu, lastw, 1);
         if (lane == 0) pw = carry_w;
-        carry_w = __shfl_sync(0xffffffffu, wb.w, 31);
+        carry_w = __shfl_sync(0xffffffffu, lastw, 31);
         swar_begin(sl, pw);
-        swar_word<false>(sl, wa.x, 0u);
-        swar_word<false>(sl, wa.y, 0u);
-        swar_word<false>(sl, wa.z, 0u);
-        swar_word<false>(sl, wa.w, 0u);
-        swar_word<false>(sl, wb.x, 0u);
-        swar_word<false>(sl, wb.y, 0u);
-        swar_word<false>(sl, wb.z, 0u);
-        swar_word<false>(sl, wb.w, 0u);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const uint4 wa = *reinterpret_cast<const uint4 *>(src + 32 * half), wb = *reinterpret_cast<const uint4 *>(src + 32 * half + 16);
+            swar_word<false>(sl, wa.x, 0u);
+            swar_word<false>(sl, wa.y, 0u);
+            swar_word<false>(sl, wa.z, 0u);
+            swar_word<false>(sl, wa.w, 0u);
+            swar_word<false>(sl, wb.x, 0u);
+            swar_word<false>(sl, wb.y, 0u);
+            swar_word<false>(sl, wb.z, 0u);
+            swar_word<false>(sl, wb.w, 0u);
+        }
     } else {
-        uint4 wa = make_uint4(0, 0, 0, 0), wb = make_uint4(0, 0, 0, 0);
-        if (o < total) wa = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes));
-        if (o + 16 < total) wb = *reinterpret_cast<const uint4 *>(buf + (o % kStageBytes) + 16);
+        uint4 w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            w[q] = make_uint4(0, 0, 0, 0);
+            if (o + 16 * q < total) w[q] = *reinterpret_cast<const uint4 *>(src + 16 * q);
+        }
         int lo_i = static_cast<int>(pstart) - static_cast<int>(o);
         int hi_i = static_cast<int>(pend) - static_cast<int>(o);
-        lo_i = lo_i < 0 ? 0 : (lo_i > 32 ? 32 : lo_i);
-        hi_i = hi_i < 0 ? 0 : (hi_i > 32 ? 32 : hi_i);
-        const uint32_t valid = low_bits(hi_i) & ~low_bits(lo_i);
-        const uint32_t mine = wb.w & expand4(valid >> 28);
+        lo_i = lo_i < 0 ? 0 : (lo_i > 64 ? 64 : lo_i);
+        hi_i = hi_i < 0 ? 0 : (hi_i > 64 ? 64 : hi_i);
+        const uint32_t va = low_bits(hi_i > 32 ? 32 : hi_i) & ~low_bits(lo_i > 32 ? 32 : lo_i);               // bytes 0..31
+        const uint32_t vb = low_bits(hi_i > 32 ? hi_i - 32 : 0) & ~low_bits(lo_i > 32 ? lo_i - 32 : 0);       // bytes 32..63
+        const uint32_t mine = w[3].w & expand4(vb >> 28);
         uint32_t pw = __shfl_up_sync(0xffffffffu, mine, 1);
         if (lane == 0) pw = carry_w;
         carry_w = __shfl_sync(0xffffffffu, mine, 31);
         swar_begin(sl, pw);
-        swar_word<true>(sl, wa.x, expand4(valid));
-        swar_word<true>(sl, wa.y, expand4(valid >> 4));
-        swar_word<true>(sl, wa.z, expand4(valid >> 8));
-        swar_word<true>(sl, wa.w, expand4(valid >> 12));
-        swar_word<true>(sl, wb.x, expand4(valid >> 16));
-        swar_word<true>(sl, wb.y, expand4(valid >> 20));
-        swar_word<true>(sl, wb.z, expand4(valid >> 24));
-        swar_word<true>(sl, wb.w, expand4(valid >> 28));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t v = (q < 2 ? va : vb) >> (16 * (q & 1));
+            swar_word<true>(sl, w[q].x, expand4(v));
+            swar_word<true>(sl, w[q].y, expand4(v >> 4));
+            swar_word<true>(sl, w[q].z, expand4(v >> 8));
+            swar_word<true>(sl, w[q].w, expand4(v >> 12));
+        }
     }
     SwarChunk r;
     r.wide = __any_sync(0xffffffffu, (sl.wide & 0x80808080u) != 0);
@@ -762,8 +777,8 @@ __device__ __noinline__ int delta_page_sum_all(WarpSmem *sm, int lane) {
     }
     PageStream st;
     stream_open(st, sm, body, len, lane);
-    const uint32_t nchunks = (st.total + kFastChunkBytes - 1) / kFastChunkBytes;
-    constexpr uint32_t kChunksPerStage = kStageBytes / kFastChunkBytes;
+    const uint32_t nchunks = (st.total + kSwarChunkBytes - 1) / kSwarChunkBytes;
+    constexpr uint32_t kChunksPerStage = kStageBytes / kSwarChunkBytes;
     int64_t S = 0;                 // this lane's share of  sum_j d_j * (n - j)
     uint32_t tb = 0, carry_w = 0;  // terminators before this chunk; last (masked) word of the previous chunk
     uint32_t last_byte = 0;
@@ -1990,7 +2005,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, BYDB_FAST_CTAS) scan_sum_ex
     }
     __syncthreads();
     const uint32_t nwork = *p.work_count;
-    constexpr uint32_t kChunksPerStage = kStageBytes / kFastChunkBytes;
+    constexpr uint32_t kChunksPerStage = kStageBytes / kSwarChunkBytes;
     uint32_t seq = 0;  // stages issued so far by this warp (mbarrier phase bookkeeping; the kernel owns the ring from start to end)
     unsigned long long st_rows = 0, st_bytes = 0;  // per-warp statistics, flushed once at the end
     uint32_t st_blocks = 0, known_types = 0;
@@ -2103,7 +2118,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, BYDB_FAST_CTAS) scan_sum_ex
                     const uint32_t ps_k = __shfl_sync(0xffffffffu, pstart, k), pe_k = __shfl_sync(0xffffffffu, pend, k);
                     const uint32_t tot_k = __shfl_sync(0xffffffffu, total, k);
                     const int64_t first_k = static_cast<int64_t>(shfl_u64(static_cast<uint64_t>(first), k));
-                    const uint32_t nchunks = (tot_k + kFastChunkBytes - 1) / kFastChunkBytes;
+                    const uint32_t nchunks = (tot_k + kSwarChunkBytes - 1) / kSwarChunkBytes;
                     int64_t S = 0;
                     uint32_t tb = 0, carry_w = 0, last_byte = 0;
                     for (uint32_t j = 0; j < nst_k; ++j) {

@@ -71,7 +71,7 @@ static bool check(const uint8_t *b, uint32_t valid, uint32_t aw, bool dual) {
 }
 
 // ---- SWAR sum decoder (swar_begin / swar_word / swar_end): a whole page emulated lane by lane exactly like the kernel
-// walks it (1 KB chunks of 32 lanes x 32 bytes, 16-byte aligned window around the page, masked first / last chunk, the
+// walks it (2 KB chunks of 32 lanes x 64 bytes, 16-byte aligned window around the page, masked first / last chunk, the
 // previous lane's last word handed on, per-chunk exclusive scan of the lanes' terminator counts), against the plain
 // definition  sum over rows of (first + prefix of the deltas).
 static bool swar_page_check(std::mt19937_64 &rng, int n_values, int max_len) {
@@ -103,29 +103,29 @@ static bool swar_page_check(std::mt19937_64 &rng, int n_values, int max_len) {
     // emulation
     int64_t S = 0;
     uint32_t tb = 0, carry_w = 0, wide = 0;
-    const uint32_t nchunks = (total + 1023) / 1024;
+    const uint32_t nchunks = (total + 2047) / 2048;
     for (uint32_t c = 0; c < nchunks; ++c) {
-        const bool interior = c * 1024 >= pstart && (c + 1) * 1024 <= pend;
+        const bool interior = c * 2048 >= pstart && (c + 1) * 2048 <= pend;
         uint32_t nl[32], lastw[32];
         int32_t T[32], Rp[32];
         for (int lane = 0; lane < 32; ++lane) {
-            const uint32_t o = c * 1024 + lane * 32;
-            uint32_t w[8];
-            for (int k = 0; k < 8; ++k) {
+            const uint32_t o = c * 2048 + lane * 64;
+            uint32_t w[16];
+            for (int k = 0; k < 16; ++k) {
                 w[k] = 0;
                 if (o + 4 * k < total) memcpy(&w[k], &win[o + 4 * k], 4);
             }
             int lo_i = static_cast<int>(pstart) - static_cast<int>(o), hi_i = static_cast<int>(pend) - static_cast<int>(o);
-            lo_i = lo_i < 0 ? 0 : (lo_i > 32 ? 32 : lo_i);
-            hi_i = hi_i < 0 ? 0 : (hi_i > 32 ? 32 : hi_i);
-            const uint32_t valid = low_bits(hi_i) & ~low_bits(lo_i);
+            lo_i = lo_i < 0 ? 0 : (lo_i > 64 ? 64 : lo_i);
+            hi_i = hi_i < 0 ? 0 : (hi_i > 64 ? 64 : hi_i);
+            const uint64_t valid = (hi_i >= 64 ? ~0ull : ((1ull << hi_i) - 1ull)) & ~(lo_i >= 64 ? ~0ull : ((1ull << lo_i) - 1ull));
             // previous lane's last word: masked like that lane saw it
             uint32_t pw = lane == 0 ? carry_w : lastw[lane - 1];
             SwarLane sl;
             swar_begin(sl, pw);
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 16; ++k) {
                 if (interior) swar_word<false>(sl, w[k], 0xffffffffu);
-                else swar_word<true>(sl, w[k], expand4(valid >> (4 * k)));
+                else swar_word<true>(sl, w[k], expand4(static_cast<uint32_t>(valid >> (4 * k))));
             }
             lastw[lane] = sl.prev_w;
             nl[lane] = swar_end(sl, T[lane], Rp[lane]);
