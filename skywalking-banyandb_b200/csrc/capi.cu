@@ -2446,33 +2446,59 @@ int bydb_scan_reduce_prepared(bydb_ctx *ctx, bydb_prepared *p, int32_t root, byd
         }
         memset(&rg.captured, 0, sizeof rg.captured);
         cudaStream_t s = es.stream;
+        cudaGetLastError();  // a stale error of an earlier call must not be blamed on the capture
         cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+        const char *bad_step = nullptr;  // first step of the capture the runtime objected to (BYDB_TRACE prints it)
         if (e == cudaSuccess) {
             Scratch fin;
-            bool ok = cudaMemcpyAsync(d_args, h_args, sizeof(CommArgs), cudaMemcpyHostToDevice, s) == cudaSuccess;
+            auto step = [&](const char *name, bool good) {
+                const cudaError_t le = cudaGetLastError();
+                if ((!good || le != cudaSuccess) && !bad_step) {
+                    bad_step = name;
+                    if (le != cudaSuccess) e = le;
+                }
+            };
+            step("args copy", cudaMemcpyAsync(d_args, h_args, sizeof(CommArgs), cudaMemcpyHostToDevice, s) == cudaSuccess);
             launch_comm_wait_args(done, 1, d_args, 1, my_err, kErrPeerTimeout, s);
-            ok = ok && run_scan(ctx, &p->q, plan, es, s, my_slot, tl, &rg.captured, 0, true) == 0;
+            step("wait for the slots", true);
+            step("scan", run_scan(ctx, &p->q, plan, es, s, my_slot, tl, &rg.captured, 0, true) == 0);
             launch_comm_signal_args(flags + cm.rank, status + cm.rank, d_args, s);
+            step("signal", true);
             if (cm.rank == root) {
                 launch_comm_wait_args(flags, static_cast<uint32_t>(cm.nranks), d_args, 0, my_err, kErrPeerTimeout, s);
+                step("wait for the ranks", true);
                 launch_combine_tables(reinterpret_cast<uint64_t *>(slots0), static_cast<uint32_t>(cm.nranks), tl.total / 8, tl.off_sum_f64 / 8,
                                       tl.off_max_f64 / 8, tl.off_max_f64 / 8, tl.off_sum_i64 / 8, tl.off_sum_i64 / 8, tl.off_max_i64 / 8, tl.off_max_i64 / 8,
                                       tl.total / 8, s, slot_bytes / 8);
-                ok = ok && finalize_enqueue(&p->q, plan, es, s, slots0, tl, p->host_off, rg.fl, fin) == 0;
+                step("combine", true);
+                step("finalize", finalize_enqueue(&p->q, plan, es, s, slots0, tl, p->host_off, rg.fl, fin) == 0);
                 launch_comm_done_args(done, d_args, s);
-                ok = ok && cudaMemcpyAsync(h_back + 8, status, sizeof(unsigned long long) * static_cast<size_t>(cm.nranks), cudaMemcpyDeviceToHost, s) == cudaSuccess;
+                step("done word", true);
+                step("status read-back",
+                     cudaMemcpyAsync(h_back + 8, status, sizeof(unsigned long long) * static_cast<size_t>(cm.nranks), cudaMemcpyDeviceToHost, s) == cudaSuccess);
                 rg.captured.kernel_launches += 3 + rg.fl.launches;
             }
-            ok = ok && cudaMemcpyAsync(h_back, my_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, s) == cudaSuccess;
+            step("error read-back", cudaMemcpyAsync(h_back, my_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, s) == cudaSuccess);
             rg.captured.kernel_launches += 2;
-            cudaGraph_t graph = nullptr;
-            e = cudaStreamEndCapture(s, &graph);
-            if (ok && e == cudaSuccess && graph) e = cudaGraphInstantiate(&rg.exec, graph, 0);
-            else e = cudaErrorUnknown;
-            if (graph) cudaGraphDestroy(graph);
         }
-        if (e != cudaSuccess || !rg.exec) {
+        cudaGraph_t graph = nullptr;
+        if (e == cudaSuccess || bad_step) {
+            const cudaError_t ee = cudaStreamEndCapture(s, &graph);  // always leave capture mode
+            if (!bad_step && ee != cudaSuccess) {
+                bad_step = "end capture";
+                e = ee;
+            }
+        }
+        if (!bad_step && graph) {
+            e = cudaGraphInstantiate(&rg.exec, graph, 0);
+            if (e != cudaSuccess) bad_step = "instantiate";
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (bad_step || !rg.exec) {
+            static const bool trace = getenv("BYDB_TRACE") != nullptr;
+            if (trace) fprintf(stderr, "[bydb] prepared collective: capture failed at '%s' (%s); keeping the plain path\n", bad_step ? bad_step : "?", cudaGetErrorString(e));
             cudaGetLastError();
+            if (rg.exec) cudaGraphExecDestroy(rg.exec);
             rg.exec = nullptr;
             p->reduce_capturable = false;  // the plain path from here on
             lk.unlock();
