@@ -1369,6 +1369,9 @@ int bydb_init(const bydb_cfg *cfg, bydb_ctx **out) {
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
         }
     }
+    preload_kernels();
+    preload_unpack_kernels();
+    preload_index_kernels();
     int occ_fast = 1, occ_slow = 1;
     scan_max_ctas_per_sm(&occ_fast, &occ_slow);
     int want = (cfg && cfg->warps_per_sm > 0) ? (cfg->warps_per_sm + kWarpsPerCta - 1) / kWarpsPerCta : 64;

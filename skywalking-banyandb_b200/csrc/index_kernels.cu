@@ -15,6 +15,7 @@
 // Names: columns are interned into a small device table ("f:<field>" / "t:<family>/<tag>"); the host maps the table to the
 // context's name ids between the two walks (a few dozen strings -- no page bytes and no index bytes are parsed on the host).
 #include "index_kernels.cuh"
+#include "scan_kernels.cuh"
 
 #include "../../include/bydb_gpu.h"
 #include "zstd_dec.cuh"
@@ -385,6 +386,16 @@ void launch_index_walk(const IndexParams &p, bool fill, cudaStream_t s) {
 void launch_index_order(const IndexParams &p, cudaStream_t s) {
     if (p.n_blocks == 0) return;
     index_order_kernel<<<static_cast<unsigned>((p.n_blocks + 255) / 256), 256, 0, s>>>(p);
+}
+
+void preload_index_kernels() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, index_meta_kernel);
+    cudaFuncGetAttributes(&a, index_inflate_kernel);
+    cudaFuncGetAttributes(&a, index_walk_kernel<true>);
+    cudaFuncGetAttributes(&a, index_walk_kernel<false>);
+    cudaFuncGetAttributes(&a, index_order_kernel);
+    cudaGetLastError();
 }
 
 }  // namespace bydb

@@ -3049,6 +3049,32 @@ void launch_finalize(const FinalizeParams &p, cudaStream_t s) {
     finalize_kernel<<<(n + threads - 1) / threads, threads, 0, s>>>(p);
 }
 
+// With lazy module loading the first launch of a kernel loads its code, and that may wait for the device to go idle.  A
+// collective's wait kernel spins until its peers arrive -- if a peer shares the device (tests, several contexts per GPU) and
+// its first-ever launch of some kernel lands behind that spin, both wait for each other until the bounded wait gives up.
+// bydb_init therefore touches every kernel of the library once on its device.
+void preload_kernels() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, plan_blocks_kernel);
+    cudaFuncGetAttributes(&a, scan_blocks_kernel<true>);
+    cudaFuncGetAttributes(&a, scan_blocks_kernel<false>);
+    cudaFuncGetAttributes(&a, scan_sum_express_kernel);
+    cudaFuncGetAttributes(&a, detect_overlap_kernel);
+    cudaFuncGetAttributes(&a, dedup_kernel);
+    cudaFuncGetAttributes(&a, series_reduce_kernel);
+    cudaFuncGetAttributes(&a, group_reduce_kernel);
+    cudaFuncGetAttributes(&a, finalize_kernel);
+    cudaFuncGetAttributes(&a, select_rows_kernel<true>);
+    cudaFuncGetAttributes(&a, select_rows_kernel<false>);
+    cudaFuncGetAttributes(&a, combine_tables_kernel);
+    cudaFuncGetAttributes(&a, comm_wait_kernel);
+    cudaFuncGetAttributes(&a, comm_signal_kernel);
+    cudaFuncGetAttributes(&a, comm_wait_args_kernel);
+    cudaFuncGetAttributes(&a, comm_signal_args_kernel);
+    cudaFuncGetAttributes(&a, comm_done_args_kernel);
+    cudaGetLastError();
+}
+
 // Go math.Pow10 (src/math/pow10.go): pow10postab32[n/32] * pow10tab[n%32].  The product is done
 // on the host in IEEE double (no FMA: a single multiply), exactly like the Go runtime.
 int upload_pow10_table() {

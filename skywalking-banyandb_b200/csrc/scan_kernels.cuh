@@ -222,5 +222,8 @@ void launch_detect_overlap(const ScanParams &p, cudaStream_t s);
 void launch_dedup(const ScanParams &p, int grid, cudaStream_t s);
 int upload_pow10_table();
 void scan_max_ctas_per_sm(int *fast, int *slow);
+void preload_kernels();          // scan_kernels.cu: forces the (lazily loaded) code of every kernel onto the current device
+void preload_unpack_kernels();   // unpack_kernels.cu
+void preload_index_kernels();    // index_kernels.cu
 
 }  // namespace bydb

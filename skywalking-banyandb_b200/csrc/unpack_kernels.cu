@@ -472,4 +472,11 @@ void launch_unpack_pages(const UnpackParams &p, int n_warps, cudaStream_t s) {
     unpack_pages_kernel<<<(n_warps + 3) / 4, 128, 0, s>>>(p);
 }
 
+void preload_unpack_kernels() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, classify_pages_kernel);
+    cudaFuncGetAttributes(&a, unpack_pages_kernel);
+    cudaGetLastError();
+}
+
 }  // namespace bydb
