@@ -190,6 +190,38 @@ int bydb_part_directory(bydb_ctx *ctx, bydb_part_h part, void *blocks_out, uint6
 /* Scan -> filter -> aggregate over parts already resident in HBM. */
 int bydb_scan_agg(bydb_ctx *ctx, const bydb_query *q, bydb_result *out);
 
+/* Group-by on a STORED tag: the key changes from row to row inside a series (a12; the vectorized path's BatchAggregation with
+ * a non-entity key column, pkg/query/vectorized/measure/aggregation.go:193-254).  A row belongs to the group
+ * (series_group of its series, value of the key tag in that row); groups come back in insertion order -- the scan order is
+ * series by series (ascending series id), by time inside a series -- or in rank order when top_n > 0 (ties: the group
+ * inserted first, top.go:62-76).  A nil cell and "" are the same key (groupby.go:226-254 encodes a string / bytes key as
+ * length + raw bytes).  The key must be a string / binary tag stored with the dictionary encoding (<= 256 distinct values
+ * per block, pkg/encoding/dictionary.go); a block that fell back to the plain bytes block makes the call return
+ * BYDB_ENOTSUP, more than max_values distinct values over the selected blocks BYDB_ENOMEM (the reference's aggregation
+ * memory budget), a value longer than 64 bytes BYDB_ENOTSUP.  Device side: one pass collects the distinct values from the
+ * dictionary pages, then ONE SCAN PASS PER VALUE (the key as an extra predicate) fills that value's slice of a composite
+ * partial table; stats count every pass.  Not available through the prepared / partial-table / multi-GPU entry points,
+ * and not over parts that overlap in time. */
+typedef struct {
+    const char *family;    /* tag family of the key tag                                      */
+    const char *tag;       /* tag name                                                       */
+    uint32_t max_values;   /* distinct key values accepted over the whole query; 0 = 64, at most 256 */
+    uint32_t reserved;
+} bydb_group_key;
+
+typedef struct {
+    bydb_result base;          /* rows as in bydb_result; base.group_id[r] = series_group of row r       */
+    const int32_t *key_id;     /* [base.n_rows] key value of row r: index into the table below           */
+    int32_t n_keys;            /* distinct key values found in the selected blocks (some may have no row) */
+    int32_t reserved;
+    const uint32_t *key_off;   /* [n_keys + 1] value k is key_bytes[key_off[k] .. key_off[k+1])          */
+    const uint8_t *key_bytes;
+    void *owner;               /* private                                                                 */
+} bydb_keyed_result;
+
+int bydb_scan_agg_keyed(bydb_ctx *ctx, const bydb_query *q, const bydb_group_key *key, bydb_keyed_result *out);
+void bydb_keyed_result_free(bydb_ctx *ctx, bydb_keyed_result *r);
+
 /* Same, but the parts come as HOST file images: they are uploaded, scanned and dropped inside the
  * call (the end-to-end path of a cold query).  q->parts / q->n_parts are ignored. */
 int bydb_scan_agg_host(bydb_ctx *ctx, uint32_t n_parts, const bydb_part_files *parts, const bydb_query *q, bydb_result *out);

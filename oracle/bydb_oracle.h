@@ -201,6 +201,11 @@ typedef struct {
     int top_desc;                /* 1 = largest first */
     int threads;                 /* decode threads (goroutine-per-block analogue, query_batch.go:195); <=1 serial */
     int per_thread_partials;     /* 0 = reference-shaped (single-thread merge+agg), 1 = best-effort all-core */
+    /* per-row group key: a stored string / binary tag (NULL = none).  A row's group is (group of its series, tag value);
+     * groups are emitted in insertion order (pkg/query/vectorized/measure/aggregation.go:193-254); a null cell and ""
+     * are the same key (groupby.go:226-254).  Runs the serial fold. */
+    const char *key_family;
+    const char *key_tag;
 } ob_query;
 
 typedef struct {
@@ -214,6 +219,10 @@ typedef struct {
     uint64_t rows_scanned;       /* rows decoded from selected blocks (before time trim) */
     uint64_t rows_matched;       /* rows folded */
     uint64_t blocks_scanned;
+    /* only with a group-key tag: group_id[r] is then the SERIES group of row r, key_id[r] its key value */
+    int32_t *key_id;             /* [n_rows] index into keys */
+    int32_t n_keys;
+    ob_bytes *keys;              /* distinct key values, first-seen order */
 } ob_result;
 
 int ob_query_run(const ob_query *q, ob_result *out);

@@ -65,14 +65,16 @@ class _Query(C.Structure):
                 ("sids", C.c_void_p), ("groups", C.c_void_p), ("n_groups", C.c_int32),
                 ("tmin", C.c_int64), ("tmax", C.c_int64), ("n_preds", C.c_int), ("preds", C.POINTER(_Pred)),
                 ("n_aggs", C.c_int), ("aggs", C.POINTER(_Agg)), ("top_n", C.c_int), ("top_agg", C.c_int),
-                ("top_desc", C.c_int), ("threads", C.c_int), ("per_thread_partials", C.c_int)]
+                ("top_desc", C.c_int), ("threads", C.c_int), ("per_thread_partials", C.c_int),
+                ("key_family", C.c_char_p), ("key_tag", C.c_char_p)]
 
 
 class _Result(C.Structure):
     _fields_ = [("n_rows", C.c_int32), ("n_aggs", C.c_int32), ("group_id", C.POINTER(C.c_int32)),
                 ("rows", C.POINTER(C.c_int64)), ("is_float", C.POINTER(C.c_uint8)),
                 ("val_i64", C.POINTER(C.c_int64)), ("val_f64", C.POINTER(C.c_double)),
-                ("rows_scanned", C.c_uint64), ("rows_matched", C.c_uint64), ("blocks_scanned", C.c_uint64)]
+                ("rows_scanned", C.c_uint64), ("rows_matched", C.c_uint64), ("blocks_scanned", C.c_uint64),
+                ("key_id", C.POINTER(C.c_int32)), ("n_keys", C.c_int32), ("keys", C.POINTER(_Bytes))]
 
 
 class _Rows(C.Structure):
@@ -508,6 +510,7 @@ class Query:
     top_desc: bool = True
     threads: int = 1
     per_thread_partials: bool = False
+    group_key: Optional[Tuple[str, str]] = None  # (family, tag): per-row group key, a stored string / binary tag
 
 
 @dataclass
@@ -520,6 +523,7 @@ class Result:
     rows_scanned: int
     rows_matched: int
     blocks_scanned: int
+    key: Optional[List[bytes]] = None  # [n_rows] key value of each row (queries with group_key)
 
     def value(self, row: int, agg: int):
         return float(self.val_f64[row, agg]) if self.is_float[agg] else int(self.val_i64[row, agg])
@@ -572,6 +576,10 @@ def _mk_query(q: Query):
     cq.n_aggs, cq.aggs = len(q.aggs), aggs
     cq.top_n, cq.top_agg, cq.top_desc = q.top_n, q.top_agg, int(q.top_desc)
     cq.threads, cq.per_thread_partials = q.threads, int(q.per_thread_partials)
+    if q.group_key is not None:
+        kf, kt = q.group_key[0].encode(), q.group_key[1].encode()
+        keep.extend([kf, kt])
+        cq.key_family, cq.key_tag = kf, kt
     return cq, keep
 
 
@@ -588,6 +596,9 @@ def run_query(q: Query) -> Result:
         val_i64=np.ctypeslib.as_array(r.val_i64, (max(n, 1) * max(a, 1),))[:n * a].copy().reshape(n, a),
         val_f64=np.ctypeslib.as_array(r.val_f64, (max(n, 1) * max(a, 1),))[:n * a].copy().reshape(n, a),
         rows_scanned=r.rows_scanned, rows_matched=r.rows_matched, blocks_scanned=r.blocks_scanned)
+    if q.group_key is not None:
+        keys = [C.string_at(r.keys[k].p, r.keys[k].len) if r.keys[k].len > 0 else b"" for k in range(r.n_keys)]
+        res.key = [keys[r.key_id[i]] for i in range(n)]
     lib().ob_result_free(C.byref(r))
     return res
 

@@ -189,6 +189,9 @@ static int decode_numeric(const uint8_t *src, size_t srclen, int value_type, siz
     return 0;
 }
 
+/* tag columns a cursor loads: one per predicate, plus the group-key tag (last) when the query has one */
+static int n_tag_cols(const ob_query *q) { return q->n_preds + (q->key_tag ? 1 : 0); }
+
 static void cursor_free(cursor *c, int n_fcols, int n_preds) {
     free(c->ts);
     free(c->ver);
@@ -291,17 +294,19 @@ static int load_cursor(scan *s, cursor *c) {
         free(full.f64);
         free(full.null);
     }
-    c->tags = (tcol *)calloc((size_t)(q->n_preds ? q->n_preds : 1), sizeof(tcol));
-    for (int t = 0; t < q->n_preds; t++) {
-        const ob_pred *pr = &q->preds[t];
+    const int n_tcols = n_tag_cols(q);
+    c->tags = (tcol *)calloc((size_t)(n_tcols ? n_tcols : 1), sizeof(tcol));
+    for (int t = 0; t < n_tcols; t++) {
+        const char *t_family = t < q->n_preds ? q->preds[t].family : q->key_family;
+        const char *t_tag = t < q->n_preds ? q->preds[t].tag : q->key_tag;
         const obi_fammeta *fm = NULL;
         for (size_t k = 0; k < c->bm.n_fams; k++)
-            if (strcmp(c->bm.fams[k].name, pr->family) == 0) fm = &c->bm.fams[k];
+            if (strcmp(c->bm.fams[k].name, t_family) == 0) fm = &c->bm.fams[k];
         if (!fm) continue;
         char fn[200];
-        snprintf(fn, sizeof fn, "%s.tfm", pr->family);
+        snprintf(fn, sizeof fn, "%s.tfm", t_family);
         obi_file *tfm = obi_part_file(p, fn, 0);
-        snprintf(fn, sizeof fn, "%s.tf", pr->family);
+        snprintf(fn, sizeof fn, "%s.tf", t_family);
         obi_file *tf = obi_part_file(p, fn, 0);
         if (!tfm || !tf || fm->offset + fm->size > tfm->data.len) {
             ob_set_error("tag family metadata out of bounds");
@@ -314,7 +319,7 @@ static int load_cursor(scan *s, cursor *c) {
             return -1;
         }
         for (size_t k = 0; k < ncm; k++) {
-            if (strcmp(cms[k].name, pr->tag) != 0) continue;
+            if (strcmp(cms[k].name, t_tag) != 0) continue;
             if (cms[k].offset + cms[k].size > tf->data.len) {
                 free(cms);
                 ob_set_error("tag page out of bounds");
@@ -469,13 +474,80 @@ typedef struct {
 
 /* ------------------------------------------------------------------ per-series merge (query.go:912-1025) */
 typedef struct {
+    int32_t gid;    /* group of the row's series */
+    int32_t key_id; /* index into folder.keys */
+} comp;
+
+typedef struct {
     scan *s;
-    group *groups;   /* [n_groups] */
+    group *groups;   /* [n_groups]; with a group-key tag: [n_comp], one per (series group, key value) in first-seen order */
     int *agg_float;  /* [n_aggs] -1 unknown, 0 int, 1 float */
     uint64_t rows_matched;
     ob_rows *rows_out; /* optional raw dump */
     size_t rows_cap;
+    /* per-row group key (a stored tag): pkg/query/vectorized/measure/aggregation.go:193-254 -- the group of a row is found by
+     * its encoded key (groupby.go:226-254: strings / bytes as length + raw bytes, so a null cell and "" are the same key),
+     * new groups are appended to the insertion list and emitted in that order */
+    int keyed;
+    comp *comps;
+    size_t n_comp, cap_comp, last_comp;
+    ob_bytes *keys; /* distinct key values, first-seen order; owned copies */
+    size_t n_keys, cap_keys;
+    int key_bad_type;
 } folder;
+
+static int32_t keyed_group(folder *fo, const cursor *c, size_t row, int32_t gid) {
+    const ob_query *q = fo->s->q;
+    const tcol *kc = &c->tags[q->n_preds];
+    const uint8_t *kp = NULL;
+    size_t kl = 0;
+    if (kc->present) {
+        if (kc->value_type != OB_VT_STR && kc->value_type != OB_VT_BINARY) {
+            fo->key_bad_type = 1;
+            return -1;
+        }
+        if (kc->cells[row].len > 0) {
+            kp = kc->cells[row].p;
+            kl = (size_t)kc->cells[row].len;
+        }
+    }
+    if (fo->n_comp) { /* runs of equal keys are the common case */
+        const comp *lc = &fo->comps[fo->last_comp];
+        const ob_bytes *lk = &fo->keys[lc->key_id];
+        if (lc->gid == gid && (size_t)lk->len == kl && (kl == 0 || memcmp(lk->p, kp, kl) == 0)) return (int32_t)fo->last_comp;
+    }
+    size_t kid = 0;
+    for (; kid < fo->n_keys; kid++)
+        if ((size_t)fo->keys[kid].len == kl && (kl == 0 || memcmp(fo->keys[kid].p, kp, kl) == 0)) break;
+    if (kid == fo->n_keys) {
+        if (fo->n_keys == fo->cap_keys) {
+            fo->cap_keys = fo->cap_keys ? fo->cap_keys * 2 : 16;
+            fo->keys = (ob_bytes *)realloc(fo->keys, sizeof(ob_bytes) * fo->cap_keys);
+        }
+        uint8_t *cp = (uint8_t *)malloc(kl ? kl : 1);
+        if (kl) memcpy(cp, kp, kl);
+        fo->keys[kid].p = cp;
+        fo->keys[kid].len = (int64_t)kl;
+        fo->n_keys++;
+    }
+    size_t ci = 0;
+    for (; ci < fo->n_comp; ci++)
+        if (fo->comps[ci].gid == gid && (size_t)fo->comps[ci].key_id == kid) break;
+    if (ci == fo->n_comp) {
+        if (fo->n_comp == fo->cap_comp) {
+            fo->cap_comp = fo->cap_comp ? fo->cap_comp * 2 : 16;
+            fo->comps = (comp *)realloc(fo->comps, sizeof(comp) * fo->cap_comp);
+            fo->groups = (group *)realloc(fo->groups, sizeof(group) * fo->cap_comp);
+        }
+        fo->comps[ci].gid = gid;
+        fo->comps[ci].key_id = (int32_t)kid;
+        memset(&fo->groups[ci], 0, sizeof(group));
+        fo->groups[ci].slots = (slot *)calloc((size_t)(q->n_aggs ? q->n_aggs : 1), sizeof(slot));
+        fo->n_comp++;
+    }
+    fo->last_comp = ci;
+    return (int32_t)ci;
+}
 
 static void fold_row(folder *fo, const cursor *c, size_t row, int32_t gid) {
     const ob_query *q = fo->s->q;
@@ -508,6 +580,10 @@ static void fold_row(folder *fo, const cursor *c, size_t row, int32_t gid) {
         }
         r->n++;
         return;
+    }
+    if (fo->keyed) {
+        gid = keyed_group(fo, c, row, gid);
+        if (gid < 0) return;
     }
     group *g = &fo->groups[gid];
     g->rows++;
@@ -644,7 +720,7 @@ static void scan_setup(scan *s, const ob_query *q) {
     }
 }
 static void scan_teardown(scan *s) {
-    for (size_t i = 0; i < s->n_cur; i++) cursor_free(&s->cur[i], s->n_fcols, s->q->n_preds);
+    for (size_t i = 0; i < s->n_cur; i++) cursor_free(&s->cur[i], s->n_fcols, n_tag_cols(s->q));
     free(s->cur);
     free(s->fcol_names);
     free(s->agg_fcol);
@@ -696,9 +772,13 @@ static folder folder_new(scan *s, int32_t n_groups) {
     return fo;
 }
 static void folder_free(folder *fo, int32_t n_groups) {
+    if (fo->keyed) n_groups = (int32_t)fo->n_comp;
     for (int32_t g = 0; g < n_groups; g++) free(fo->groups[g].slots);
     free(fo->groups);
     free(fo->agg_float);
+    for (size_t k = 0; k < fo->n_keys; k++) free((void *)fo->keys[k].p);
+    free(fo->keys);
+    free(fo->comps);
 }
 
 typedef struct {
@@ -741,9 +821,11 @@ int ob_query_run(const ob_query *q, ob_result *out) {
     for (size_t i = 0; i < s.n_cur; i++) sorted[i] = &s.cur[i];
     qsort(sorted, s.n_cur, sizeof(cursor *), cursor_cmp);
 
-    folder total = folder_new(&s, ng);
+    const int keyed = q->key_tag != NULL;
+    folder total = folder_new(&s, keyed ? 0 : ng);
+    total.keyed = keyed;
     int rc = 0;
-    if (q->per_thread_partials && q->threads > 1) {
+    if (q->per_thread_partials && q->threads > 1 && !keyed) { /* insertion order needs the serial fold */
         /* best-effort all-core: whole series per worker, per-thread partials, Reduce-combine in worker order */
         int nt = q->threads;
         part_job *jobs = (part_job *)calloc((size_t)nt, sizeof(part_job));
@@ -799,12 +881,17 @@ int ob_query_run(const ob_query *q, ob_result *out) {
             fold_range(&total, sorted, 0, w);
         }
     }
+    if (rc == 0 && total.key_bad_type) {
+        ob_set_error("group key must be a string / binary tag");
+        rc = -1;
+    }
     if (rc != 0) {
         free(sorted);
         folder_free(&total, ng);
         scan_teardown(&s);
         return -1;
     }
+    if (keyed) ng = (int32_t)total.n_comp; /* composite groups, insertion order */
     out->rows_matched = total.rows_matched;
     out->n_aggs = q->n_aggs;
     out->is_float = (uint8_t *)calloc((size_t)(q->n_aggs ? q->n_aggs : 1), 1);
@@ -836,6 +923,17 @@ int ob_query_run(const ob_query *q, ob_result *out) {
         if (nrows > q->top_n) nrows = q->top_n;
     }
     out->n_rows = nrows;
+    if (keyed) {
+        out->key_id = (int32_t *)calloc((size_t)(nrows ? nrows : 1), sizeof(int32_t));
+        out->n_keys = (int32_t)total.n_keys;
+        out->keys = (ob_bytes *)calloc(total.n_keys ? total.n_keys : 1, sizeof(ob_bytes));
+        for (size_t k2 = 0; k2 < total.n_keys; k2++) {
+            uint8_t *cp = (uint8_t *)malloc(total.keys[k2].len ? (size_t)total.keys[k2].len : 1);
+            memcpy(cp, total.keys[k2].p, (size_t)total.keys[k2].len);
+            out->keys[k2].p = cp;
+            out->keys[k2].len = total.keys[k2].len;
+        }
+    }
     out->group_id = (int32_t *)calloc((size_t)(nrows ? nrows : 1), sizeof(int32_t));
     out->rows = (int64_t *)calloc((size_t)(nrows ? nrows : 1), sizeof(int64_t));
     size_t nv = (size_t)(nrows ? nrows : 1) * (size_t)(q->n_aggs ? q->n_aggs : 1);
@@ -843,7 +941,8 @@ int ob_query_run(const ob_query *q, ob_result *out) {
     out->val_f64 = (double *)calloc(nv, sizeof(double));
     for (int32_t r = 0; r < nrows; r++) {
         int32_t g = ents[r].g;
-        out->group_id[r] = g;
+        out->group_id[r] = keyed ? total.comps[g].gid : g;
+        if (keyed) out->key_id[r] = total.comps[g].key_id;
         out->rows[r] = total.groups[g].rows;
         for (int a = 0; a < q->n_aggs; a++) {
             const slot *sl = &total.groups[g].slots[a];
@@ -861,6 +960,9 @@ int ob_query_run(const ob_query *q, ob_result *out) {
 }
 
 void ob_result_free(ob_result *r) {
+    for (int32_t k = 0; k < r->n_keys; k++) free((void *)r->keys[k].p);
+    free(r->keys);
+    free(r->key_id);
     free(r->group_id);
     free(r->rows);
     free(r->is_float);

@@ -69,6 +69,15 @@ class _Result(C.Structure):
                 ("owner", C.c_void_p)]
 
 
+class _GroupKey(C.Structure):
+    _fields_ = [("family", C.c_char_p), ("tag", C.c_char_p), ("max_values", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class _KeyedResult(C.Structure):
+    _fields_ = [("base", _Result), ("key_id", C.POINTER(C.c_int32)), ("n_keys", C.c_int32), ("reserved", C.c_int32),
+                ("key_off", C.POINTER(C.c_uint32)), ("key_bytes", C.POINTER(C.c_uint8)), ("owner", C.c_void_p)]
+
+
 class _PartialRows(C.Structure):
     _fields_ = [("n_rows", C.c_int32), ("n_aggs", C.c_int32), ("group_id", C.POINTER(C.c_int32)), ("is_float", C.POINTER(C.c_uint8)),
                 ("val_i64", C.POINTER(C.c_int64)), ("val_f64", C.POINTER(C.c_double)), ("cnt_i64", C.POINTER(C.c_int64)),
@@ -118,6 +127,9 @@ def load_library():
     L.bydb_scan_agg.argtypes = [C.c_void_p, C.POINTER(_Query), C.POINTER(_Result)]
     L.bydb_scan_agg_host.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_PartFiles), C.POINTER(_Query), C.POINTER(_Result)]
     L.bydb_result_free.argtypes = [C.c_void_p, C.POINTER(_Result)]
+    L.bydb_scan_agg_keyed.argtypes = [C.c_void_p, C.POINTER(_Query), C.POINTER(_GroupKey), C.POINTER(_KeyedResult)]
+    L.bydb_keyed_result_free.argtypes = [C.c_void_p, C.POINTER(_KeyedResult)]
+    L.bydb_keyed_result_free.restype = None
     L.bydb_query_prepare.argtypes = [C.c_void_p, C.POINTER(_Query), C.POINTER(C.c_void_p)]
     L.bydb_scan_agg_prepared.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Result)]
     L.bydb_query_release.argtypes = [C.c_void_p, C.c_void_p]
@@ -200,6 +212,8 @@ class Result:
     val_i64: np.ndarray   # [n_rows, n_aggs]
     val_f64: np.ndarray
     stats: Stats
+    key: Optional[List[bytes]] = None   # scan_agg_keyed only: key value of each row
+    n_keys: int = 0                      # scan_agg_keyed only: distinct key values found in the selected blocks
 
     def value(self, row: int, agg: int):
         return float(self.val_f64[row, agg]) if self.is_float[agg] else int(self.val_i64[row, agg])
@@ -402,6 +416,28 @@ class Context:
             return _read_result(r)
         finally:
             self._L.bydb_result_free(self._h, C.byref(r))
+
+    def scan_agg_keyed(self, q: Query, family: str, tag: str, max_values: int = 0) -> Result:
+        """Group-by on a stored tag (bydb_scan_agg_keyed): rows carry (series group, key value)."""
+        keep: list = []
+        cq = _mk_query(q, keep)
+        fb, tb = family.encode(), tag.encode()
+        gk = _GroupKey(fb, tb, max_values, 0)
+        r = _KeyedResult()
+        _check(self._L.bydb_scan_agg_keyed(self._h, C.byref(cq), C.byref(gk), C.byref(r)))
+        try:
+            if r.base.n_rows == 0 and not r.base.owner:
+                a = len(q.aggs)
+                res = Result(np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(a, bool), np.zeros((0, a), np.int64),
+                             np.zeros((0, a), np.float64), Stats.of(r.base.stats))
+            else:
+                res = _read_result(r.base)
+            keys = [bytes(r.key_bytes[r.key_off[k]:r.key_off[k + 1]]) for k in range(r.n_keys)]
+            res.key = [keys[r.key_id[i]] for i in range(r.base.n_rows)]
+            res.n_keys = r.n_keys
+            return res
+        finally:
+            self._L.bydb_keyed_result_free(self._h, C.byref(r))
 
     # ---- prepared queries replayed as one captured CUDA graph (bydb_query_prepare / bydb_scan_agg_prepared)
     def prepare_graph(self, q: Query) -> "GraphQuery":

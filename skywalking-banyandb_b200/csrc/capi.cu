@@ -270,10 +270,12 @@ const char *dev_err_text(uint32_t code) {
         case kErrPredType: return "predicate literal type does not match the stored tag column type";
         case kErrTmaTimeout: return "internal error: a TMA bulk copy did not complete";
         case kErrPeerTimeout: return "multi-GPU reduce: a peer rank did not deliver its partial table in time";
+        case kErrKeyCap: return "per-row group key: more distinct key values than bydb_group_key.max_values";
+        case kErrKeyLong: return "per-row group key: a key value longer than 64 bytes";
     }
     return "unknown device error";
 }
-int dev_err_code(uint32_t code) { return (code == kErrCorrupt || code == kErrBadEnc || code == kErrTypeMix || code == kErrPredType) ? BYDB_EINVAL : (code == kErrTmaTimeout || code == kErrPeerTimeout) ? BYDB_EIO : BYDB_ENOTSUP; }
+int dev_err_code(uint32_t code) { return code == kErrKeyCap ? BYDB_ENOMEM : (code == kErrCorrupt || code == kErrBadEnc || code == kErrTypeMix || code == kErrPredType) ? BYDB_EINVAL : (code == kErrTmaTimeout || code == kErrPeerTimeout) ? BYDB_EIO : BYDB_ENOTSUP; }
 
 int validate_query(const bydb_query *q, bool need_parts) {
     if (!q) return fail(BYDB_EINVAL, "query is NULL");
@@ -784,8 +786,16 @@ struct Scratch {
 
 // Runs plan -> scan -> series_reduce -> group_reduce on `stream`, leaving the partial table at
 // `d_table` (device).  Synchronises the stream.  Fills stats.
+// one pass of a group-key query (bydb_scan_agg_keyed): where in the composite table the pass writes, and its side outputs
+struct KeyedPass {
+    size_t group_off;   // first group row of this pass's slice
+    int64_t *coltype;   // [F] the pass's own column types + status (merged by permute_table)
+    int64_t *kts;       // [n_series] see ReduceParams::Kts
+    uint32_t *krow;     // [n_series]
+};
+
 int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cudaStream_t stream, uint8_t *d_table, const TableLayout &tl,
-             bydb_stats *stats, int batch = 0, bool presized = false) {
+             bydb_stats *stats, int batch = 0, bool presized = false, const KeyedPass *kp = nullptr) {
     cudaEvent_t *ev = slot.ev + 4 * batch;
     uint8_t *zpage = slot.zpage + 256 * batch;
     memset(zpage, 0, 256);  // a failure before the read-back is enqueued must not leave a previous call's status behind
@@ -821,6 +831,7 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
     const size_t off_qsid = carve(NB * 4);
     const size_t off_P = carve(NB * F * sizeof(BlockPartial));
     const size_t off_Prows = carve(NB * 4);
+    const size_t off_Pfirst = carve(kp ? NB * 4 : 0);
     const size_t off_S = carve(NS * F * sizeof(BlockPartial));
     const size_t off_Srows = carve(NS * 8);
     const size_t n_first = NS * plan.parts.size();
@@ -904,6 +915,7 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
     sp.first_block = use_first ? reinterpret_cast<uint32_t *>(d + off_first) : nullptr;
     sp.P = reinterpret_cast<BlockPartial *>(d + off_P);
     sp.Prows = reinterpret_cast<uint32_t *>(d + off_Prows);
+    sp.Pfirst = kp ? reinterpret_cast<uint32_t *>(d + off_Pfirst) : nullptr;
 
     rp.n_series = static_cast<uint32_t>(NS);
     rp.n_fcols = static_cast<uint32_t>(F);
@@ -928,6 +940,16 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
     rp.max_i64 = reinterpret_cast<int64_t *>(d_table + tl.off_max_i64);
     rp.notmin_i64 = reinterpret_cast<int64_t *>(d_table + tl.off_notmin_i64);
     rp.coltype = reinterpret_cast<int64_t *>(d_table + tl.off_coltype);
+    if (kp) {
+        const size_t go = kp->group_off, gf = kp->group_off * F;
+        rp.sum_f64 += gf, rp.max_f64 += gf, rp.negmin_f64 += gf;
+        rp.sum_i64 += gf, rp.cnt += gf, rp.max_i64 += gf, rp.notmin_i64 += gf;
+        rp.rows += go;
+        rp.coltype = kp->coltype;
+        rp.Pfirst = sp.Pfirst;
+        rp.Kts = kp->kts;
+        rp.Krow = kp->krow;
+    }
 
     CUDA_TRY(cudaEventRecord(ev[0], stream));
     launch_plan_blocks(sp, stream);
@@ -1526,6 +1548,264 @@ int bydb_scan_agg(bydb_ctx *ctx, const bydb_query *q, bydb_result *out) {
 // predicate tags -- into one arena image per slice: [DevBlock[] | DevCol[] | file table | pages], every page offset
 // rewritten into the arena.  The image goes up through the pinned staging ring in 64 MB chunks.
 // ------------------------------------------------------------------------------------------------
+
+namespace {
+struct KeyedOwner {
+    std::vector<int32_t> key_id;
+    std::vector<uint32_t> key_off;
+    std::vector<uint8_t> key_bytes;
+};
+}  // namespace
+
+void bydb_keyed_result_free(bydb_ctx *ctx, bydb_keyed_result *r);
+
+// Group-by on a stored tag (per-row key): see "Group key" in scan_kernels.cu for the device side.
+int bydb_scan_agg_keyed(bydb_ctx *ctx, const bydb_query *q, const bydb_group_key *key, bydb_keyed_result *out) {
+    return guarded([&]() -> int {
+    if (!ctx || !out) return fail(BYDB_EINVAL, "ctx/out is NULL");
+    memset(out, 0, sizeof *out);
+    int rc = validate_query(q, true);
+    if (rc) return rc;
+    if (!key || !key->family || !key->tag) return fail(BYDB_EINVAL, "group key without family/tag");
+    const uint32_t cap = key->max_values ? key->max_values : 64u;
+    if (cap > kMaxKeyValues) return fail(BYDB_EINVAL, "bydb_group_key.max_values above 256");
+    if (q->n_preds + 1 > kMaxPreds) return fail(BYDB_ENOTSUP, "a group-key query takes at most 7 predicates");
+    g_last_dev_err = 0;
+    Plan plan;
+    rc = make_plan(ctx, q, nullptr, plan);
+    if (rc) return rc;
+    for (size_t a = 0; a < plan.parts.size(); ++a)
+        for (size_t b = a + 1; b < plan.parts.size(); ++b) {
+            const PartDir &x = plan.parts[a]->dir, &y = plan.parts[b]->dir;
+            if (x.blocks.empty() || y.blocks.empty()) continue;
+            if (std::max(std::max(x.min_ts, y.min_ts), q->tmin) <= std::min(std::min(x.max_ts, y.max_ts), q->tmax))
+                return fail(BYDB_ENOTSUP, "group-key query over parts that overlap in time (version dedup) is not supported on the device path");
+        }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    SlotLease lease(ctx);
+    if (lease.init()) return fail(BYDB_EIO, "cannot create stream");
+    ExecSlot &slot = *lease.slot;
+    cudaStream_t stream = slot.stream;
+    const size_t F = plan.fcols.size(), NS = q->n_series, NB = plan.total_blocks, G = static_cast<size_t>(plan.n_groups);
+    memset(&out->base.stats, 0, sizeof out->base.stats);
+
+    // ---- 1. the distinct key values of the selected blocks
+    size_t o = 0;
+    auto carve = [&](size_t bytes) {
+        size_t at = o;
+        o = align_up(o + bytes, 256);
+        return at;
+    };
+    const size_t a_sids = carve(NS * 8), a_slots = carve(kKeySlots * 8), a_ctl = carve(16), a_vals = carve(static_cast<size_t>(cap) * kMaxLit),
+                 a_lens = carve(static_cast<size_t>(cap) * 4);
+    const size_t a_total = o;
+    Scratch ka;
+    ka.stream = stream;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&ka.base), a_total, stream));
+    const size_t back_bytes = a_total - a_ctl;  // ctl | vals | lens come back in one copy
+    if (slot.ensure_pinned(std::max(back_bytes, NS * 8) + 256)) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
+    if (NS) memcpy(slot.pinned, q->series_ids, NS * 8);
+    if (NS) CUDA_TRY(cudaMemcpyAsync(ka.base + a_sids, slot.pinned, NS * 8, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemsetAsync(ka.base + a_slots, 0, a_total - a_slots, stream));
+    KeyParams kpar;
+    memset(&kpar, 0, sizeof kpar);
+    {
+        uint32_t base = 0;
+        for (size_t i = 0; i < plan.parts.size(); ++i) {
+            DevPartRef r;
+            r.blocks = plan.parts[i]->d_blocks;
+            r.cols = plan.parts[i]->d_cols;
+            r.files = plan.parts[i]->d_files;
+            r.n_blocks = static_cast<uint32_t>(plan.parts[i]->dir.blocks.size());
+            r.block_base = base;
+            base += r.n_blocks;
+            kpar.parts[i] = r;
+        }
+    }
+    kpar.n_parts = static_cast<uint32_t>(plan.parts.size());
+    kpar.total_blocks = static_cast<uint32_t>(NB);
+    kpar.q_sids = reinterpret_cast<const uint64_t *>(ka.base + a_sids);
+    kpar.n_series = static_cast<uint32_t>(NS);
+    kpar.cap = cap;
+    kpar.tmin = q->tmin;
+    kpar.tmax = q->tmax;
+    kpar.key_name = ctx->names.find(std::string("t:") + key->family + "/" + key->tag);
+    kpar.slots = reinterpret_cast<unsigned long long *>(ka.base + a_slots);
+    kpar.count = reinterpret_cast<uint32_t *>(ka.base + a_ctl);
+    kpar.err = reinterpret_cast<uint32_t *>(ka.base + a_ctl) + 1;
+    kpar.vals = ka.base + a_vals;
+    kpar.lens = reinterpret_cast<uint32_t *>(ka.base + a_lens);
+    launch_key_values(kpar, ctx->sm_count * 4, stream);
+    CUDA_TRY(cudaStreamSynchronize(stream));  // the staging of the series ids must be consumed before the read-back reuses it
+    CUDA_TRY(cudaMemcpyAsync(slot.pinned, ka.base + a_ctl, back_bytes, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaGetLastError());
+    out->base.stats.kernel_launches += 2;
+    out->base.stats.h2d_bytes += NS * 8;
+    out->base.stats.d2h_bytes += back_bytes;
+    const uint32_t *ctl = reinterpret_cast<const uint32_t *>(slot.pinned);
+    if (ctl[1] != 0) {
+        g_last_dev_err = ctl[1];
+        char buf[64];
+        snprintf(buf, sizeof buf, " (block #%u)", ctl[2]);
+        return fail(dev_err_code(ctl[1]), std::string(dev_err_text(ctl[1])) + buf);
+    }
+    const size_t V = std::min<size_t>(ctl[0], cap);
+    std::vector<std::vector<uint8_t>> values(V);
+    {
+        const uint8_t *hv = slot.pinned + (a_vals - a_ctl);
+        const uint32_t *hl = reinterpret_cast<const uint32_t *>(slot.pinned + (a_lens - a_ctl));
+        for (size_t v = 0; v < V; ++v) values[v].assign(hv + v * kMaxLit, hv + v * kMaxLit + hl[v]);
+    }
+    auto owner = new KeyedOwner();
+    out->owner = owner;
+    bool done = false;
+    struct Undo {  // a failure past this point must not leave a half-filled result with the caller
+        bydb_ctx *ctx;
+        bydb_keyed_result *out;
+        bool *done;
+        ~Undo() {
+            if (!*done) bydb_keyed_result_free(ctx, out);
+        }
+    } undo{ctx, out, &done};
+    owner->key_off.push_back(0);
+    for (size_t v = 0; v < V; ++v) {
+        owner->key_bytes.insert(owner->key_bytes.end(), values[v].begin(), values[v].end());
+        owner->key_off.push_back(static_cast<uint32_t>(owner->key_bytes.size()));
+    }
+    if (owner->key_bytes.empty()) owner->key_bytes.push_back(0);
+    out->n_keys = static_cast<int32_t>(V);
+    out->key_off = owner->key_off.data();
+    out->key_bytes = owner->key_bytes.data();
+    if (V == 0) {  // no block selected: no rows (n_rows = 0)
+        done = true;
+        return 0;
+    }
+
+    // ---- 2. one scan pass per value into slice v of the composite table (V x G groups, value-major)
+    const size_t GP = G * V;
+    if (GP > 0x7fffffffull / std::max<size_t>(F, 1)) return fail(BYDB_ENOMEM, "group-key query: too many composite groups");
+    TableLayout tlc(GP, F);
+    o = 0;
+    const size_t b_src = carve(tlc.total), b_dst = carve(tlc.total), b_ct = carve(V * F * 8), b_kts = carve(V * NS * 8), b_krow = carve(V * NS * 4),
+                 b_slot = carve(NS * V * 4), b_first = carve(GP * 4), b_perm = carve(GP * 4), b_np = carve(16);
+    Scratch kb;
+    kb.stream = stream;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&kb.base), o, stream));
+    CUDA_TRY(cudaMemsetAsync(kb.base + b_ct, 0, V * F * 8, stream));
+    CUDA_TRY(cudaMemsetAsync(kb.base + b_slot, 0xff, NS * V * 4, stream));
+    {
+        const size_t A = q->n_aggs;
+        if (slot.ensure_pinned(NS * 12 + (G + 1) * 4 + GP * (12 + 16 * A) + 16 * A + 8192)) return fail(BYDB_ENOMEM, "cudaMallocHost failed");
+    }
+    std::vector<bydb_pred> preds(q->preds, q->preds + q->n_preds);
+    preds.emplace_back();
+    bydb_query qv = *q;
+    qv.n_preds = q->n_preds + 1;
+    for (size_t v = 0; v < V; ++v) {
+        bydb_pred &kpred = preds.back();
+        memset(&kpred, 0, sizeof kpred);
+        kpred.family = key->family;
+        kpred.tag = key->tag;
+        kpred.op = values[v].empty() ? kOpEqOrNil : BYDB_OP_EQ;  // a nil cell and "" are the same key (groupby.go:226-254)
+        kpred.value_type = BYDB_VT_STR;
+        kpred.lit = values[v].data();
+        kpred.lit_len = values[v].size();
+        qv.preds = preds.data();
+        KeyedPass pass;
+        pass.group_off = v * G;
+        pass.coltype = reinterpret_cast<int64_t *>(kb.base + b_ct) + v * F;
+        pass.kts = reinterpret_cast<int64_t *>(kb.base + b_kts) + v * NS;
+        pass.krow = reinterpret_cast<uint32_t *>(kb.base + b_krow) + v * NS;
+        rc = run_scan(ctx, &qv, plan, slot, stream, kb.base + b_src, tlc, &out->base.stats, 0, true, &pass);
+        cudaError_t ce = cudaStreamSynchronize(stream);  // also on failure: nothing may be in flight when the slot goes back
+        if (!rc && ce != cudaSuccess) rc = fail(BYDB_EIO, cudaGetErrorString(ce));
+        if (!rc) rc = collect_scan(slot, &out->base.stats);
+        if (rc) return rc;
+    }
+
+    // ---- 3. insertion order of the composite groups, table reordered, ordinary finalisation / Top-N on it
+    KeyOrderParams ko;
+    memset(&ko, 0, sizeof ko);
+    ko.n_groups = static_cast<int32_t>(G);
+    ko.n_values = static_cast<uint32_t>(V);
+    ko.n_series = static_cast<uint32_t>(NS);
+    // order | group_start of the series groups: rebuilt here (run_scan's copies live in its own scratch)
+    std::vector<int32_t> order(NS), gstart(G + 1, 0);
+    if (q->series_group) {
+        for (size_t i = 0; i < NS; ++i) gstart[static_cast<size_t>(q->series_group[i]) + 1]++;
+        for (size_t g = 0; g < G; ++g) gstart[g + 1] += gstart[g];
+        std::vector<int32_t> cur(gstart.begin(), gstart.end() - 1);
+        for (size_t i = 0; i < NS; ++i) order[cur[q->series_group[i]]++] = static_cast<int32_t>(i);
+    } else {
+        for (size_t i = 0; i < NS; ++i) order[i] = static_cast<int32_t>(i);
+        gstart[1] = static_cast<int32_t>(NS);
+    }
+    Scratch kc;
+    kc.stream = stream;
+    const size_t c_order = 0, c_gstart = align_up(NS * 4, 256);
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&kc.base), c_gstart + (G + 1) * 4, stream));
+    if (NS) memcpy(slot.pinned, order.data(), NS * 4);
+    memcpy(slot.pinned + c_gstart, gstart.data(), (G + 1) * 4);
+    CUDA_TRY(cudaMemcpyAsync(kc.base, slot.pinned, c_gstart + (G + 1) * 4, cudaMemcpyHostToDevice, stream));
+    ko.order = reinterpret_cast<const int32_t *>(kc.base + c_order);
+    ko.group_start = reinterpret_cast<const int32_t *>(kc.base + c_gstart);
+    ko.Kts = reinterpret_cast<const int64_t *>(kb.base + b_kts);
+    ko.Krow = reinterpret_cast<const uint32_t *>(kb.base + b_krow);
+    ko.slot = reinterpret_cast<int32_t *>(kb.base + b_slot);
+    ko.first_series = reinterpret_cast<int32_t *>(kb.base + b_first);
+    ko.perm = reinterpret_cast<int32_t *>(kb.base + b_perm);
+    ko.n_present = reinterpret_cast<uint32_t *>(kb.base + b_np);
+    launch_key_order(ko, stream);
+    auto table_ptrs = [&](uint8_t *t) {
+        TablePtrs tp;
+        tp.sum_f64 = reinterpret_cast<double *>(t + tlc.off_sum_f64);
+        tp.max_f64 = reinterpret_cast<double *>(t + tlc.off_max_f64);
+        tp.negmin_f64 = reinterpret_cast<double *>(t + tlc.off_negmin_f64);
+        tp.sum_i64 = reinterpret_cast<int64_t *>(t + tlc.off_sum_i64);
+        tp.cnt = reinterpret_cast<int64_t *>(t + tlc.off_cnt);
+        tp.rows = reinterpret_cast<int64_t *>(t + tlc.off_rows);
+        tp.max_i64 = reinterpret_cast<int64_t *>(t + tlc.off_max_i64);
+        tp.notmin_i64 = reinterpret_cast<int64_t *>(t + tlc.off_notmin_i64);
+        tp.coltype = reinterpret_cast<int64_t *>(t + tlc.off_coltype);
+        return tp;
+    };
+    launch_permute_table(table_ptrs(kb.base + b_dst), table_ptrs(kb.base + b_src), ko.perm, static_cast<uint32_t>(GP), static_cast<uint32_t>(F),
+                         reinterpret_cast<const int64_t *>(kb.base + b_ct), static_cast<uint32_t>(V), stream);
+    CUDA_TRY(cudaStreamSynchronize(stream));  // the staging above is reused by the finalisation's read-back
+    out->base.stats.kernel_launches += 3;
+    Plan planc = plan;
+    planc.n_groups = static_cast<int32_t>(GP);
+    rc = finalize_to_host(ctx, q, planc, slot, stream, kb.base + b_dst, tlc, &out->base, true);
+    if (rc) {
+        cudaStreamSynchronize(stream);
+        return rc;
+    }
+    std::vector<int32_t> perm(GP);
+    CUDA_TRY(cudaMemcpyAsync(perm.data(), kb.base + b_perm, GP * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    out->base.stats.d2h_bytes += GP * 4;
+    // rows carry the position in insertion order: back to (group of the series, key value)
+    auto *ro = static_cast<ResultOwner *>(out->base.owner);
+    owner->key_id.resize(ro->group_id.size());
+    for (size_t r = 0; r < ro->group_id.size(); ++r) {
+        const int32_t comp = perm[static_cast<size_t>(ro->group_id[r])];
+        owner->key_id[r] = comp / static_cast<int32_t>(G);
+        ro->group_id[r] = comp % static_cast<int32_t>(G);
+    }
+    out->key_id = owner->key_id.data();
+    done = true;
+    return 0;
+    });
+}
+
+void bydb_keyed_result_free(bydb_ctx *ctx, bydb_keyed_result *r) {
+    if (!r) return;
+    bydb_result_free(ctx, &r->base);
+    delete static_cast<KeyedOwner *>(r->owner);
+    memset(r, 0, sizeof *r);
+}
+
 struct GatherSeg {
     const uint8_t *src;
     size_t dst;

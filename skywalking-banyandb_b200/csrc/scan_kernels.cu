@@ -328,6 +328,7 @@ __device__ __forceinline__ bool cmp_op(int op, bool have, int cmp) {
         case BYDB_OP_LE: return have && cmp <= 0;
         case BYDB_OP_GT: return have && cmp > 0;
         case BYDB_OP_GE: return have && cmp >= 0;
+        case kOpEqOrNil: return !have || cmp == 0;
     }
     return false;
 }
@@ -1705,6 +1706,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? BYDB_FAST_CTAS 
 
         // ---- 2. tag predicates -> row bitmask
         uint32_t rows = empty ? 0 : (r1 - r0 + 1);
+        uint32_t first_row = r0;
         const int32_t ddi = p.dd_index ? p.dd_index[g] : -1;
         const bool use_mask = p.n_preds > 0 || ddi >= 0;
         if (use_mask && !empty && err == kErrNone && !defer) {
@@ -1831,6 +1833,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? BYDB_FAST_CTAS 
 #pragma unroll
                     for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
                     rows = c;
+                    if (p.Pfirst) {  // group-key passes: where the key value first shows in this block
+                        uint32_t f = 0xffffffffu;
+                        for (uint32_t w = lane; w < nwords && f == 0xffffffffu; w += 32) {
+                            const uint32_t m = sm->mask[w];
+                            if (m) f = w * 32u + static_cast<uint32_t>(__ffs(m)) - 1u;
+                        }
+                        first_row = __reduce_min_sync(0xffffffffu, f);
+                    }
                 }
             }
         }
@@ -1944,6 +1954,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kFastLane ? BYDB_FAST_CTAS 
         }
         if (lane == 0) {
             p.Prows[g] = rows;
+            if (p.Pfirst) p.Pfirst[g] = first_row;
             sm->st_rows += count;
             sm->st_matched += rows;
             sm->st_bytes += page_bytes;
@@ -2426,6 +2437,8 @@ __global__ void __launch_bounds__(256) series_reduce_kernel(const __grid_constan
         acc[c].cnt = 0;
     }
     int64_t rows = 0;
+    int64_t kts = INT64_MAX;  // group-key passes: (ts_min, row) of the first surviving row of the series, lane-local until the end
+    uint32_t krow = 0;
     int64_t span_lo[4], span_hi[4];
     int nspan = 0;
     bool overlap = false;
@@ -2453,6 +2466,10 @@ __global__ void __launch_bounds__(256) series_reduce_kernel(const __grid_constan
                 r = p.Prows[g];
                 tlo = part.blocks[b].ts_min;
                 thi = part.blocks[b].ts_max;
+            }
+            if (p.Kts && r > 0 && tlo < kts) {
+                kts = tlo;
+                krow = p.Pfirst[g];
             }
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) {
@@ -2489,6 +2506,21 @@ __global__ void __launch_bounds__(256) series_reduce_kernel(const __grid_constan
                 span_lo[3] = plo < span_lo[3] ? plo : span_lo[3];
                 span_hi[3] = phi > span_hi[3] ? phi : span_hi[3];
             }
+        }
+    }
+    if (p.Kts) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const int64_t ot = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(kts), m));
+            const uint32_t orow = __shfl_xor_sync(0xffffffffu, krow, m);
+            if (ot < kts) {
+                kts = ot;
+                krow = orow;
+            }
+        }
+        if (lane == 0) {
+            p.Kts[i] = kts;
+            p.Krow[i] = krow;
         }
     }
     if (lane != 0) return;
@@ -2872,6 +2904,249 @@ __global__ void combine_tables_kernel(uint64_t *t, uint32_t n, uint64_t words, u
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
+
+// ------------------------------------------------------------------------------------------------
+// Group key: group-by on a stored dictionary tag, whose value changes from row to row inside a series
+// (pkg/query/vectorized/measure/aggregation.go:193-254 Consume: key of the row -> group, new groups appended to the
+// insertion list; groupby.go:226-254: a string / bytes key is its length + raw bytes, so a nil cell and "" are one key).
+//   1. key_values_kernel: one warp per selected block reads the tag's dictionary page (<= 256 values per block,
+//      pkg/encoding/dictionary.go:52-88) and enters every value into a small open-addressing table in global memory; a
+//      slot holds the device address and length of the bytes inside the part, the bytes themselves never move.
+//   2. the host runs one ordinary scan pass per distinct value v (predicate "tag is v"); group_reduce of pass v writes
+//      slice v of a composite partial table of V x G groups, series_reduce records where each series first shows v.
+//   3. key_order_kernel / key_perm_kernel put the composite groups into insertion order: the scan order is series by
+//      series (ascending series id) and by time inside a series, so a group's first row is (first series that shows the
+//      value, rank of the value among that series' values by first row); permute_table_kernel reorders the table and the
+//      ordinary finalisation / Top-N runs on it unchanged (ties in Top-N go to the group inserted first, top.go:62-76).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void key_err(const KeyParams &p, uint32_t code, uint32_t g) {
+    if (atomicCAS(&p.err[0], 0u, code) == 0u) p.err[1] = g;
+}
+
+__device__ void key_insert(const KeyParams &p, const uint8_t *bytes, uint32_t len, uint32_t g) {
+    if (len > kMaxLit) {
+        key_err(p, kErrKeyLong, g);
+        return;
+    }
+    uint64_t h = 0xcbf29ce484222325ull;  // FNV-1a
+    for (uint32_t i = 0; i < len; ++i) h = (h ^ __ldg(bytes + i)) * 0x100000001b3ull;
+    const unsigned long long mine =
+        (1ull << 63) | (static_cast<unsigned long long>(len) << 48) | (len ? (reinterpret_cast<uintptr_t>(bytes) & 0xffffffffffffull) : 0ull);
+    uint32_t s = static_cast<uint32_t>(h ^ (h >> 32)) & (kKeySlots - 1);
+    for (uint32_t probe = 0; probe < kKeySlots; ++probe) {
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&p.slots[s]);
+        if (cur == 0) {
+            cur = atomicCAS(&p.slots[s], 0ull, mine);
+            if (cur == 0) {
+                if (atomicAdd(p.count, 1u) >= p.cap) key_err(p, kErrKeyCap, g);
+                return;
+            }
+        }
+        if (((cur >> 48) & 0x7fffu) == len) {
+            const uint8_t *o = reinterpret_cast<const uint8_t *>(static_cast<uintptr_t>(cur & 0xffffffffffffull));
+            bool eq = true;
+            for (uint32_t i = 0; i < len && eq; ++i) eq = __ldg(o + i) == __ldg(bytes + i);
+            if (eq) return;
+        }
+        s = (s + 1) & (kKeySlots - 1);
+    }
+    key_err(p, kErrKeyCap, g);
+}
+
+__global__ void __launch_bounds__(256) key_values_kernel(const __grid_constant__ KeyParams p) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < p.total_blocks; g += n_warps) {
+        uint32_t stop = lane == 0 ? *reinterpret_cast<volatile uint32_t *>(&p.err[0]) : 0u;
+        stop = __shfl_sync(0xffffffffu, stop, 0);
+        if (stop != 0u) return;  // warp-uniform
+        uint32_t pi = 0;
+        while (pi + 1 < p.n_parts && g >= p.parts[pi + 1].block_base) ++pi;
+        const DevPartRef &part = p.parts[pi];
+        const DevBlock blk = part.blocks[g - part.block_base];
+        // the selection of plan_blocks_kernel
+        uint32_t lo = 0, hi = p.n_series;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (p.q_sids[mid] < blk.sid) lo = mid + 1;
+            else hi = mid;
+        }
+        if (!(lo < p.n_series && p.q_sids[lo] == blk.sid) || blk.ts_max < p.tmin || blk.ts_min > p.tmax) continue;
+        DevCol col;
+        if (!find_col(part, blk, p.key_name, col, lane)) {
+            if (lane == 0) key_insert(p, nullptr, 0, g);  // column absent in this block: every cell is nil (block.go:226-233)
+            continue;
+        }
+        uint32_t err = kErrNone;
+        const uint8_t *page = part.files[col.file_id] + col.off;
+        const uint8_t *q = page + 1, *end = page + col.size;
+        uint64_t nvals = 0;
+        uint32_t llen = 0, dlen = 0, width = 1;
+        const uint8_t *lens = nullptr, *data = nullptr;
+        if (col.value_type != BYDB_VT_STR && col.value_type != BYDB_VT_BINARY) err = kErrPredType;
+        else if (col.size < 2) err = kErrCorrupt;
+        else if (__ldg(page) == 9) err = kErrTagPlain;
+        else if (__ldg(page) != 10) err = kErrBadEnc;
+        else if (!read_varuint_seq(q, end, nvals) || nvals == 0 || nvals > 256) err = kErrCorrupt;
+        if (err == kErrNone) err = read_cblock_header(q, end, llen, kErrZstdDict);
+        if (err == kErrNone) {
+            const uint8_t wt = llen >= 1 ? __ldg(q) : 4;
+            width = 1u << (wt & 3);
+            if (wt > 3 || llen != 1 + nvals * width) err = kErrCorrupt;
+            lens = q + 1;
+            q += llen;
+        }
+        if (err == kErrNone) err = read_cblock_header(q, end, dlen, kErrZstdDict);
+        data = q;
+        if (err != kErrNone) {
+            if (lane == 0) key_err(p, err, g);
+            continue;
+        }
+        uint32_t off_carry = 0;
+        for (uint32_t base = 0; base < nvals; base += 32) {
+            const uint32_t k = base + lane;
+            uint32_t L = 0;
+            if (k < nvals)
+                for (uint32_t i = 0; i < width; ++i) L = (L << 8) | __ldg(lens + k * width + i);
+            const uint32_t vlen = L > 0 ? L - 1 : 0;
+            uint32_t incl = vlen;
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, sft);
+                if (lane >= sft) incl += o;
+            }
+            const uint32_t off = off_carry + incl - vlen;
+            off_carry += __shfl_sync(0xffffffffu, incl, 31);
+            if (k < nvals) {
+                if (off + vlen > dlen) key_err(p, kErrCorrupt, g);
+                else key_insert(p, data + off, vlen, g);
+            }
+        }
+    }
+}
+
+// one warp: the occupied slots, in slot order, packed into vals / lens (read back by the host: the values become the
+// literals of the per-value passes and the key column of the result)
+__global__ void key_pack_kernel(const __grid_constant__ KeyParams p) {
+    const int lane = threadIdx.x;
+    uint32_t n = 0;
+    for (uint32_t s = 0; s < kKeySlots && n < p.cap; ++s) {
+        const unsigned long long cur = p.slots[s];
+        if (cur == 0) continue;
+        const uint32_t len = static_cast<uint32_t>((cur >> 48) & 0x7fffu);
+        const uint8_t *o = reinterpret_cast<const uint8_t *>(static_cast<uintptr_t>(cur & 0xffffffffffffull));
+        for (uint32_t i = lane; i < len; i += 32) p.vals[static_cast<size_t>(n) * kMaxLit + i] = __ldg(o + i);
+        if (lane == 0) p.lens[n] = len;
+        ++n;
+    }
+}
+
+void launch_key_values(const KeyParams &p, int grid, cudaStream_t s) {
+    if (p.total_blocks) key_values_kernel<<<grid, 256, 0, s>>>(p);
+    key_pack_kernel<<<1, 32, 0, s>>>(p);
+}
+
+// one warp per composite group (v, g): its first series and the rank of v among that series' values
+__global__ void __launch_bounds__(256) key_order_kernel(const __grid_constant__ KeyOrderParams p) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t gp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t G = static_cast<uint32_t>(p.n_groups);
+    if (gp >= G * p.n_values) return;
+    const uint32_t v = gp / G, g = gp % G;
+    const int64_t *kts = p.Kts + static_cast<size_t>(v) * p.n_series;
+    int32_t best = INT32_MAX;
+    for (int32_t k = p.group_start[g] + lane; k < p.group_start[g + 1]; k += 32) {
+        const int32_t i = p.order[k];
+        if (kts[i] != INT64_MAX && i < best) best = i;
+    }
+    best = __reduce_min_sync(0xffffffffu, best);
+    if (best == INT32_MAX) {
+        if (lane == 0) p.first_series[gp] = -1;
+        return;
+    }
+    const int64_t mts = kts[best];
+    const uint32_t mrow = p.Krow[static_cast<size_t>(v) * p.n_series + best];
+    uint32_t rank = 0;
+    for (uint32_t v2 = lane; v2 < p.n_values; v2 += 32) {
+        const int64_t t = p.Kts[static_cast<size_t>(v2) * p.n_series + best];
+        if (t != INT64_MAX && (t < mts || (t == mts && p.Krow[static_cast<size_t>(v2) * p.n_series + best] < mrow))) ++rank;
+    }
+    rank = __reduce_add_sync(0xffffffffu, rank);
+    if (lane == 0) {
+        p.first_series[gp] = best;
+        p.slot[static_cast<size_t>(best) * p.n_values + rank] = static_cast<int32_t>(gp);
+    }
+}
+
+// one CTA: ordered compaction of the (series, rank) slots -> perm; the composite groups that never appeared follow
+__global__ void __launch_bounds__(1024) key_perm_kernel(const __grid_constant__ KeyOrderParams p) {
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t tid = threadIdx.x;
+    const size_t n_slots = static_cast<size_t>(p.n_series) * p.n_values;
+    const uint32_t n_comp = static_cast<uint32_t>(p.n_groups) * p.n_values;
+    uint32_t base = 0;
+    for (size_t chunk = 0; chunk < n_slots; chunk += 1024) {
+        const size_t idx = chunk + tid;
+        const int32_t gp = idx < n_slots ? p.slot[idx] : -1;
+        uint32_t total = 0;
+        const uint32_t pos = block_excl_scan(gp >= 0 ? 1u : 0u, warp_tot, total);
+        if (gp >= 0) p.perm[base + pos] = gp;
+        base += total;
+        __syncthreads();
+    }
+    if (tid == 0) *p.n_present = base;
+    for (uint32_t chunk = 0; chunk < n_comp; chunk += 1024) {
+        const uint32_t gp = chunk + tid;
+        const bool absent = gp < n_comp && p.first_series[gp] < 0;
+        uint32_t total = 0;
+        const uint32_t pos = block_excl_scan(absent ? 1u : 0u, warp_tot, total);
+        if (absent) p.perm[base + pos] = static_cast<int32_t>(gp);
+        base += total;
+        __syncthreads();
+    }
+}
+
+void launch_key_order(const KeyOrderParams &p, cudaStream_t s) {
+    const uint32_t n_comp = static_cast<uint32_t>(p.n_groups) * p.n_values;
+    if (n_comp == 0) return;
+    key_order_kernel<<<(n_comp + 7) / 8, 256, 0, s>>>(p);
+    key_perm_kernel<<<1, 1024, 0, s>>>(p);
+}
+
+__global__ void permute_table_kernel(TablePtrs dst, TablePtrs src, const int32_t *perm, uint32_t n_groups, uint32_t n_fcols,
+                                     const int64_t *pass_coltype, uint32_t n_passes) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_fcols) {
+        // column type of the query = the type any pass saw; two passes that disagree are a type mix; the worst status wins
+        int64_t typ = 0, err = 0;
+        for (uint32_t v = 0; v < n_passes; ++v) {
+            const int64_t w = pass_coltype[static_cast<size_t>(v) * n_fcols + t];
+            const int64_t wt = w & 0xff, we = w >> 8;
+            if (wt != 0 && typ != 0 && wt != typ) err = err > static_cast<int64_t>(kErrTypeMix) ? err : static_cast<int64_t>(kErrTypeMix);
+            if (typ == 0) typ = wt;
+            err = we > err ? we : err;
+        }
+        dst.coltype[t] = typ | (err << 8);
+    }
+    if (t >= n_groups * n_fcols) return;
+    const uint32_t j = t / n_fcols, c = t % n_fcols;
+    const size_t so = static_cast<size_t>(perm[j]) * n_fcols + c;
+    dst.sum_f64[t] = src.sum_f64[so];
+    dst.max_f64[t] = src.max_f64[so];
+    dst.negmin_f64[t] = src.negmin_f64[so];
+    dst.sum_i64[t] = src.sum_i64[so];
+    dst.cnt[t] = src.cnt[so];
+    dst.max_i64[t] = src.max_i64[so];
+    dst.notmin_i64[t] = src.notmin_i64[so];
+    if (c == 0) dst.rows[j] = src.rows[perm[j]];
+}
+
+void launch_permute_table(const TablePtrs &dst, const TablePtrs &src, const int32_t *perm, uint32_t n_groups, uint32_t n_fcols,
+                          const int64_t *pass_coltype, uint32_t n_passes, cudaStream_t s) {
+    const uint32_t n = n_groups * n_fcols > n_fcols ? n_groups * n_fcols : n_fcols;
+    permute_table_kernel<<<(n + 255) / 256, 256, 0, s>>>(dst, src, perm, n_groups, n_fcols, pass_coltype, n_passes);
+}
+
 void launch_plan_blocks(const ScanParams &p, cudaStream_t s) {
     if (p.total_blocks == 0) return;
     const int threads = 256;
@@ -3054,6 +3329,12 @@ void launch_finalize(const FinalizeParams &p, cudaStream_t s) {
 // its first-ever launch of some kernel lands behind that spin, both wait for each other until the bounded wait gives up.
 // bydb_init therefore touches every kernel of the library once on its device.
 void preload_kernels() {
+    cudaFuncAttributes ka;
+    (void)cudaFuncGetAttributes(&ka, key_values_kernel);
+    (void)cudaFuncGetAttributes(&ka, key_pack_kernel);
+    (void)cudaFuncGetAttributes(&ka, key_order_kernel);
+    (void)cudaFuncGetAttributes(&ka, key_perm_kernel);
+    (void)cudaFuncGetAttributes(&ka, permute_table_kernel);
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, plan_blocks_kernel);
     cudaFuncGetAttributes(&a, scan_blocks_kernel<true>);

@@ -43,7 +43,10 @@ enum DevErr : uint32_t {
     kErrPredType = 9,       // predicate literal type does not match the stored tag column type
     kErrTmaTimeout = 10,    // a bulk copy never completed (internal error)
     kErrPeerTimeout = 11,   // multi-GPU reduce: a peer rank never delivered its partial table / never freed the slot
+    kErrKeyCap = 12,        // per-row group key: more distinct values than the caller's max_values
+    kErrKeyLong = 13,       // per-row group key: a value longer than kMaxLit bytes
 };
+constexpr int kOpEqOrNil = 7;  // internal predicate operator of the group-key passes: the cell is nil or equals the literal
 
 struct DevPartRef {
     const DevBlock *blocks;
@@ -95,6 +98,7 @@ struct ScanParams {
     uint32_t *first_block;        // [n_parts * n_series] first block of the series in the part (0xffffffff = none); may be NULL
     BlockPartial *P;              // [total_blocks * n_fcols]
     uint32_t *Prows;              // [total_blocks] rows that passed range + predicates
+    uint32_t *Pfirst;             // [total_blocks] first surviving row of the block (group-key passes only, else NULL)
     int32_t *col_type;            // [n_fcols] 0 unknown / BYDB_VT_INT64 / BYDB_VT_FLOAT64
     uint32_t *err;                // [2]
     unsigned long long *stats;    // [0] rows_scanned [1] rows_matched [2] page_bytes [3] blocks
@@ -128,6 +132,11 @@ struct ReduceParams {
     uint32_t *err;
     uint32_t dedup_done;          // 1 = overlapping parts were resolved by the dedup kernels
     uint32_t pad2;
+    // group-key passes only (else NULL): where the series first shows the pass's key value -- (ts_min of the earliest block
+    // with a surviving row, that row's index); INT64_MAX = the series never shows it
+    const uint32_t *Pfirst;
+    int64_t *Kts;                 // [n_series]
+    uint32_t *Krow;               // [n_series]
     // partial table (see bydb_gpu.h): written by group_reduce
     double *sum_f64, *max_f64, *negmin_f64;
     int64_t *sum_i64, *cnt, *rows, *max_i64, *notmin_i64, *coltype;
@@ -167,6 +176,47 @@ struct SelectParams {
     uint32_t *sel_count;
 };
 void launch_select_rows(const SelectParams &p, cudaStream_t s);
+
+// ---- per-row group key (a stored dictionary tag): see "Group key" in scan_kernels.cu
+constexpr uint32_t kKeySlots = 1024;   // open-addressing table of the distinct key values (at most 256 are accepted)
+constexpr uint32_t kMaxKeyValues = 256;
+struct KeyParams {
+    DevPartRef parts[kMaxParts];
+    uint32_t n_parts, total_blocks;
+    const uint64_t *q_sids;
+    uint32_t n_series;
+    uint32_t cap;                 // distinct values the caller accepts
+    int64_t tmin, tmax;
+    uint16_t key_name;
+    uint16_t pad[3];
+    unsigned long long *slots;    // [kKeySlots] 0 = empty, else bit63 | len << 48 | device address of the bytes
+    uint32_t *count;              // distinct values found
+    uint32_t *err;                // [2]
+    uint8_t *vals;                // [cap * kMaxLit] packed by key_pack
+    uint32_t *lens;               // [cap]
+};
+void launch_key_values(const KeyParams &p, int grid, cudaStream_t s);
+struct KeyOrderParams {
+    int32_t n_groups;             // G: groups of series
+    uint32_t n_values;            // V
+    uint32_t n_series;
+    uint32_t pad;
+    const int32_t *order, *group_start;
+    const int64_t *Kts;           // [V * n_series]
+    const uint32_t *Krow;         // [V * n_series]
+    int32_t *slot;                // [n_series * V] preset to -1: composite group whose first row is (series, rank)
+    int32_t *first_series;        // [V * G] -1 = the composite group never appeared
+    int32_t *perm;                // [V * G] composite groups in insertion order, then the ones that never appeared
+    uint32_t *n_present;
+};
+void launch_key_order(const KeyOrderParams &p, cudaStream_t s);
+struct TablePtrs {
+    double *sum_f64, *max_f64, *negmin_f64;
+    int64_t *sum_i64, *cnt, *rows, *max_i64, *notmin_i64, *coltype;
+};
+// dst[j] = src[perm[j]] for every group row of a partial table; coltype = the passes' column types merged
+void launch_permute_table(const TablePtrs &dst, const TablePtrs &src, const int32_t *perm, uint32_t n_groups, uint32_t n_fcols,
+                          const int64_t *pass_coltype, uint32_t n_passes, cudaStream_t s);
 constexpr int kFusedFinalizeGroups = 8192;  // up to here one CTA finalises and selects in a single launch
 struct FinalizeParams;
 uint32_t launch_finalize_select(const FinalizeParams &fp, const SelectParams &p, cudaStream_t s);  // -> kernels launched

@@ -1276,3 +1276,113 @@ def test_block_index_decoded_on_the_device_equals_the_host_parser(bydb):
                 ctx.register_part(9, bad)
             h = ctx.register_part(10, files)   # and the context is still usable
             ctx.release_part(h)
+
+
+def _keyed_both(bydb, gpu_ctx, parts, oq, family, tag, max_values=0):
+    from tests.helpers import to_gpu_query
+    pid0 = _next_pid()
+    handles = [gpu_ctx.register_part(pid0 + i, p.files()) for i, p in enumerate(parts)]
+    try:
+        got = gpu_ctx.scan_agg_keyed(to_gpu_query(bydb, handles, oq), family, tag, max_values)
+    finally:
+        for h in handles:
+            gpu_ctx.release_part(h)
+    import dataclasses
+    want = O.run_query(dataclasses.replace(oq, group_key=(family, tag)))
+    return got, want
+
+
+def test_group_by_stored_tag_insertion_order_and_topn(bydb, gpu_ctx):
+    # a12: the group key is a stored dictionary tag, so it changes from row to row (aggregation.go:193-254); nil and "" are one key
+    rng = np.random.default_rng(0xA12)
+    sids, ts, ver = grid(23, 9000, sid0=3, sid_step=2)   # 8193-row block + a tail block per series
+    n = sids.size
+    lat = np.round(25 + rng.normal(0, 5, n), 2)
+    calls = rng.integers(-5000, 5000, n)
+    code = rng.integers(0, 4, n) * 100
+    # runs of equal values of random length (what RLE dictionary pages hold), a few nil and "" cells, one value only late in time
+    region = []
+    while len(region) < n:
+        v = rng.integers(0, 7)
+        region.extend([b"region-%d" % v] * int(rng.integers(1, 40)))
+    region = region[:n]
+    for i in range(0, n, 977):
+        region[i] = None
+    for i in range(5, n, 1409):
+        region[i] = b""
+    for s in range(23):
+        region[s * 9000 + 8800: s * 9000 + 8810] = [b"late"] * 10
+    part = build_part(sids, ts, ver, [("latency", O.VT_FLOAT64, lat, None), ("calls", O.VT_INT64, calls, None)],
+                      [("default", [("region", O.VT_STR, region, None), ("code", O.VT_INT64, code, None)])])
+    usid = np.unique(sids)
+    groups = (np.arange(usid.size) % 3).astype(np.int32)
+    aggs = [("latency", O.AGG_SUM), ("latency", O.AGG_MAX), ("calls", O.AGG_SUM), ("calls", O.AGG_MIN), ("calls", O.AGG_COUNT),
+            ("latency", O.AGG_MEAN)]
+    oq = O.Query([part], usid, aggs, groups=groups, n_groups=3, tmin=T0 + 100 * STEP, tmax=T0 + 8900 * STEP,
+                 preds=[O.Pred("default", "code", O.OP_NE, 300)])
+    got, want = _keyed_both(bydb, gpu_ctx, [part], oq, "default", "region")
+    assert got.key == want.key, "key values in insertion order"
+    assert_parity(got, want, aggs, "keyed")
+    assert b"" in got.key and b"late" in got.key and len(got.key) == 3 * 9
+    # no series groups: pure group-by-tag
+    oq1 = O.Query([part], usid[::2], [("calls", O.AGG_SUM), ("calls", O.AGG_COUNT)], tmin=T0 + 50 * STEP, tmax=T0 + 8700 * STEP)
+    got, want = _keyed_both(bydb, gpu_ctx, [part], oq1, "default", "region")
+    assert got.key == want.key and b"late" not in got.key
+    assert_parity(got, want, oq1.aggs, "keyed, one series group")
+    # Top-N over the composite groups, both directions; COUNT ties go to the group inserted first
+    for desc in (True, False):
+        oqt = O.Query([part], usid, [("calls", O.AGG_COUNT), ("latency", O.AGG_MAX)], groups=groups, n_groups=3, top_n=7, top_agg=0,
+                      top_desc=desc)
+        got, want = _keyed_both(bydb, gpu_ctx, [part], oqt, "default", "region")
+        assert got.key == want.key
+        assert_parity(got, want, oqt.aggs, f"keyed top desc={desc}")
+    # two parts that follow each other in time: a value that first shows in the second part is inserted later
+    half = ts < T0 + 4000 * STEP
+    pa = build_part(sids[half], ts[half], ver[half], [("calls", O.VT_INT64, calls[half], None)],
+                    [("default", [("region", O.VT_STR, [r for r, h in zip(region, half) if h], None)])])
+    pb = build_part(sids[~half], ts[~half], ver[~half], [("calls", O.VT_INT64, calls[~half], None)],
+                    [("default", [("region", O.VT_STR, [r for r, h in zip(region, half) if not h], None)])])
+    oq2 = O.Query([pa, pb], usid, [("calls", O.AGG_SUM), ("calls", O.AGG_MAX)], groups=groups, n_groups=3)
+    got, want = _keyed_both(bydb, gpu_ctx, [pa, pb], oq2, "default", "region")
+    assert got.key == want.key
+    assert_parity(got, want, oq2.aggs, "keyed, two parts")
+    # a tag no block stores: every cell is nil -> the single key ""
+    got, want = _keyed_both(bydb, gpu_ctx, [part], oq1, "default", "nosuchtag")
+    assert got.key == want.key == [b""]
+    assert_parity(got, want, oq1.aggs, "keyed, absent tag")
+    # nothing selected
+    oq0 = O.Query([part], np.array([999999], dtype=np.uint64), [("calls", O.AGG_SUM)])
+    got, want = _keyed_both(bydb, gpu_ctx, [part], oq0, "default", "region")
+    assert got.key == want.key == [] and got.rows.size == 0
+
+
+def test_group_by_stored_tag_limits(bydb, gpu_ctx):
+    rng = np.random.default_rng(7)
+    sids, ts, ver = grid(4, 3000)
+    n = sids.size
+    calls = rng.integers(0, 100, n)
+    region = [b"r%d" % v for v in rng.integers(0, 12, n)]
+    longv = [b"x" * 70 if i % 500 == 0 else b"ok" for i in range(n)]
+    code = rng.integers(0, 4, n)
+    part = build_part(sids, ts, ver, [("calls", O.VT_INT64, calls, None)],
+                      [("default", [("region", O.VT_STR, region, None), ("long", O.VT_STR, longv, None), ("code", O.VT_INT64, code, None)])])
+    h = gpu_ctx.register_part(_next_pid(), part.files())
+    try:
+        q = bydb.Query(parts=[h], series_ids=np.unique(sids), aggs=[("calls", O.AGG_SUM)])
+        with pytest.raises(bydb.BydbError) as e:
+            gpu_ctx.scan_agg_keyed(q, "default", "region", max_values=8)   # 12 distinct values
+        assert e.value.code == bydb.capi.ENOMEM
+        assert len(gpu_ctx.scan_agg_keyed(q, "default", "region", max_values=12).key) == 12
+        with pytest.raises(bydb.BydbError) as e:
+            gpu_ctx.scan_agg_keyed(q, "default", "long")
+        assert e.value.code == bydb.capi.ENOTSUP
+        with pytest.raises(bydb.BydbError) as e:
+            gpu_ctx.scan_agg_keyed(q, "default", "code")                   # an int64 tag is not a dictionary page
+        assert e.value.code == bydb.capi.EINVAL
+        with pytest.raises(bydb.BydbError) as e:
+            gpu_ctx.scan_agg_keyed(q, "default", "region", max_values=1000)
+        assert e.value.code == bydb.capi.EINVAL
+        # the context is still healthy
+        assert gpu_ctx.scan_agg(q).val_i64[0, 0] == int(calls.sum())
+    finally:
+        gpu_ctx.release_part(h)

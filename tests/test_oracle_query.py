@@ -256,3 +256,58 @@ def test_block_selection_part_iter_test_go():
                                 tmin=1, tmax=220))
         assert r.blocks_scanned == len(want) and r.rows_scanned == 2 * len(want)
         assert [sids[g] for g in r.group_id.tolist()] == want and r.rows.tolist() == [2] * len(want)
+
+
+def _model_keyed(sids, ts, f_int, f_flt, region, usid, groups, tmin, tmax, pred_code=None, code=None):
+    """Insertion-ordered group-by on (group of the series, region value): aggregation.go:193-254."""
+    order = np.lexsort((ts, sids))
+    gmap = {int(s): int(g) for s, g in zip(usid, groups)}
+    out = {}
+    for i in order:
+        if int(sids[i]) not in gmap or not (tmin <= ts[i] <= tmax):
+            continue
+        if pred_code is not None and code[i] != pred_code:
+            continue
+        rv = region[i] if region[i] is not None else b""
+        k = (gmap[int(sids[i])], rv)
+        e = out.setdefault(k, {"rows": 0, "si": 0, "sf": 0.0, "mx": -np.inf})
+        e["rows"] += 1
+        e["si"] += int(f_int[i])
+        e["sf"] += float(f_flt[i])
+        e["mx"] = max(e["mx"], float(f_flt[i]))
+    return out
+
+
+def test_group_by_row_tag_insertion_order():
+    # a12: the key is a stored tag, so it changes from row to row inside a series
+    sids, ts, ver, f_int, f_flt, region, code, _ = _synthetic(n_series=9, n_pts=400, seed=5)
+    region = [None if (i % 53 == 0) else (b"" if i % 47 == 0 else r) for i, r in enumerate(region)]  # nil and "" are one key
+    part = _build(sids, ts, ver, f_int, f_flt, region, code)
+    usid = np.unique(sids)
+    groups = (np.arange(usid.size) % 2).astype(np.int32)
+    tmin, tmax = T0 + 10 * STEP, T0 + 350 * STEP
+    aggs = [("calls", O.AGG_SUM), ("latency", O.AGG_SUM), ("latency", O.AGG_MAX), ("calls", O.AGG_COUNT)]
+    q = O.Query([part], usid, aggs, groups=groups, n_groups=2, tmin=tmin, tmax=tmax,
+                preds=[O.Pred("default", "code", O.OP_EQ, 200)], group_key=("default", "region"))
+    r = O.run_query(q)
+    want = _model_keyed(sids, ts, f_int, f_flt, region, usid, groups, tmin, tmax, pred_code=200, code=code)
+    assert [(int(g), k) for g, k in zip(r.group_id, r.key)] == list(want.keys())
+    for i, e in enumerate(want.values()):
+        assert r.rows[i] == e["rows"] and r.val_i64[i, 0] == e["si"] and r.val_i64[i, 3] == e["rows"]
+        assert abs(r.val_f64[i, 1] - e["sf"]) <= 1e-9 * abs(e["sf"]) and r.val_f64[i, 2] == e["mx"]
+    assert (b"" in r.key) and len(set(zip(r.group_id.tolist(), r.key))) == len(r.key)
+    # Top-N over the composite groups; ties go to the group inserted first (top.go:62-76)
+    qt = O.Query([part], usid, [("calls", O.AGG_COUNT)], groups=groups, n_groups=2, tmin=tmin, tmax=tmax,
+                 group_key=("default", "region"), top_n=5, top_agg=0, top_desc=True)
+    rt = O.run_query(qt)
+    full = _model_keyed(sids, ts, f_int, f_flt, region, usid, groups, tmin, tmax)
+    ranked = sorted(enumerate(full.items()), key=lambda t: (-t[1][1]["rows"], t[0]))[:5]
+    assert [(int(g), k) for g, k in zip(rt.group_id, rt.key)] == [kv[0] for _, kv in ranked]
+    assert rt.val_i64[:, 0].tolist() == [kv[1]["rows"] for _, kv in ranked]
+
+
+def test_group_by_row_tag_rejects_numeric_tag():
+    sids, ts, ver, f_int, f_flt, region, code, _ = _synthetic(n_series=2, n_pts=20)
+    part = _build(sids, ts, ver, f_int, f_flt, region, code)
+    with pytest.raises(RuntimeError, match="group key"):
+        O.run_query(O.Query([part], np.unique(sids), [("calls", O.AGG_SUM)], group_key=("default", "code")))
