@@ -25,6 +25,17 @@ int main(void) {
     int (*f_prep)(bydb_ctx *, const bydb_query *, bydb_prepared **) = bydb_query_prepare;
     int (*f_run)(bydb_ctx *, bydb_prepared *, bydb_result *) = bydb_scan_agg_prepared;
     void (*f_qrel)(bydb_ctx *, bydb_prepared *) = bydb_query_release;
+    int (*f_dir)(bydb_ctx *, bydb_part_h, void *, uint64_t, void *, uint64_t, uint64_t *, uint64_t *) = bydb_part_directory;
+    int (*f_keyed)(bydb_ctx *, const bydb_query *, const bydb_group_key *, bydb_keyed_result *) = bydb_scan_agg_keyed;
+    void (*f_kfree)(bydb_ctx *, bydb_keyed_result *) = bydb_keyed_result_free;
+    int (*f_prow)(bydb_ctx *, const bydb_query *, const void *, uint64_t, void *, bydb_partial_rows *) = bydb_partials_rows;
+    void (*f_prfree)(bydb_ctx *, bydb_partial_rows *) = bydb_partial_rows_free;
+    int (*f_cexp)(bydb_ctx *, uint64_t, int32_t, bydb_comm_handle *) = bydb_comm_export;
+    int (*f_ccon)(bydb_ctx *, int32_t, int32_t, const bydb_comm_handle *) = bydb_comm_connect;
+    int (*f_red)(bydb_ctx *, const bydb_query *, int32_t, bydb_result *) = bydb_scan_reduce;
+    int (*f_redp)(bydb_ctx *, bydb_prepared *, int32_t, bydb_result *) = bydb_scan_reduce_prepared;
+    int (*f_redh)(bydb_ctx *, uint32_t, const bydb_part_files *, const bydb_query *, int32_t, bydb_result *) = bydb_scan_reduce_host;
+    (void)f_dir; (void)f_prow; (void)f_prfree; (void)f_cexp; (void)f_ccon; (void)f_red; (void)f_redp; (void)f_redh;
     (void)f_prep; (void)f_run; (void)f_qrel;
     (void)f_shutdown; (void)f_reg; (void)f_rel; (void)f_info; (void)f_fb; (void)f_scan; (void)f_host; (void)f_free; (void)f_part; (void)f_comb; (void)f_fin;
 
@@ -65,6 +76,38 @@ int main(void) {
     int rc = f_init(NULL, &ctx);
     if (rc == 0) {
         printf("init ok (GPU present)\n");
+        /* group-by on a stored tag from plain C: count(latency) per value of default/region over 3 series x 2000 points */
+        sp.n_points = 2000; sp.region_values = 4; sp.region_run = 8;
+        if (bydb_synth_part(&sp, &img) != 0 || !img) { printf("synth failed\n"); return 1; }
+        bydb_file files[16];
+        uint32_t nf = bydb_part_image_n_files(img);
+        if (nf > 16) return 1;
+        for (uint32_t i = 0; i < nf; ++i) {
+            files[i].name = bydb_part_image_file_name(img, i);
+            files[i].data = bydb_part_image_file_data(img, i, &files[i].len);
+        }
+        bydb_part_files pf = {nf, files};
+        bydb_part_h h = 0;
+        if (f_reg(ctx, 42, &pf, &h) != 0) { printf("register failed: %s\n", bydb_last_error()); return 1; }
+        bydb_agg cnt = {"latency", BYDB_AGG_COUNT, 0};
+        uint64_t s3[3] = {1, 2, 3};
+        bydb_query kq;
+        memset(&kq, 0, sizeof kq);
+        kq.parts = &h; kq.n_parts = 1; kq.series_ids = s3; kq.n_series = 3; kq.aggs = &cnt; kq.n_aggs = 1;
+        kq.tmin = INT64_MIN; kq.tmax = INT64_MAX;
+        bydb_group_key gk = {"default", "region", 0, 0};
+        bydb_keyed_result kr;
+        if (f_keyed(ctx, &kq, &gk, &kr) != 0) { printf("keyed scan failed: %s\n", bydb_last_error()); return 1; }
+        int64_t total = 0;
+        for (int32_t r = 0; r < kr.base.n_rows; ++r) {
+            const uint32_t a = kr.key_off[kr.key_id[r]], b = kr.key_off[kr.key_id[r] + 1];
+            if (b - a != 2 || kr.key_bytes[a] != 'r' || kr.base.group_id[r] != 0) { printf("bad key row %d\n", r); return 1; }
+            total += kr.base.val_i64[r];
+        }
+        if (kr.base.n_rows != 4 || kr.n_keys != 4 || total != 6000) { printf("keyed result: %d rows, %d keys, %lld\n", kr.base.n_rows, kr.n_keys, (long long)total); return 1; }
+        f_kfree(ctx, &kr);
+        f_rel(ctx, h);
+        bydb_part_image_free(img);
         bydb_shutdown(ctx);
     } else {
         printf("init refused: %d %s\n", rc, bydb_last_error());

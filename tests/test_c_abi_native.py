@@ -10,7 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_c_caller_links_and_runs(tmp_path, bydb):
+def _run_c_caller(tmp_path, bydb):
     if shutil.which("gcc") is None:
         pytest.skip("no gcc")
     lib_dir = os.path.dirname(bydb.library_path())
@@ -19,9 +19,20 @@ def test_c_caller_links_and_runs(tmp_path, bydb):
                            os.path.join(ROOT, "tests", "native", "c_abi_caller.c"), "-L", lib_dir, "-lbydbgpu", "-Wl,-rpath," + lib_dir])
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
+    return out.stdout
+
+
+def test_c_caller_links_and_runs(tmp_path, bydb):
+    out = _run_c_caller(tmp_path, bydb)
     import torch
     if not torch.cuda.is_available():
-        assert "init refused" in out.stdout
+        assert "init refused" in out
+
+
+@pytest.mark.gpu
+def test_c_caller_on_the_device(tmp_path, bydb):
+    """The same C99 program on a GPU box: registers a synthetic part and runs the group-by-stored-tag call from plain C."""
+    assert "init ok" in _run_c_caller(tmp_path, bydb)
 
 
 @pytest.mark.gpu
