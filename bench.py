@@ -523,6 +523,17 @@ def main():
                                  "achieved_GBps": r2.stats.rows_scanned * B_ALG_C2 / (s2 * 1e-3) / 1e9, "encoded_page_bytes": int(r2.stats.page_bytes),
                                  "rows_matched": int(r2.rows[0]), "mean_latency": float(r2.val_f64[0, 0]), "max_walk": float(r2.val_f64[0, 1]),
                                  "blocks_slow_lane": int(r2.stats.blocks_slow_lane)}
+            # third leg: group-by on a STORED tag (a12): sum + count of latency per value of default/region (8 values) -- one
+            # scan pass per value behind bydb_scan_agg_keyed
+            qk = pkg.Query(parts=[h], series_ids=sids, aggs=[("latency", pkg.AGG_SUM), ("latency", pkg.AGG_COUNT)])
+            rk = ctx.scan_agg_keyed(qk, "default", "region")
+            nk = 3
+            dk, rk = timed(lambda: ctx.scan_agg_keyed(qk, "default", "region"), nk)
+            extra["stored_tag_group_by"] = {"query": "sum(latency), count(latency) GROUP BY region (a stored tag, 8 values)", "api": "bydb_scan_agg_keyed",
+                                            "ms_per_step": dk / nk * 1e3, "datapoints_per_step": int(rows_step), "value": rows_step * nk / dk,
+                                            "unit": "datapoints/s", "groups": [k.decode() for k in rk.key],
+                                            "rows_per_group": [int(x) for x in rk.rows], "all_rows_accounted": bool(int(rk.rows.sum()) == int(rows_step)),
+                                            "kernel_launches": int(rk.stats.kernel_launches)}
 
     # ------------------------------------------------------------------ end to end: host buffers in, result out
     e2e = None
