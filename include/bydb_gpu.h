@@ -222,6 +222,33 @@ typedef struct {
 int bydb_scan_agg_keyed(bydb_ctx *ctx, const bydb_query *q, const bydb_group_key *key, bydb_keyed_result *out);
 void bydb_keyed_result_free(bydb_ctx *ctx, bydb_keyed_result *r);
 
+/* Write side: numeric field pages encoded ON THE DEVICE, byte for byte what banyand/measure/column.go:113-234
+ * (encodeInt64Column / encodeFloat64Column -> pkg/encoding/int_list.go:27-53, float.go:30-124) writes into fv.bin for a block:
+ * [encode type][decimal exponent, float64 only][first value][zig-zag varint body].  The building block of a device-side merger
+ * (decoded blocks in, pages out).  A float64 block that needs the reference's general shortest-digits search, holds NaN / Inf or
+ * overflows on the common exponent is not encoded here: needs_cpu[b] = 1 and its page is empty -- the CPU writer (which owns the
+ * EncodeTypePlain fallback page) takes it.  Columns with null cells are not accepted (they always take the fallback page). */
+typedef struct {
+    int32_t value_type;          /* BYDB_VT_INT64 / BYDB_VT_FLOAT64                                  */
+    uint32_t n_blocks;
+    const uint32_t *block_rows;  /* [n_blocks] rows of each block (>= 1)                              */
+    const void *values;          /* HOST memory: int64_t / double values, the blocks back to back     */
+} bydb_encode_input;
+
+typedef struct {
+    uint32_t n_blocks;
+    uint32_t reserved;
+    const uint64_t *page_off;    /* [n_blocks + 1] page b = bytes[page_off[b] .. page_off[b+1])       */
+    const uint8_t *bytes;
+    const uint8_t *needs_cpu;    /* [n_blocks]                                                        */
+    uint64_t n_cpu_blocks;
+    double device_ms;            /* CUDA-event time of the two kernels (encode + gather)              */
+    void *owner;                 /* private                                                           */
+} bydb_encoded_pages;
+
+int bydb_encode_pages(bydb_ctx *ctx, const bydb_encode_input *in, bydb_encoded_pages *out);
+void bydb_encoded_pages_free(bydb_ctx *ctx, bydb_encoded_pages *r);
+
 /* Same, but the parts come as HOST file images: they are uploaded, scanned and dropped inside the
  * call (the end-to-end path of a cold query).  q->parts / q->n_parts are ignored. */
 int bydb_scan_agg_host(bydb_ctx *ctx, uint32_t n_parts, const bydb_part_files *parts, const bydb_query *q, bydb_result *out);

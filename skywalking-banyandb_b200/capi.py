@@ -78,6 +78,15 @@ class _KeyedResult(C.Structure):
                 ("key_off", C.POINTER(C.c_uint32)), ("key_bytes", C.POINTER(C.c_uint8)), ("owner", C.c_void_p)]
 
 
+class _EncodeInput(C.Structure):
+    _fields_ = [("value_type", C.c_int32), ("n_blocks", C.c_uint32), ("block_rows", C.c_void_p), ("values", C.c_void_p)]
+
+
+class _EncodedPages(C.Structure):
+    _fields_ = [("n_blocks", C.c_uint32), ("reserved", C.c_uint32), ("page_off", C.POINTER(C.c_uint64)), ("bytes", C.POINTER(C.c_uint8)),
+                ("needs_cpu", C.POINTER(C.c_uint8)), ("n_cpu_blocks", C.c_uint64), ("device_ms", C.c_double), ("owner", C.c_void_p)]
+
+
 class _PartialRows(C.Structure):
     _fields_ = [("n_rows", C.c_int32), ("n_aggs", C.c_int32), ("group_id", C.POINTER(C.c_int32)), ("is_float", C.POINTER(C.c_uint8)),
                 ("val_i64", C.POINTER(C.c_int64)), ("val_f64", C.POINTER(C.c_double)), ("cnt_i64", C.POINTER(C.c_int64)),
@@ -130,6 +139,9 @@ def load_library():
     L.bydb_scan_agg_keyed.argtypes = [C.c_void_p, C.POINTER(_Query), C.POINTER(_GroupKey), C.POINTER(_KeyedResult)]
     L.bydb_keyed_result_free.argtypes = [C.c_void_p, C.POINTER(_KeyedResult)]
     L.bydb_keyed_result_free.restype = None
+    L.bydb_encode_pages.argtypes = [C.c_void_p, C.POINTER(_EncodeInput), C.POINTER(_EncodedPages)]
+    L.bydb_encoded_pages_free.argtypes = [C.c_void_p, C.POINTER(_EncodedPages)]
+    L.bydb_encoded_pages_free.restype = None
     L.bydb_query_prepare.argtypes = [C.c_void_p, C.POINTER(_Query), C.POINTER(C.c_void_p)]
     L.bydb_scan_agg_prepared.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Result)]
     L.bydb_query_release.argtypes = [C.c_void_p, C.c_void_p]
@@ -438,6 +450,26 @@ class Context:
             return res
         finally:
             self._L.bydb_keyed_result_free(self._h, C.byref(r))
+
+    def encode_pages(self, values: np.ndarray, block_rows: Sequence[int]):
+        """Write side (bydb_encode_pages): int64 / float64 value blocks -> ([page bytes or None per block], device ms).
+        None = the block needs the CPU writer."""
+        vt = VT_FLOAT64 if values.dtype == np.float64 else VT_INT64
+        vals = np.ascontiguousarray(values, dtype=np.float64 if vt == VT_FLOAT64 else np.int64)
+        rows = np.ascontiguousarray(block_rows, dtype=np.uint32)
+        assert int(rows.sum()) == vals.size
+        inp = _EncodeInput(vt, rows.size, rows.ctypes.data, vals.ctypes.data)
+        r = _EncodedPages()
+        _check(self._L.bydb_encode_pages(self._h, C.byref(inp), C.byref(r)))
+        try:
+            n = r.n_blocks
+            off = np.ctypeslib.as_array(r.page_off, (n + 1,)).copy() if n else np.zeros(1, np.uint64)
+            total = int(off[-1])
+            data = np.ctypeslib.as_array(r.bytes, (max(total, 1),))[:total].tobytes()
+            pages = [None if r.needs_cpu[b] else data[int(off[b]):int(off[b + 1])] for b in range(n)]
+            return pages, float(r.device_ms)
+        finally:
+            self._L.bydb_encoded_pages_free(self._h, C.byref(r))
 
     # ---- prepared queries replayed as one captured CUDA graph (bydb_query_prepare / bydb_scan_agg_prepared)
     def prepare_graph(self, q: Query) -> "GraphQuery":

@@ -1394,6 +1394,7 @@ int bydb_init(const bydb_cfg *cfg, bydb_ctx **out) {
     preload_kernels();
     preload_unpack_kernels();
     preload_index_kernels();
+    preload_encode_kernels();
     int occ_fast = 1, occ_slow = 1;
     scan_max_ctas_per_sm(&occ_fast, &occ_slow);
     int want = (cfg && cfg->warps_per_sm > 0) ? (cfg->warps_per_sm + kWarpsPerCta - 1) / kWarpsPerCta : 64;
@@ -1558,6 +1559,7 @@ struct KeyedOwner {
 }  // namespace
 
 void bydb_keyed_result_free(bydb_ctx *ctx, bydb_keyed_result *r);
+void bydb_encoded_pages_free(bydb_ctx *ctx, bydb_encoded_pages *r);
 
 // Group-by on a stored tag (per-row key): see "Group key" in scan_kernels.cu for the device side.
 int bydb_scan_agg_keyed(bydb_ctx *ctx, const bydb_query *q, const bydb_group_key *key, bydb_keyed_result *out) {
@@ -1803,6 +1805,122 @@ void bydb_keyed_result_free(bydb_ctx *ctx, bydb_keyed_result *r) {
     if (!r) return;
     bydb_result_free(ctx, &r->base);
     delete static_cast<KeyedOwner *>(r->owner);
+    memset(r, 0, sizeof *r);
+}
+
+
+namespace {
+struct EncodedOwner {
+    std::vector<uint64_t> page_off;
+    std::vector<uint8_t> bytes, needs_cpu;
+};
+}  // namespace
+
+// Write side (f4): numeric field pages encoded on the device, see encode_kernels.cu.
+int bydb_encode_pages(bydb_ctx *ctx, const bydb_encode_input *in, bydb_encoded_pages *out) {
+    return guarded([&]() -> int {
+    if (!ctx || !in || !out) return fail(BYDB_EINVAL, "ctx/in/out is NULL");
+    memset(out, 0, sizeof *out);
+    if (in->value_type != BYDB_VT_INT64 && in->value_type != BYDB_VT_FLOAT64) return fail(BYDB_EINVAL, "bydb_encode_pages takes int64 or float64 columns");
+    if (in->n_blocks > 0 && (!in->block_rows || !in->values)) return fail(BYDB_EINVAL, "block_rows / values is NULL");
+    const size_t NB = in->n_blocks;
+    const bool is_float = in->value_type == BYDB_VT_FLOAT64;
+    std::vector<uint64_t> block_off(NB + 1, 0), slot_off(NB + 1, 0);
+    for (size_t b = 0; b < NB; ++b) {
+        if (in->block_rows[b] == 0) return fail(BYDB_EINVAL, "a block without rows");
+        block_off[b + 1] = block_off[b] + in->block_rows[b];
+        slot_off[b + 1] = slot_off[b] + align_up(11 + 10 * static_cast<size_t>(in->block_rows[b]), 16);  // a varint takes at most 10 bytes
+    }
+    const size_t NV = block_off[NB];
+    auto owner = new EncodedOwner();
+    out->owner = owner;
+    out->n_blocks = in->n_blocks;
+    owner->page_off.assign(NB + 1, 0);
+    owner->needs_cpu.assign(std::max<size_t>(NB, 1), 0);
+    owner->bytes.assign(1, 0);
+    out->page_off = owner->page_off.data();
+    out->needs_cpu = owner->needs_cpu.data();
+    out->bytes = owner->bytes.data();
+    if (NB == 0) return 0;
+    bool done = false;
+    struct Undo {
+        bydb_ctx *ctx;
+        bydb_encoded_pages *out;
+        bool *done;
+        ~Undo() {
+            if (!*done) bydb_encoded_pages_free(ctx, out);
+        }
+    } undo{ctx, out, &done};
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    SlotLease lease(ctx);
+    if (lease.init()) return fail(BYDB_EIO, "cannot create stream");
+    cudaStream_t stream = lease.slot->stream;
+    size_t o = 0;
+    auto carve = [&](size_t bytes) {
+        size_t at = o;
+        o = align_up(o + bytes, 256);
+        return at;
+    };
+    const size_t d_vals = carve(NV * 8), d_boff = carve((NB + 1) * 8), d_soff = carve((NB + 1) * 8), d_scr = carve(is_float ? NV * 8 : 0),
+                 d_exp = carve(is_float ? NV * 2 : 0), d_len = carve(NB * 4), d_st = carve(NB), d_ooff = carve((NB + 1) * 8), d_slots = carve(slot_off[NB]);
+    Scratch sc;
+    sc.stream = stream;
+    if (cudaMallocAsync(reinterpret_cast<void **>(&sc.base), o, stream) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(BYDB_ENOMEM, "bydb_encode_pages: device allocation failed");
+    }
+    uint8_t *d = sc.base;
+    cudaEvent_t ev0 = lease.slot->ev[0], ev1 = lease.slot->ev[1];
+    CUDA_TRY(cudaMemcpyAsync(d + d_vals, in->values, NV * 8, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(d + d_boff, block_off.data(), (NB + 1) * 8, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(d + d_soff, slot_off.data(), (NB + 1) * 8, cudaMemcpyHostToDevice, stream));
+    EncodeParams ep;
+    memset(&ep, 0, sizeof ep);
+    ep.values = d + d_vals;
+    ep.block_off = reinterpret_cast<const uint64_t *>(d + d_boff);
+    ep.n_blocks = static_cast<uint32_t>(NB);
+    ep.is_float = is_float ? 1u : 0u;
+    ep.scratch = reinterpret_cast<int64_t *>(d + d_scr);
+    ep.exps = reinterpret_cast<int16_t *>(d + d_exp);
+    ep.slots = d + d_slots;
+    ep.slot_off = reinterpret_cast<const uint64_t *>(d + d_soff);
+    ep.page_len = reinterpret_cast<uint32_t *>(d + d_len);
+    ep.status = d + d_st;
+    const int grid = ctx->sm_count * 4;
+    CUDA_TRY(cudaEventRecord(ev0, stream));
+    launch_encode_pages(ep, grid, stream);
+    std::vector<uint32_t> page_len(NB);
+    CUDA_TRY(cudaMemcpyAsync(page_len.data(), d + d_len, NB * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(owner->needs_cpu.data(), d + d_st, NB, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaGetLastError());
+    for (size_t b = 0; b < NB; ++b) {
+        owner->page_off[b + 1] = owner->page_off[b] + page_len[b];
+        out->n_cpu_blocks += owner->needs_cpu[b] ? 1u : 0u;
+    }
+    const size_t total = owner->page_off[NB];
+    owner->bytes.assign(std::max<size_t>(total, 1), 0);
+    out->bytes = owner->bytes.data();
+    Scratch compact;
+    compact.stream = stream;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&compact.base), std::max<size_t>(total, 256), stream));
+    CUDA_TRY(cudaMemcpyAsync(d + d_ooff, owner->page_off.data(), (NB + 1) * 8, cudaMemcpyHostToDevice, stream));
+    launch_gather_pages(ep, reinterpret_cast<const uint64_t *>(d + d_ooff), compact.base, grid, stream);
+    CUDA_TRY(cudaEventRecord(ev1, stream));
+    if (total) CUDA_TRY(cudaMemcpyAsync(owner->bytes.data(), compact.base, total, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    out->device_ms = ms;
+    done = true;
+    return 0;
+    });
+}
+
+void bydb_encoded_pages_free(bydb_ctx *, bydb_encoded_pages *r) {
+    if (!r) return;
+    delete static_cast<EncodedOwner *>(r->owner);
     memset(r, 0, sizeof *r);
 }
 

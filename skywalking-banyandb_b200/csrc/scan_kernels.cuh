@@ -262,6 +262,23 @@ size_t unpack_scratch_stride();
 void launch_classify_pages(const UnpackParams &p, cudaStream_t s);
 void launch_unpack_pages(const UnpackParams &p, int n_warps, cudaStream_t s);
 
+// ---- write side: numeric field pages encoded on the device (encode_kernels.cu)
+struct EncodeParams {
+    const void *values;           // int64 / double, the blocks back to back
+    const uint64_t *block_off;    // [n_blocks + 1] value offsets
+    uint32_t n_blocks;
+    uint32_t is_float;
+    int64_t *scratch;             // [n_values] decimal integers of a float64 column
+    int16_t *exps;                // [n_values]
+    uint8_t *slots;               // worst-case page slots
+    const uint64_t *slot_off;     // [n_blocks + 1]
+    uint32_t *page_len;           // [n_blocks] 0 = the block goes to the CPU writer
+    uint8_t *status;              // [n_blocks] 1 = not encoded here
+};
+void launch_encode_pages(const EncodeParams &p, int grid, cudaStream_t s);
+void launch_gather_pages(const EncodeParams &p, const uint64_t *out_off, uint8_t *out, int grid, cudaStream_t s);
+void preload_encode_kernels();   // encode_kernels.cu
+
 size_t scan_smem_bytes();
 void launch_plan_blocks(const ScanParams &p, cudaStream_t s);
 void launch_scan_blocks(const ScanParams &p, int grid_fast, int grid_slow, cudaStream_t s);

@@ -35,6 +35,9 @@ int main(void) {
     int (*f_red)(bydb_ctx *, const bydb_query *, int32_t, bydb_result *) = bydb_scan_reduce;
     int (*f_redp)(bydb_ctx *, bydb_prepared *, int32_t, bydb_result *) = bydb_scan_reduce_prepared;
     int (*f_redh)(bydb_ctx *, uint32_t, const bydb_part_files *, const bydb_query *, int32_t, bydb_result *) = bydb_scan_reduce_host;
+    int (*f_enc)(bydb_ctx *, const bydb_encode_input *, bydb_encoded_pages *) = bydb_encode_pages;
+    void (*f_encfree)(bydb_ctx *, bydb_encoded_pages *) = bydb_encoded_pages_free;
+    (void)f_enc; (void)f_encfree;
     (void)f_dir; (void)f_prow; (void)f_prfree; (void)f_cexp; (void)f_ccon; (void)f_red; (void)f_redp; (void)f_redh;
     (void)f_prep; (void)f_run; (void)f_qrel;
     (void)f_shutdown; (void)f_reg; (void)f_rel; (void)f_info; (void)f_fb; (void)f_scan; (void)f_host; (void)f_free; (void)f_part; (void)f_comb; (void)f_fin;
