@@ -858,7 +858,6 @@ __device__ __forceinline__ void sparse_flush(WarpSmem *sm, uint32_t m, uint32_t 
         base = sm->q_base[lane];
     }
     const uint32_t lo = static_cast<uint32_t>(d >> 16) & 0xffu, hi = static_cast<uint32_t>(d >> 24) & 0xffu;
-    const bool all_full = __all_sync(0xffffffffu, !mine || (lo == 0 && hi == 64));
     if (mine) {
         const uint8_t *src = &sm->stage[0][0] + (static_cast<uint32_t>(d) & 0xffffu);
         uint32_t accv = static_cast<uint32_t>(d >> 40) & 0x3fffu, sh = static_cast<uint32_t>(d >> 32) & 0xffu;
@@ -880,8 +879,8 @@ __device__ __forceinline__ void sparse_flush(WarpSmem *sm, uint32_t m, uint32_t 
             const uint32_t term = valid & ~msb;
             const uint32_t nh = __popc(term);
             const uint32_t a32 = static_cast<uint32_t>(a) & low_bits(nh);
-            if (all_full) fast_lane_decode<true, kNeed>(wa, wb, valid, term, a32, accv, sh, P, sumP, minP, maxP);
-            else fast_lane_decode<false, kNeed>(wa, wb, valid, term, a32, accv, sh, P, sumP, minP, maxP);
+            // one decode variant (the masked one) for interior and edge windows alike: code size, see delta_page_sparse
+            fast_lane_decode<false, kNeed>(wa, wb, valid, term, a32, accv, sh, P, sumP, minP, maxP);
             a = nh >= 32 ? (a >> 16) >> 16 : (a >> nh);
         }
         const uint32_t cntA = static_cast<uint32_t>(__popcll(aw));
@@ -958,43 +957,39 @@ __device__ __noinline__ int delta_page_sparse(WarpSmem *sm, int lane) {
         hi_i = hi_i < 0 ? 0 : (hi_i > 64 ? 64 : hi_i);
         SwarLite sl;
         uint32_t lastw;
+        // the word loops stay ROLLED (4 words per trip): unrolled, the two light passes and the two decode variants of one
+        // instantiation are ~25 KB of hot code, and a query with two aggregated fields runs two instantiations -- ncu r02l: the
+        // warps then wait for instructions 6.8 cycles per issue
         if (interior) {
             lastw = *reinterpret_cast<const uint32_t *>(src + kSwarLaneBytes - 4);
             uint32_t pw = __shfl_up_sync(0xffffffffu, lastw, 1);
             if (lane == 0) pw = carry_w;
             swar_lite_begin(sl, pw);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const uint4 wa = *reinterpret_cast<const uint4 *>(src + 32 * half), wb = *reinterpret_cast<const uint4 *>(src + 32 * half + 16);
-                swar_lite_word<false>(sl, wa.x, 0u);
-                swar_lite_word<false>(sl, wa.y, 0u);
-                swar_lite_word<false>(sl, wa.z, 0u);
-                swar_lite_word<false>(sl, wa.w, 0u);
-                swar_lite_word<false>(sl, wb.x, 0u);
-                swar_lite_word<false>(sl, wb.y, 0u);
-                swar_lite_word<false>(sl, wb.z, 0u);
-                swar_lite_word<false>(sl, wb.w, 0u);
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                const uint4 w = *reinterpret_cast<const uint4 *>(src + 16 * q);
+                swar_lite_word<false>(sl, w.x, 0u);
+                swar_lite_word<false>(sl, w.y, 0u);
+                swar_lite_word<false>(sl, w.z, 0u);
+                swar_lite_word<false>(sl, w.w, 0u);
             }
         } else {
-            uint4 w[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                w[q] = make_uint4(0, 0, 0, 0);
-                if (o + 16 * q < st.total) w[q] = *reinterpret_cast<const uint4 *>(src + 16 * q);
-            }
             const uint32_t va = low_bits(hi_i > 32 ? 32 : hi_i) & ~low_bits(lo_i > 32 ? 32 : lo_i);
             const uint32_t vb = low_bits(hi_i > 32 ? hi_i - 32 : 0) & ~low_bits(lo_i > 32 ? lo_i - 32 : 0);
-            lastw = w[3].w & expand4(vb >> 28);
+            lastw = 0;
+            if (o + 48 < st.total) lastw = *reinterpret_cast<const uint32_t *>(src + kSwarLaneBytes - 4) & expand4(vb >> 28);
             uint32_t pw = __shfl_up_sync(0xffffffffu, lastw, 1);
             if (lane == 0) pw = carry_w;
             swar_lite_begin(sl, pw);
-#pragma unroll
+#pragma unroll 1
             for (int q = 0; q < 4; ++q) {
+                uint4 w = make_uint4(0, 0, 0, 0);
+                if (o + 16 * q < st.total) w = *reinterpret_cast<const uint4 *>(src + 16 * q);
                 const uint32_t v = (q < 2 ? va : vb) >> (16 * (q & 1));
-                swar_lite_word<true>(sl, w[q].x, expand4(v));
-                swar_lite_word<true>(sl, w[q].y, expand4(v >> 4));
-                swar_lite_word<true>(sl, w[q].z, expand4(v >> 8));
-                swar_lite_word<true>(sl, w[q].w, expand4(v >> 12));
+                swar_lite_word<true>(sl, w.x, expand4(v));
+                swar_lite_word<true>(sl, w.y, expand4(v >> 4));
+                swar_lite_word<true>(sl, w.z, expand4(v >> 8));
+                swar_lite_word<true>(sl, w.w, expand4(v >> 12));
             }
         }
         carry_w = __shfl_sync(0xffffffffu, lastw, 31);
