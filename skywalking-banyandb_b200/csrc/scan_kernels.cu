@@ -63,7 +63,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 // ------------------------------------------------------------------------------------------------
 // per-warp shared memory
 // ------------------------------------------------------------------------------------------------
-constexpr int kSparseQueue = 64;  // at most 32 windows of the previous chunk + 32 of the current one
+constexpr int kSparseQueue = BYDB_SPARSE ? 64 : 1;  // at most 32 windows of the previous chunk + 32 of the current one
 
 struct __align__(128) WarpSmem {
     uint8_t stage[kStages][kStageBytes];
@@ -1740,9 +1740,6 @@ __device__ __noinline__ int delta_pred_fast(WarpSmem *sm, int lane) {
 // kDeferSlow is returned by the fast lane when a page needs the general decoder
 constexpr uint32_t kDeferSlow = 0xffffffffu;
 
-#ifndef BYDB_SPARSE
-#define BYDB_SPARSE 1   // 0: masked / ranged delta pages keep the serial decoder (A/B timing)
-#endif
 template <int kMode>
 __device__ __forceinline__ int sparse_dispatch(WarpSmem *sm, uint32_t need, int lane) {
     if constexpr (kMode == kRowsAll) {

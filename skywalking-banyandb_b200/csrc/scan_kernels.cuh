@@ -15,7 +15,10 @@ constexpr int kWarpsPerCta = 8;          // 256 threads; every warp is an indepe
 #define BYDB_STAGE_BYTES 2048            // experiment knobs (make variant EXTRA="-DBYDB_STAGE_BYTES=4096 -DBYDB_STAGES=3")
 #endif
 #ifndef BYDB_STAGES
-#define BYDB_STAGES 3
+#define BYDB_STAGES 2
+#endif
+#ifndef BYDB_SPARSE
+#define BYDB_SPARSE 0                    // 1: masked / ranged delta pages take delta_page_sparse (measured slower; make variant EXTRA="-DBYDB_SPARSE=1 -DBYDB_STAGES=3")
 #endif
 #ifndef BYDB_FAST_CTAS
 #define BYDB_FAST_CTAS 3                 // resident CTAs per SM the fast lane is compiled for (register cap 65536 / (256 x n))
