@@ -574,6 +574,29 @@ def main():
                        + ("; bydb_scan_reduce_host on every rank: host images in on all ranks, the partial tables meet in rank 0's mailbox, one "
                           "result out on rank 0 -- the collective is inside the timed call" if world > 1 else ""))
         e2e["pin_copy_s_outside_timed_region"] = t_pin
+        if world == 1:
+            # one more, untimed, step with the library's host-side timeline (BYDB_TRACE) captured from stderr: shows whether a slow
+            # step waited for the block-index parsers (host cores) or for the copies (PCIe)
+            import tempfile
+            try:
+                with tempfile.TemporaryFile() as tf:
+                    sys.stderr.flush()
+                    saved = os.dup(2)
+                    os.dup2(tf.fileno(), 2)
+                    os.environ["BYDB_TRACE"] = "1"
+                    try:
+                        t1 = time.perf_counter()
+                        ctx.scan_agg_host([pinned], c3_query(pkg, [], sids, services, flags=Q_HOST_ZERO_COPY))
+                        traced_ms = (time.perf_counter() - t1) * 1e3
+                    finally:
+                        os.environ.pop("BYDB_TRACE", None)
+                        os.dup2(saved, 2)
+                        os.close(saved)
+                    tf.seek(0)
+                    lines = [ln.strip() for ln in tf.read().decode(errors="replace").splitlines() if "[bydb cold]" in ln]
+                e2e["traced_step"] = {"ms": traced_ms, "timeline": lines[:40]}
+            except Exception as ex:  # noqa: BLE001
+                e2e["traced_step"] = {"error": str(ex)[:200]}
         if last is not None and r_e2e is not None:
             # the cold path scans in slices and combines their tables: float sums may differ from the resident run in the last bits
             e2e["same_result_as_resident"] = bool(r_e2e.group_id.tolist() == last.group_id.tolist() and r_e2e.val_i64.tolist() == last.val_i64.tolist()

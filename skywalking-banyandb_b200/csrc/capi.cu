@@ -2098,7 +2098,7 @@ static int scan_agg_host_pipelined(bydb_ctx *ctx, const bydb_part_files *files, 
         int rc = 0;
     };
     const size_t T = std::max<size_t>(1, std::min<size_t>(n_primary, 32));
-    static const bool trace = getenv("BYDB_TRACE") != nullptr;  // host-side timeline of the cold path on stderr
+    const bool trace = getenv("BYDB_TRACE") != nullptr;  // host-side timeline of the cold path on stderr (read per call: a caller can trace one step)
     const auto t_begin = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); };
     std::vector<std::future<Parsed>> parses;
