@@ -98,15 +98,34 @@ struct ExecSlot {
         if (busy_pending) cudaEventSynchronize(busy);
         busy_pending = false;
     }
+    // Page-locked allocations (and frees) are implicit synchronisation points of the device: no kernel issued after one starts
+    // before every kernel issued before it has finished.  When several ranks share a device, a rank whose wait kernel is spinning
+    // for a peer would then never see that peer's kernels start (the peer's call just allocated staging memory) -- a 60 s
+    // stall ending in BYDB_EIO.  So: every slot is created with kInitialPinned bytes at bydb_init, grows geometrically and
+    // rarely, and nothing is freed before bydb_shutdown.
+    static constexpr size_t kInitialPinned = 1u << 20;
+    std::vector<uint8_t *> retired;
     int ensure_pinned(size_t n) {
         if (n <= pinned_bytes) return 0;
-        if (pinned) cudaFreeHost(pinned);
-        pinned = nullptr;
-        pinned_bytes = 0;
-        size_t want = align_up(n, 1 << 16);
-        if (cudaMallocHost(reinterpret_cast<void **>(&pinned), want) != cudaSuccess) return -1;
+        size_t want = align_up(std::max(n, 2 * pinned_bytes), 1 << 16);
+        uint8_t *fresh = nullptr;
+        if (cudaMallocHost(reinterpret_cast<void **>(&fresh), want) != cudaSuccess) {
+            cudaGetLastError();
+            want = align_up(n, 1 << 16);
+            if (cudaMallocHost(reinterpret_cast<void **>(&fresh), want) != cudaSuccess) return -1;
+        }
+        if (pinned) retired.push_back(pinned);  // copies from it may still be in flight; freed at shutdown
+        pinned = fresh;
         pinned_bytes = want;
         return 0;
+    }
+    int create() {
+        if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return -1;
+        for (auto &e : ev)
+            if (cudaEventCreate(&e) != cudaSuccess) return -1;
+        if (cudaMallocHost(reinterpret_cast<void **>(&zpage), 256 * kMaxBatches) != cudaSuccess) return -1;
+        if (cudaEventCreateWithFlags(&busy, cudaEventDisableTiming) != cudaSuccess) return -1;
+        return ensure_pinned(kInitialPinned);
     }
 };
 
@@ -224,13 +243,8 @@ struct SlotLease {
             slot->wait_idle();  // its pinned staging may still feed an asynchronous call's copies
             return 0;
         }
-        slot.reset(new ExecSlot());
-        if (cudaStreamCreateWithFlags(&slot->stream, cudaStreamNonBlocking) != cudaSuccess) return -1;
-        for (auto &e : slot->ev)
-            if (cudaEventCreate(&e) != cudaSuccess) return -1;
-        if (cudaMallocHost(reinterpret_cast<void **>(&slot->zpage), 256 * ExecSlot::kMaxBatches) != cudaSuccess) return -1;
-        if (cudaEventCreateWithFlags(&slot->busy, cudaEventDisableTiming) != cudaSuccess) return -1;
-        return 0;
+        slot.reset(new ExecSlot());   // more concurrent callers than slots made at bydb_init
+        return slot->create();
     }
     ~SlotLease() {
         if (!slot) return;
@@ -1295,6 +1309,7 @@ void prepared_destroy(bydb_prepared *p) {
             if (e) cudaEventDestroy(e);
         if (p->slot->busy) cudaEventDestroy(p->slot->busy);
         if (p->slot->pinned) cudaFreeHost(p->slot->pinned);
+        for (uint8_t *r : p->slot->retired) cudaFreeHost(r);
         if (p->slot->zpage) cudaFreeHost(p->slot->zpage);
     }
     delete p;
@@ -1391,6 +1406,15 @@ int bydb_init(const bydb_cfg *cfg, bydb_ctx **out) {
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
         }
     }
+    // execution slots (stream, events, pinned staging) for the first concurrent callers: made now, not inside a query
+    for (int i = 0; i < 2; ++i) {
+        std::unique_ptr<ExecSlot> sl(new ExecSlot());
+        if (sl->create() != 0) {
+            cudaGetLastError();
+            break;
+        }
+        ctx->free_slots.push_back(std::move(sl));
+    }
     preload_kernels();
     preload_unpack_kernels();
     preload_index_kernels();
@@ -1415,6 +1439,7 @@ void bydb_shutdown(bydb_ctx *ctx) {
             if (e) cudaEventDestroy(e);
         if (s->busy) cudaEventDestroy(s->busy);
         if (s->pinned) cudaFreeHost(s->pinned);
+        for (uint8_t *r : s->retired) cudaFreeHost(r);
         if (s->zpage) cudaFreeHost(s->zpage);
     }
     ctx->free_slots.clear();
@@ -2000,7 +2025,9 @@ static int plan_gather(bydb_ctx *ctx, const std::vector<FileImage> &imgs, const 
 }
 
 // uploads the image through the staging ring onto `stream`; the copies of one chunk are spread over the worker pool
-static int upload_gather(bydb_ctx *ctx, GatherImage &g, uint8_t *d_arena, cudaStream_t stream) {
+// the pinned staging ring of the gather path: made at the first pageable cold query -- or at bydb_comm_connect, because a
+// page-locked allocation INSIDE a collective can stall peers that share the device (see ExecSlot::ensure_pinned)
+static int ensure_stage_ring(bydb_ctx *ctx) {
     StageRing &ring = ctx->stage;
     for (int i = 0; i < StageRing::kBufs; ++i) {
         if (ring.buf[i]) continue;
@@ -2008,6 +2035,12 @@ static int upload_gather(bydb_ctx *ctx, GatherImage &g, uint8_t *d_arena, cudaSt
             cudaEventCreateWithFlags(&ring.done[i], cudaEventDisableTiming) != cudaSuccess)
             return fail(BYDB_ENOMEM, "cannot allocate the pinned staging ring");
     }
+    return 0;
+}
+
+static int upload_gather(bydb_ctx *ctx, GatherImage &g, uint8_t *d_arena, cudaStream_t stream) {
+    StageRing &ring = ctx->stage;
+    if (int rrc = ensure_stage_ring(ctx)) return rrc;
     const uint8_t *table[2] = {d_arena, d_arena};  // every page lives in the arena: "file" 0 (and a spare slot)
     size_t si = 0;
     for (size_t c0 = 0; c0 < g.bytes; c0 += StageRing::kBytes) {
@@ -2403,10 +2436,12 @@ int bydb_query_prepare(bydb_ctx *ctx, const bydb_query *q, bydb_prepared **out) 
     p->q.preds = p->preds.data();
     // a dedicated slot: stream, events, pinned staging
     p->slot.reset(new ExecSlot());
-    bool ok = cudaStreamCreateWithFlags(&p->slot->stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (auto &e : p->slot->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
-    ok = ok && cudaMallocHost(reinterpret_cast<void **>(&p->slot->zpage), 256 * ExecSlot::kMaxBatches) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&p->slot->busy, cudaEventDisableTiming) == cudaSuccess;
+    bool ok = p->slot->create() == 0;  // with its pinned staging: nothing page-locked is allocated inside an execution
+    if (ok) {
+        // sized for this query now (see ExecSlot::ensure_pinned: a page-locked allocation inside a collective can stall the peers)
+        const size_t G = q->series_group ? static_cast<size_t>(q->n_groups) : 1, A = q->n_aggs, NS = q->n_series;
+        ok = p->slot->ensure_pinned(NS * 12 + (G + 1) * 4 + G * (12 + 16 * A) + 16 * A + 16384) == 0;
+    }
     ok = ok && cudaEventCreate(&p->t0) == cudaSuccess && cudaEventCreate(&p->t1) == cudaSuccess;
     if (!ok) {
         prepared_destroy(p);
@@ -2627,6 +2662,7 @@ int bydb_comm_connect(bydb_ctx *ctx, int32_t rank, int32_t nranks, const bydb_co
     std::vector<uint8_t *> peer(static_cast<size_t>(nranks), nullptr);
     std::vector<bool> opened(static_cast<size_t>(nranks), false);
     std::vector<size_t> slots(static_cast<size_t>(nranks), 0);
+    bool shares_device = false;  // another rank lives on this GPU (tests, a box with fewer GPUs than ranks)
     for (int r = 0; r < nranks; ++r) {
         CommBlob b;
         memcpy(&b, &all[r], sizeof b);
@@ -2634,6 +2670,7 @@ int bydb_comm_connect(bydb_ctx *ctx, int32_t rank, int32_t nranks, const bydb_co
         if (kCommCtl + 2 * static_cast<uint64_t>(nranks) * b.slot_bytes > b.mailbox_bytes)
             return fail(BYDB_EINVAL, "mailbox of rank " + std::to_string(r) + " was exported for fewer ranks");
         slots[r] = b.slot_bytes;
+        if (r != rank && static_cast<int>(b.device) == ctx->device) shares_device = true;
         if (r == rank) {
             if (b.raw_ptr != reinterpret_cast<uint64_t>(cm.mine)) return fail(BYDB_EINVAL, "handles[rank] is not this context's own handle");
             peer[r] = cm.mine;
@@ -2667,6 +2704,9 @@ int bydb_comm_connect(bydb_ctx *ctx, int32_t rank, int32_t nranks, const bydb_co
     cm.nranks = nranks;
     cm.epoch = 0;
     cm.last_use.assign(2 * static_cast<size_t>(nranks), 0);
+    // ranks that share a device must not make page-locked allocations inside a collective (ExecSlot::ensure_pinned): the
+    // staging ring of the pageable cold path is made now
+    if (shares_device && ensure_stage_ring(ctx) != 0) g_last_error.clear();
     return 0;
     });
 }
