@@ -1404,6 +1404,11 @@ int bydb_init(const bydb_cfg *cfg, bydb_ctx **out) {
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             uint64_t thr = UINT64_MAX;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            // never let the allocator satisfy a request by making the requesting stream wait for ANOTHER stream's pending free:
+            // with several ranks on one device that other stream may sit behind a wait kernel spinning for this very rank
+            // (the collective then stalls until the 60 s bound; seen as a test that failed only after the pool had history)
+            int no = 0;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &no);
         }
     }
     // execution slots (stream, events, pinned staging) for the first concurrent callers: made now, not inside a query

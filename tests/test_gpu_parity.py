@@ -945,9 +945,25 @@ def test_scan_reduce_peer_mailboxes_equal_the_single_context_answer(bydb, gpu_ct
     # they share the device, on a multi-GPU box each takes its own), every rank scans its shard and writes its partial table into
     # the root's mailbox, the root combines in rank order and finalises -- the liaison reduce of measure_plan_aggregation.go:96-124.
     # Must equal one context scanning everything, for grouped Top-N, MEAN / MIN / MAX finalisation and a rank without matching rows.
+    import faulthandler
+    import gc
     import threading
     import torch
     n_dev = torch.cuda.device_count()
+    # On a one-GPU box the ranks share the device.  A finaliser of some earlier test's object (a prepared query, a context) that runs
+    # on a rank's thread in the middle of a collective frees page-locked memory -- an implicit device synchronisation that waits for
+    # the peers' spinning wait kernels, i.e. for the very rank that is stuck in it.  Nothing unrelated may be torn down here.
+    gc.collect()
+    gc.disable()
+    faulthandler.dump_traceback_later(25, exit=False)   # a stalled collective shows where every thread sits
+    try:
+        _scan_reduce_body(bydb, gpu_ctx, threading, n_dev)
+    finally:
+        faulthandler.cancel_dump_traceback_later()
+        gc.enable()
+
+
+def _scan_reduce_body(bydb, gpu_ctx, threading, n_dev):
     rng = np.random.default_rng(314)
     R = 3
     sids, ts, ver = grid(30, 2600)
