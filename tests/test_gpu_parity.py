@@ -1471,3 +1471,51 @@ def test_device_page_encoder_matches_the_reference_writer(bydb, gpu_ctx):
     assert pages == []
     with pytest.raises(bydb.BydbError):
         gpu_ctx.encode_pages(np.zeros(3, np.int64), [0, 3])   # a block without rows
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_sweep_stored_tag_group_by(bydb, gpu_ctx, seed):
+    # randomised a12 queries: key cardinality, run lengths, nil cells, series groups, predicates, ranges, aggregates, Top-N
+    rng = np.random.default_rng(0xA1200 + seed)
+    n_series, n_pts = int(rng.integers(3, 18)), int(rng.integers(200, 9500))
+    sids, ts, ver = grid(n_series, n_pts, sid0=int(rng.integers(1, 50)), sid_step=int(rng.integers(1, 4)))
+    n = sids.size
+    lat = np.round(rng.normal(40, 15, n), int(rng.integers(0, 4)))
+    calls = rng.integers(-(10 ** int(rng.integers(1, 7))), 10 ** int(rng.integers(1, 7)), n)
+    code = rng.integers(0, 5, n) * 100
+    n_vals, max_run = int(rng.integers(1, 10)), int(rng.integers(1, 60))
+    key = []
+    while len(key) < n:
+        v = int(rng.integers(0, n_vals))
+        key.extend([b"k%d" % v if v else b""] * int(rng.integers(1, max_run + 1)))   # value 0 is the empty string
+    key = key[:n]
+    if rng.random() < 0.5:
+        for i in rng.integers(0, n, max(1, n // 300)):
+            key[int(i)] = None
+    part = build_part(sids, ts, ver, [("latency", O.VT_FLOAT64, lat, None), ("calls", O.VT_INT64, calls, None)],
+                      [("default", [("key", O.VT_STR, key, None), ("code", O.VT_INT64, code, None)])])
+    usid = np.unique(sids)
+    pick = usid[rng.random(usid.size) < 0.8] if usid.size > 3 else usid
+    if pick.size == 0:
+        pick = usid[:1]
+    n_groups = int(rng.integers(1, 5))
+    groups = rng.integers(0, n_groups, pick.size).astype(np.int32)
+    # group ids in first-appearance order of the series, like the caller densifies them
+    remap, dense = {}, []
+    for g in groups.tolist():
+        dense.append(remap.setdefault(g, len(remap)))
+    groups = np.array(dense, dtype=np.int32)
+    funcs = [O.AGG_SUM, O.AGG_COUNT, O.AGG_MIN, O.AGG_MAX, O.AGG_MEAN]
+    aggs = [(str(rng.choice(["latency", "calls"])), int(rng.choice(funcs))) for _ in range(int(rng.integers(1, 5)))]
+    kw = {}
+    if rng.random() < 0.6:
+        kw["preds"] = [O.Pred("default", "code", int(rng.choice([O.OP_EQ, O.OP_NE, O.OP_GE, O.OP_LT])), int(rng.integers(0, 5)) * 100)]
+    if rng.random() < 0.6:
+        a, b = sorted(rng.integers(0, n_pts, 2).tolist())
+        kw["tmin"], kw["tmax"] = T0 + a * STEP, T0 + b * STEP
+    if rng.random() < 0.4:
+        kw["top_n"], kw["top_agg"], kw["top_desc"] = int(rng.integers(1, 8)), int(rng.integers(0, len(aggs))), bool(rng.integers(0, 2))
+    oq = O.Query([part], pick, aggs, groups=groups, n_groups=len(remap), **kw)
+    got, want = _keyed_both(bydb, gpu_ctx, [part], oq, "default", "key")
+    assert got.key == want.key, (seed, got.key, want.key)
+    assert_parity(got, want, aggs, f"keyed sweep {seed}")
