@@ -836,9 +836,10 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
         return at;
     };
     const size_t off_zero = carve(256);  // work_count, work_next, err[2], stats[4], col_type[F]
-    const size_t off_sids = carve(NS * 8);
-    const size_t off_order = carve(NS * 4);
-    const size_t off_gstart = carve((static_cast<size_t>(G) + 1) * 4);
+    // sids | order | group_start sit back to back, exactly like in the pinned staging: one copy brings all three
+    const size_t off_sids = carve(NS * 12 + (static_cast<size_t>(G) + 1) * 4);
+    const size_t off_order = off_sids + NS * 8;
+    const size_t off_gstart = off_sids + NS * 12;
     const size_t off_worklist = carve(NB * 4);
     const size_t off_slowlist = carve(NB * 4);
     const size_t off_restlist = carve(NB * 4);
@@ -866,9 +867,7 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
     memcpy(h + NS * 12, gstart.data(), (static_cast<size_t>(G) + 1) * 4);
     CUDA_TRY(cudaMemsetAsync(d + off_zero, 0, 256, stream));
     if (use_first) CUDA_TRY(cudaMemsetAsync(d + off_first, 0xff, n_first * 4, stream));
-    if (NS) CUDA_TRY(cudaMemcpyAsync(d + off_sids, h, NS * 8, cudaMemcpyHostToDevice, stream));
-    if (NS) CUDA_TRY(cudaMemcpyAsync(d + off_order, h + NS * 8, NS * 4, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaMemcpyAsync(d + off_gstart, h + NS * 12, (static_cast<size_t>(G) + 1) * 4, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(d + off_sids, h, stage_bytes, cudaMemcpyHostToDevice, stream));
     if (stats) stats->h2d_bytes += stage_bytes;
 
     // zero page: [0] work_count [1] work_next [2..3] err [4..11] stats (u64 x4) [16..] col_type
@@ -1022,7 +1021,9 @@ int run_scan(bydb_ctx *ctx, const bydb_query *q, Plan &plan, ExecSlot &slot, cud
     launch_scan_blocks(sp, ctx->sm_count * ctx->ctas_per_sm_fast, ctx->sm_count * ctx->ctas_per_sm, stream);
     CUDA_TRY(cudaEventRecord(ev[2], stream));
     launch_series_reduce(rp, stream);
-    launch_group_reduce(rp, stream);
+    bool small_groups = true;  // every group has at most 32 series: the warp-per-group reduce (bit-identical sums)
+    for (int32_t g = 0; g < G && small_groups; ++g) small_groups = gstart[g + 1] - gstart[g] <= 32;
+    launch_group_reduce(rp, stream, small_groups);
     CUDA_TRY(cudaEventRecord(ev[3], stream));
     // read back the zero page (errors + counters); the caller synchronises and then calls collect_scan
     CUDA_TRY(cudaMemcpyAsync(zpage, d + off_zero, 256, cudaMemcpyDeviceToHost, stream));

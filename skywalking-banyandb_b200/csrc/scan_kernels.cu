@@ -2856,6 +2856,54 @@ __global__ void __launch_bounds__(256) group_reduce_kernel(const __grid_constant
     }
 }
 
+// The same reduce for groups of at most 32 series (a service with a handful of instances): one WARP per group, eight groups per
+// CTA.  The CTA version above degenerates to exactly this tree for such a group (thread k < 32 holds series k, warps 1..7 hold
+// nothing), so the sums are bit-identical; what goes away is a thousand 256-thread CTAs with two barriers each.
+__global__ void __launch_bounds__(256) group_reduce_small_kernel(const __grid_constant__ ReduceParams p) {
+    const int lane = threadIdx.x & 31;
+    const int32_t g = static_cast<int32_t>((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (g >= p.n_groups) return;
+    const int32_t lo = p.group_start[g], hi = p.group_start[g + 1];
+    const int32_t k = lo + lane;
+    int64_t rows = k < hi ? p.Srows[p.order[k]] : 0;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) rows += static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(rows), m));
+    if (lane == 0) p.rows[g] = rows;
+    for (uint32_t c = 0; c < p.n_fcols; ++c) {
+        const bool is_float = p.col_type[c] == BYDB_VT_FLOAT64;
+        BlockPartial acc;
+        acc.sum.i = 0;
+        acc.mn.i = 0;
+        acc.mx.i = 0;
+        acc.cnt = 0;
+        if (k < hi) combine(acc, p.S[static_cast<size_t>(p.order[k]) * p.n_fcols + c], is_float);
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            BlockPartial o;
+            o.sum.i = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(acc.sum.i), m));
+            o.mn.i = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(acc.mn.i), m));
+            o.mx.i = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(acc.mx.i), m));
+            o.cnt = static_cast<int64_t>(shfl_xor_u64(static_cast<uint64_t>(acc.cnt), m));
+            BlockPartial a = (lane & m) ? o : acc, b = (lane & m) ? acc : o;
+            combine(a, b, is_float);
+            acc = a;
+        }
+        if (lane == 0) {
+            const BlockPartial &t = acc;
+            const size_t o = static_cast<size_t>(g) * p.n_fcols + c;
+            const bool have = t.cnt > 0;
+            p.cnt[o] = t.cnt;
+            p.sum_f64[o] = (have && is_float) ? t.sum.f : 0.0;
+            p.max_f64[o] = (have && is_float) ? t.mx.f : -INFINITY;
+            p.negmin_f64[o] = (have && is_float) ? -t.mn.f : -INFINITY;
+            p.sum_i64[o] = (have && !is_float) ? t.sum.i : 0;
+            p.max_i64[o] = (have && !is_float) ? t.mx.i : INT64_MIN;
+            p.notmin_i64[o] = (have && !is_float) ? ~t.mn.i : INT64_MIN;
+            if (g == 0) p.coltype[c] = static_cast<int64_t>(p.col_type[c]) | (static_cast<int64_t>(p.err[0]) << 8);
+        }
+    }
+}
+
 // finalisation: pkg/query/aggregation/function.go Val() + output typing aggregation.go:425-430
 __device__ __forceinline__ void finalize_header(const FinalizeParams &p) {
     for (uint32_t a = 0; a < p.n_aggs; ++a)
@@ -3101,6 +3149,50 @@ __global__ void __launch_bounds__(1024) select_rows_kernel(const __grid_constant
         s_gid[i] = INT32_MAX;
     }
     __syncthreads();
+    if (P2 <= blockDim.x) {
+        // one element per thread, kept in registers: compare-exchange steps inside a warp (j < 32: 40 of the 55 steps for 1024
+        // elements) are two shuffles and no barrier; only the wider steps go through shared memory
+        uint64_t mk = 0;
+        int32_t mg = INT32_MAX;
+        const uint32_t t = static_cast<uint32_t>(tid);
+        if (t < P2) {
+            mk = s_key[t];
+            mg = s_gid[t];
+        }
+        for (uint32_t k2 = 2; k2 <= P2; k2 <<= 1) {
+            for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
+                uint64_t ok;
+                int32_t og;
+                if (j < 32) {
+                    ok = shfl_xor_u64(mk, static_cast<int>(j));
+                    og = __shfl_xor_sync(0xffffffffu, mg, static_cast<int>(j));
+                } else {
+                    __syncthreads();  // the previous wide step's reads are done
+                    if (t < P2) {
+                        s_key[t] = mk;
+                        s_gid[t] = mg;
+                    }
+                    __syncthreads();
+                    ok = t < P2 ? s_key[t ^ j] : 0;
+                    og = t < P2 ? s_gid[t ^ j] : INT32_MAX;
+                }
+                const bool up = (t & k2) == 0, lower = (t & j) == 0;
+                const bool mine_first = mk > ok || (mk == ok && mg < og);  // mine precedes the partner in the output
+                // the lower position of the pair holds the preceding element when the run ascends (`up`), the other one otherwise
+                const bool keep = lower ? (mine_first == up) : (mine_first != up);
+                if (!keep) {
+                    mk = ok;
+                    mg = og;
+                }
+            }
+        }
+        __syncthreads();
+        if (t < P2) {
+            s_key[t] = mk;
+            s_gid[t] = mg;
+        }
+        __syncthreads();
+    } else
     for (uint32_t k2 = 2; k2 <= P2; k2 <<= 1) {
         for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
             for (uint32_t i = tid; i < P2; i += blockDim.x) {
@@ -3466,9 +3558,10 @@ void launch_series_reduce(const ReduceParams &p, cudaStream_t s) {
     const int threads = 256;  // 8 series (one warp each) per CTA
     series_reduce_kernel<<<(p.n_series + 7) / 8, threads, 0, s>>>(p);
 }
-void launch_group_reduce(const ReduceParams &p, cudaStream_t s) {
+void launch_group_reduce(const ReduceParams &p, cudaStream_t s, bool small_groups) {
     if (p.n_groups <= 0) return;
-    group_reduce_kernel<<<p.n_groups, 256, 0, s>>>(p);
+    if (small_groups) group_reduce_small_kernel<<<(p.n_groups + 7) / 8, 256, 0, s>>>(p);
+    else group_reduce_kernel<<<p.n_groups, 256, 0, s>>>(p);
 }
 void launch_combine_tables(uint64_t *tables, uint32_t n_tables, uint64_t words, uint64_t sum_f64_lo, uint64_t sum_f64_hi, uint64_t max_f64_lo,
                            uint64_t max_f64_hi, uint64_t sum_i64_lo, uint64_t sum_i64_hi, uint64_t max_i64_lo, uint64_t max_i64_hi, cudaStream_t s,
@@ -3608,6 +3701,7 @@ void preload_kernels() {
     cudaFuncGetAttributes(&a, dedup_kernel);
     cudaFuncGetAttributes(&a, series_reduce_kernel);
     cudaFuncGetAttributes(&a, group_reduce_kernel);
+    cudaFuncGetAttributes(&a, group_reduce_small_kernel);
     cudaFuncGetAttributes(&a, finalize_kernel);
     cudaFuncGetAttributes(&a, select_rows_kernel<true>);
     cudaFuncGetAttributes(&a, select_rows_kernel<false>);

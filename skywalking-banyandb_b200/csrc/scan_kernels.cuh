@@ -286,7 +286,7 @@ size_t scan_smem_bytes();
 void launch_plan_blocks(const ScanParams &p, cudaStream_t s);
 void launch_scan_blocks(const ScanParams &p, int grid_fast, int grid_slow, cudaStream_t s);
 void launch_series_reduce(const ReduceParams &p, cudaStream_t s);
-void launch_group_reduce(const ReduceParams &p, cudaStream_t s);
+void launch_group_reduce(const ReduceParams &p, cudaStream_t s, bool small_groups = false);  // small_groups: no group has more than 32 series
 void launch_finalize(const FinalizeParams &p, cudaStream_t s);
 void launch_detect_overlap(const ScanParams &p, cudaStream_t s);
 void launch_dedup(const ScanParams &p, int grid, cudaStream_t s);
