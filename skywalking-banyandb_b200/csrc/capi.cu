@@ -193,6 +193,15 @@ struct Comm {
     uint64_t epoch = 0;
     std::vector<uint64_t> last_use;     // [root * 2 + parity] epoch of the previous collective that used that root's slots of that parity
     std::mutex mu;                      // collective calls are issued one at a time per context
+    // A peer lives on THIS GPU (tests on a one-GPU box, more ranks than GPUs): no wait kernel may spin there.  CUDA gives no
+    // forward-progress guarantee between streams of one device -- they share a handful of hardware queues, and work queued
+    // behind the dependants of a spinning kernel in the same queue never launches, so a rank could wait forever for a peer
+    // whose kernels sit behind its own wait kernel (seen as collectives that stalled until the 60 s bound, depending on how
+    // many streams the process had created before).  In this mode the HOST polls the flags and the prepared form keeps the
+    // plain path.  Ranks on different GPUs keep the device-side waits.
+    bool shared_device = false;
+    cudaStream_t poll_stream = nullptr;
+    unsigned long long *poll_buf = nullptr;  // pinned, kCommMaxRanks words
 };
 
 // Pinned staging ring of the gather path (host images in PAGEABLE memory): the pages a query touches are collected into
@@ -1457,6 +1466,8 @@ void bydb_shutdown(bydb_ctx *ctx) {
     for (size_t r = 0; r < ctx->comm.peer.size(); ++r)
         if (ctx->comm.ipc_opened[r] && ctx->comm.peer[r]) cudaIpcCloseMemHandle(ctx->comm.peer[r]);
     if (ctx->comm.mine) cudaFree(ctx->comm.mine);
+    if (ctx->comm.poll_stream) cudaStreamDestroy(ctx->comm.poll_stream);
+    if (ctx->comm.poll_buf) cudaFreeHost(ctx->comm.poll_buf);
     delete ctx;
 }
 
@@ -2619,6 +2630,7 @@ struct CommBlob {  // what travels inside a bydb_comm_handle
     uint32_t magic, device;
     uint64_t pid, raw_ptr, slot_bytes, mailbox_bytes;
     cudaIpcMemHandle_t ipc;
+    unsigned char uuid[16];  // the physical GPU (device ordinals differ between processes under CUDA_VISIBLE_DEVICES)
 };
 static_assert(sizeof(CommBlob) <= sizeof(bydb_comm_handle), "bydb_comm_handle too small");
 
@@ -2652,6 +2664,12 @@ int bydb_comm_export(bydb_ctx *ctx, uint64_t max_table_bytes, int32_t max_ranks,
     b.slot_bytes = cm.slot_bytes;
     b.mailbox_bytes = cm.mailbox_bytes;
     CUDA_TRY(cudaIpcGetMemHandle(&b.ipc, cm.mine));
+    {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
+        static_assert(sizeof prop.uuid.bytes == sizeof b.uuid, "uuid size");
+        memcpy(b.uuid, prop.uuid.bytes, sizeof b.uuid);
+    }
     memset(out, 0, sizeof *out);
     memcpy(out, &b, sizeof b);
     return 0;
@@ -2671,6 +2689,12 @@ int bydb_comm_connect(bydb_ctx *ctx, int32_t rank, int32_t nranks, const bydb_co
     std::vector<bool> opened(static_cast<size_t>(nranks), false);
     std::vector<size_t> slots(static_cast<size_t>(nranks), 0);
     bool shares_device = false;  // another rank lives on this GPU (tests, a box with fewer GPUs than ranks)
+    unsigned char my_uuid[16];
+    {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
+        memcpy(my_uuid, prop.uuid.bytes, sizeof my_uuid);
+    }
     for (int r = 0; r < nranks; ++r) {
         CommBlob b;
         memcpy(&b, &all[r], sizeof b);
@@ -2678,7 +2702,7 @@ int bydb_comm_connect(bydb_ctx *ctx, int32_t rank, int32_t nranks, const bydb_co
         if (kCommCtl + 2 * static_cast<uint64_t>(nranks) * b.slot_bytes > b.mailbox_bytes)
             return fail(BYDB_EINVAL, "mailbox of rank " + std::to_string(r) + " was exported for fewer ranks");
         slots[r] = b.slot_bytes;
-        if (r != rank && static_cast<int>(b.device) == ctx->device) shares_device = true;
+        if (r != rank && memcmp(b.uuid, my_uuid, sizeof my_uuid) == 0) shares_device = true;
         if (r == rank) {
             if (b.raw_ptr != reinterpret_cast<uint64_t>(cm.mine)) return fail(BYDB_EINVAL, "handles[rank] is not this context's own handle");
             peer[r] = cm.mine;
@@ -2715,12 +2739,38 @@ int bydb_comm_connect(bydb_ctx *ctx, int32_t rank, int32_t nranks, const bydb_co
     // ranks that share a device must not make page-locked allocations inside a collective (ExecSlot::ensure_pinned): the
     // staging ring of the pageable cold path is made now
     if (shares_device && ensure_stage_ring(ctx) != 0) g_last_error.clear();
+    if (shares_device) {
+        // host-polled waits (see Comm::shared_device): the polling stream and its pinned words are made now
+        if (cudaStreamCreateWithFlags(&cm.poll_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaMallocHost(reinterpret_cast<void **>(&cm.poll_buf), sizeof(unsigned long long) * kCommMaxRanks) != cudaSuccess)
+            return fail(BYDB_EIO, "cannot create the polling stream of a shared-device collective");
+        cm.shared_device = true;
+    }
     return 0;
     });
 }
 
 // given: the parts to scan instead of q->parts (the host-buffer form); pre_rc: a failure that already happened on this
 // rank (its transient parts could not be admitted) -- the rank still takes part in the collective and reports it
+// Host-side form of comm_wait_kernel for ranks that share a device (Comm::shared_device): polls n words until all have reached
+// `epoch`; bounded like the kernel (60 s).  Returns 0 or kErrPeerTimeout.
+static uint32_t comm_wait_host(Comm &cm, const unsigned long long *dev_words, uint32_t n, unsigned long long epoch) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t spins = 0;; ++spins) {
+        if (cudaMemcpyAsync(cm.poll_buf, dev_words, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, cm.poll_stream) != cudaSuccess ||
+            cudaStreamSynchronize(cm.poll_stream) != cudaSuccess) {
+            cudaGetLastError();
+            return kErrPeerTimeout;
+        }
+        bool all = true;
+        for (uint32_t i = 0; i < n; ++i) all = all && cm.poll_buf[i] >= epoch;
+        if (all) return 0;
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60)) return kErrPeerTimeout;
+        if (spins > 64) std::this_thread::sleep_for(std::chrono::microseconds(20));
+        else std::this_thread::yield();
+    }
+}
+
 static int scan_reduce_impl(bydb_ctx *ctx, const bydb_query *q, const std::vector<std::shared_ptr<Part>> *given, int pre_rc, uint64_t h2d_pre, int32_t root,
                             bydb_result *out) {
     {
@@ -2761,7 +2811,11 @@ static int scan_reduce_impl(bydb_ctx *ctx, const bydb_query *q, const std::vecto
     // consumed by the root (its `done` word only ever grows) before they are overwritten
     const uint64_t prev_use = cm.last_use[2 * static_cast<size_t>(root) + parity];
     cm.last_use[2 * static_cast<size_t>(root) + parity] = epoch;
-    if (prev_use) launch_comm_wait(done, 1, prev_use, my_err, kErrPeerTimeout, s);
+    uint32_t host_perr = 0;  // outcome of the host-polled waits (shared-device mode)
+    if (prev_use) {
+        if (cm.shared_device) host_perr = comm_wait_host(cm, done, 1, prev_use);
+        else launch_comm_wait(done, 1, prev_use, my_err, kErrPeerTimeout, s);
+    }
     // map: this rank's group_reduce writes the table straight into the root's memory (P2P stores over NVLink)
     if (!rc) rc = run_scan(ctx, q, plan, es, s, my_slot, tl, &out->stats);
     const std::string my_msg = rc ? g_last_error : std::string();
@@ -2773,7 +2827,12 @@ static int scan_reduce_impl(bydb_ctx *ctx, const bydb_query *q, const std::vecto
     int frc = 0;
     if (cm.rank == root) {
         // reduce: wait for every rank's table, combine in rank order (deterministic float sums), finalise
-        launch_comm_wait(flags, static_cast<uint32_t>(cm.nranks), epoch, my_err, kErrPeerTimeout, s);
+        if (cm.shared_device) {
+            const uint32_t e2 = comm_wait_host(cm, flags, static_cast<uint32_t>(cm.nranks), epoch);  // own flag included: own table is complete
+            host_perr = host_perr ? host_perr : e2;
+        } else {
+            launch_comm_wait(flags, static_cast<uint32_t>(cm.nranks), epoch, my_err, kErrPeerTimeout, s);
+        }
         if (!rc) {
             launch_combine_tables(reinterpret_cast<uint64_t *>(slots0), static_cast<uint32_t>(cm.nranks), tl.total / 8, tl.off_sum_f64 / 8, tl.off_max_f64 / 8,
                                   tl.off_max_f64 / 8, tl.off_sum_i64 / 8, tl.off_sum_i64 / 8, tl.off_max_i64 / 8, tl.off_max_i64 / 8, tl.total / 8, s,
@@ -2790,6 +2849,7 @@ static int scan_reduce_impl(bydb_ctx *ctx, const bydb_query *q, const std::vecto
     cudaStreamSynchronize(s);
     uint32_t perr = 0;
     if (cudaMemcpy(&perr, my_err, sizeof perr, cudaMemcpyDeviceToHost) == cudaSuccess && perr != 0) cudaMemset(my_err, 0, sizeof perr);
+    if (!perr) perr = host_perr;
     // ---- outcome, most specific first: this rank's own host-side failure, its device-side scan error, a peer's failure
     if (rc) {
         if (finalized) bydb_result_free(ctx, out);
@@ -2833,7 +2893,7 @@ int bydb_scan_reduce_prepared(bydb_ctx *ctx, bydb_prepared *p, int32_t root, byd
     CUDA_TRY(cudaSetDevice(ctx->device));
     g_last_dev_err = 0;
     const uint64_t run = p->reduce_runs++;
-    if (run == 0 || !p->reduce_capturable) return scan_reduce_impl(ctx, &p->q, nullptr, 0, 0, root, out);
+    if (run == 0 || !p->reduce_capturable || cm.shared_device) return scan_reduce_impl(ctx, &p->q, nullptr, 0, 0, root, out);
     std::unique_lock<std::mutex> lk(cm.mu);
     const uint64_t epoch = cm.epoch + 1;
     const size_t parity = static_cast<size_t>(epoch & 1u);
