@@ -342,6 +342,84 @@ BYDB_LANE_FN void swar_tail(uint32_t lw, uint32_t &accv, uint32_t &sh, int32_t &
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// SWAR sum decoder under a row mask (delta_page_sum_masked in scan_kernels.cu): SUM / MEAN / COUNT over the ACTIVE rows only.
+//     sum over active rows r of value_r  =  A * first + sum_j d_j * W_j ,   W_j = number of active rows >= j,
+// so the byte weights of the all-rows decoder,  (n - 1) - #terminators before the byte,  become
+//     (A - a_0) - #ACTIVE terminators before the byte
+// (A = active rows, a_0 = row 0 active): the same dot products with the rank taken over active terminators only.  The lane
+// brings the activity of the rows that end in it as a bit string (bit i = i-th terminator of the lane is an active row); per
+// word the next <= 4 bits are deposited onto the word's terminator bytes with one byte gather (PRMT): byte j takes bit e_j of
+// the nibble, e_j = terminators before byte j inside the word.
+// ------------------------------------------------------------------------------------------------
+struct SwarMasked {
+    int32_t T0, T1, T2, R0, R1, R2;
+    uint32_t wide;
+    int32_t nact;      // 1 + ACTIVE terminators seen so far in this lane
+    uint32_t prev_w;
+    uint32_t aw_lo, aw_hi;  // activity bits of the terminators still to come in this lane
+};
+BYDB_LANE_FN void swar_masked_begin(SwarMasked &s, uint32_t prev_w, uint32_t aw_lo, uint32_t aw_hi) {
+    s.T0 = s.T1 = s.T2 = s.R0 = s.R1 = s.R2 = 0;
+    s.wide = 0;
+    s.nact = 1;
+    s.prev_w = prev_w;
+    s.aw_lo = aw_lo;
+    s.aw_hi = aw_hi;
+}
+template <bool kMasked>
+BYDB_LANE_FN void swar_masked_word(SwarMasked &s, uint32_t w_in, uint32_t vm) {
+    const uint32_t w = kMasked ? (w_in & vm) : w_in;
+    const uint32_t pw = s.prev_w;
+    const uint32_t p = w & 0x7f7f7f7fu;
+    const uint32_t M1 = lane_prmt(w, pw, 0xA98Fu);
+    const uint32_t M2 = lane_prmt(w, pw, 0x98FEu);
+    const uint32_t sb = imad_u32(w, 128u, 0u);
+    const uint32_t psb = imad_u32(pw, 128u, 0u);
+    const uint32_t S0 = lane_prmt(sb, 0u, 0xBA98u);
+    const uint32_t S1 = lane_prmt(sb, psb, 0xA98Fu);
+    const uint32_t S2 = lane_prmt(sb, psb, 0x98FEu);
+    const uint32_t S12 = (M2 & S2) | (~M2 & S1);
+    const uint32_t x0 = (p ^ S0) & ~M1;
+    const uint32_t p1 = p & M1 & ~M2;
+    const uint32_t q2 = w & M1 & M2;
+    const uint32_t wT = S12 | 0x01010101u;
+    uint32_t t01 = ~mulhi_u32(w, 1u << 25) & 0x01010101u;  // 1 where the byte terminates a varint
+    if (kMasked) t01 &= vm;
+    // ---- the word's terminators that are active rows: byte j <- bit e_j of the next activity bits
+    const uint32_t e = imad_u32(t01, 0x01010100u, 0u);                  // byte j = terminators before byte j inside the word (0..3)
+    const uint32_t a4 = imad_u32(s.aw_lo & 15u, 0x00204081u, 0u) & 0x01010101u;  // bits 0..3 of the activity string as four 0/1 bytes
+    // the e_j (<= 3 each) as selector nibbles: x = e | e >> 4 holds (e_0, e_1) in byte 0 and (e_2, e_3) in byte 2
+    const uint32_t sel = lane_prmt(e | (e >> 4), 0u, 0x4420u);
+    const uint32_t a01 = lane_prmt(a4, 0u, sel) & t01;                  // 1 where an ACTIVE row ends
+    const uint32_t ntw = (e >> 24) + (t01 >> 24);                       // terminators in this word (bytes 0..2, plus byte 3)
+    // shift the activity string by the terminators consumed (<= 4)
+    const uint64_t aw = ((static_cast<uint64_t>(s.aw_hi) << 32) | s.aw_lo) >> ntw;
+    s.aw_lo = static_cast<uint32_t>(aw);
+    s.aw_hi = static_cast<uint32_t>(aw >> 32);
+    const uint32_t base = imad_u32(static_cast<uint32_t>(s.nact), 0x01010101u, 0u);
+    const uint32_t rinc = imad_u32(a01, 0x01010101u, base);    // inclusive active count + 1
+    const uint32_t rank1 = imad_u32(a01, 0xffffffffu, rinc);   // exclusive active count + 1
+    s.nact = dp4a_su(0x01010101u, a01, s.nact);
+    const uint32_t wR = imad_u32(S12 & 0x01010101u, 1u, rank1 ^ S12);
+    s.T0 = dp4a_su(x0, 0x01010101u, s.T0);
+    s.R0 = dp4a_su(x0, rank1, s.R0);
+    s.T1 = dp4a_us(p1, wT, s.T1);
+    s.R1 = dp4a_us(p1, wR, s.R1);
+    s.T2 = dp4a_us(q2, wT, s.T2);
+    s.R2 = dp4a_us(q2, wR, s.R2);
+    s.wide |= q2;
+    s.prev_w = w;
+}
+// -> ACTIVE terminators of the lane; T and R' (active ranks)
+BYDB_LANE_FN uint32_t swar_masked_end(const SwarMasked &s, int32_t &T, int32_t &Rp) {
+    T = (s.T0 >> 1) + 64 * s.T1 + 8192 * s.T2;
+    Rp = (s.R0 >> 1) + 64 * s.R1 + 8192 * s.R2;
+    return static_cast<uint32_t>(s.nact - 1);
+}
+// terminators among the 64 bytes of a lane (first pass: the lanes' row offsets must be known before the activity bits can be cut)
+BYDB_LANE_FN uint32_t count_terminators(uint32_t w, uint32_t vm) { return lane_popc(~w & 0x80808080u & vm); }
+
 // 4 bits -> 4 byte masks (bit j -> 0xff in byte j): bit j times 2^(7j) lands on bit 8j, nothing else does
 BYDB_LANE_FN uint32_t expand4(uint32_t n) { return (((n & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu; }
 

@@ -828,6 +828,147 @@ __device__ __noinline__ int delta_page_sum_all(WarpSmem *sm, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// SWAR sum decoder under a row mask / time range: SUM / MEAN / COUNT of an EncodeTypeDelta page over the ACTIVE rows, without
+// decoding a value (lane_decode.cuh: swar_masked_word).  Two passes per 2 KB chunk: (1) the lanes' terminator counts -- a lane
+// must know the rows that end in it before it can cut their activity bits out of the row mask; (2) the byte-linear sums with the
+// rank taken over active terminators.  Lane contribution: ((A - a_0) - active terminators before the lane + 1) * T - R'.
+// One hot loop, like delta_page_sum_all.  Returns like delta_page_fast.
+// ------------------------------------------------------------------------------------------------
+template <int kMode>
+__device__ __noinline__ int delta_page_sum_masked(WarpSmem *sm, int lane) {
+    static_assert(kMode != kRowsAll, "every row active: delta_page_sum_all");
+    const uint8_t *body = sm->a_body;
+    const uint32_t len = sm->a_len, count = sm->a_count, r0 = sm->a_r0, r1 = sm->a_r1;
+    const int64_t first = sm->a_first;
+    uint32_t A_total, a0;
+    if (kMode == kRowsRange) {
+        A_total = r1 - r0 + 1u;
+        a0 = r0 == 0 ? 1u : 0u;
+    } else {
+        uint32_t c = 0;
+        for (uint32_t w = lane; w < ((count + 31u) >> 5); w += 32) c += __popc(sm->mask[w]);
+        A_total = __reduce_add_sync(0xffffffffu, c);
+        a0 = sm->mask[0] & 1u;
+    }
+    AggAcc acc;
+    acc.init();
+    if (lane == 0) {
+        acc.add_scaled(first, A_total);
+        acc.cnt = A_total;
+    }
+    if (len == 0) {
+        publish_acc(sm, acc, lane);
+        return count == 1 ? 0 : 2;
+    }
+    PageStream st;
+    stream_open(st, sm, body, len, lane);
+    const uint32_t nchunks = (st.total + kSwarChunkBytes - 1) / kSwarChunkBytes;
+    constexpr uint32_t kChunksPerStage = kStageBytes / kSwarChunkBytes;
+    int64_t S = 0;
+    uint32_t tb = 0, atb = 0, carry_w = 0, last_byte = 0;
+    const uint8_t *buf = nullptr;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const uint32_t k = c / kChunksPerStage;
+        if ((c % kChunksPerStage) == 0) buf = stream_wait(st, sm, k);
+        const uint32_t o = c * kSwarChunkBytes + lane * kSwarLaneBytes;
+        const bool interior = c * kSwarChunkBytes >= st.pstart && (c + 1) * kSwarChunkBytes <= st.pend;  // warp-uniform
+        const uint8_t *src = buf + (o % kStageBytes);
+        int lo_i = static_cast<int>(st.pstart) - static_cast<int>(o);
+        int hi_i = static_cast<int>(st.pend) - static_cast<int>(o);
+        lo_i = lo_i < 0 ? 0 : (lo_i > 64 ? 64 : lo_i);
+        hi_i = hi_i < 0 ? 0 : (hi_i > 64 ? 64 : hi_i);
+        const uint32_t va = interior ? 0xffffffffu : (low_bits(hi_i > 32 ? 32 : hi_i) & ~low_bits(lo_i > 32 ? 32 : lo_i));
+        const uint32_t vb = interior ? 0xffffffffu : (low_bits(hi_i > 32 ? hi_i - 32 : 0) & ~low_bits(lo_i > 32 ? lo_i - 32 : 0));
+        // ---- pass 1: terminators of the lane -> its first row
+        uint32_t n_all = 0, lastw = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 w = make_uint4(0, 0, 0, 0);
+            if (interior || o + 16 * q < st.total) w = *reinterpret_cast<const uint4 *>(src + 16 * q);
+            const uint32_t v = (q < 2 ? va : vb) >> (16 * (q & 1));
+            n_all += count_terminators(w.x, expand4(v)) + count_terminators(w.y, expand4(v >> 4)) + count_terminators(w.z, expand4(v >> 8)) +
+                     count_terminators(w.w, expand4(v >> 12));
+            if (q == 3) lastw = w.w & expand4(v >> 12);
+        }
+        uint32_t n_in = n_all;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const uint32_t on = __shfl_up_sync(0xffffffffu, n_in, sft);
+            if (lane >= sft) n_in += on;
+        }
+        const uint32_t row0 = 1u + tb + n_in - n_all;
+        unsigned long long aw;
+        const unsigned long long nbits = n_all >= 64 ? ~0ull : ((1ull << n_all) - 1ull);
+        if (kMode == kRowsRange) {
+            const uint32_t a = r0 > row0 ? min(r0 - row0, 64u) : 0u;
+            const uint32_t b = r1 + 1u > row0 ? min(r1 + 1u - row0, 64u) : 0u;
+            const unsigned long long mb = b >= 64 ? ~0ull : ((1ull << b) - 1ull), ma = a >= 64 ? ~0ull : ((1ull << a) - 1ull);
+            aw = mb & ~ma & nbits;
+        } else {
+            const uint32_t wi = min(row0 >> 5, static_cast<uint32_t>(kMaskWords));
+            const uint32_t m0 = sm->mask[wi], m1 = sm->mask[wi + 1], m2 = sm->mask[wi + 2];
+            const uint32_t sft = row0 & 31u;
+            aw = (static_cast<unsigned long long>(__funnelshift_r(m1, m2, sft)) << 32 | __funnelshift_r(m0, m1, sft)) & nbits;
+        }
+        uint32_t pw = __shfl_up_sync(0xffffffffu, lastw, 1);
+        if (lane == 0) pw = carry_w;
+        carry_w = __shfl_sync(0xffffffffu, lastw, 31);
+        // ---- pass 2: byte-linear sums, ranks over the active terminators
+        SwarMasked sl;
+        swar_masked_begin(sl, pw, static_cast<uint32_t>(aw), static_cast<uint32_t>(aw >> 32));
+        if (interior) {
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                const uint4 w = *reinterpret_cast<const uint4 *>(src + 16 * q);
+                swar_masked_word<false>(sl, w.x, 0u);
+                swar_masked_word<false>(sl, w.y, 0u);
+                swar_masked_word<false>(sl, w.z, 0u);
+                swar_masked_word<false>(sl, w.w, 0u);
+            }
+        } else {
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                uint4 w = make_uint4(0, 0, 0, 0);
+                if (o + 16 * q < st.total) w = *reinterpret_cast<const uint4 *>(src + 16 * q);
+                const uint32_t v = (q < 2 ? va : vb) >> (16 * (q & 1));
+                swar_masked_word<true>(sl, w.x, expand4(v));
+                swar_masked_word<true>(sl, w.y, expand4(v >> 4));
+                swar_masked_word<true>(sl, w.z, expand4(v >> 8));
+                swar_masked_word<true>(sl, w.w, expand4(v >> 12));
+            }
+        }
+        if (__any_sync(0xffffffffu, (sl.wide & 0x80808080u) != 0)) {
+            stream_drain(st, sm, k);
+            if (lane == 0) sm->seq = st.seq0 + min(st.nstages, k + static_cast<uint32_t>(kStages));
+            __syncwarp();
+            return 1;
+        }
+        int32_t T, Rp;
+        const uint32_t na = swar_masked_end(sl, T, Rp);
+        uint32_t a_in = na;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const uint32_t on = __shfl_up_sync(0xffffffffu, a_in, sft);
+            if (lane >= sft) a_in += on;
+        }
+        const int64_t A1a = static_cast<int64_t>(A_total - a0) - static_cast<int64_t>(atb) - static_cast<int64_t>(a_in - na) + 1;
+        S += A1a * static_cast<int64_t>(T) - static_cast<int64_t>(Rp);
+        tb += __shfl_sync(0xffffffffu, n_in, 31);
+        atb += __shfl_sync(0xffffffffu, a_in, 31);
+        if (c == nchunks - 1 && lane == 0) last_byte = buf[(st.pend - 1) % kStageBytes];
+        if ((c % kChunksPerStage) == kChunksPerStage - 1 || c == nchunks - 1) stream_release(st, sm, k, lane);
+    }
+    {
+        const uint64_t us = static_cast<uint64_t>(S);
+        acc.lo += us;
+        acc.hi += (S >> 63) + (acc.lo < us ? 1 : 0);
+    }
+    publish_acc(sm, acc, lane);
+    last_byte = __shfl_sync(0xffffffffu, last_byte, 0);
+    return (tb + 1 == count && last_byte < 0x80u) ? 0 : 2;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Sparse masked decode of an EncodeTypeDelta page (row predicate and / or time range, narrow deltas): the selective pass.
 // With a dictionary predicate that keeps one row in eight, in runs, two thirds of the 64-byte lane windows of a field page hold
 // no active row at all; the serial decoder (delta_page_fast) still walks every byte of every window because the next window's
@@ -1741,6 +1882,12 @@ __device__ __noinline__ int delta_pred_fast(WarpSmem *sm, int lane) {
 constexpr uint32_t kDeferSlow = 0xffffffffu;
 
 template <int kMode>
+__device__ __forceinline__ int masked_sum_dispatch(WarpSmem *sm, int lane) {
+    if constexpr (kMode == kRowsAll) return 2;  // not reached
+    else return delta_page_sum_masked<kMode>(sm, lane);
+}
+
+template <int kMode>
 __device__ __forceinline__ int sparse_dispatch(WarpSmem *sm, uint32_t need, int lane) {
     if constexpr (kMode == kRowsAll) {
         return 2;  // not reached: every-row pages take delta_page_sum_all / delta_page_fast
@@ -1807,6 +1954,7 @@ __device__ __noinline__ uint32_t agg_field_page(WarpSmem *sm, int lane) {
         __syncwarp();
         if (enc == 3) {
             if (need == kNeedSum && kMode == kRowsAll) rc = delta_page_sum_all(sm, lane);
+            else if (need == kNeedSum && kMode != kRowsAll && kFastLane && BYDB_MASKED_SWAR) rc = masked_sum_dispatch<kMode>(sm, lane);
             else if (kMode != kRowsAll && kFastLane && BYDB_SPARSE) rc = sparse_dispatch<kMode>(sm, need, lane);
             else if (need == kNeedSum) rc = delta_page_fast<kMode, kNeedSum>(sm, lane);
             else if (need == kNeedMinMax) rc = delta_page_fast<kMode, kNeedMinMax>(sm, lane);

@@ -308,6 +308,105 @@ static bool sparse_page_check(std::mt19937_64 &rng, int n_values, int density_pc
     return true;
 }
 
+// ---- SWAR sum under a row mask (swar_masked_*): a page emulated the way delta_page_sum_masked walks it -- first the lanes' terminator
+// counts (row offsets), then the words with the rank taken over ACTIVE terminators -- against the plain masked sum.
+static bool swar_masked_page_check(std::mt19937_64 &rng, int n_values, int density_pct) {
+    std::vector<int64_t> d;
+    const uint32_t pstart = static_cast<uint32_t>(rng() % 16);
+    std::vector<uint8_t> win(pstart);
+    for (auto &x : win) x = static_cast<uint8_t>(rng());
+    for (int i = 0; i < n_values; ++i) {
+        const int L = 1 + static_cast<int>(rng() % 3);
+        uint32_t u = static_cast<uint32_t>(rng()) & ((1u << (7 * L)) - 1u);
+        if (L > 1 && (u >> (7 * (L - 1))) == 0) u |= 1u << (7 * (L - 1));
+        if (rng() % 7 == 0) u &= ~0x3f80u;
+        if (L > 1 && (u >> (7 * (L - 1))) == 0) u |= 1u << (7 * (L - 1));
+        d.push_back(zz(u));
+        for (int k = 0; k < L; ++k) win.push_back(static_cast<uint8_t>(((u >> (7 * k)) & 0x7f) | (k < L - 1 ? 0x80 : 0)));
+    }
+    const uint32_t pend = static_cast<uint32_t>(win.size());
+    while (win.size() % 16) win.push_back(static_cast<uint8_t>(rng()));
+    const uint32_t total = static_cast<uint32_t>(win.size());
+    win.resize(win.size() + 2048, 0xAB);
+    const int64_t first = static_cast<int64_t>(rng() % 2000001) - 1000000;
+    std::vector<uint8_t> act(n_values + 1 + 128, 0);
+    for (size_t r = 0; r < static_cast<size_t>(n_values) + 1;) {
+        const size_t run = 1 + rng() % 40;
+        const bool on = static_cast<int>(rng() % 100) < density_pct;
+        for (size_t k = 0; k < run && r < static_cast<size_t>(n_values) + 1; ++k) act[r++] = on;
+    }
+    int64_t want = 0, A_total = 0, v = first;
+    for (int r = 0; r <= n_values; ++r) {
+        if (r > 0) v += d[r - 1];
+        if (act[r]) {
+            want += v;
+            A_total++;
+        }
+    }
+    int64_t S = 0;
+    uint32_t row_base = 1, atb = 0, carry_w = 0;
+    const uint32_t nchunks = (total + 2047) / 2048;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const bool interior = c * 2048 >= pstart && (c + 1) * 2048 <= pend;
+        uint32_t lastw[32], nall[32], nact[32];
+        int32_t T[32], Rp[32];
+        uint64_t valid[32];
+        uint32_t w[32][16];
+        for (int lane = 0; lane < 32; ++lane) {
+            const uint32_t o = c * 2048 + lane * 64;
+            for (int k = 0; k < 16; ++k) {
+                w[lane][k] = 0;
+                if (o + 4 * k < total) memcpy(&w[lane][k], &win[o + 4 * k], 4);
+            }
+            int lo_i = static_cast<int>(pstart) - static_cast<int>(o), hi_i = static_cast<int>(pend) - static_cast<int>(o);
+            lo_i = lo_i < 0 ? 0 : (lo_i > 64 ? 64 : lo_i);
+            hi_i = hi_i < 0 ? 0 : (hi_i > 64 ? 64 : hi_i);
+            valid[lane] = (hi_i >= 64 ? ~0ull : ((1ull << hi_i) - 1ull)) & ~(lo_i >= 64 ? ~0ull : ((1ull << lo_i) - 1ull));
+            nall[lane] = 0;
+            for (int k = 0; k < 16; ++k) nall[lane] += count_terminators(w[lane][k], interior ? 0xffffffffu : expand4(static_cast<uint32_t>(valid[lane] >> (4 * k))));
+        }
+        uint32_t lb = 0;
+        for (int lane = 0; lane < 32; ++lane) {
+            const uint32_t row0 = row_base + lb;
+            uint64_t aw = 0;
+            for (uint32_t i = 0; i < nall[lane] && i < 64; ++i) aw |= static_cast<uint64_t>(act[row0 + i]) << i;
+            SwarMasked sl;
+            swar_masked_begin(sl, lane == 0 ? carry_w : lastw[lane - 1], static_cast<uint32_t>(aw), static_cast<uint32_t>(aw >> 32));
+            for (int k = 0; k < 16; ++k) {
+                if (interior) swar_masked_word<false>(sl, w[lane][k], 0xffffffffu);
+                else swar_masked_word<true>(sl, w[lane][k], expand4(static_cast<uint32_t>(valid[lane] >> (4 * k))));
+            }
+            lastw[lane] = sl.prev_w;
+            nact[lane] = swar_masked_end(sl, T[lane], Rp[lane]);
+            if ((sl.wide & 0x80808080u) != 0) {
+                std::printf("FAIL masked swar: narrow page flagged wide\n");
+                return false;
+            }
+            if (nact[lane] != static_cast<uint32_t>(__builtin_popcountll(aw))) {
+                std::printf("FAIL masked swar: active terminators %u vs %d (chunk %u lane %d)\n", nact[lane], __builtin_popcountll(aw), c, lane);
+                return false;
+            }
+            lb += nall[lane];
+        }
+        carry_w = lastw[31];
+        uint32_t alb = 0;
+        for (int lane = 0; lane < 32; ++lane) {
+            const int64_t A1a = (A_total - act[0]) - static_cast<int64_t>(atb) - static_cast<int64_t>(alb) + 1;
+            S += A1a * static_cast<int64_t>(T[lane]) - static_cast<int64_t>(Rp[lane]);
+            alb += nact[lane];
+        }
+        atb += alb;
+        row_base += lb;
+    }
+    const int64_t got = A_total * first + S;
+    if (row_base != static_cast<uint32_t>(n_values) + 1 || got != want || static_cast<int64_t>(atb) + act[0] != A_total) {
+        std::printf("FAIL masked swar page: n_values=%d pstart=%u rows=%u got=%lld want=%lld active=%u/%lld\n", n_values, pstart, row_base,
+                    static_cast<long long>(got), static_cast<long long>(want), atb + act[0], static_cast<long long>(A_total));
+        return false;
+    }
+    return true;
+}
+
 int main() {
     std::mt19937_64 rng(20260922);
     long n = 0;
@@ -360,6 +459,10 @@ int main() {
     for (int it = 0; it < 3000; ++it) {
         const int nv = it < 50 ? it : 1 + static_cast<int>(rng() % 9000);
         if (!sparse_page_check(rng, nv, it % 3 == 0 ? 12 : (it % 3 == 1 ? 50 : 100))) return 1;
+    }
+    for (int it = 0; it < 3000; ++it) {
+        const int nv = it < 50 ? it : 1 + static_cast<int>(rng() % 9000);
+        if (!swar_masked_page_check(rng, nv, it % 4 == 0 ? 12 : (it % 4 == 1 ? 50 : (it % 4 == 2 ? 100 : 0)))) return 1;
     }
     std::printf("OK %ld lane decodes\n", n);
     return 0;
